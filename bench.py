@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — MuRaL-snv genome-wide predict (BASELINE.json configs[1]) on N B200s.
+
+Workload: synthetic 100 Mb genome (4 x 25 Mb, iid ACGT, seed 1234, N runs at chromosome ends and 20 random
+5 kb N runs per chromosome, seed 1235), sites = every A ('+') / T ('-') in genomic order,
+Network2 with the shipped Homo_sapiens/SNV/AT weights (tests/golden/snv_hs_AT.npz; local ±7 bp 3-mers,
+expanded ±1 kb, C=32), one *step* = the hot path (gather -> network -> log-probs) over one batch of
+`--sites-per-step` consecutive sites.  Each rank owns a contiguous genomic interval (no collectives on the
+data path; weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|bf16] [--impl reference]
+
+`value`  : sites/s with the site records already in HBM (device-timed with CUDA events per step, max over ranks)
+`e2e`    : sites/s through the C-ABI host entry point (pinned host buffers, H2D + D2H inside the timed region)
+`roofline`: dominant kernel (the Conv1d stack) — algorithmic FLOPs per launch / mean launch duration from the
+            library's own CUDA-event profile of a second, identical pass
+`cpu_baseline` / `--impl reference`: the oracle port of the reference CPU path (numpy encoders + torch CPU fp32
+            network, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHROM_LEN = 25_000_000
+N_CHROM = 4
+FLOP_STACK = 6_352_896 + 43_112       # stage-S forward FLOPs/site at L=2001
+FLOP_CONV_ONLY = 6_352_896
+
+
+# ------------------------------------------------------------------------------------------ workload
+def synth_chromosome(ci):
+    rng = np.random.default_rng(1234 + ci)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, CHROM_LEN, dtype=np.uint8)]
+    seq = seq.copy()
+    seq[:10_000] = ord("N"); seq[-10_000:] = ord("N")
+    r2 = np.random.default_rng(1235 + ci)
+    for s in r2.integers(20_000, CHROM_LEN - 30_000, 20):
+        seq[s:s + 5_000] = ord("N")
+    return seq
+
+
+def rank_sites(chroms, rank, world, need):
+    """First `need` A/T sites of this rank's genomic interval -> (pos int32, meta int32)."""
+    from mural_b200.data import pack_meta
+    N_CHROM = len(chroms)
+    total = CHROM_LEN * N_CHROM
+    lo = total * rank // world
+    pos_l, meta_l, got = [], [], 0
+    g = lo
+    while got < need:
+        ci, off = (g // CHROM_LEN) % N_CHROM, g % CHROM_LEN
+        span = min(CHROM_LEN - off, int((need - got) * 2.2) + 100_000)
+        sl = chroms[ci][off:off + span]
+        isA, isT = sl == ord("A"), sl == ord("T")
+        idx = np.flatnonzero(isA | isT)[: need - got]
+        pos_l.append((idx + off).astype(np.int32))
+        meta_l.append(pack_meta(isT[idx].astype(np.int64), np.zeros(len(idx), np.int64), np.full(len(idx), ci)))
+        got += len(idx)
+        g = (g + span) % total
+    return np.concatenate(pos_l), np.concatenate(meta_l)
+
+
+def load_weights():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "snv_hs_AT.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    state = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    return cfg, state, int(z["n_cat"])
+
+
+def build_model(cfg, state, n_cat, mode):
+    import torch
+    from mural_b200 import model_choice
+    common = dict(emb_dims=[(65, 2)] * n_cat, n_cont=0, n_class=cfg["n_class"], distal_order=1, in_channels=4)
+    m = model_choice(2, cfg, common, "snv")
+    sd = m.state_dict()
+    alias = {"1": "bn1", "2": "conv1", "4": "bn2", "5": "conv2"}
+    for k in sd:
+        src = k
+        if ".layer." in k:
+            head, rest = k.split(".layer.")
+            src = head + "." + alias[rest.split(".")[0]] + "." + rest.split(".", 1)[1]
+        sd[k] = torch.from_numpy(np.asarray(state[src]))
+    m.load_state_dict(sd, strict=True)
+    m.to("cuda").eval()
+    m.compute_mode = mode
+    return m
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
+    """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
+    import torch
+    from oracle import encode_np as E
+    from oracle import network_t as NT
+    torch.set_num_threads(os.cpu_count())
+    comp_lut = E._ASCII2SYM
+    syms = {}
+    t0 = time.perf_counter()
+    n = len(pos)
+    out = []
+    with torch.no_grad():
+        for b0 in range(0, n, batch):
+            p, mt = pos[b0:b0 + batch], meta[b0:b0 + batch]
+            ch = mt >> 8
+            cat = np.empty((len(p), 2 * cfg["local_radius"] + 1 - (cfg["local_order"] - 1)), np.int64)
+            oh = np.empty((len(p), 4, 2 * cfg["distal_radius"] + 1), np.float32)
+            for c in np.unique(ch):
+                if c not in syms:
+                    syms[c] = comp_lut[chroms[c]]
+                m = ch == c
+                cat[m] = E.kmer_windows(syms[c], p[m], mt[m] & 1, cfg["local_radius"], cfg["local_order"])
+                oh[m] = E.onehot_windows(syms[c], p[m], mt[m] & 1, cfg["distal_radius"])
+            out.append(NT.network2_forward(state, cat, oh, torch.float32))
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mural_b200", choices=["mural_b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("MURAL_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--sites-per-step", type=int, default=262144)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg, state, n_cat = load_weights()
+    workload = ("MuRaL-snv genome-wide predict, Homo_sapiens/SNV/AT weights, synthetic 100 Mb genome (4x25 Mb), "
+                "every A(+)/T(-) site, local 7bp 3-mers + expanded 1 Kb (L=2001), C=32, n_class=4")
+    base_cfg = {"workload": workload, "sites_per_step_per_gpu": a.sites_per_step, "parallelism": "interval-sharded x%d" % world}
+
+    # -------------------------------------------------------------------- reference arm (CPU oracle port)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        chroms = [synth_chromosome(0)]                # the bounded sample lives on the first chromosome
+        per_step = min(a.cpu_sample, a.sites_per_step)
+        pos, meta = rank_sites(chroms, 0, 1, per_step * (a.steps + a.warmup))
+        for w in range(a.warmup):
+            cpu_port_sites_per_sec(chroms, pos[w * per_step:(w + 1) * per_step][:2048], meta[w * per_step:(w + 1) * per_step][:2048], cfg, state)
+        t = 0.0
+        for s in range(a.warmup, a.warmup + a.steps):
+            _, dt = cpu_port_sites_per_sec(chroms, pos[s * per_step:(s + 1) * per_step], meta[s * per_step:(s + 1) * per_step], cfg, state)
+            t += dt
+        v = per_step * a.steps / t
+        line = {"impl": "reference", "metric": "sites/sec (predict)", "value": v, "unit": "sites/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": dict(base_cfg, sites_per_step_per_gpu=per_step),
+                "cpu_baseline": {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "%d consecutive A/T sites of chr0 per step, batch 1024, numpy encoders + torch CPU fp32" % per_step},
+                "e2e": {"value": v, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # -------------------------------------------------------------------- mural_b200 arm
+    import torch
+    import torch.distributed as dist
+    from mural_b200 import PackedGenome, SiteBatch, _lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = _lib.lib()
+    mode = a.mode
+    if mode == "auto":
+        mode = "probe"
+    chroms = [synth_chromosome(ci) for ci in range(N_CHROM)]
+    genome = PackedGenome({"chr%d" % (i + 1): c.tobytes() for i, c in enumerate(chroms)})
+    S, K, W = a.sites_per_step, a.steps, a.warmup
+    pos, meta = rank_sites(chroms, rank, world, S * (K + W))
+    model = build_model(cfg, state, n_cat, "fp32" if mode == "probe" else mode)
+    if mode == "probe":
+        model.refresh()
+        mode = "bf16" if L.mural_snv_tc_available(model._h) == 1 else "fp32"
+        model.compute_mode = mode
+    d_pos, d_meta = torch.from_numpy(pos).cuda(), torch.from_numpy(meta).cuda()
+    out = torch.empty((S, cfg["n_class"]), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        _lib.check(L.mural_snv_forward(model._h, genome.handle, C.c_void_p(d_pos.data_ptr() + 4 * i * S),
+                                       C.c_void_p(d_meta.data_ptr() + 4 * i * S), S, _lib.MODES[mode], _lib.ptr(out),
+                                       C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model.refresh()
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    L.mural_reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)                       # L2 flush (256 MiB write), outside the per-step event pair
+        ev[i][0].record(stream)
+        step(W + i)
+        ev[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = int(L.mural_launch_count())
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * S * K / (dev_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI host entry point
+    h_pos = torch.from_numpy(pos).pin_memory(); h_meta = torch.from_numpy(meta).pin_memory()
+    h_out = torch.empty((S, cfg["n_class"]), dtype=torch.float32).pin_memory()
+
+    def step_host(i):
+        _lib.check(L.mural_snv_predict_host(model._h, genome.handle, C.c_void_p(h_pos.data_ptr() + 4 * i * S),
+                                            C.c_void_p(h_meta.data_ptr() + 4 * i * S), S, _lib.MODES[mode], _lib.ptr(h_out),
+                                            C.c_void_p(stream.cuda_stream)))
+    for i in range(min(W, 2)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_host(W + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * S * K / float(te.item())
+
+    # ---- roofline of the dominant kernel: library-side CUDA-event profile over an identical pass
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(L, step, W, K, S, mode, cfg, barrier)
+    line = {"metric": "sites/sec (predict)", "value": value, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
+            "config": dict(base_cfg, mode=mode, l2="flushed between steps (256 MiB write outside the per-step CUDA-event pairs); "
+                           "per-step activation workspace > L2", wall_s_timed_region=t_wall),
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
+            "roofline": roof}
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:
+            n_s = a.cpu_sample
+            v, dt = cpu_port_sites_per_sec(chroms, pos[:n_s], meta[:n_s], cfg, state)
+            line["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "first %d sites of the step-0 batch, batch 1024, numpy encoders + torch CPU fp32 (%.1f s)" % (n_s, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def kernel_roofline(L, step, W, K, S, mode, cfg, barrier):
+    if not hasattr(L, "mural_profile_begin"):
+        return None
+    peaks = {}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    src = "measured"
+    if os.path.exists(p):
+        peaks = json.load(open(p))
+    else:
+        peaks, src = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+    L.mural_profile_begin()
+    for i in range(K):
+        step(W + i)
+    barrier()
+    buf = C.create_string_buffer(1 << 16)
+    L.mural_profile_end(buf, len(buf))
+    prof = json.loads(buf.value.decode() or "{}")
+    conv = {k: v for k, v in prof.items() if "conv" in k}
+    if not conv:
+        return None
+    ms = sum(v["ms"] for v in conv.values()); n = sum(v["count"] for v in conv.values())
+    total_ms = sum(v["ms"] for v in prof.values())
+    flops_per_launch = FLOP_CONV_ONLY * S * K / n
+    achieved = flops_per_launch / (ms / n * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "+".join(sorted(conv)), "launches": n, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,
+            "peak_source": src + " (bf16 sustained, kernel timed inside a long step)",
+            "flops_per_launch": flops_per_launch, "profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

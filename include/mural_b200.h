@@ -1,0 +1,157 @@
+/*
+ * mural_b200.h — C ABI of the B200-native MuRaL hot path (libmural_b200.so).
+ *
+ * The reference (CaiLiLab/MuRaL v1.2.0) is pure Python and has no FFI; its drop-in seams are three
+ * Python call sites.  Every entry point below names the reference function(s) whose
+ * work it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes stubs a
+ * MuRaL maintainer would add at those call sites.
+ *
+ * Conventions
+ *  - plain C types only; `d_*` arguments are CUDA device pointers, `h_*` host pointers;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); nothing here
+ *    synchronises the device unless the name ends in `_host` (those copy H2D/D2H and sync `stream`);
+ *  - every function returns 0 on success, non-zero on error; mural_last_error() gives the message of
+ *    the last failure on the calling thread.  Nothing calls exit() (the reference sys.exit()s);
+ *  - a *site* is (pos, meta): pos = 0-based BED start on its chromosome (int32), meta packs
+ *    strand | label<<1 | chrom_index<<8   (strand: 0 '+', 1 '-').
+ */
+#ifndef MURAL_B200_H
+#define MURAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MURAL_ABI_VERSION 1
+
+#define MURAL_MODEL_SNV 0
+#define MURAL_MODEL_INDEL 1
+
+#define MURAL_META(strand, label, chrom) ((int32_t)(((chrom) << 8) | (((label) & 0x7f) << 1) | ((strand) & 1)))
+
+/* compute modes of the conv stack */
+#define MURAL_MODE_FP32 0 /* CUDA-core fp32 FMA; the "fp32-equivalent" mode (1e-3 gate)           */
+#define MURAL_MODE_BF16 1 /* tcgen05 implicit GEMM, bf16 operands, fp32 accumulate (5e-3 gate)   */
+
+const char* mural_last_error(void);
+int mural_abi_version(void);
+/* number of kernel launches issued by this library since the last mural_reset_launch_count() */
+int64_t mural_launch_count(void);
+void mural_reset_launch_count(void);
+/* optional per-kernel CUDA-event profile: between begin and end every launch of this library is bracketed
+ * by two events on its stream; end() synchronises the device and writes
+ * {"<kernel>": {"count": n, "ms": total}, ...} as JSON into buf; returns the number of launches seen. */
+void mural_profile_begin(void);
+int64_t mural_profile_end(char* buf, int64_t cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed reference genome (replaces SeqIO.to_dict(...) + the python `str` genome,
+ * MuRaL/data/preprocessing.py:836, and the per-character dict lookups at :698-700, :809-813).
+ *
+ * Layout in HBM: 2 bits/base (A0 C1 G2 T3, 16 bases per uint32, little-endian within the word),
+ * 1 bit/base "not ACGT" mask (32 bases per uint32) and a sorted run table
+ * (global start, global end, symbol 4..14 = R Y M S W K B D H V N) for the masked bases.
+ * Chromosomes are concatenated, each starting on a 64-base boundary.
+ * Characters are case-folded; anything outside ACGTRYMSWKBDHVN is an error (the reference raises
+ * KeyError on it).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_genome mural_genome_t;
+
+int mural_genome_create(int32_t n_chrom, const char* const* h_seqs, const int64_t* h_lens, int device,
+                        mural_genome_t** out);
+void mural_genome_destroy(mural_genome_t* g);
+int32_t mural_genome_n_chrom(const mural_genome_t* g);
+int64_t mural_genome_chrom_len(const mural_genome_t* g, int32_t chrom);
+int64_t mural_genome_device_bytes(const mural_genome_t* g);
+int64_t mural_genome_n_exception_runs(const mural_genome_t* g);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoders (bit-exact with the reference; exposed for parity tests and for callers that still want
+ * the reference tensors).
+ *
+ * mural_encode_local  : seq_digit_encoder + process_local_seq_* (preprocessing.py:636-723, 479-522)
+ *                       -> int64 [n, 2R+1-(k-1)] (snv) / [n, 2R-(k-1)] (indel)
+ * mural_encode_onehot : seq_ohe_encoder + distal_encoding_by_region (preprocessing.py:756-816, 978-999)
+ *                       -> float32 [n, 4, W], W = 2R+1 (snv) / 2R (indel)
+ * ---------------------------------------------------------------------------------------------- */
+int mural_encode_local(const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
+                       int32_t radius, int32_t order, int32_t model_type, int64_t* d_out, void* stream);
+int mural_encode_onehot(const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
+                        int32_t radius, int32_t model_type, float* d_out, void* stream);
+int mural_encode_local_host(const mural_genome_t* g, const int32_t* h_pos, const int32_t* h_meta, int64_t n,
+                            int32_t radius, int32_t order, int32_t model_type, int64_t* h_out);
+int mural_encode_onehot_host(const mural_genome_t* g, const int32_t* h_pos, const int32_t* h_meta, int64_t n,
+                             int32_t radius, int32_t model_type, float* h_out);
+/* one-hot tensor -> symbol codes (0..14, 255 = not a reference one-hot column); lets the drop-in
+ * Network2.forward(distal_x) accept the reference's own input tensors. */
+int mural_onehot_to_symbols(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MuRaL-snv network (Network2, MuRaL/model/model_snv.py:290-525).
+ *
+ * Parameters are exchanged as ONE flat fp32 blob whose layout is queried by name: entry i has the
+ * reference state_dict key (e.g. "RBs1_2.0.conv1.weight"), an element offset and a size.  The
+ * aliased "*.layer.N.*" duplicates of the reference state_dict are not part of the blob.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_snv_config {
+  int32_t local_radius;   /* config['local_radius']                      */
+  int32_t local_order;    /* config['local_order'] (k of the k-mer)      */
+  int32_t distal_radius;  /* config['distal_radius'] -> L = 2R+1         */
+  int32_t hidden1;        /* config['local_hidden1_size']                */
+  int32_t hidden2;        /* config['local_hidden2_size']                */
+  int32_t channels;       /* config['CNN_out_channels']                  */
+  int32_t kernel_size;    /* config['CNN_kernel_size'] (conv1/2/3)       */
+  int32_t n_class;        /* config['n_class']                           */
+} mural_snv_config_t;
+
+typedef struct mural_snv_model mural_snv_model_t;
+
+int mural_snv_model_create(const mural_snv_config_t* cfg, int device, mural_snv_model_t** out);
+void mural_snv_model_destroy(mural_snv_model_t* m);
+int32_t mural_snv_model_n_tensors(const mural_snv_model_t* m);
+/* is_buffer: 0 = trainable parameter, 1 = BatchNorm running statistic.  All trainable tensors come
+ * first in the blob, so blob[0 : n_trainable) is the flat parameter vector optimisers work on. */
+int mural_snv_model_tensor(const mural_snv_model_t* m, int32_t i, const char** name, int64_t* offset,
+                           int64_t* numel, int32_t* is_buffer);
+int64_t mural_snv_model_n_params(const mural_snv_model_t* m);    /* blob length in floats */
+int64_t mural_snv_model_n_trainable(const mural_snv_model_t* m); /* leading trainable part   */
+/* Load eval-mode weights (BatchNorm running stats included in the blob); folds and uploads. */
+int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, int64_t n);
+
+/* model_predict_m body (MuRaL/model/nn_utils.py:48-65) for n sites: gather + Network2.forward (eval).
+ * d_logp: float32 [n, n_class] log-probabilities, exactly what Network2.forward returns. */
+int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, const int32_t* d_pos,
+                      const int32_t* d_meta, int64_t n, int32_t mode, float* d_logp, void* stream);
+/* Same network on the reference's own tensors (cat_x int64 [n,n_cat], distal_x float32 [n,4,L]). */
+int mural_snv_forward_tensors(mural_snv_model_t* m, const int64_t* d_cat, const float* d_distal, int64_t n,
+                              int32_t L, int32_t mode, float* d_logp, void* stream);
+/* End-to-end: host site arrays in, host log-probs out (H2D + kernels + D2H + stream sync). */
+int mural_snv_predict_host(mural_snv_model_t* m, const mural_genome_t* g, const int32_t* h_pos,
+                           const int32_t* h_meta, int64_t n, int32_t mode, float* h_logp, void* stream);
+/* CrossEntropyLoss(reduction='sum') over d_logp with labels from meta (nn_utils.py:64): adds into *d_loss */
+int mural_ce_sum(const float* d_logp, const int32_t* d_meta, int64_t n, int32_t n_class, double* d_loss,
+                 void* stream);
+/* 1 when the tcgen05 (MURAL_MODE_BF16) path is compiled in and supports this model's shape */
+int mural_snv_tc_available(const mural_snv_model_t* m);
+/* sites per workspace chunk of the forward (0 = default); parity-test switch for debug taps */
+int mural_snv_set_chunk(mural_snv_model_t* m, int64_t chunk_sites);
+int mural_snv_set_debug(mural_snv_model_t* m, int32_t on);
+/* debug/parity taps: copies an intermediate activation of the LAST forward chunk to the host.
+ * name in {"pool1","pool1_2","rb1_2","conv2_2","rb2_2","gmax","gmax_2","logit_local","logit_mid","logit_large"} */
+int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, int64_t max_floats,
+                        int64_t* n_written);
+
+/* ------------------------------------------------------------------------------------------------
+ * Calibration epilogue (run_predict.py:214-225): softmax(logp) -> FullDirichlet apply
+ * (dirichletcal/calib/fulldirichlet.py:78-80, multinomial.py:60-64,235-244) -> optional Poisson
+ * calibration (MuRaL/model/calibration.py:10-23).  h_weights: fp64 [k, k+1] or NULL.  Output fp64 [n,k].
+ * ---------------------------------------------------------------------------------------------- */
+int mural_calibrate(const float* d_logp, int64_t n, int32_t n_class, const double* h_weights,
+                    int32_t poisson, double* d_prob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MURAL_B200_H */

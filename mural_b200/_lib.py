@@ -1,0 +1,99 @@
+"""ctypes binding of libmural_b200.so (include/mural_b200.h).
+
+There is no CPU fallback: if the library is missing the import of anything that needs it raises.
+`python -m mural_b200.build` (or __graft_entry__.build()) produces the library in-tree.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmural_b200.so")
+
+MODEL_SNV, MODEL_INDEL = 0, 1
+MODE_FP32, MODE_BF16 = 0, 1
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+
+
+class SnvConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("local_radius", "local_order", "distal_radius", "hidden1", "hidden2",
+                                          "channels", "kernel_size", "n_class")]
+
+
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against include/mural_b200.h.
+PROTOTYPES = {
+    "mural_last_error": (C.c_char_p, []),
+    "mural_abi_version": (C.c_int, []),
+    "mural_launch_count": (_i64, []),
+    "mural_reset_launch_count": (None, []),
+    "mural_profile_begin": (None, []),
+    "mural_profile_end": (_i64, [C.c_char_p, _i64]),
+    "mural_snv_tc_available": (C.c_int, [_vp]),
+    "mural_genome_create": (C.c_int, [_i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.c_int, C.POINTER(_vp)]),
+    "mural_genome_destroy": (None, [_vp]),
+    "mural_genome_n_chrom": (_i32, [_vp]),
+    "mural_genome_chrom_len": (_i64, [_vp, _i32]),
+    "mural_genome_device_bytes": (_i64, [_vp]),
+    "mural_genome_n_exception_runs": (_i64, [_vp]),
+    "mural_encode_local": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "mural_encode_onehot": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "mural_encode_local_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "mural_encode_onehot_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "mural_onehot_to_symbols": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "mural_snv_model_create": (C.c_int, [C.POINTER(SnvConfig), C.c_int, C.POINTER(_vp)]),
+    "mural_snv_model_destroy": (None, [_vp]),
+    "mural_snv_model_n_tensors": (_i32, [_vp]),
+    "mural_snv_model_tensor": (C.c_int, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "mural_snv_model_n_params": (_i64, [_vp]),
+    "mural_snv_model_n_trainable": (_i64, [_vp]),
+    "mural_snv_model_load": (C.c_int, [_vp, _vp, _i64]),
+    "mural_snv_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mural_snv_forward_tensors": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "mural_snv_predict_host": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mural_ce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "mural_snv_set_chunk": (C.c_int, [_vp, _i64]),
+    "mural_snv_set_debug": (C.c_int, [_vp, _i32]),
+    "mural_snv_debug_tap": (C.c_int, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64)]),
+    "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("mural_b200: %s is missing — build it with `python -m mural_b200.build` "
+                               "(there is no CPU/PyTorch fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().mural_last_error().decode("utf-8", "replace")
+        if "KeyError" in msg:
+            raise KeyError(msg)
+        if "IndexError" in msg:
+            raise IndexError(msg)
+        raise RuntimeError("mural_b200: " + msg)
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """data pointer of a torch tensor / numpy array (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)

@@ -1,0 +1,633 @@
+// MuRaL-snv Network2 eval forward, fp32 CUDA-core path ("fp32-equivalent" mode) + shared stem/head kernels.
+// Reference forward: MuRaL/model/model_snv.py:439-525; loop body of model_predict_m: MuRaL/model/nn_utils.py:48-65.
+//
+// Pipeline per chunk of sites (activations channels-last fp32 [site][pos][C] in a reusable workspace):
+//   k_stem      gather 2-bit window -> smem symbols -> (BN(4)+Conv1d(4->C)) as table lookups -> max-pool 1,
+//               for both CNN branches; also emits the local k-mer indices             (E4,E5,M3,M4 of SURVEY §8a)
+//   k_local_mlp embedding gather + 3 Linear layers with BN folded forward               (M1,M2)
+//   k_conv      Conv1d(C,C,ks) with ReLU/BN prologue, zero padding per site, bias, up to two residuals (M5,M6)
+//   k_pool      MaxPool1d (-inf padding)                                                (M4)
+//   k_head      global max, BN+Linear heads, 3 softmaxes, average, clamp, log           (M7,M8)
+#include <float.h>
+#include <string.h>
+
+#include "snv_model.cuh"
+
+namespace mural {
+
+// ------------------------------------------------------------------------------------------------ stem
+struct StemBranch {
+  const float* T;     // [ks][16][C]
+  const float* bias;  // [C]
+  float* out;         // [n][L1][C]
+  int L0, off0, L1, pk, ps, pp;
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) k_stem(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
+                                              const uint8_t* __restrict__ sym_in, int R, int L, int ks, StemBranch b0,
+                                              StemBranch b1, int local_R, int order, int n_cat, int32_t* __restrict__ cat_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sT = reinterpret_cast<float*>(smem_raw);  // [2][ks][16][C]
+  float* sB = sT + 2 * ks * 16 * C;                // [2][C]
+  uint8_t* sym = reinterpret_cast<uint8_t*>(sB + 2 * C);
+  const int64_t site = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < ks * 16 * C; e += blockDim.x) {
+    sT[e] = b0.T[e];
+    sT[ks * 16 * C + e] = b1.T[e];
+  }
+  for (int e = tid; e < C; e += blockDim.x) {
+    sB[e] = b0.bias[e];
+    sB[C + e] = b1.bias[e];
+  }
+  if (sym_in) {
+    for (int i = tid; i < L; i += blockDim.x) sym[i] = sym_in[site * L + i];
+  } else {
+    const int m = meta[site];
+    load_window(G, int(uint32_t(m) >> 8), int64_t(pos[site]) - R, L, m & 1, sym);
+  }
+  __syncthreads();
+  const int half = ks / 2;
+#pragma unroll 1
+  for (int br = 0; br < 2; ++br) {
+    const StemBranch& B = br ? b1 : b0;
+    const float* T = sT + br * ks * 16 * C;
+    const uint8_t* s0 = sym + B.off0;
+    float* out = B.out + site * int64_t(B.L1) * C;
+    for (int e = tid; e < B.L1 * C; e += blockDim.x) {
+      const int j = e / C, c = e - j * C;
+      int lo = j * B.ps - B.pp, hi = lo + B.pk;
+      lo = lo < 0 ? 0 : lo;
+      hi = hi > B.L0 ? B.L0 : hi;
+      float mx = -FLT_MAX;
+      for (int p = lo; p < hi; ++p) {
+        float v = sB[br * C + c];
+        for (int t = 0; t < ks; ++t) {
+          const int q = p + t - half;
+          const int s = (q >= 0 && q < B.L0) ? s0[q] : SYM_PAD;
+          v += T[(t * 16 + s) * C + c];
+        }
+        mx = fmaxf(mx, v);
+      }
+      out[e] = mx;
+    }
+  }
+  // local k-mer indices from the centre of the already oriented window (seq_digit_encoder semantics)
+  if (cat_out) {
+    for (int j = tid; j < n_cat; j += blockDim.x) {
+      int idx = 0;
+      bool bad = false;
+      for (int d = 0; d < order; ++d) {
+        const int s = sym[R - local_R + j + d];
+        bad |= s > 3;
+        idx = idx * 4 + (s & 3);
+      }
+      cat_out[site * n_cat + j] = bad ? (1 << (2 * order)) : idx;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ local MLP
+constexpr int MLP_TS = 8;  // sites per CTA
+
+__global__ void __launch_bounds__(128) k_local_mlp(LocalDev P, const int32_t* __restrict__ cat32,
+                                                   const int64_t* __restrict__ cat64, int64_t n, int n_cat, int emb_rows,
+                                                   int K1, int H1, int H2, int NC, float* __restrict__ logits,
+                                                   int* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* x = reinterpret_cast<float*>(smem_raw);  // [TS][K1]
+  float* h1 = x + MLP_TS * K1;                    // [TS][H1]
+  float* h2 = h1 + MLP_TS * H1;                   // [TS][H2]
+  const int64_t site0 = int64_t(blockIdx.x) * MLP_TS;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < MLP_TS * K1; e += blockDim.x) {
+    const int s = e / K1, k = e - s * K1;
+    float v = 0.f;
+    if (site0 + s < n) {
+      const int64_t ci = (site0 + s) * n_cat + k / 5;
+      int64_t idx = cat64 ? cat64[ci] : int64_t(cat32[ci]);
+      if (idx < 0 || idx >= emb_rows) {  // nn.Embedding would raise IndexError
+        if (err_flag) atomicOr(err_flag, 2);
+        idx = 0;
+      }
+      v = P.emb[idx * 5 + k % 5];
+    }
+    x[e] = v;
+  }
+  __syncthreads();
+  for (int o = tid; o < H1; o += blockDim.x) {
+    float acc[MLP_TS];
+#pragma unroll
+    for (int s = 0; s < MLP_TS; ++s) acc[s] = P.b1[o];
+    for (int k = 0; k < K1; ++k) {
+      const float w = P.W1t[k * H1 + o];
+#pragma unroll
+      for (int s = 0; s < MLP_TS; ++s) acc[s] = fmaf(x[s * K1 + k], w, acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < MLP_TS; ++s) h1[s * H1 + o] = fmaxf(acc[s], 0.f);
+  }
+  __syncthreads();
+  for (int o = tid; o < H2; o += blockDim.x) {
+    float acc[MLP_TS];
+#pragma unroll
+    for (int s = 0; s < MLP_TS; ++s) acc[s] = P.b2[o];
+    for (int k = 0; k < H1; ++k) {
+      const float w = P.W2t[k * H2 + o];
+#pragma unroll
+      for (int s = 0; s < MLP_TS; ++s) acc[s] = fmaf(h1[s * H1 + k], w, acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < MLP_TS; ++s) h2[s * H2 + o] = fmaxf(acc[s], 0.f);
+  }
+  __syncthreads();
+  for (int e = tid; e < MLP_TS * NC; e += blockDim.x) {
+    const int s = e / NC, o = e - s * NC;
+    if (site0 + s >= n) continue;
+    float acc = P.b3[o];
+    for (int k = 0; k < H2; ++k) acc = fmaf(h2[s * H2 + k], P.W3t[k * NC + o], acc);
+    logits[(site0 + s) * NC + o] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv
+// rows = n_sites*L flattened; a CTA computes TP consecutive rows x C channels.  Zero padding is per site:
+// the contribution of tap t to output row r is dropped when (r % L) + t - ks/2 falls outside [0, L).
+template <int C>
+struct ConvTile {
+  static constexpr int CG = C / 4;     // channel groups (4 channels each)
+  static constexpr int RG = 128 / CG;  // row groups (4 rows each)
+  static constexpr int TP = RG * 4;    // rows per CTA
+  static constexpr int XS = C + 1;     // padded smem row stride
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) k_conv(const float* __restrict__ in, float* __restrict__ out,
+                                              const float* __restrict__ res1, const float* __restrict__ res2,
+                                              int64_t rows, int L, ConvLayerDev P, int relu_out) {
+  using T = ConvTile<C>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* ws = reinterpret_cast<float*>(smem_raw);  // [ks][C][C]
+  float* xs = ws + P.ks * C * C;                   // [TP+ks-1][C+1]
+  const int ks = P.ks, half = ks / 2;
+  const int tid = threadIdx.x;
+  const int64_t r0 = int64_t(blockIdx.x) * T::TP;
+  for (int e = tid * 4; e < ks * C * C; e += 128 * 4) *reinterpret_cast<float4*>(ws + e) = *reinterpret_cast<const float4*>(P.Wt + e);
+  for (int e = tid; e < (T::TP + ks - 1) * C; e += 128) {
+    const int k = e / C, ci = e - k * C;
+    const int64_t r = r0 - half + k;
+    float v = 0.f;
+    if (r >= 0 && r < rows) {
+      v = in[r * C + ci];
+      if (P.relu_in) v = fmaxf(v, 0.f);
+      v = fmaf(v, P.a[ci], P.b[ci]);
+    }
+    xs[k * T::XS + ci] = v;
+  }
+  __syncthreads();
+  const int tc = tid % T::CG, tr = tid / T::CG;
+  int pin[4];  // position of each of this thread's rows inside its site
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pin[i] = int((r0 + tr * 4 + i) % L);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int t = 0; t < ks; ++t) {
+    float tmp[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmp[i][j] = 0.f;
+    const float* wt = ws + t * C * C + 4 * tc;
+    const float* xt = xs + (tr * 4 + t) * T::XS;
+#pragma unroll 8
+    for (int ci = 0; ci < C; ++ci) {
+      const float4 w = *reinterpret_cast<const float4*>(wt + ci * C);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = xt[i * T::XS + ci];
+        tmp[i][0] = fmaf(x, w.x, tmp[i][0]);
+        tmp[i][1] = fmaf(x, w.y, tmp[i][1]);
+        tmp[i][2] = fmaf(x, w.z, tmp[i][2]);
+        tmp[i][3] = fmaf(x, w.w, tmp[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = pin[i] + t - half;
+      if (q >= 0 && q < L) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += tmp[i][j];
+      }
+    }
+  }
+  const float4 bias = *reinterpret_cast<const float4*>(P.bias + 4 * tc);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + tr * 4 + i;
+    if (r >= rows) continue;
+    float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+    if (res1) {
+      const float4 q = *reinterpret_cast<const float4*>(res1 + r * C + 4 * tc);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (res2) {
+      const float4 q = *reinterpret_cast<const float4*>(res2 + r * C + 4 * tc);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (relu_out) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    *reinterpret_cast<float4*>(out + r * C + 4 * tc) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pool
+__global__ void k_pool(const float* __restrict__ in, float* __restrict__ out, int64_t n, int Lin, int Lout, int C, int pk,
+                       int ps, int pp) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= n * Lout * C) return;
+  const int c = int(e % C);
+  const int64_t sj = e / C;
+  const int j = int(sj % Lout);
+  const int64_t site = sj / Lout;
+  int lo = j * ps - pp, hi = lo + pk;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > Lin ? Lin : hi;
+  float mx = -FLT_MAX;
+  for (int p = lo; p < hi; ++p) mx = fmaxf(mx, in[(site * Lin + p) * C + c]);
+  out[e] = mx;
+}
+
+// ------------------------------------------------------------------------------------------------ head
+struct HeadBranch {
+  const float* x;  // [n][L3][C]  conv3 output after ReLU
+  const float* Wfc;
+  const float* bfc;
+  int L3;
+};
+
+__global__ void __launch_bounds__(128) k_head(HeadBranch b0, HeadBranch b1, const float* __restrict__ local_logits, int64_t n,
+                                              int C, int NC, float* __restrict__ logp, float* __restrict__ tap_gmax0,
+                                              float* __restrict__ tap_gmax1, float* __restrict__ tap_logit0,
+                                              float* __restrict__ tap_logit1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t site = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (site >= n) return;
+  float lg[2][16];
+#pragma unroll 1
+  for (int br = 0; br < 2; ++br) {
+    const HeadBranch& B = br ? b1 : b0;
+    float part[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) part[o] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float mx = -FLT_MAX;
+      for (int p = 0; p < B.L3; ++p) mx = fmaxf(mx, B.x[(site * B.L3 + p) * C + c]);  // torch.max(dim=2), model_snv.py:489,511
+      float* tg = br ? tap_gmax1 : tap_gmax0;
+      if (tg) tg[site * C + c] = mx;
+#pragma unroll
+      for (int o = 0; o < 16; ++o)
+        if (o < NC) part[o] = fmaf(mx, B.Wfc[c * NC + o], part[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < NC) lg[br][o] = warp_sum(part[o]) + B.bfc[o];
+  }
+  if (lane != 0) return;
+  float sm[3][16];
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    float mx = -FLT_MAX, sum = 0.f;
+    for (int o = 0; o < NC; ++o) {
+      const float v = k == 2 ? local_logits[site * NC + o] : lg[k][o];
+      sm[k][o] = v;
+      mx = fmaxf(mx, v);
+    }
+    for (int o = 0; o < NC; ++o) {
+      sm[k][o] = expf(sm[k][o] - mx);
+      sum += sm[k][o];
+    }
+    for (int o = 0; o < NC; ++o) sm[k][o] /= sum;
+  }
+  for (int o = 0; o < NC; ++o) {
+    if (tap_logit0) tap_logit0[site * NC + o] = lg[0][o];
+    if (tap_logit1) tap_logit1[site * NC + o] = lg[1][o];
+    const float distal = (sm[0][o] + sm[1][o]) / 2.f;                  // model_snv.py:515
+    logp[site * NC + o] = logf(fmaxf((sm[2][o] + distal) / 2.f, 1e-9f));  // :523
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+__global__ void k_ce_sum(const float* __restrict__ logp, const int32_t* __restrict__ meta, int64_t n, int NC,
+                         double* __restrict__ loss) {
+  // CrossEntropyLoss(reduction='sum') applied to log-probs: -log_softmax(logp)[y]  (nn_utils.py:64)
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  float v = 0.f;
+  if (i < n) {
+    const float* p = logp + i * NC;
+    float mx = -FLT_MAX;
+    for (int o = 0; o < NC; ++o) mx = fmaxf(mx, p[o]);
+    float s = 0.f;
+    for (int o = 0; o < NC; ++o) s += expf(p[o] - mx);
+    const int y = (meta[i] >> 1) & 0x7f;
+    v = -(p[y < NC ? y : 0] - mx - logf(s));
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(loss, double(v));
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <int C>
+static int conv_launch(const float* in, float* out, const float* r1, const float* r2, int64_t n, int L, const ConvLayerDev& P,
+                       int relu_out, cudaStream_t st) {
+  using T = ConvTile<C>;
+  const int64_t rows = n * L;
+  const size_t smem = sizeof(float) * (size_t(P.ks) * C * C + size_t(T::TP + P.ks - 1) * T::XS);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CUDA_TRY(cudaFuncSetAttribute(k_conv<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  LAUNCH(k_conv<C>, (unsigned)cdiv(rows, T::TP), 128, smem, st, in, out, r1, r2, rows, L, P, relu_out);
+  return 0;
+}
+
+static int conv_any(int C, const float* in, float* out, const float* r1, const float* r2, int64_t n, int L,
+                    const ConvLayerDev& P, int relu_out, cudaStream_t st) {
+  switch (C) {
+    case 16: return conv_launch<16>(in, out, r1, r2, n, L, P, relu_out, st);
+    case 32: return conv_launch<32>(in, out, r1, r2, n, L, P, relu_out, st);
+    case 64: return conv_launch<64>(in, out, r1, r2, n, L, P, relu_out, st);
+  }
+  MURAL_FAIL("unsupported channel count");
+}
+
+static int pool_launch(const float* in, float* out, int64_t n, int Lin, int Lout, int C, const int* p, cudaStream_t st) {
+  const int64_t tot = n * Lout * C;
+  LAUNCH(k_pool, (unsigned)cdiv(tot, 256), 256, 0, st, in, out, n, Lin, Lout, C, p[0], p[1], p[2]);
+  return 0;
+}
+
+static int save_tap(mural_snv_model* m, const char* name, const float* d, int64_t floats, cudaStream_t st) {
+  if (!m->debug) return 0;
+  std::vector<float>& v = m->tap_store[name];
+  v.resize(floats);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpy(v.data(), d, floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                    const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st) {
+  const int C = m->cfg.channels, ks = m->cfg.kernel_size, L = m->L, R = m->cfg.distal_radius;
+  StemBranch sb[2];
+  for (int br = 0; br < 2; ++br) {
+    const BranchDev& B = m->br[br];
+    sb[br] = StemBranch{B.T, B.bias1, br ? large_out : mid_out, B.L0, br ? 0 : L / 2 - 100, B.L1, B.pool[0][0], B.pool[0][1],
+                        B.pool[0][2]};
+  }
+  const size_t smem = sizeof(float) * (2 * size_t(ks) * 16 * C + 2 * C) + ((size_t(L) + 15) & ~size_t(15));
+  GenomeView gv = G ? *G : GenomeView{};
+#define STEM_CASE(CC)                                                                                                    \
+  case CC: {                                                                                                             \
+    static size_t configured = 0;                                                                                        \
+    if (smem > 48 * 1024 && smem > configured) {                                                                         \
+      CUDA_TRY(cudaFuncSetAttribute(k_stem<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+      configured = smem;                                                                                                 \
+    }                                                                                                                    \
+    LAUNCH(k_stem<CC>, (unsigned)ns, 128, smem, st, gv, d_pos, d_meta, d_sym, R, L, ks, sb[0], sb[1], m->cfg.local_radius, \
+           m->cfg.local_order, m->n_cat, cat_out);                                                                       \
+  } break;
+  switch (C) {
+    STEM_CASE(16)
+    STEM_CASE(32)
+    STEM_CASE(64)
+    default: MURAL_FAIL("unsupported channel count");
+  }
+#undef STEM_CASE
+  return 0;
+}
+
+int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
+                     cudaStream_t st) {
+  const int K1 = m->k1, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2;
+  const size_t smem = sizeof(float) * MLP_TS * size_t(K1 + H1 + H2);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CUDA_TRY(cudaFuncSetAttribute(k_local_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  LAUNCH(k_local_mlp, (unsigned)cdiv(ns, MLP_TS), 128, smem, st, m->local, cat32, cat64, ns, m->n_cat, m->emb_rows, K1, H1, H2,
+         m->cfg.n_class, logits, err_flag);
+  return 0;
+}
+
+int snv_head_launch(mural_snv_model* m, const float* h_mid, const float* h_large, const float* local_logits, int64_t ns,
+                    float* logp, float* tg0, float* tg1, float* tl0, float* tl1, cudaStream_t st) {
+  HeadBranch hb[2] = {{h_mid, m->br[0].Wfc, m->br[0].bfc, m->br[0].L3}, {h_large, m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
+  LAUNCH(k_head, (unsigned)cdiv(ns * 32, 128), 128, 0, st, hb[0], hb[1], local_logits, ns, m->cfg.channels, m->cfg.n_class, logp,
+         tg0, tg1, tl0, tl1);
+  return 0;
+}
+
+int snv_ensure_workspace(mural_snv_model* m, int64_t bytes) {
+  if (m->ws_bytes >= bytes) return 0;
+  cudaFree(m->d_ws);
+  m->d_ws = nullptr;
+  m->ws_bytes = 0;
+  CUDA_TRY(cudaMalloc(&m->d_ws, bytes));
+  m->ws_bytes = bytes;
+  return 0;
+}
+
+int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st) {
+  const int C = m->cfg.channels, NC = m->cfg.n_class;
+  const BranchDev &Bm = m->br[0], &Bl = m->br[1];
+  const int64_t Lmax = Bl.L1 > Bm.L1 ? Bl.L1 : Bm.L1;
+  // floats per site: 4 rotating activation buffers at the widest length, the mid branch pool-1 output,
+  // both conv3 outputs, local logits, tap scratch, k-mer indices
+  const int64_t per_site = 4 * Lmax * C + int64_t(Bm.L1) * C + int64_t(Bm.L3 + Bl.L3) * C + 3 * NC + 2 * C + m->n_cat;
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 2048;
+  if (chunk > n) chunk = n;
+  if (int rc = snv_ensure_workspace(m, chunk * per_site * 4 + 256)) return rc;
+  float* w = (float*)m->d_ws;
+  float* buf[4];
+  for (int i = 0; i < 4; ++i) { buf[i] = w; w += chunk * Lmax * C; }
+  float* mid0 = w; w += chunk * int64_t(Bm.L1) * C;
+  float* hmid = w; w += chunk * int64_t(Bm.L3) * C;
+  float* hlarge = w; w += chunk * int64_t(Bl.L3) * C;
+  float* llog = w; w += chunk * NC;
+  float* tl0 = w; w += chunk * NC;
+  float* tl1 = w; w += chunk * NC;
+  float* tg0 = w; w += chunk * C;
+  float* tg1 = w; w += chunk * C;
+  int32_t* cat32 = (int32_t*)w; w += chunk * m->n_cat;
+  int* err_flag = (int*)w;
+  CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
+
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
+    if (int rc = snv_stem_launch(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
+                                 d_sym ? d_sym + s0 * m->L : nullptr, ns, mid0, buf[0], d_cat ? nullptr : cat32, st))
+      return rc;
+    if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, ns, llog, err_flag, st))
+      return rc;
+    for (int br = 1; br >= 0; --br) {  // large first (its pool-1 output sits in buf[0]), then mid
+      const BranchDev& B = m->br[br];
+      float* P = br ? buf[0] : mid0;
+      float *Q = buf[1], *Rb = buf[2], *U = buf[3];
+      const char* sfx = br ? "_2" : "";
+      if (int rc = save_tap(m, (std::string("pool1") + sfx).c_str(), P, ns * B.L1 * C, st)) return rc;
+      // ---- stage 1 at length L1: two ResBlocks + outer skip (model_snv.py:477-479 / 499-501)
+      if (int rc = conv_any(C, P, Q, nullptr, nullptr, ns, B.L1, B.rb1[0], 0, st)) return rc;
+      if (int rc = conv_any(C, Q, Rb, P, nullptr, ns, B.L1, B.rb1[1], 0, st)) return rc;   // y1 = x0 + f(x0)
+      if (int rc = conv_any(C, Rb, Q, nullptr, nullptr, ns, B.L1, B.rb1[2], 0, st)) return rc;
+      if (int rc = conv_any(C, Q, U, Rb, P, ns, B.L1, B.rb1[3], 0, st)) return rc;          // y2 + jump = y1 + f(y1) + x0
+      if (int rc = save_tap(m, (std::string("rb1") + sfx).c_str(), U, ns * B.L1 * C, st)) return rc;
+      // ---- pool 2, conv2, stage 2 (:480-485 / 502-507)
+      float* X2 = br ? P : buf[0];  // mid0 is smaller than needed? no: reuse buf[0] for the mid branch
+      if (int rc = pool_launch(U, X2, ns, B.L1, B.L2, C, B.pool[1], st)) return rc;
+      if (int rc = conv_any(C, X2, Q, nullptr, nullptr, ns, B.L2, B.conv2, 0, st)) return rc;  // jump2
+      if (int rc = save_tap(m, (std::string("conv2") + sfx).c_str(), Q, ns * B.L2 * C, st)) return rc;
+      if (int rc = conv_any(C, Q, Rb, nullptr, nullptr, ns, B.L2, B.rb2[0], 0, st)) return rc;
+      if (int rc = conv_any(C, Rb, U, Q, nullptr, ns, B.L2, B.rb2[1], 0, st)) return rc;
+      if (int rc = conv_any(C, U, Rb, nullptr, nullptr, ns, B.L2, B.rb2[2], 0, st)) return rc;
+      if (int rc = conv_any(C, Rb, X2, U, Q, ns, B.L2, B.rb2[3], 0, st)) return rc;
+      if (int rc = save_tap(m, (std::string("rb2") + sfx).c_str(), X2, ns * B.L2 * C, st)) return rc;
+      // ---- pool 3, conv3 + ReLU (:486-488 / 508-510)
+      if (int rc = pool_launch(X2, Rb, ns, B.L2, B.L3, C, B.pool[2], st)) return rc;
+      if (int rc = conv_any(C, Rb, br ? hlarge : hmid, nullptr, nullptr, ns, B.L3, B.conv3, 1, st)) return rc;
+    }
+    if (int rc = snv_head_launch(m, hmid, hlarge, llog, ns, d_logp + s0 * NC, m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr,
+                                 m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr, st))
+      return rc;
+    if (m->debug) {
+      if (int rc = save_tap(m, "gmax", tg0, ns * C, st)) return rc;
+      if (int rc = save_tap(m, "gmax_2", tg1, ns * C, st)) return rc;
+      if (int rc = save_tap(m, "logit_mid", tl0, ns * NC, st)) return rc;
+      if (int rc = save_tap(m, "logit_large", tl1, ns * NC, st)) return rc;
+      if (int rc = save_tap(m, "logit_local", llog, ns * NC, st)) return rc;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (d_cat) {  // tensor path: surface out-of-range embedding indices like nn.Embedding would
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, err_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    MURAL_CHECK((flag & 2) == 0, "IndexError: index out of range in embedding lookup");
+  }
+  return 0;
+}
+
+}  // namespace mural
+
+using namespace mural;
+
+static int check_model(const mural_snv_model_t* m) {
+  MURAL_CHECK(m != nullptr, "model is NULL");
+  MURAL_CHECK(m->loaded, "model weights not loaded (call mural_snv_model_load first)");
+  return 0;
+}
+
+extern "C" int mural_snv_set_debug(mural_snv_model_t* m, int32_t on) {
+  MURAL_CHECK(m != nullptr, "model is NULL");
+  m->debug = on != 0;
+  m->tap_store.clear();
+  return 0;
+}
+extern "C" int mural_snv_set_chunk(mural_snv_model_t* m, int64_t chunk_sites) {
+  MURAL_CHECK(m != nullptr && chunk_sites >= 0, "bad argument");
+  m->chunk_sites = chunk_sites;
+  return 0;
+}
+
+extern "C" int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta,
+                                 int64_t n, int32_t mode, float* d_logp, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  MURAL_CHECK(g && (n == 0 || (d_pos && d_meta && d_logp)), "NULL argument");
+  MURAL_CHECK(g->device == m->device, "genome and model live on different devices");
+  if (n == 0) return 0;
+  if (mode == MURAL_MODE_FP32) return snv_forward_fp32(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
+  if (mode == MURAL_MODE_BF16) return snv_forward_tc(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
+  MURAL_FAIL("unknown compute mode");
+}
+
+extern "C" int mural_snv_forward_tensors(mural_snv_model_t* m, const int64_t* d_cat, const float* d_distal, int64_t n, int32_t L,
+                                         int32_t mode, float* d_logp, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  MURAL_CHECK(n == 0 || (d_cat && d_distal && d_logp), "NULL argument");
+  MURAL_CHECK(L == m->L, "distal_x length does not match the model's distal_radius");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* d_sym = nullptr;
+  const int64_t sym_bytes = (n * int64_t(L) + 255) & ~int64_t(255);
+  CUDA_TRY(cudaMalloc((void**)&d_sym, sym_bytes + 256));
+  int* d_bad = (int*)(d_sym + sym_bytes);
+  cudaMemsetAsync(d_bad, 0, 4, st);
+  int rc = onehot_to_symbols_checked(d_distal, n, L, d_sym, d_bad, st);
+  if (rc == 0) {
+    // any column that is not one of the reference's 15 one-hot vectors cannot go through the table stem
+    int bad = 0;
+    cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (bad) rc = fail(__FILE__, __LINE__, "distal_x holds columns that are not reference one-hot vectors (bigWig channels / arbitrary floats are not supported by the table stem)");
+  }
+  if (rc == 0) {
+    rc = mode == MURAL_MODE_BF16 ? snv_forward_tc(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
+                                 : snv_forward_fp32(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(d_sym);
+  return rc;
+}
+
+extern "C" int mural_snv_predict_host(mural_snv_model_t* m, const mural_genome_t* g, const int32_t* h_pos,
+                                      const int32_t* h_meta, int64_t n, int32_t mode, float* h_logp, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  MURAL_CHECK(g && (n == 0 || (h_pos && h_meta && h_logp)), "NULL argument");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(m->device));
+  const int NC = m->cfg.n_class;
+  // persistent staging buffers (grown on demand) so repeated calls do not pay cudaMalloc
+  const int64_t need = n * (8 + 4 * NC);
+  if (m->io_bytes < need) {
+    cudaFree(m->d_io);
+    m->d_io = nullptr;
+    m->io_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_io, need));
+    m->io_bytes = need;
+  }
+  int32_t* d_pos = (int32_t*)m->d_io;
+  int32_t* d_meta = d_pos + n;
+  float* d_logp = (float*)(d_meta + n);
+  CUDA_TRY(cudaMemcpyAsync(d_pos, h_pos, n * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_meta, h_meta, n * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = mural_snv_forward(m, g, d_pos, d_meta, n, mode, d_logp, stream)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_logp, d_logp, n * NC * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mural_ce_sum(const float* d_logp, const int32_t* d_meta, int64_t n, int32_t n_class, double* d_loss,
+                            void* stream) {
+  MURAL_CHECK(d_logp && d_meta && d_loss && n_class >= 2, "bad argument");
+  if (n == 0) return 0;
+  LAUNCH(k_ce_sum, (unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream, d_logp, d_meta, n, n_class, d_loss);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, int64_t max_floats,
+                                   int64_t* n_written) {
+  MURAL_CHECK(m && name && n_written, "NULL argument");
+  auto it = m->tap_store.find(name);
+  MURAL_CHECK(it != m->tap_store.end(), std::string("no such tap (enable mural_snv_set_debug first): ") + name);
+  const int64_t k = (int64_t)it->second.size() < max_floats ? (int64_t)it->second.size() : max_floats;
+  if (h_out && k) memcpy(h_out, it->second.data(), k * sizeof(float));
+  *n_written = (int64_t)it->second.size();
+  return 0;
+}

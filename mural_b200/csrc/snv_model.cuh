@@ -1,0 +1,99 @@
+// MuRaL-snv Network2 (MuRaL/model/model_snv.py:290-525): parameter layout + device-resident prepared weights.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mural {
+
+struct TensorEntry {
+  std::string name;  // reference state_dict key
+  int64_t offset;    // element offset in the flat fp32 blob
+  int64_t numel;
+  int32_t is_buffer;  // 0 trainable parameter, 1 BatchNorm running statistic
+};
+
+// One Conv1d(C,C,ks) with its preceding BatchNorm (and optional ReLU before the BN), eval-folded:
+//   y = bias + sum_tap sum_ci Wt[tap][ci][co] * pad0( a[ci]*act(x[.,ci]) + b[ci] )
+struct ConvLayerDev {
+  const float* Wt;    // [ks][C][C]  (tap, ci, co)
+  const float* bias;  // [C]
+  const float* a;     // [C] BN scale  gamma/sqrt(var+eps)
+  const float* b;     // [C] BN shift  beta - mean*a
+  int ks;
+  int relu_in;  // ReLU applied to the input before the BN affine (ResBlock convs)
+};
+
+struct BranchDev {
+  const float* T;      // stem table [ks][16 symbols][C]: conv1 applied to BN(4)(one-hot column)
+  const float* bias1;  // [C]
+  ConvLayerDev rb1[4];  // RBs1.0.conv1, RBs1.0.conv2, RBs1.1.conv1, RBs1.1.conv2
+  ConvLayerDev conv2;
+  ConvLayerDev rb2[4];
+  ConvLayerDev conv3;
+  const float* Wfc;  // [C][n_class]   BN(distal_fc.0) folded into Linear(distal_fc.2)
+  const float* bfc;  // [n_class]
+  int pool[3][3];    // (kernel, stride, pad) of the three max-pools
+  int L0, L1, L2, L3;  // lengths: input, after pool1, after pool2, after pool3
+};
+
+struct LocalDev {
+  const float* emb;  // [4^k+1][5]
+  const float* W1t;  // [5*n_cat][h1]
+  const float* b1;   // [h1]
+  const float* W2t;  // [h1][h2]   bn_layers.0 folded in
+  const float* b2;
+  const float* W3t;  // [h2][n_class]  bn_layers.1 folded in (local_fc)
+  const float* b3;
+};
+
+}  // namespace mural
+
+struct mural_snv_model {
+  mural_snv_config_t cfg;
+  int device;
+  int n_cat, emb_rows, k1;  // k1 = 5*n_cat
+  int L;                    // 2R+1
+  std::vector<mural::TensorEntry> layout;
+  std::map<std::string, int> index;
+  int64_t n_blob, n_trainable;
+  // prepared eval weights
+  float* d_prep = nullptr;
+  int64_t prep_floats = 0;
+  mural::LocalDev local;
+  mural::BranchDev br[2];  // 0 = middle-scale (201 bp), 1 = large-scale (full window)
+  bool loaded = false;
+  // bf16 tcgen05 path (snv_tc.cu)
+  void* tc = nullptr;
+  // forward workspace (grown on demand)
+  void* d_ws = nullptr;
+  int64_t ws_bytes = 0;
+  int64_t chunk_sites = 0;
+  // persistent H2D/D2H staging of mural_snv_predict_host
+  void* d_io = nullptr;
+  int64_t io_bytes = 0;
+  // debug taps (parity tests): host copies of intermediate activations of the last chunk
+  bool debug = false;
+  std::map<std::string, std::vector<float>> tap_store;
+};
+
+namespace mural {
+// bf16 tcgen05 path (snv_tc.cu): prepared bf16 weights live behind m->tc
+int snv_tc_prepare(mural_snv_model* m, const float* h_blob);
+void snv_tc_destroy(mural_snv_model* m);
+int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                   const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st);
+// shared launch helpers (snv_forward.cu)
+int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                    const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st);
+int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
+                     cudaStream_t st);
+int snv_head_launch(mural_snv_model* m, const float* h_mid, const float* h_large, const float* local_logits, int64_t ns,
+                    float* logp, float* tg0, float* tg1, float* tl0, float* tl1, cudaStream_t st);
+int snv_ensure_workspace(mural_snv_model* m, int64_t bytes);
+int onehot_to_symbols_checked(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, int* d_flag, cudaStream_t st);
+int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st);
+}

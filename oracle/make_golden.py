@@ -174,6 +174,7 @@ def main():
         sd = torch.load(os.path.join(REF, rel, "model"), map_location="cpu")
         model.load_state_dict(sd)
         model.eval()
+        manifest.setdefault("state_dict_keys", {})[tag] = [[k, list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()]
         bp, bm = ("A", "T") if "AT" in tag or tag.startswith("ex") else ("C", "G")
         ch, stt, sd_ = pick_sites(genome, rng, per_chrom=n_eval // 3, base_plus=bp, base_minus=bm)
         central = int(cfg.get("segment_center", 300000))
@@ -220,6 +221,7 @@ def main():
         down = cfg["down_list"]
         model = indel.UNet_Small(n_class, ch8, ks, down, use_reverse=use_rev)
         model.load_state_dict(sd); model.eval()
+        manifest.setdefault("state_dict_keys", {})[tag] = [[k, list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()]
         Rd = int(cfg["distal_radius"])
         ch, stt, sd_ = pick_sites(genome, rng, per_chrom=8)
         sd_[:] = 0                                   # reference indel data are '+' only

@@ -1,0 +1,88 @@
+"""CPU: host-side logic of mural_b200 (ordering, BED/FASTA ingest, batching, state_dict contract)."""
+import gzip
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encode_np as E
+
+
+def test_segment_order_matches_oracle_state_machine(kat):
+    from mural_b200.data import segment_order
+    z, _ = kat
+    rng = np.random.default_rng(5)
+    for central in (1, 13, 999, 5000, 300000):
+        perm, sizes = segment_order(z["chrom"], z["start"], z["strand"], central)
+        lit = E.bed_batches(z["chrom"], z["start"], z["strand"], central)
+        assert np.array_equal(perm, np.concatenate([np.array(b[0]) for b in lit]))
+        assert list(sizes) == [len(b[0]) for b in lit]
+    for _ in range(20):                              # ragged / unsorted / repeated chromosomes
+        n = int(rng.integers(1, 300))
+        ch = rng.integers(0, 4, n); st = rng.integers(0, 20000, n); sd = rng.integers(0, 2, n)
+        c = int(rng.integers(1, 5000))
+        perm, sizes = segment_order(ch, st, sd, c)
+        lit = E.bed_batches(ch, st, sd, c)
+        assert np.array_equal(perm, np.concatenate([np.array(b[0]) for b in lit]))
+    perm, sizes = segment_order([], [], [], 10)
+    assert len(perm) == 0 and len(sizes) == 0
+
+
+def test_bed_and_fasta_ingest(tmp_path):
+    from mural_b200.data import SiteTable
+    from mural_b200.genome import read_fasta
+    bed = tmp_path / "a.bed.gz"
+    with gzip.open(bed, "wt") as f:
+        f.write("chr2\t10\t11\t.\t0\t+\nchr2\t15\t16\t.\t3\t-\nchr1\t7\t8\t.\t1\t+\n")
+    t = SiteTable.from_bed(str(bed))
+    assert t.chrom_names == ["chr2", "chr1"] and list(t.start) == [10, 15, 7]
+    assert list(t.strand) == [0, 1, 0] and list(t.label) == [0, 3, 1]
+    fa = tmp_path / "g.fa"
+    fa.write_text(">chr1 desc\nACGT\nacgn\n>chr2\nTTTT\n")
+    g = read_fasta(str(fa))
+    assert g == {"chr1": b"ACGTacgn", "chr2": b"TTTT"}
+    fa.write_text(">x\nAC\n>x\nGT\n")
+    with pytest.raises(ValueError):
+        read_fasta(str(fa))
+
+
+class _FakeGenome:
+    device = torch.device("cpu")
+    chrom_index = {"chrA": 0, "chrB": 1, "chrC": 2}
+
+
+def test_batches_preserve_reference_order(kat):
+    """predict path: concatenated batches == bed_reader emission order (tail is carried to the next pool)."""
+    from mural_b200.data import PackedSiteDataset, SiteTable, generate_site_batches
+    z, genome = kat
+    t = SiteTable(list(genome), z["chrom"], z["start"], z["start"] + 1, z["strand"], z["start"] % 4)
+    ds = PackedSiteDataset(t, _FakeGenome(), 5000, 7, 3, 1000)
+    for bs, pool in ((16, 1), (128, 10), (7, 3)):
+        got = torch.cat([b.pos for b in generate_site_batches(ds, pool, bs, shuffle=False, device="cpu")]).numpy()
+        assert np.array_equal(got, ds.pos)
+        sizes = [len(b) for b in generate_site_batches(ds, pool, bs, shuffle=False, device="cpu")]
+        assert all(s == bs for s in sizes[:-1]) and 0 < sizes[-1] <= bs
+    # shuffled: a permutation of the same multiset
+    got = torch.cat([b.pos for b in generate_site_batches(ds, 4, 32, shuffle=True, seed=1, device="cpu")]).numpy()
+    assert np.array_equal(np.sort(got), np.sort(ds.pos))
+    # meta packing round-trips
+    assert np.array_equal(ds.meta & 1, ds.strand) and np.array_equal((ds.meta >> 1) & 0x7f, ds.label)
+    assert np.array_equal(ds.meta >> 8, ds.chrom)
+
+
+def test_state_dict_contract(manifest):
+    """Same keys, shapes and dtypes as the reference Network2 (incl. '.layer.N.' aliases)."""
+    from mural_b200 import model_choice
+    cfg = {"local_radius": 7, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": 1000,
+           "emb_dropout": .1, "local_dropout": .1, "CNN_kernel_size": 3, "CNN_out_channels": 32, "distal_fc_dropout": .25,
+           "n_class": 4, "model_no": 2}
+    common = dict(emb_dims=[(65, 2)] * 13, n_cont=0, n_class=4, distal_order=1, in_channels=4)
+    m = model_choice(2, cfg, common, "snv")
+    ref = manifest["state_dict_keys"]["hs_AT"]
+    sd = m.state_dict()
+    assert [k for k, _, _ in ref] == list(sd.keys())
+    for k, shape, dt in ref:
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dt, k
+    assert sum(p.numel() for p in m.parameters()) == 86904
+    with pytest.raises(ValueError):
+        model_choice(1, cfg, common, "snv")

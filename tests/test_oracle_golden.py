@@ -1,0 +1,109 @@
+"""CPU: the oracle (oracle/) against the fixtures generated from the real reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import INDEL_TAGS, SNV_TAGS, load_snv_golden, GOLD
+from oracle import encode_np as E
+from oracle import network_t as NT
+
+CASES = range(6)
+
+
+def _oracle_case(z, genome, ci):
+    mt, R_l, order, R_d, central = [int(v) for v in z["case%d_cfg" % ci]]
+    mt = "snv" if mt == 0 else "indel"
+    names = list(genome)
+    ch, st, sd = z["chrom"], z["start"], z["strand"]
+    perm, sizes = E.order_sites(ch, st, sd, central)
+    syms = [E.seq_to_symbols(genome[n]) for n in names]
+    cat = np.empty((len(perm), E.window_length(R_l, mt) - (order - 1)), dtype=np.int64)
+    oh = np.empty((len(perm), 4, E.window_length(R_d, mt)), dtype=np.float32)
+    for c in range(len(names)):
+        m = ch[perm] == c
+        cat[m] = E.kmer_windows(syms[c], st[perm][m], sd[perm][m], R_l, order, mt)
+        oh[m] = E.onehot_windows(syms[c], st[perm][m], sd[perm][m], R_d, mt)
+    return perm, sizes, cat, oh
+
+
+@pytest.mark.parametrize("ci", CASES)
+def test_encoders_match_reference_fixture(kat, ci):
+    z, genome = kat
+    perm, sizes, cat, oh = _oracle_case(z, genome, ci)
+    assert np.array_equal(perm, z["case%d_perm" % ci])
+    assert np.array_equal(sizes, z["case%d_sizes" % ci])
+    assert np.array_equal(cat, z["case%d_cat" % ci])                      # integer: bit exact
+    rows = z["case%d_oh_rows" % ci]
+    assert np.array_equal(oh[rows].view(np.uint32), z["case%d_oh" % ci].view(np.uint32))   # fp32 bit patterns
+
+
+def test_literal_bed_reader_equals_vectorised(kat):
+    z, _ = kat
+    rng = np.random.default_rng(0)
+    for central in (1, 7, 333, 5000, 10 ** 6):
+        lit = E.bed_batches(z["chrom"], z["start"], z["strand"], central)
+        perm, sizes = E.order_sites(z["chrom"], z["start"], z["strand"], central)
+        assert np.array_equal(np.concatenate([np.array(b[0]) for b in lit]), perm)
+        assert [len(b[0]) for b in lit] == list(sizes)
+    # unsorted / interleaved chromosomes: the state machine never moves a window backwards
+    ch = rng.integers(0, 3, 500); st = rng.integers(0, 50000, 500); sd = rng.integers(0, 2, 500)
+    lit = E.bed_batches(ch, st, sd, 4000)
+    perm, sizes = E.order_sites(ch, st, sd, 4000)
+    assert np.array_equal(np.concatenate([np.array(b[0]) for b in lit]), perm)
+
+
+def test_unknown_character_is_keyerror():
+    with pytest.raises(KeyError):
+        E.seq_to_symbols("ACGTX")
+
+
+@pytest.mark.parametrize("tag", SNV_TAGS)
+def test_network2_oracle_matches_reference_logits(kat, tag, manifest):
+    z, cfg, state = load_snv_golden(tag)
+    _, genome = kat
+    names = list(genome)
+    syms = [E.seq_to_symbols(genome[n]) for n in names]
+    ch, st, sd = z["chrom"], z["start"], z["strand"]
+    n = len(st)
+    cat = np.empty((n, int(z["n_cat"])), dtype=np.int64)
+    oh = np.empty((n, 4, 2 * cfg["distal_radius"] + 1), dtype=np.float32)
+    for c in range(len(names)):
+        m = ch == c
+        cat[m] = E.kmer_windows(syms[c], st[m], sd[m], cfg["local_radius"], cfg["local_order"])
+        oh[m] = E.onehot_windows(syms[c], st[m], sd[m], cfg["distal_radius"])
+    with torch.no_grad():
+        taps = {}
+        lp = NT.network2_forward(state, cat, oh, torch.float32, taps=taps).numpy()
+    assert np.abs(lp - z["ref_logp"]).max() < 2e-5        # fp32 CPU vs the reference module's fp32 CPU
+    assert np.abs(taps["pool1_2"].numpy()[:16] - z["tap_pool1_2"]).max() < 1e-5
+    # calibrator apply restatement vs the fixture computed at generation time
+    prob = torch.softmax(torch.from_numpy(z["ref_logp"]), 1).numpy()
+    assert np.allclose(NT.dirichlet_apply(z["cal_weights"], prob), z["cal_prob"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", INDEL_TAGS)
+def test_unet_oracle_matches_reference(kat, tag):
+    import os
+    z = np.load(os.path.join(GOLD, "indel_%s.npz" % tag))
+    state = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    _, genome = kat
+    names = list(genome)
+    syms = [E.seq_to_symbols(genome[n]) for n in names]
+    ch, st, sd = z["chrom"], z["start"], z["strand"]
+    Rd = int(z["distal_radius"])
+    oh = np.empty((len(st), 4, 2 * Rd), dtype=np.float32)
+    for c in range(len(names)):
+        m = ch == c
+        oh[m] = E.onehot_windows(syms[c], st[m], sd[m], Rd, "indel")
+    with torch.no_grad():
+        o = NT.unet_small_forward(state, oh, [int(v) for v in z["down"]], bool(z["use_reverse"]), torch.float32).numpy()
+    assert np.abs(o - z["ref_out"]).max() < 1e-4
+
+
+def test_poisson_calibrate_properties():
+    rng = np.random.default_rng(3)
+    p = rng.dirichlet([50, 1, 1, 1], 100)
+    q = NT.poisson_calibrate(p)
+    lam = -np.log(p[:, 0])
+    assert np.allclose(q[:, 0], 1 - lam)
+    assert np.allclose(q[:, 1:].sum(1), lam)          # non-reference classes re-scaled to sum to lambda
