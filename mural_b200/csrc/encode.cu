@@ -83,7 +83,7 @@ using namespace mural;
 
 extern "C" int mural_encode_local(const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                                   int32_t radius, int32_t order, int32_t model_type, int64_t* d_out, void* stream) {
-  MURAL_CHECK(g && d_out, "NULL argument");
+  MURAL_CHECK(g && (n == 0 || (d_pos && d_meta && d_out)), "NULL argument");
   MURAL_CHECK(order >= 1 && order <= 12, "local_order must be in [1,12]");
   MURAL_CHECK(model_type == MURAL_MODEL_SNV || model_type == MURAL_MODEL_INDEL, "model_type must be snv or indel");
   const int W = window_len(radius, model_type);
@@ -99,7 +99,7 @@ extern "C" int mural_encode_local(const mural_genome_t* g, const int32_t* d_pos,
 
 extern "C" int mural_encode_onehot(const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                                    int32_t radius, int32_t model_type, float* d_out, void* stream) {
-  MURAL_CHECK(g && d_out, "NULL argument");
+  MURAL_CHECK(g && (n == 0 || (d_pos && d_meta && d_out)), "NULL argument");
   MURAL_CHECK(model_type == MURAL_MODEL_SNV || model_type == MURAL_MODEL_INDEL, "model_type must be snv or indel");
   const int W = window_len(radius, model_type);
   MURAL_CHECK(radius >= 0 && W > 0, "empty window");

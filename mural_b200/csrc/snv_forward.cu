@@ -19,7 +19,8 @@ namespace mural {
 struct StemBranch {
   const float* T;     // [ks][16][C]
   const float* bias;  // [C]
-  float* out;         // [n][L1][C]
+  float* out;         // [n][L1][C], or fp32 planes [C/4][rows_alloc][4] with row(s,p) = 1 + s*(L1+1) + p
+  int64_t rows_alloc;  // 0: dense site-major layout
   int L0, off0, L1, pk, ps, pp;
 };
 
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(128) k_stem(GenomeView G, const int32_t* __res
         }
         mx = fmaxf(mx, v);
       }
-      out[e] = mx;
+      if (B.rows_alloc) B.out[(int64_t(c >> 2) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 4 + (c & 3)] = mx;
+      else out[e] = mx;
     }
   }
   // local k-mer indices from the centre of the already oriented window (seq_digit_encoder semantics)
@@ -381,12 +383,18 @@ static int save_tap(mural_snv_model* m, const char* name, const float* d, int64_
 
 int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                     const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st) {
+  return snv_stem_launch_planes(m, G, d_pos, d_meta, d_sym, ns, mid_out, 0, large_out, 0, cat_out, st);
+}
+
+int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
+                           const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
+                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st) {
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, L = m->L, R = m->cfg.distal_radius;
   StemBranch sb[2];
   for (int br = 0; br < 2; ++br) {
     const BranchDev& B = m->br[br];
-    sb[br] = StemBranch{B.T, B.bias1, br ? large_out : mid_out, B.L0, br ? 0 : L / 2 - 100, B.L1, B.pool[0][0], B.pool[0][1],
-                        B.pool[0][2]};
+    sb[br] = StemBranch{B.T, B.bias1, br ? large_out : mid_out, br ? large_rows_alloc : mid_rows_alloc, B.L0,
+                        br ? 0 : L / 2 - 100, B.L1, B.pool[0][0], B.pool[0][1], B.pool[0][2]};
   }
   const size_t smem = sizeof(float) * (2 * size_t(ks) * 16 * C + 2 * C) + ((size_t(L) + 15) & ~size_t(15));
   GenomeView gv = G ? *G : GenomeView{};

@@ -1,14 +1,533 @@
-// bf16 tcgen05 implicit-GEMM path of the Network2 conv stack (placeholder until the kernel lands).
+// bf16 tcgen05 path of the Network2 conv stack (MURAL_MODE_BF16): one kernel per *stage* of a branch, the whole
+// chain of Conv1d(32,32,3) layers of that stage executed back to back on 128-row tiles with every
+// intermediate activation kept on chip (TMEM accumulator -> registers -> bf16 A operand in shared memory).
+// Reference arithmetic: MuRaL/model/model_snv.py:475-488 / 497-510 and ResBlock :794-812.
+//
+// Row space of a stage: the L positions of every site of the chunk laid end to end with ONE all-zero
+// separator row between sites (and before the first / after the last):  row(s, p) = 1 + s*(L+1) + p.
+// The separator is the conv's zero padding, so a 3-tap convolution is three MMAs whose A operand is the
+// same shared-memory tile shifted by one 16-byte row (SWIZZLE_NONE K-major core matrices are row-linear):
+//     D[128 x 32] (TMEM, fp32) += A_tap[128 x 32ci] (smem bf16) * W_tap[32ci x 32co] (smem bf16),  tap = 0,1,2
+// i.e. 6 tcgen05.mma (M=128, N=32, K=16) per layer per tile, issued by one thread, completion via
+// tcgen05.commit -> mbarrier.  BatchNorm (eval) in front of each conv is folded into the bf16 weights and a
+// bias; because the reference pads AFTER the BN, the two rows at the site edges get a per-edge correction.
+// Global activations are fp32 in a plane-major layout  buf[plane = c/4][row][4 floats]  so that a warp
+// whose lanes own consecutive rows reads/writes 512 contiguous bytes per instruction.
+#include <cuda_bf16.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
 #include "snv_model.cuh"
 
 namespace mural {
-int snv_tc_prepare(mural_snv_model* m, const float* h_blob) { (void)m; (void)h_blob; return 0; }
-void snv_tc_destroy(mural_snv_model* m) { (void)m; }
+namespace tc {
+
+constexpr int TILE = 128;
+constexpr int A_ROWS = TILE + 2;       // one zero halo row above and below the tile
+constexpr int A_PLANE = A_ROWS * 16;   // bytes per 8-channel plane
+constexpr int A_BYTES = 4 * A_PLANE;   // 8320
+constexpr int W_LAYER = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
+constexpr int B_LAYER = 3 * 32;           // floats: bias_full, e_left, e_right
+constexpr int MAX_LAYERS = 5;
+// instruction descriptor, kind::f16: D=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), K-major A and B, N=32, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+enum Mode { RB4 = 0, C_RB4 = 1, SINGLE = 2 };
+__host__ __device__ constexpr int n_layers(int mode) { return mode == RB4 ? 4 : (mode == C_RB4 ? 5 : 1); }
+
+struct StageArgs {
+  const float* in;      // fp32 planes [8][in_rows_alloc][4]
+  float* out;           // fp32 planes [8][out_rows_alloc][4]
+  const uint8_t* wblob;  // n_layers * W_LAYER bytes of bf16 weights, then n_layers * B_LAYER floats
+  int64_t in_rows_alloc, out_rows_alloc;
+  int64_t rows;          // n_sites*(L+1)+1 rows of this stage
+  int L;                 // site length at this stage
+  int Lin;               // site length of the input buffer (== L when not pooled)
+  int pk, ps, pp;        // max-pool fused into the loader (pk == 0: none)
+  int n_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// SWIZZLE_NONE, K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((saddr >> 4) & 0x3FFFu) | (uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+#define TMEM_LD32(r, taddr)                                                                                          \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                      \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                      \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                    \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+      : "r"(taddr)                                                                                                   \
+      : "memory")
+
+// One stage of one branch.  128 threads; thread m owns tile row m through the whole layer chain, so the
+// residual stream (x0 / jump and the first ResBlock's output) lives in its registers.
+template <int MODE>
+__global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
+  constexpr int NL = n_layers(MODE);
+  constexpr int STRIDE = TILE - 2 * NL;  // valid output rows per tile (the chain eats NL rows on each side)
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;                                          // [4 planes][130 rows][16 B]
+  unsigned char* sW = smem + ((A_BYTES + 127) & ~127);               // [NL][W_LAYER]
+  float* sB = reinterpret_cast<float*>(sW + NL * W_LAYER);           // [NL][3][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + NL * B_LAYER);    // mbarrier
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  // ---- one-time setup: weights -> smem, zero halo rows, mbarrier, TMEM allocation (32 columns)
+  for (int e = tid * 16; e < NL * W_LAYER; e += 128 * 16)
+    *reinterpret_cast<uint4*>(sW + e) = *reinterpret_cast<const uint4*>(a.wblob + e);
+  {
+    const float* gb = reinterpret_cast<const float*>(a.wblob + NL * W_LAYER);
+    for (int e = tid; e < NL * B_LAYER; e += 128) sB[e] = gb[e];
+  }
+  if (tid < 8) {  // rows 0 and 129 of the four planes stay zero for the whole kernel
+    const int plane = tid >> 1, row = (tid & 1) ? (A_ROWS - 1) : 0;
+    *reinterpret_cast<uint4*>(sA + plane * A_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_row = tmem_base + (uint32_t(warp * 32) << 16);  // this warp's lane quarter
+  const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW), bar_u = smem_u32(bar);
+  uint32_t phase = 0;
+  const int Lp1 = a.L + 1;
+
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t r = int64_t(tile) * STRIDE - NL + tid;  // this thread's row in the stage's row space
+    int pos = -1;                                          // position inside the site; -1 = separator / outside
+    int64_t site = 0;
+    if (r > 0 && r < a.rows) {
+      site = r / Lp1;
+      pos = int(r - site * Lp1) - 1;
+    }
+    const bool live = pos >= 0;
+    float keep0[32], keep1[32];  // residual stream: x0 (or jump) and the first ResBlock's output
+    // ---------------------------------------------------------------- load the chain's input row
+    if (live) {
+      if (a.pk == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(a.in) + q * a.in_rows_alloc + r);
+          keep0[4 * q] = v.x; keep0[4 * q + 1] = v.y; keep0[4 * q + 2] = v.z; keep0[4 * q + 3] = v.w;
+        }
+      } else {  // MaxPool1d(pk, ps, pp) fused into the load; padding never wins (-inf), :361,371,404,414
+        int lo = pos * a.ps - a.pp, hi = lo + a.pk;
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > a.Lin ? a.Lin : hi;
+        const int64_t base = 1 + site * (a.Lin + 1);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) keep0[c] = -FLT_MAX;
+        for (int p = lo; p < hi; ++p) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.in) + q * a.in_rows_alloc + base + p);
+            keep0[4 * q] = fmaxf(keep0[4 * q], v.x); keep0[4 * q + 1] = fmaxf(keep0[4 * q + 1], v.y);
+            keep0[4 * q + 2] = fmaxf(keep0[4 * q + 2], v.z); keep0[4 * q + 3] = fmaxf(keep0[4 * q + 3], v.w);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) keep0[c] = 0.f;
+    }
+    // first A operand: relu(x0) for a ResBlock chain, x itself when the chain starts with BN->Conv (conv2/conv3)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pk4;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float x0 = keep0[8 * q + 2 * k], x1 = keep0[8 * q + 2 * k + 1];
+        if (MODE == RB4) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        w[k] = pack_bf16(x0, x1);
+      }
+      *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
+    }
+
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      // make the generic-proxy smem writes visible to the tensor core (async proxy), order prior tcgen05.ld
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t da = umma_desc(sA_u + (2 * h) * A_PLANE + t * 16, A_PLANE, 128);
+            const uint64_t db = umma_desc(sW_u + l * W_LAYER + (t * 4 + 2 * h) * 512, 512, 128);
+            umma_bf16(tmem_base, da, db, (t | h) ? 1u : 0u);
+          }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u) : "memory");
+      }
+      mbar_wait(bar_u, phase);
+      phase ^= 1;
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t acc[32];
+      TMEM_LD32(acc, tmem_row);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const float* bl = sB + l * B_LAYER;
+      float v[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float x = __uint_as_float(acc[c]) + bl[c];
+        if (pos == 0) x -= bl[32 + c];            // left tap fell on the zero padding, not on BN(0)
+        if (pos == a.L - 1) x -= bl[64 + c];      // right tap likewise
+        v[c] = x;
+      }
+      // residual wiring of the chain
+      const bool is_last = (l == NL - 1);
+      if (MODE == RB4) {
+        if (l == 1) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { v[c] += keep0[c]; keep1[c] = v[c]; }      // y1 = x0 + f1(x0)
+        } else if (l == 3) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += keep1[c] + keep0[c];                 // y2 + jump
+        }
+      } else if (MODE == C_RB4) {
+        if (l == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) keep0[c] = v[c];                             // jump = conv2(x)
+        } else if (l == 2) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { v[c] += keep0[c]; keep1[c] = v[c]; }
+        } else if (l == 4) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] += keep1[c] + keep0[c];
+        }
+      }
+      if (!is_last) {
+        // next layer's A operand: relu (every non-final layer feeds a ReLU->BN->Conv), zero on separators
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk4;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            w[k] = live ? pack_bf16(fmaxf(v[8 * q + 2 * k], 0.f), fmaxf(v[8 * q + 2 * k + 1], 0.f)) : 0u;
+          *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
+        }
+      } else {
+        const bool valid = live && tid >= NL && tid < TILE - NL;
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (MODE == SINGLE) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *(reinterpret_cast<float4*>(a.out) + q * a.out_rows_alloc + r) = o;
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+}
+
+// head for the plane layout: global max over the site's L3 rows of both branches, folded BN+Linear, combine
+struct HeadTc {
+  const float* x;  // fp32 planes [8][rows_alloc][4], conv3 output after ReLU
+  int64_t rows_alloc;
+  const float* Wfc;
+  const float* bfc;
+  int L3;
+};
+
+__global__ void __launch_bounds__(128) k_head_tc(HeadTc b0, HeadTc b1, const float* __restrict__ local_logits, int64_t n, int NC,
+                                                 float* __restrict__ logp, float* __restrict__ tg0, float* __restrict__ tg1,
+                                                 float* __restrict__ tl0, float* __restrict__ tl1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t site = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (site >= n) return;
+  float lg[2][16];
+#pragma unroll 1
+  for (int br = 0; br < 2; ++br) {
+    const HeadTc& B = br ? b1 : b0;
+    const int64_t base = 1 + site * (B.L3 + 1);
+    float mx = -FLT_MAX;  // lane = channel (C == 32)
+    for (int p = 0; p < B.L3; ++p) mx = fmaxf(mx, B.x[((lane >> 2) * B.rows_alloc + base + p) * 4 + (lane & 3)]);
+    float* tg = br ? tg1 : tg0;
+    if (tg) tg[site * 32 + lane] = mx;
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < NC) lg[br][o] = warp_sum(mx * B.Wfc[lane * NC + o]) + B.bfc[o];
+  }
+  if (lane != 0) return;
+  float sm[3][16];
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    float mx = -FLT_MAX, sum = 0.f;
+    for (int o = 0; o < NC; ++o) {
+      const float v = k == 2 ? local_logits[site * NC + o] : lg[k][o];
+      sm[k][o] = v;
+      mx = fmaxf(mx, v);
+    }
+    for (int o = 0; o < NC; ++o) { sm[k][o] = expf(sm[k][o] - mx); sum += sm[k][o]; }
+    for (int o = 0; o < NC; ++o) sm[k][o] /= sum;
+  }
+  for (int o = 0; o < NC; ++o) {
+    if (tl0) tl0[site * NC + o] = lg[0][o];
+    if (tl1) tl1[site * NC + o] = lg[1][o];
+    logp[site * NC + o] = logf(fmaxf((sm[2][o] + (sm[0][o] + sm[1][o]) / 2.f) / 2.f, 1e-9f));
+  }
+}
+
+struct TcState {
+  uint8_t* d_w = nullptr;         // all stage blobs back to back
+  const uint8_t* blob[2][3] = {};  // [branch][stage]
+};
+
+static inline int64_t rows_of(int64_t ns, int L) { return ns * (L + 1) + 1; }
+static inline int64_t rows_alloc(int64_t ns, int L) { return (rows_of(ns, L) + 7 + 8) & ~int64_t(7); }
+
+template <int MODE>
+static int launch_stage(const StageArgs& a, cudaStream_t st) {
+  constexpr int NL = n_layers(MODE);
+  const size_t smem = ((A_BYTES + 127) & ~127) + NL * W_LAYER + NL * B_LAYER * 4 + 16;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(k_stage_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int grid = a.n_tiles < 148 * 3 ? a.n_tiles : 148 * 3;
+  LAUNCH(k_stage_tc<MODE>, grid, 128, smem, st, a);
+  return 0;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------- host
+int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
+  snv_tc_destroy(m);
+  if (m->cfg.channels != 32 || m->cfg.kernel_size != 3) return 0;  // tcgen05 path is specialised; fp32 path serves the rest
+  using namespace tc;
+  auto T = [&](const std::string& n) { return h_blob + m->layout[m->index.at(n)].offset; };
+  std::vector<uint8_t> all;
+  size_t offs[2][3];
+  for (int br = 0; br < 2; ++br) {
+    const std::string s = br ? "_2" : "";
+    std::vector<std::pair<std::string, std::string>> chains[3];  // (bn, conv) per layer
+    for (int g = 1; g <= 2; ++g) {
+      if (g == 2) chains[1].push_back({"conv2" + s + ".0", "conv2" + s + ".1"});
+      for (int i = 0; i < 2; ++i) {
+        const std::string p = "RBs" + std::to_string(g) + s + "." + std::to_string(i);
+        chains[g - 1].push_back({p + ".bn1", p + ".conv1"});
+        chains[g - 1].push_back({p + ".bn2", p + ".conv2"});
+      }
+    }
+    chains[2].push_back({"conv3" + s + ".0", "conv3" + s + ".1"});
+    for (int stg = 0; stg < 3; ++stg) {
+      const int NL = (int)chains[stg].size();
+      while (all.size() % 256) all.push_back(0);
+      offs[br][stg] = all.size();
+      std::vector<uint8_t> wb(size_t(NL) * W_LAYER);
+      std::vector<float> fb(size_t(NL) * B_LAYER);
+      for (int l = 0; l < NL; ++l) {
+        const std::string &bn = chains[stg][l].first, &cv = chains[stg][l].second;
+        const float *g = T(bn + ".weight"), *be = T(bn + ".bias"), *mu = T(bn + ".running_mean"), *var = T(bn + ".running_var");
+        const float *W = T(cv + ".weight"), *bi = T(cv + ".bias");  // [co][ci][tap]
+        double a[32], b[32];
+        for (int c = 0; c < 32; ++c) {
+          a[c] = double(g[c]) / sqrt(double(var[c]) + 1e-5);
+          b[c] = double(be[c]) - double(mu[c]) * a[c];
+        }
+        __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(wb.data() + size_t(l) * W_LAYER);
+        for (int t = 0; t < 3; ++t)
+          for (int ci = 0; ci < 32; ++ci)
+            for (int co = 0; co < 32; ++co)
+              wl[((t * 4 + ci / 8) * 32 + co) * 8 + (ci % 8)] = __float2bfloat16(float(double(W[(co * 32 + ci) * 3 + t]) * a[ci]));
+        for (int co = 0; co < 32; ++co) {
+          double e[3] = {0, 0, 0};
+          for (int t = 0; t < 3; ++t)
+            for (int ci = 0; ci < 32; ++ci) e[t] += double(W[(co * 32 + ci) * 3 + t]) * b[ci];
+          fb[size_t(l) * B_LAYER + co] = float(double(bi[co]) + e[0] + e[1] + e[2]);
+          fb[size_t(l) * B_LAYER + 32 + co] = float(e[0]);
+          fb[size_t(l) * B_LAYER + 64 + co] = float(e[2]);
+        }
+      }
+      all.insert(all.end(), wb.begin(), wb.end());
+      const uint8_t* fp = reinterpret_cast<const uint8_t*>(fb.data());
+      all.insert(all.end(), fp, fp + fb.size() * 4);
+    }
+  }
+  TcState* S = new TcState();
+  if (cudaMalloc((void**)&S->d_w, all.size()) != cudaSuccess) {
+    delete S;
+    MURAL_FAIL("cudaMalloc of the tcgen05 weight blob failed");
+  }
+  cudaMemcpy(S->d_w, all.data(), all.size(), cudaMemcpyHostToDevice);
+  for (int br = 0; br < 2; ++br)
+    for (int stg = 0; stg < 3; ++stg) S->blob[br][stg] = S->d_w + offs[br][stg];
+  m->tc = S;
+  return 0;
+}
+
+void snv_tc_destroy(mural_snv_model* m) {
+  if (!m->tc) return;
+  tc::TcState* S = (tc::TcState*)m->tc;
+  cudaFree(S->d_w);
+  delete S;
+  m->tc = nullptr;
+}
+
+// de-plane a [8][rows_alloc][4] buffer into host [site][L][32] for the parity taps
+static int save_tap_planes(mural_snv_model* m, const char* name, const float* d, int64_t ralloc, int64_t ns, int L,
+                           cudaStream_t st) {
+  if (!m->debug) return 0;
+  std::vector<float> raw(size_t(8) * ralloc * 4);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaMemcpy(raw.data(), d, raw.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<float>& v = m->tap_store[name];
+  v.resize(size_t(ns) * L * 32);
+  for (int64_t s = 0; s < ns; ++s)
+    for (int p = 0; p < L; ++p)
+      for (int c = 0; c < 32; ++c) v[(s * L + p) * 32 + c] = raw[((c / 4) * ralloc + 1 + s * (L + 1) + p) * 4 + (c % 4)];
+  return 0;
+}
+
 int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                    const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st) {
-  (void)m; (void)G; (void)d_pos; (void)d_meta; (void)d_sym; (void)d_cat; (void)n; (void)d_logp; (void)st;
-  MURAL_FAIL("MURAL_MODE_BF16 is not available in this build");
+  using namespace tc;
+  MURAL_CHECK(m->tc != nullptr, "MURAL_MODE_BF16 needs CNN_out_channels == 32 and CNN_kernel_size == 3");
+  TcState* S = (TcState*)m->tc;
+  const int NC = m->cfg.n_class;
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 4096;
+  if (chunk > n) chunk = n;
+  // workspace: per branch X0 (stem out), Z1, Z2, H as fp32 planes; + local logits, taps, k-mer indices
+  int64_t floats = 0;
+  int64_t ra[2][4];
+  for (int br = 0; br < 2; ++br) {
+    const BranchDev& B = m->br[br];
+    ra[br][0] = rows_alloc(chunk, B.L1);
+    ra[br][1] = ra[br][0];
+    ra[br][2] = rows_alloc(chunk, B.L2);
+    ra[br][3] = rows_alloc(chunk, B.L3);
+    for (int k = 0; k < 4; ++k) floats += 32 * ra[br][k];
+  }
+  floats += chunk * (3 * NC + 64 + m->n_cat) + 64;
+  if (int rc = snv_ensure_workspace(m, floats * 4 + 256)) return rc;
+  float* w = (float*)m->d_ws;
+  float* bufs[2][4];
+  for (int br = 0; br < 2; ++br)
+    for (int k = 0; k < 4; ++k) { bufs[br][k] = w; w += 32 * ra[br][k]; }
+  float* llog = w; w += chunk * NC;
+  float* tl0 = w; w += chunk * NC;
+  float* tl1 = w; w += chunk * NC;
+  float* tg0 = w; w += chunk * 32;
+  float* tg1 = w; w += chunk * 32;
+  int32_t* cat32 = (int32_t*)w; w += chunk * m->n_cat;
+  int* err_flag = (int*)w;
+  CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
+
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
+    if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
+                                        d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
+                                        d_cat ? nullptr : cat32, st))
+      return rc;
+    if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, ns, llog, err_flag, st))
+      return rc;
+    for (int br = 1; br >= 0; --br) {
+      const BranchDev& B = m->br[br];
+      const char* sfx = br ? "_2" : "";
+      if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], ra[br][0], ns, B.L1, st)) return rc;
+      StageArgs a{};
+      // stage 1: two ResBlocks + outer skip at length L1
+      a.in = bufs[br][0]; a.out = bufs[br][1]; a.wblob = S->blob[br][0];
+      a.in_rows_alloc = ra[br][0]; a.out_rows_alloc = ra[br][1];
+      a.rows = rows_of(ns, B.L1); a.L = B.L1; a.Lin = B.L1; a.pk = 0; a.ps = 1; a.pp = 0;
+      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 4);
+      if (int rc = launch_stage<RB4>(a, st)) return rc;
+      if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], ra[br][1], ns, B.L1, st)) return rc;
+      // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
+      a.in = bufs[br][1]; a.out = bufs[br][2]; a.wblob = S->blob[br][1];
+      a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
+      a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
+      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 5);
+      if (int rc = launch_stage<C_RB4>(a, st)) return rc;
+      if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], ra[br][2], ns, B.L2, st)) return rc;
+      // stage 3: pool3 + conv3 + ReLU at length L3
+      a.in = bufs[br][2]; a.out = bufs[br][3]; a.wblob = S->blob[br][2];
+      a.in_rows_alloc = ra[br][2]; a.out_rows_alloc = ra[br][3];
+      a.rows = rows_of(ns, B.L3); a.L = B.L3; a.Lin = B.L2; a.pk = B.pool[2][0]; a.ps = B.pool[2][1]; a.pp = B.pool[2][2];
+      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 1);
+      if (int rc = launch_stage<SINGLE>(a, st)) return rc;
+    }
+    HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
+                    {bufs[1][3], ra[1][3], m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
+    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 32, 128), 128, 0, st, hb[0], hb[1], llog, ns, NC, d_logp + s0 * NC,
+           m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr);
+    if (m->debug) {
+      auto flat = [&](const char* nm, const float* d, int64_t k) -> int {
+        std::vector<float>& v = m->tap_store[nm];
+        v.resize(k);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(v.data(), d, k * 4, cudaMemcpyDeviceToHost));
+        return 0;
+      };
+      if (int rc = flat("gmax", tg0, ns * 32)) return rc;
+      if (int rc = flat("gmax_2", tg1, ns * 32)) return rc;
+      if (int rc = flat("logit_mid", tl0, ns * NC)) return rc;
+      if (int rc = flat("logit_large", tl1, ns * NC)) return rc;
+      if (int rc = flat("logit_local", llog, ns * NC)) return rc;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (d_cat) {
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, err_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    MURAL_CHECK((flag & 2) == 0, "IndexError: index out of range in embedding lookup");
+  }
+  return 0;
 }
+
 }  // namespace mural
 
-extern "C" int mural_snv_tc_available(const mural_snv_model_t* m) { (void)m; return 0; }
+extern "C" int mural_snv_tc_available(const mural_snv_model_t* m) { return (m && m->tc) ? 1 : 0; }

@@ -1,0 +1,83 @@
+"""GPU: bf16 tcgen05 path (MURAL_MODE_BF16) of Network2 vs the reference logits; gate 5e-3 on probabilities."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SNV_TAGS, load_snv_golden
+from test_gpu_snv_forward import build_model, probs, site_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bf16_taps_close_to_reference(kat, cuda_genome):
+    """Stage outputs of the chained tcgen05 kernels: relative error at bf16 level, catches layout/descriptor bugs."""
+    z, cfg, state = load_snv_golden("hs_AT")
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    m.set_debug(True, chunk=0)
+    with torch.no_grad():
+        m.forward(None, site_batch(z, cuda_genome))
+    C = cfg["CNN_out_channels"]
+    report = {}
+    for name in ("pool1", "pool1_2", "rb1", "rb1_2", "rb2", "rb2_2"):
+        if "tap_" + name not in z.files:
+            continue
+        ref = z["tap_" + name]
+        got = m.debug_tap(name).reshape(len(z["start"]), -1, C)[:16].transpose(0, 2, 1)
+        assert got.shape == ref.shape, name
+        report[name] = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    for name in ("gmax", "gmax_2", "logit_local", "logit_mid", "logit_large"):
+        ref = z["tap_" + name]
+        got = m.debug_tap(name).reshape(len(z["start"]), -1)[:16]
+        report[name] = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    print("bf16 tap relative errors:", report)
+    assert report["pool1_2"] < 1e-5 and report["logit_local"] < 1e-4     # fp32 parts of the path
+    for k, v in report.items():
+        assert v < 3e-2, (k, v, report)
+    m.set_debug(False)
+
+
+@pytest.mark.parametrize("tag", SNV_TAGS)
+def test_bf16_forward_matches_reference(kat, cuda_genome, tag):
+    z, cfg, state = load_snv_golden(tag)
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    with torch.no_grad():
+        lp = m.forward(None, site_batch(z, cuda_genome)).cpu().numpy()
+    d = np.abs(probs(lp) - probs(z["ref_logp"])).max()
+    print(tag, "bf16 max|dp| = %.3e" % d)
+    assert d <= 5e-3
+
+
+def test_bf16_chunking_and_tensor_path(kat, cuda_genome):
+    z, cfg, state = load_snv_golden("hs_nonCpG")
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    sb = site_batch(z, cuda_genome)
+    with torch.no_grad():
+        a = m.forward(None, sb)
+        m.set_debug(False, chunk=29)
+        b = m.forward(None, sb)
+        m.set_debug(False, chunk=0)
+        cat = cuda_genome.encode_local(sb.pos, sb.meta, cfg["local_radius"], cfg["local_order"])
+        oh = cuda_genome.encode_onehot(sb.pos, sb.meta, cfg["distal_radius"])
+        c = m.forward((None, cat), oh)
+    assert torch.equal(a, b), float((a - b).abs().max())     # tiling must not change any row's arithmetic
+    assert torch.equal(a, c)
+
+
+def test_bf16_large_batch_matches_fp32_path(kat, cuda_genome):
+    """Many tiles per CTA (persistent loop, phase flips): bf16 vs the fp32 kernels on 20k sites."""
+    from mural_b200 import SiteBatch, pack_meta
+    z, cfg, state = load_snv_golden("hs_AT")
+    _, genome = kat
+    rng = np.random.default_rng(4)
+    n = 20000
+    st = rng.integers(0, 30000, n).astype(np.int32)
+    sd = rng.integers(0, 2, n)
+    sb = SiteBatch(torch.from_numpy(st).cuda(), torch.from_numpy(pack_meta(sd, 0 * sd, 0 * sd)).cuda(), cuda_genome)
+    m = build_model(cfg, state, int(z["n_cat"]), mode="fp32")
+    with torch.no_grad():
+        a = m.forward(None, sb)
+        m.compute_mode = "bf16"
+        b = m.forward(None, sb)
+    d = (torch.softmax(a, 1) - torch.softmax(b, 1)).abs().max().item()
+    print("bf16 vs fp32 kernels, 20k sites: max|dp| = %.3e" % d)
+    assert d <= 5e-3
