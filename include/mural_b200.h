@@ -137,7 +137,7 @@ int mural_ce_sum(const float* d_logp, const int32_t* d_meta, int64_t n, int32_t 
 int mural_snv_tc_available(const mural_snv_model_t* m);
 /* sites per workspace chunk of the forward (0 = default); parity-test switch for debug taps */
 int mural_snv_set_chunk(mural_snv_model_t* m, int64_t chunk_sites);
-int mural_snv_set_debug(mural_snv_model_t* m, int32_t on);
+int mural_snv_set_debug(mural_snv_model_t* m, int32_t flags); /* bit0: keep taps, bit1: force the generic stem kernel */
 /* debug/parity taps: copies an intermediate activation of the LAST forward chunk to the host.
  * name in {"pool1","pool1_2","rb1_2","conv2_2","rb2_2","gmax","gmax_2","logit_local","logit_mid","logit_large"} */
 int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, int64_t max_floats,

@@ -19,6 +19,7 @@ namespace mural {
 struct StemBranch {
   const float* T;     // [ks][16][C]
   const float* bias;  // [C]
+  const float* T4;    // [256][C] pair table of the fast stem (ks == 3), may be NULL
   float* out;         // [n][L1][C], or fp32 planes [C/4][rows_alloc][4] with row(s,p) = 1 + s*(L1+1) + p
   int64_t rows_alloc;  // 0: dense site-major layout
   int L0, off0, L1, pk, ps, pp;
@@ -86,6 +87,115 @@ __global__ void __launch_bounds__(128) k_stem(GenomeView G, const int32_t* __res
         idx = idx * 4 + (s & 3);
       }
       cat_out[site * n_cat + j] = bad ? (1 << (2 * order)) : idx;
+    }
+  }
+}
+
+// Fast stem (ks == 3): persistent CTAs keep both branches' 4-mer pair tables in shared memory.  For an
+// all-ACGT window a pooled bin of 15 positions is the max of 8 table rows (2 rows for the 3-wide pool of the
+// middle branch); bins touching the window edge (missing tap = zero padding) and windows holding N/IUPAC
+// symbols or chromosome overhang go through the exact per-tap tables.  Lane mapping: C/4 lanes share a bin and
+// read one contiguous table row (conflict-free LDS.128), and write one 16-byte chunk each.
+template <int C>
+__device__ __forceinline__ float4 stem_bin_generic(const float* __restrict__ T, const float* __restrict__ bias,
+                                                   const uint8_t* __restrict__ s0, int L0, int lo, int hi, int q) {
+  float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+  for (int p = lo; p < hi; ++p) {
+    float4 v = b;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int x = p + t - 1;
+      const int sy = (x >= 0 && x < L0) ? s0[x] : SYM_PAD;
+      const float4 w = *reinterpret_cast<const float4*>(T + (t * 16 + sy) * C + 4 * q);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+  }
+  return mx;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256, 2) k_stem_fast(GenomeView G, const int32_t* __restrict__ pos,
+                                                      const int32_t* __restrict__ meta, const uint8_t* __restrict__ sym_in,
+                                                      int64_t ns, int R, int L, StemBranch b0, StemBranch b1, int local_R,
+                                                      int order, int n_cat, int32_t* __restrict__ cat_out) {
+  constexpr int CG = C / 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sT4 = reinterpret_cast<float*>(smem_raw);  // [2][256][C]
+  float* sT = sT4 + 2 * 256 * C;                    // [2][3][16][C]
+  float* sB = sT + 2 * 3 * 16 * C;                  // [2][C]
+  uint8_t* sym = reinterpret_cast<uint8_t*>(sB + 2 * C);
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  for (int e = tid * 4; e < 256 * C; e += 256 * 4) {
+    *reinterpret_cast<float4*>(sT4 + e) = *reinterpret_cast<const float4*>(b0.T4 + e);
+    *reinterpret_cast<float4*>(sT4 + 256 * C + e) = *reinterpret_cast<const float4*>(b1.T4 + e);
+  }
+  for (int e = tid; e < 3 * 16 * C; e += 256) {
+    sT[e] = b0.T[e];
+    sT[3 * 16 * C + e] = b1.T[e];
+  }
+  for (int e = tid; e < C; e += 256) {
+    sB[e] = b0.bias[e];
+    sB[C + e] = b1.bias[e];
+  }
+  const int Lw = (L + 3) >> 2;
+  for (int64_t site = blockIdx.x; site < ns; site += gridDim.x) {
+    __syncthreads();  // previous site's readers are done with sym / s_bad; tables visible on the first pass
+    if (tid == 0) s_bad = 0;
+    if (sym_in) {
+      for (int i = tid; i < L; i += 256) sym[i] = sym_in[site * L + i];
+    } else {
+      const int m = meta[site];
+      load_window(G, int(uint32_t(m) >> 8), int64_t(pos[site]) - R, L, m & 1, sym);
+    }
+    if (tid < 4) sym[L + tid] = 0;  // tail of the last word
+    __syncthreads();
+    {
+      bool bad = false;
+      for (int i = tid; i < Lw; i += 256) bad |= (reinterpret_cast<const uint32_t*>(sym)[i] & 0xFCFCFCFCu) != 0u;
+      if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    const bool slow = s_bad != 0;
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      const StemBranch& B = br ? b1 : b0;
+      const float* T4 = sT4 + br * 256 * C;
+      const uint8_t* s0 = sym + B.off0;
+      for (int item = tid; item < B.L1 * CG; item += 256) {
+        const int j = item / CG, q = item - j * CG;
+        int lo = j * B.ps - B.pp, hi = lo + B.pk;
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > B.L0 ? B.L0 : hi;
+        float4 mx;
+        if (slow || lo == 0 || hi == B.L0 || hi - lo < 2) {
+          mx = stem_bin_generic<C>(sT + br * 3 * 16 * C, sB + br * C, s0, B.L0, lo, hi, q);
+        } else {
+          mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+          for (int p = lo; p < hi; p += 2) {
+            const int pp = (p + 1 < hi) ? p : hi - 2;  // odd tail: overlap the last pair (max is idempotent)
+            const int k4 = s0[pp - 1] | (s0[pp] << 2) | (s0[pp + 1] << 4) | (s0[pp + 2] << 6);
+            const float4 w = *reinterpret_cast<const float4*>(T4 + k4 * C + 4 * q);
+            mx.x = fmaxf(mx.x, w.x); mx.y = fmaxf(mx.y, w.y); mx.z = fmaxf(mx.z, w.z); mx.w = fmaxf(mx.w, w.w);
+          }
+        }
+        if (B.rows_alloc) *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = mx;
+        else *reinterpret_cast<float4*>(B.out + (site * B.L1 + j) * int64_t(C) + 4 * q) = mx;
+      }
+    }
+    if (cat_out) {
+      for (int j = tid; j < n_cat; j += 256) {
+        int idx = 0;
+        bool bad = false;
+        for (int d = 0; d < order; ++d) {
+          const int sy = sym[R - local_R + j + d];
+          bad |= sy > 3;
+          idx = idx * 4 + (sy & 3);
+        }
+        cat_out[site * n_cat + j] = bad ? (1 << (2 * order)) : idx;
+      }
     }
   }
 }
@@ -393,8 +503,31 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
   StemBranch sb[2];
   for (int br = 0; br < 2; ++br) {
     const BranchDev& B = m->br[br];
-    sb[br] = StemBranch{B.T, B.bias1, br ? large_out : mid_out, br ? large_rows_alloc : mid_rows_alloc, B.L0,
+    sb[br] = StemBranch{B.T, B.bias1, B.T4, br ? large_out : mid_out, br ? large_rows_alloc : mid_rows_alloc, B.L0,
                         br ? 0 : L / 2 - 100, B.L1, B.pool[0][0], B.pool[0][1], B.pool[0][2]};
+  }
+  GenomeView gvf = G ? *G : GenomeView{};
+  if (ks == 3 && !m->slow_stem) {
+    const size_t smem_f = sizeof(float) * (2 * size_t(256) * C + 2 * 3 * 16 * size_t(C) + 2 * C) + ((size_t(L) + 4 + 15) & ~size_t(15));
+    int grid = int(ns < 148 * 2 ? ns : 148 * 2);
+#define STEMF_CASE(CC)                                                                                                     \
+  case CC: {                                                                                                              \
+    static size_t configured = 0;                                                                                         \
+    if (smem_f > configured) {                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(k_stem_fast<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));          \
+      configured = smem_f;                                                                                                \
+    }                                                                                                                     \
+    LAUNCH(k_stem_fast<CC>, grid, 256, smem_f, st, gvf, d_pos, d_meta, d_sym, ns, R, L, sb[0], sb[1], m->cfg.local_radius, \
+           m->cfg.local_order, m->n_cat, cat_out);                                                                        \
+  } break;
+    switch (C) {
+      STEMF_CASE(16)
+      STEMF_CASE(32)
+      STEMF_CASE(64)
+      default: MURAL_FAIL("unsupported channel count");
+    }
+#undef STEMF_CASE
+    return 0;
   }
   const size_t smem = sizeof(float) * (2 * size_t(ks) * 16 * C + 2 * C) + ((size_t(L) + 15) & ~size_t(15));
   GenomeView gv = G ? *G : GenomeView{};
@@ -542,7 +675,8 @@ static int check_model(const mural_snv_model_t* m) {
 
 extern "C" int mural_snv_set_debug(mural_snv_model_t* m, int32_t on) {
   MURAL_CHECK(m != nullptr, "model is NULL");
-  m->debug = on != 0;
+  m->debug = (on & 1) != 0;      // bit 0: keep parity taps of the last chunk
+  m->slow_stem = (on & 2) != 0;  // bit 1: force the generic per-tap stem kernel
   m->tap_store.clear();
   return 0;
 }

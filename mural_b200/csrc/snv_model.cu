@@ -230,7 +230,7 @@ extern "C" int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, i
     }
   }
   // ---- CNN branches
-  struct BrOff { int64_t T, bias1, Wfc, bfc; ConvOff rb1[4], conv2, rb2[4], conv3; } bo[2];
+  struct BrOff { int64_t T, bias1, T4, Wfc, bfc; ConvOff rb1[4], conv2, rb2[4], conv3; } bo[2];
   for (int br = 0; br < 2; ++br) {
     const std::string s = br ? "_2" : "";
     // stem table: BN(4) then Conv1d(4->C) applied to a one-hot column == table lookup per tap.
@@ -254,6 +254,22 @@ extern "C" int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, i
           }
           F.prep[bo[br].T + (int64_t(t) * 16 + sy) * C + co] = (float)acc;
         }
+    // 4-mer table of the fast stem (ks == 3): both positions of a pair share one lookup.  Built in float with
+    // the same summation order as the per-tap path (bias + tap0 + tap1 + tap2) so both paths agree bitwise.
+    bo[br].T4 = -1;
+    if (ks == 3) {
+      bo[br].T4 = F.alloc(int64_t(256) * C);
+      for (int k4 = 0; k4 < 256; ++k4) {
+        const int b0 = k4 & 3, b1 = (k4 >> 2) & 3, b2 = (k4 >> 4) & 3, b3 = (k4 >> 6) & 3;
+        for (int co = 0; co < C; ++co) {
+          const float* Tt = &F.prep[bo[br].T];
+          float v1 = F.prep[bo[br].bias1 + co], v2 = v1;
+          v1 += Tt[(0 * 16 + b0) * C + co]; v1 += Tt[(1 * 16 + b1) * C + co]; v1 += Tt[(2 * 16 + b2) * C + co];
+          v2 += Tt[(0 * 16 + b1) * C + co]; v2 += Tt[(1 * 16 + b2) * C + co]; v2 += Tt[(2 * 16 + b3) * C + co];
+          F.prep[bo[br].T4 + int64_t(k4) * C + co] = v1 > v2 ? v1 : v2;
+        }
+      }
+    }
     for (int g = 1; g <= 2; ++g) {
       ConvOff* rb = g == 1 ? bo[br].rb1 : bo[br].rb2;
       for (int i = 0; i < 2; ++i) {
@@ -294,6 +310,7 @@ extern "C" int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, i
     BranchDev& B = m->br[br];
     B.T = D + bo[br].T;
     B.bias1 = D + bo[br].bias1;
+    B.T4 = bo[br].T4 >= 0 ? D + bo[br].T4 : nullptr;
     B.Wfc = D + bo[br].Wfc;
     B.bfc = D + bo[br].bfc;
     for (int i = 0; i < 4; ++i) { B.rb1[i] = mk(bo[br].rb1[i]); B.rb2[i] = mk(bo[br].rb2[i]); }

@@ -29,6 +29,7 @@ struct ConvLayerDev {
 struct BranchDev {
   const float* T;      // stem table [ks][16 symbols][C]: conv1 applied to BN(4)(one-hot column)
   const float* bias1;  // [C]
+  const float* T4;     // ks==3 only: [256 4-mers][C] = max(conv1 at p, conv1 at p+1) incl. bias; index b(p-1) | b(p)<<2 | b(p+1)<<4 | b(p+2)<<6
   ConvLayerDev rb1[4];  // RBs1.0.conv1, RBs1.0.conv2, RBs1.1.conv1, RBs1.1.conv2
   ConvLayerDev conv2;
   ConvLayerDev rb2[4];
@@ -76,6 +77,7 @@ struct mural_snv_model {
   int64_t io_bytes = 0;
   // debug taps (parity tests): host copies of intermediate activations of the last chunk
   bool debug = false;
+  bool slow_stem = false;  // parity switch: force the generic per-tap stem kernel
   std::map<std::string, std::vector<float>> tap_store;
 };
 

@@ -148,3 +148,21 @@ def test_window_sweep_and_local10_vs_oracle(cuda_genome, kat):
             exp = NT.network2_forward(state, cat, oh, torch.float64).numpy()
         assert np.abs(probs(got) - probs(exp)).max() <= 1e-3, (R_d, R_l, ks)
         assert np.abs(got - exp).max() < 2e-4, (R_d, R_l, ks)
+
+
+def test_fast_stem_equals_generic_stem(kat, cuda_genome):
+    """4-mer pair-table stem == per-tap table stem, bit for bit (incl. N / IUPAC / chromosome-edge windows)."""
+    for tag in ("hs_AT", "ex_ckpt6"):
+        z, cfg, state = load_snv_golden(tag)
+        m = build_model(cfg, state, int(z["n_cat"]))
+        sb = site_batch(z, cuda_genome)
+        taps = {}
+        for flags in (1, 3):
+            m.set_debug(flags)
+            with torch.no_grad():
+                out = m.forward(None, sb)
+            taps[flags] = (m.debug_tap("pool1").copy(), m.debug_tap("pool1_2").copy(), out.clone())
+        m.set_debug(0)
+        assert np.array_equal(taps[1][0].view(np.uint32), taps[3][0].view(np.uint32))
+        assert np.array_equal(taps[1][1].view(np.uint32), taps[3][1].view(np.uint32))
+        assert torch.equal(taps[1][2], taps[3][2])
