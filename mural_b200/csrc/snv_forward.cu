@@ -201,20 +201,23 @@ __global__ void __launch_bounds__(256, 2) k_stem_fast(GenomeView G, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------ local MLP
-constexpr int MLP_TS = 8;  // sites per CTA
+constexpr int MLP_TS = 32;       // sites per CTA
+constexpr int MLP_THREADS = 160;
 
-__global__ void __launch_bounds__(128) k_local_mlp(LocalDev P, const int32_t* __restrict__ cat32,
-                                                   const int64_t* __restrict__ cat64, int64_t n, int n_cat, int emb_rows,
-                                                   int K1, int H1, int H2, int NC, float* __restrict__ logits,
-                                                   int* __restrict__ err_flag) {
+// Activations are kept transposed in shared memory ([feature][site]) so one LDS.128 feeds four FMAs of the
+// same weight; each thread owns one output neuron for all (or half) of the CTA's sites.
+__global__ void __launch_bounds__(MLP_THREADS) k_local_mlp(LocalDev P, const int32_t* __restrict__ cat32,
+                                                           const int64_t* __restrict__ cat64, int64_t n, int n_cat,
+                                                           int emb_rows, int K1, int H1, int H2, int NC,
+                                                           float* __restrict__ logits, int* __restrict__ err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* x = reinterpret_cast<float*>(smem_raw);  // [TS][K1]
-  float* h1 = x + MLP_TS * K1;                    // [TS][H1]
-  float* h2 = h1 + MLP_TS * H1;                   // [TS][H2]
+  float* xT = reinterpret_cast<float*>(smem_raw);  // [K1][TS]
+  float* h1T = xT + K1 * MLP_TS;                   // [H1][TS]
+  float* h2T = h1T + H1 * MLP_TS;                  // [H2][TS]
   const int64_t site0 = int64_t(blockIdx.x) * MLP_TS;
   const int tid = threadIdx.x;
-  for (int e = tid; e < MLP_TS * K1; e += blockDim.x) {
-    const int s = e / K1, k = e - s * K1;
+  for (int e = tid; e < MLP_TS * K1; e += MLP_THREADS) {
+    const int k = e / MLP_TS, s = e - k * MLP_TS;
     float v = 0.f;
     if (site0 + s < n) {
       const int64_t ci = (site0 + s) * n_cat + k / 5;
@@ -225,40 +228,57 @@ __global__ void __launch_bounds__(128) k_local_mlp(LocalDev P, const int32_t* __
       }
       v = P.emb[idx * 5 + k % 5];
     }
-    x[e] = v;
+    xT[e] = v;
   }
   __syncthreads();
-  for (int o = tid; o < H1; o += blockDim.x) {
+  for (int o = tid; o < H1; o += MLP_THREADS) {
     float acc[MLP_TS];
+    const float b = P.b1[o];
 #pragma unroll
-    for (int s = 0; s < MLP_TS; ++s) acc[s] = P.b1[o];
+    for (int s = 0; s < MLP_TS; ++s) acc[s] = b;
+#pragma unroll 4
     for (int k = 0; k < K1; ++k) {
-      const float w = P.W1t[k * H1 + o];
+      const float w = __ldg(P.W1t + k * H1 + o);
 #pragma unroll
-      for (int s = 0; s < MLP_TS; ++s) acc[s] = fmaf(x[s * K1 + k], w, acc[s]);
+      for (int s4 = 0; s4 < MLP_TS / 4; ++s4) {
+        const float4 x = *reinterpret_cast<const float4*>(xT + k * MLP_TS + 4 * s4);
+        acc[4 * s4] = fmaf(x.x, w, acc[4 * s4]); acc[4 * s4 + 1] = fmaf(x.y, w, acc[4 * s4 + 1]);
+        acc[4 * s4 + 2] = fmaf(x.z, w, acc[4 * s4 + 2]); acc[4 * s4 + 3] = fmaf(x.w, w, acc[4 * s4 + 3]);
+      }
     }
 #pragma unroll
-    for (int s = 0; s < MLP_TS; ++s) h1[s * H1 + o] = fmaxf(acc[s], 0.f);
+    for (int s4 = 0; s4 < MLP_TS / 4; ++s4)
+      *reinterpret_cast<float4*>(h1T + o * MLP_TS + 4 * s4) =
+          make_float4(fmaxf(acc[4 * s4], 0.f), fmaxf(acc[4 * s4 + 1], 0.f), fmaxf(acc[4 * s4 + 2], 0.f), fmaxf(acc[4 * s4 + 3], 0.f));
   }
   __syncthreads();
-  for (int o = tid; o < H2; o += blockDim.x) {
-    float acc[MLP_TS];
+  for (int item = tid; item < 2 * H2; item += MLP_THREADS) {  // (output neuron, half of the sites)
+    const int o = item % H2, hs = (item / H2) * (MLP_TS / 2);
+    float acc[MLP_TS / 2];
+    const float b = P.b2[o];
 #pragma unroll
-    for (int s = 0; s < MLP_TS; ++s) acc[s] = P.b2[o];
+    for (int s = 0; s < MLP_TS / 2; ++s) acc[s] = b;
+#pragma unroll 4
     for (int k = 0; k < H1; ++k) {
-      const float w = P.W2t[k * H2 + o];
+      const float w = __ldg(P.W2t + k * H2 + o);
 #pragma unroll
-      for (int s = 0; s < MLP_TS; ++s) acc[s] = fmaf(h1[s * H1 + k], w, acc[s]);
+      for (int s4 = 0; s4 < MLP_TS / 8; ++s4) {
+        const float4 x = *reinterpret_cast<const float4*>(h1T + k * MLP_TS + hs + 4 * s4);
+        acc[4 * s4] = fmaf(x.x, w, acc[4 * s4]); acc[4 * s4 + 1] = fmaf(x.y, w, acc[4 * s4 + 1]);
+        acc[4 * s4 + 2] = fmaf(x.z, w, acc[4 * s4 + 2]); acc[4 * s4 + 3] = fmaf(x.w, w, acc[4 * s4 + 3]);
+      }
     }
 #pragma unroll
-    for (int s = 0; s < MLP_TS; ++s) h2[s * H2 + o] = fmaxf(acc[s], 0.f);
+    for (int s4 = 0; s4 < MLP_TS / 8; ++s4)
+      *reinterpret_cast<float4*>(h2T + o * MLP_TS + hs + 4 * s4) =
+          make_float4(fmaxf(acc[4 * s4], 0.f), fmaxf(acc[4 * s4 + 1], 0.f), fmaxf(acc[4 * s4 + 2], 0.f), fmaxf(acc[4 * s4 + 3], 0.f));
   }
   __syncthreads();
-  for (int e = tid; e < MLP_TS * NC; e += blockDim.x) {
+  for (int e = tid; e < MLP_TS * NC; e += MLP_THREADS) {
     const int s = e / NC, o = e - s * NC;
     if (site0 + s >= n) continue;
     float acc = P.b3[o];
-    for (int k = 0; k < H2; ++k) acc = fmaf(h2[s * H2 + k], P.W3t[k * NC + o], acc);
+    for (int k = 0; k < H2; ++k) acc = fmaf(h2T[k * MLP_TS + s], __ldg(P.W3t + k * NC + o), acc);
     logits[(site0 + s) * NC + o] = acc;
   }
 }
@@ -560,7 +580,7 @@ int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* ca
     CUDA_TRY(cudaFuncSetAttribute(k_local_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  LAUNCH(k_local_mlp, (unsigned)cdiv(ns, MLP_TS), 128, smem, st, m->local, cat32, cat64, ns, m->n_cat, m->emb_rows, K1, H1, H2,
+  LAUNCH(k_local_mlp, (unsigned)cdiv(ns, MLP_TS), MLP_THREADS, smem, st, m->local, cat32, cat64, ns, m->n_cat, m->emb_rows, K1, H1, H2,
          m->cfg.n_class, logits, err_flag);
   return 0;
 }

@@ -27,9 +27,11 @@ constexpr int TILE = 128;
 constexpr int A_ROWS = TILE + 2;       // one zero halo row above and below the tile
 constexpr int A_PLANE = A_ROWS * 16;   // bytes per 8-channel plane
 constexpr int A_BYTES = 4 * A_PLANE;   // 8320
-constexpr int W_LAYER = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
-constexpr int B_LAYER = 3 * 32;           // floats: bias_full, e_left, e_right
-constexpr int MAX_LAYERS = 5;
+constexpr int AC_PLANE = TILE * 16;    // constant-column operand: [2 planes][128 rows][16 B]
+constexpr int AC_BYTES = 2 * AC_PLANE;
+constexpr int W_CONV = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
+constexpr int W_BIAS = 2 * 32 * 16;      // bf16 [k/8][co][8]: bias / edge-correction rows of the 7th MMA = 1024 bytes
+constexpr int W_LAYER = W_CONV + W_BIAS;
 // instruction descriptor, kind::f16: D=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), K-major A and B, N=32, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -39,7 +41,7 @@ __host__ __device__ constexpr int n_layers(int mode) { return mode == RB4 ? 4 : 
 struct StageArgs {
   const float* in;      // fp32 planes [8][in_rows_alloc][4]
   float* out;           // fp32 planes [8][out_rows_alloc][4]
-  const uint8_t* wblob;  // n_layers * W_LAYER bytes of bf16 weights, then n_layers * B_LAYER floats
+  const uint8_t* wblob;  // n_layers * W_LAYER bytes
   int64_t in_rows_alloc, out_rows_alloc;
   int64_t rows;          // n_sites*(L+1)+1 rows of this stage
   int L;                 // site length at this stage
@@ -73,8 +75,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// two fp32 -> packed bf16x2 (round to nearest even) with ReLU applied on the packed pair
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.f, 0.f));
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
@@ -92,29 +99,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 // One stage of one branch.  128 threads; thread m owns tile row m through the whole layer chain, so the
 // residual stream (x0 / jump and the first ResBlock's output) lives in its registers.
+// Per layer: 7 tcgen05.mma — one K=16 "constant column" MMA that deposits bias and the two site-edge
+// corrections (A row = {1,1, [pos==0]x2, [pos==L-1]x2, 0,0}, B rows = hi/lo bf16 splits of the fp32 constants)
+// followed by the 3 taps x 2 K-halves of the convolution — then one tcgen05.ld and a lean epilogue.
 template <int MODE>
-__global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
+__global__ void __launch_bounds__(128, 4) k_stage_tc(StageArgs a) {
   constexpr int NL = n_layers(MODE);
   constexpr int STRIDE = TILE - 2 * NL;  // valid output rows per tile (the chain eats NL rows on each side)
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sA = smem;                                          // [4 planes][130 rows][16 B]
-  unsigned char* sW = smem + ((A_BYTES + 127) & ~127);               // [NL][W_LAYER]
-  float* sB = reinterpret_cast<float*>(sW + NL * W_LAYER);           // [NL][3][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + NL * B_LAYER);    // mbarrier
+  unsigned char* sA = smem;                                  // [4 planes][130 rows][16 B]
+  unsigned char* sC = smem + ((A_BYTES + 127) & ~127);       // [2 planes][128 rows][16 B]
+  unsigned char* sW = sC + AC_BYTES;                         // [NL][W_LAYER]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sW + NL * W_LAYER);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
 
-  // ---- one-time setup: weights -> smem, zero halo rows, mbarrier, TMEM allocation (32 columns)
+  // ---- one-time setup: weights -> smem, zero halo rows / constant plane 1, mbarrier, TMEM allocation (32 columns)
   for (int e = tid * 16; e < NL * W_LAYER; e += 128 * 16)
     *reinterpret_cast<uint4*>(sW + e) = *reinterpret_cast<const uint4*>(a.wblob + e);
-  {
-    const float* gb = reinterpret_cast<const float*>(a.wblob + NL * W_LAYER);
-    for (int e = tid; e < NL * B_LAYER; e += 128) sB[e] = gb[e];
-  }
   if (tid < 8) {  // rows 0 and 129 of the four planes stay zero for the whole kernel
     const int plane = tid >> 1, row = (tid & 1) ? (A_ROWS - 1) : 0;
     *reinterpret_cast<uint4*>(sA + plane * A_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
   }
+  *reinterpret_cast<uint4*>(sC + AC_PLANE + tid * 16) = make_uint4(0, 0, 0, 0);  // K columns 8..15 are unused
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,9 +135,10 @@ __global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_row = tmem_base + (uint32_t(warp * 32) << 16);  // this warp's lane quarter
-  const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW), bar_u = smem_u32(bar);
+  const uint32_t sA_u = smem_u32(sA), sC_u = smem_u32(sC), sW_u = smem_u32(sW), bar_u = smem_u32(bar);
   uint32_t phase = 0;
   const int Lp1 = a.L + 1;
+  const float4* in4 = reinterpret_cast<const float4*>(a.in);
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t r = int64_t(tile) * STRIDE - NL + tid;  // this thread's row in the stage's row space
@@ -143,44 +151,58 @@ __global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
     const bool live = pos >= 0;
     float keep0[32], keep1[32];  // residual stream: x0 (or jump) and the first ResBlock's output
     // ---------------------------------------------------------------- load the chain's input row
-    if (live) {
-      if (a.pk == 0) {
+    if (MODE == RB4) {
+      if (live) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(a.in) + q * a.in_rows_alloc + r);
+          const float4 v = __ldg(in4 + q * a.in_rows_alloc + r);
           keep0[4 * q] = v.x; keep0[4 * q + 1] = v.y; keep0[4 * q + 2] = v.z; keep0[4 * q + 3] = v.w;
         }
-      } else {  // MaxPool1d(pk, ps, pp) fused into the load; padding never wins (-inf), :361,371,404,414
-        int lo = pos * a.ps - a.pp, hi = lo + a.pk;
-        lo = lo < 0 ? 0 : lo;
-        hi = hi > a.Lin ? a.Lin : hi;
-        const int64_t base = 1 + site * (a.Lin + 1);
+      } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) keep0[c] = -FLT_MAX;
-        for (int p = lo; p < hi; ++p) {
+        for (int c = 0; c < 32; ++c) keep0[c] = 0.f;
+      }
+    } else {  // MaxPool1d(pk, ps, pp) fused into the load; padding never wins (-inf), model_snv.py:361,371,404,414
+      int lo = pos * a.ps - a.pp, hi = lo + a.pk;
+      lo = lo < 0 ? 0 : lo;
+      hi = hi > a.Lin ? a.Lin : hi;
+      if (!live) hi = lo;
+      const int64_t base = 1 + site * (a.Lin + 1);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(a.in) + q * a.in_rows_alloc + base + p);
-            keep0[4 * q] = fmaxf(keep0[4 * q], v.x); keep0[4 * q + 1] = fmaxf(keep0[4 * q + 1], v.y);
-            keep0[4 * q + 2] = fmaxf(keep0[4 * q + 2], v.z); keep0[4 * q + 3] = fmaxf(keep0[4 * q + 3], v.w);
+      for (int c = 0; c < 32; ++c) keep0[c] = live ? -FLT_MAX : 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // two channel halves keep 4*7 loads in flight without 8*7 registers
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {         // pk <= 7 for every pool of Network2 (checked on the host)
+          const int p = lo + u;
+          if (p < hi) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int qq = half * 4 + q;
+              const float4 v = __ldg(in4 + qq * a.in_rows_alloc + base + p);
+              keep0[4 * qq] = fmaxf(keep0[4 * qq], v.x); keep0[4 * qq + 1] = fmaxf(keep0[4 * qq + 1], v.y);
+              keep0[4 * qq + 2] = fmaxf(keep0[4 * qq + 2], v.z); keep0[4 * qq + 3] = fmaxf(keep0[4 * qq + 3], v.w);
+            }
           }
         }
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) keep0[c] = 0.f;
     }
-    // first A operand: relu(x0) for a ResBlock chain, x itself when the chain starts with BN->Conv (conv2/conv3)
+    // constant-column operand row: {1, 1, [pos==0], [pos==0], [pos==L-1], [pos==L-1], 0, 0} in bf16 (1.0 = 0x3F80)
+    {
+      const uint32_t one2 = 0x3F803F80u;
+      uint4 cr = make_uint4(live ? one2 : 0u, pos == 0 ? one2 : 0u, (live && pos == a.L - 1) ? one2 : 0u, 0u);
+      *reinterpret_cast<uint4*>(sC + tid * 16) = cr;
+    }
+    // first A operand: relu(x0) for a ResBlock chain, x itself when the chain starts with BN->Conv (conv2/conv3);
+    // separator rows are written as zeros here and never touched again during the chain
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 pk4;
       uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float x0 = keep0[8 * q + 2 * k], x1 = keep0[8 * q + 2 * k + 1];
-        if (MODE == RB4) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        w[k] = pack_bf16(x0, x1);
-      }
+      for (int k = 0; k < 4; ++k)
+        w[k] = (MODE == RB4) ? pack_bf16_relu(keep0[8 * q + 2 * k], keep0[8 * q + 2 * k + 1])
+                             : pack_bf16(keep0[8 * q + 2 * k], keep0[8 * q + 2 * k + 1]);
       *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
     }
 
@@ -192,13 +214,14 @@ __global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
       __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        umma_bf16(tmem_base, umma_desc(sC_u, AC_PLANE, 128), umma_desc(sW_u + l * W_LAYER + W_CONV, 512, 128), 0u);
 #pragma unroll
         for (int t = 0; t < 3; ++t)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint64_t da = umma_desc(sA_u + (2 * h) * A_PLANE + t * 16, A_PLANE, 128);
             const uint64_t db = umma_desc(sW_u + l * W_LAYER + (t * 4 + 2 * h) * 512, 512, 128);
-            umma_bf16(tmem_base, da, db, (t | h) ? 1u : 0u);
+            umma_bf16(tmem_base, da, db, 1u);
           }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u) : "memory");
       }
@@ -209,15 +232,9 @@ __global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
       uint32_t acc[32];
       TMEM_LD32(acc, tmem_row);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const float* bl = sB + l * B_LAYER;
       float v[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float x = __uint_as_float(acc[c]) + bl[c];
-        if (pos == 0) x -= bl[32 + c];            // left tap fell on the zero padding, not on BN(0)
-        if (pos == a.L - 1) x -= bl[64 + c];      // right tap likewise
-        v[c] = x;
-      }
+      for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
       // residual wiring of the chain
       const bool is_last = (l == NL - 1);
       if (MODE == RB4) {
@@ -241,15 +258,16 @@ __global__ void __launch_bounds__(128, 3) k_stage_tc(StageArgs a) {
         }
       }
       if (!is_last) {
-        // next layer's A operand: relu (every non-final layer feeds a ReLU->BN->Conv), zero on separators
+        // next layer's A operand: every non-final layer feeds a ReLU->BN->Conv
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 pk4;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk4;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            w[k] = live ? pack_bf16(fmaxf(v[8 * q + 2 * k], 0.f), fmaxf(v[8 * q + 2 * k + 1], 0.f)) : 0u;
-          *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
+            for (int k = 0; k < 4; ++k) w[k] = pack_bf16_relu(v[8 * q + 2 * k], v[8 * q + 2 * k + 1]);
+            *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
+          }
         }
       } else {
         const bool valid = live && tid >= NL && tid < TILE - NL;
@@ -329,13 +347,13 @@ static inline int64_t rows_alloc(int64_t ns, int L) { return (rows_of(ns, L) + 7
 template <int MODE>
 static int launch_stage(const StageArgs& a, cudaStream_t st) {
   constexpr int NL = n_layers(MODE);
-  const size_t smem = ((A_BYTES + 127) & ~127) + NL * W_LAYER + NL * B_LAYER * 4 + 16;
+  const size_t smem = ((A_BYTES + 127) & ~127) + AC_BYTES + NL * W_LAYER + 16;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(k_stage_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  int grid = a.n_tiles < 148 * 3 ? a.n_tiles : 148 * 3;
+  int grid = a.n_tiles < 148 * 4 ? a.n_tiles : 148 * 4;
   LAUNCH(k_stage_tc<MODE>, grid, 128, smem, st, a);
   return 0;
 }
@@ -366,8 +384,7 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
       const int NL = (int)chains[stg].size();
       while (all.size() % 256) all.push_back(0);
       offs[br][stg] = all.size();
-      std::vector<uint8_t> wb(size_t(NL) * W_LAYER);
-      std::vector<float> fb(size_t(NL) * B_LAYER);
+      std::vector<uint8_t> wb(size_t(NL) * W_LAYER, 0);
       for (int l = 0; l < NL; ++l) {
         const std::string &bn = chains[stg][l].first, &cv = chains[stg][l].second;
         const float *g = T(bn + ".weight"), *be = T(bn + ".bias"), *mu = T(bn + ".running_mean"), *var = T(bn + ".running_var");
@@ -382,18 +399,22 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
           for (int ci = 0; ci < 32; ++ci)
             for (int co = 0; co < 32; ++co)
               wl[((t * 4 + ci / 8) * 32 + co) * 8 + (ci % 8)] = __float2bfloat16(float(double(W[(co * 32 + ci) * 3 + t]) * a[ci]));
+        // constant-column MMA operand: row co = {bias_hi, bias_lo, -e_left_hi, -e_left_lo, -e_right_hi, -e_right_lo, 0, 0}
+        __nv_bfloat16* cl = reinterpret_cast<__nv_bfloat16*>(wb.data() + size_t(l) * W_LAYER + W_CONV);
+        auto split = [](double x, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+          *hi = __float2bfloat16(float(x));
+          *lo = __float2bfloat16(float(x - double(__bfloat162float(*hi))));
+        };
         for (int co = 0; co < 32; ++co) {
           double e[3] = {0, 0, 0};
           for (int t = 0; t < 3; ++t)
             for (int ci = 0; ci < 32; ++ci) e[t] += double(W[(co * 32 + ci) * 3 + t]) * b[ci];
-          fb[size_t(l) * B_LAYER + co] = float(double(bi[co]) + e[0] + e[1] + e[2]);
-          fb[size_t(l) * B_LAYER + 32 + co] = float(e[0]);
-          fb[size_t(l) * B_LAYER + 64 + co] = float(e[2]);
+          split(double(bi[co]) + e[0] + e[1] + e[2], &cl[co * 8 + 0], &cl[co * 8 + 1]);
+          split(-e[0], &cl[co * 8 + 2], &cl[co * 8 + 3]);
+          split(-e[2], &cl[co * 8 + 4], &cl[co * 8 + 5]);
         }
       }
       all.insert(all.end(), wb.begin(), wb.end());
-      const uint8_t* fp = reinterpret_cast<const uint8_t*>(fb.data());
-      all.insert(all.end(), fp, fp + fb.size() * 4);
     }
   }
   TcState* S = new TcState();
