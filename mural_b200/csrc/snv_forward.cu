@@ -8,6 +8,7 @@
 //   k_conv      Conv1d(C,C,ks) with ReLU/BN prologue, zero padding per site, bias, up to two residuals (M5,M6)
 //   k_pool      MaxPool1d (-inf padding)                                                (M4)
 //   k_head      global max, BN+Linear heads, 3 softmaxes, average, clamp, log           (M7,M8)
+#include <cuda_bf16.h>
 #include <float.h>
 #include <string.h>
 
@@ -22,6 +23,7 @@ struct StemBranch {
   const float* T4;    // [256][C] pair table of the fast stem (ks == 3), may be NULL
   float* out;         // [n][L1][C], or fp32 planes [C/4][rows_alloc][4] with row(s,p) = 1 + s*(L1+1) + p
   int64_t rows_alloc;  // 0: dense site-major layout
+  int out_bf16;        // planes of 8 bf16 channels (16 B per row) instead of 4 fp32 channels
   int L0, off0, L1, pk, ps, pp;
 };
 
@@ -72,7 +74,10 @@ __global__ void __launch_bounds__(128) k_stem(GenomeView G, const int32_t* __res
         }
         mx = fmaxf(mx, v);
       }
-      if (B.rows_alloc) B.out[(int64_t(c >> 2) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 4 + (c & 3)] = mx;
+      if (B.rows_alloc && B.out_bf16)
+        reinterpret_cast<__nv_bfloat16*>(B.out)[(int64_t(c >> 3) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 8 + (c & 7)] =
+            __float2bfloat16(mx);
+      else if (B.rows_alloc) B.out[(int64_t(c >> 2) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 4 + (c & 3)] = mx;
       else out[e] = mx;
     }
   }
@@ -181,7 +186,12 @@ __global__ void __launch_bounds__(256, 2) k_stem_fast(GenomeView G, const int32_
             mx.x = fmaxf(mx.x, w.x); mx.y = fmaxf(mx.y, w.y); mx.z = fmaxf(mx.z, w.z); mx.w = fmaxf(mx.w, w.w);
           }
         }
-        if (B.rows_alloc) *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = mx;
+        if (B.rows_alloc && B.out_bf16) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(mx.x, mx.y), p1 = __floats2bfloat162_rn(mx.z, mx.w);
+          uint2 pk2 = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(B.out) +
+                                    (int64_t(q >> 1) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 16 + (q & 1) * 8) = pk2;
+        } else if (B.rows_alloc) *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = mx;
         else *reinterpret_cast<float4*>(B.out + (site * B.L1 + j) * int64_t(C) + 4 * q) = mx;
       }
     }
@@ -518,12 +528,12 @@ int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_po
 
 int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                            const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
-                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st) {
+                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16) {
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, L = m->L, R = m->cfg.distal_radius;
   StemBranch sb[2];
   for (int br = 0; br < 2; ++br) {
     const BranchDev& B = m->br[br];
-    sb[br] = StemBranch{B.T, B.bias1, B.T4, br ? large_out : mid_out, br ? large_rows_alloc : mid_rows_alloc, B.L0,
+    sb[br] = StemBranch{B.T, B.bias1, B.T4, br ? large_out : mid_out, br ? large_rows_alloc : mid_rows_alloc, out_bf16 ? 1 : 0, B.L0,
                         br ? 0 : L / 2 - 100, B.L1, B.pool[0][0], B.pool[0][1], B.pool[0][2]};
   }
   GenomeView gvf = G ? *G : GenomeView{};

@@ -24,14 +24,20 @@ namespace mural {
 namespace tc {
 
 constexpr int TILE = 128;
-constexpr int A_ROWS = TILE + 2;       // one zero halo row above and below the tile
-constexpr int A_PLANE = A_ROWS * 16;   // bytes per 8-channel plane
-constexpr int A_BYTES = 4 * A_PLANE;   // 8320
-constexpr int AC_PLANE = TILE * 16;    // constant-column operand: [2 planes][128 rows][16 B]
+constexpr int A_ROWS = TILE + 2;         // one zero halo row above and below the tile
+constexpr int A_PLANE = A_ROWS * 16;     // bytes per 8-channel plane
+constexpr int A_BYTES = 4 * A_PLANE;     // 8320
+constexpr int A_SLOT = (A_BYTES + 127) & ~127;
+constexpr int AC_PLANE = TILE * 16;      // constant-column operand: [2 planes][128 rows][16 B]
 constexpr int AC_BYTES = 2 * AC_PLANE;
+constexpr int SLOT_BYTES = A_SLOT + AC_BYTES;
 constexpr int W_CONV = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
 constexpr int W_BIAS = 2 * 32 * 16;      // bf16 [k/8][co][8]: bias / edge-correction rows of the 7th MMA = 1024 bytes
 constexpr int W_LAYER = W_CONV + W_BIAS;
+constexpr int NGROUP = 4;                // thread groups (128 threads = one tile's rows) per CTA
+constexpr int NINFL = 2;                 // tiles in flight per group
+constexpr int NSLOT = NGROUP * NINFL;    // 8 slots x 64 TMEM columns = all 512 columns of the SM
+constexpr int THREADS = NGROUP * 128;
 // instruction descriptor, kind::f16: D=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), K-major A and B, N=32, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -39,14 +45,14 @@ enum Mode { RB4 = 0, C_RB4 = 1, SINGLE = 2 };
 __host__ __device__ constexpr int n_layers(int mode) { return mode == RB4 ? 4 : (mode == C_RB4 ? 5 : 1); }
 
 struct StageArgs {
-  const float* in;      // fp32 planes [8][in_rows_alloc][4]
-  float* out;           // fp32 planes [8][out_rows_alloc][4]
+  const uint4* in;       // bf16 planes [4][in_rows_alloc] (one uint4 = 8 channels of one row)
+  void* out;             // bf16 planes [4][out_rows_alloc] (RB4, C_RB4) or fp32 planes [8][out_rows_alloc] float4 (SINGLE)
   const uint8_t* wblob;  // n_layers * W_LAYER bytes
   int64_t in_rows_alloc, out_rows_alloc;
   int64_t rows;          // n_sites*(L+1)+1 rows of this stage
   int L;                 // site length at this stage
   int Lin;               // site length of the input buffer (== L when not pooled)
-  int pk, ps, pp;        // max-pool fused into the loader (pk == 0: none)
+  int pk, ps, pp;        // max-pool fused into the loader (RB4: none)
   int n_tiles;
 };
 
@@ -75,15 +81,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-// two fp32 -> packed bf16x2 (round to nearest even) with ReLU applied on the packed pair
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), __floats2bfloat162_rn(0.f, 0.f));
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {
+  __nv_bfloat162 v = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w), __floats2bfloat162_rn(0.f, 0.f));
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 v = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 #define TMEM_LD32(r, taddr)                                                                                          \
   asm volatile(                                                                                                      \
@@ -97,195 +108,272 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
       : "r"(taddr)                                                                                                   \
       : "memory")
 
-// One stage of one branch.  128 threads; thread m owns tile row m through the whole layer chain, so the
-// residual stream (x0 / jump and the first ResBlock's output) lives in its registers.
-// Per layer: 7 tcgen05.mma — one K=16 "constant column" MMA that deposits bias and the two site-edge
-// corrections (A row = {1,1, [pos==0]x2, [pos==L-1]x2, 0,0}, B rows = hi/lo bf16 splits of the fp32 constants)
-// followed by the 3 taps x 2 K-halves of the convolution — then one tcgen05.ld and a lean epilogue.
+#define TMEM_ST32(taddr, r)                                                                                          \
+  asm volatile(                                                                                                      \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                     \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),             \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),  \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),    \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),    \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                                 \
+      : "memory")
+
+// One stage of one branch, persistent: one CTA per SM, 4 thread groups x 2 tiles in flight.
+//
+// A group's 128 threads own the 128 rows of a tile (thread = row = TMEM lane).  Per layer the group's warp 0
+// issues 7 tcgen05.mma (constant-column MMA for bias + site-edge corrections, then 3 taps x 2 K-halves) and
+// commits to the slot's mbarrier; while those run, the group serves its other in-flight tile.  Warps 1-3 only
+// bar.arrive on the slot's named barrier and run ahead.  The residual stream never leaves the tensor core:
+// TMEM region R (32 columns) is pre-loaded with x0 (tcgen05.st) and the second conv of each ResBlock
+// ACCUMULATES onto it, the first conv of each ResBlock goes to a scratch region T.  The epilogue of a layer is
+// therefore only  tcgen05.ld -> bf16 -> ReLU -> st.shared  (the next layer's A operand).
 template <int MODE>
-__global__ void __launch_bounds__(128, 4) k_stage_tc(StageArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   constexpr int NL = n_layers(MODE);
   constexpr int STRIDE = TILE - 2 * NL;  // valid output rows per tile (the chain eats NL rows on each side)
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* sA = smem;                                  // [4 planes][130 rows][16 B]
-  unsigned char* sC = smem + ((A_BYTES + 127) & ~127);       // [2 planes][128 rows][16 B]
-  unsigned char* sW = sC + AC_BYTES;                         // [NL][W_LAYER]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sW + NL * W_LAYER);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  unsigned char* sW = smem;                              // [NL][W_LAYER], shared by all slots
+  unsigned char* sSlots = sW + NL * W_LAYER;             // [NSLOT][SLOT_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlots + NSLOT * SLOT_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int g = tid >> 7, lt = tid & 127;
 
-  // ---- one-time setup: weights -> smem, zero halo rows / constant plane 1, mbarrier, TMEM allocation (32 columns)
-  for (int e = tid * 16; e < NL * W_LAYER; e += 128 * 16)
-    *reinterpret_cast<uint4*>(sW + e) = *reinterpret_cast<const uint4*>(a.wblob + e);
-  if (tid < 8) {  // rows 0 and 129 of the four planes stay zero for the whole kernel
-    const int plane = tid >> 1, row = (tid & 1) ? (A_ROWS - 1) : 0;
-    *reinterpret_cast<uint4*>(sA + plane * A_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  // ---- one-time setup
+  {
+    constexpr int NV = NL * W_LAYER / 16;  // uint4 count
+    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+#pragma unroll
+    for (int i = 0; i < (NV + THREADS - 1) / THREADS; ++i) {
+      const int e = tid + i * THREADS;
+      if (e < NV) dst[e] = __ldg(src + e);
+    }
   }
-  *reinterpret_cast<uint4*>(sC + AC_PLANE + tid * 16) = make_uint4(0, 0, 0, 0);  // K columns 8..15 are unused
+  for (int e = tid; e < NSLOT * 8; e += THREADS) {  // halo rows 0 and 129 of the 4 planes of every slot
+    const int sl = e >> 3, plane = (e >> 1) & 3, row = (e & 1) ? (A_ROWS - 1) : 0;
+    *reinterpret_cast<uint4*>(sSlots + sl * SLOT_BYTES + plane * A_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  }
+  for (int e = tid; e < NSLOT * TILE; e += THREADS) {  // K columns 8..15 of the constant operand are unused
+    const int sl = e >> 7, row = e & 127;
+    *reinterpret_cast<uint4*>(sSlots + sl * SLOT_BYTES + A_SLOT + AC_PLANE + row * 16) = make_uint4(0, 0, 0, 0);
+  }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_row = tmem_base + (uint32_t(warp * 32) << 16);  // this warp's lane quarter
-  const uint32_t sA_u = smem_u32(sA), sC_u = smem_u32(sC), sW_u = smem_u32(sW), bar_u = smem_u32(bar);
-  uint32_t phase = 0;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
   const int Lp1 = a.L + 1;
-  const float4* in4 = reinterpret_cast<const float4*>(a.in);
+  const int tile_step = gridDim.x * NSLOT;
+  // descriptor bases (start-address field is the low 14 bits: offsets below never carry out of it)
+  const uint64_t dW0 = umma_desc(smem_u32(sW), 512, 128);
+  const uint64_t dA0 = umma_desc(smem_u32(sSlots), A_PLANE, 128);
+  const uint64_t dC0 = umma_desc(smem_u32(sSlots) + A_SLOT, AC_PLANE, 128);
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int64_t r = int64_t(tile) * STRIDE - NL + tid;  // this thread's row in the stage's row space
-    int pos = -1;                                          // position inside the site; -1 = separator / outside
+  // per in-flight tile state (registers; the k loops below are fully unrolled)
+  int tile[NINFL], layer[NINFL], pos[NINFL];
+  uint32_t phase[NINFL];
+  int64_t row[NINFL];
+  bool active[NINFL];
+
+  auto slot_of = [&](int k) { return g * NINFL + k; };
+  auto sA_of = [&](int k) { return sSlots + slot_of(k) * SLOT_BYTES; };
+
+  // publish the slot's operands to the tensor core: warps 1-3 of the group arrive and run ahead, warp 0 waits for
+  // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
+  // One named barrier per slot so that a warp running one step ahead never double-arrives.
+  auto sync_and_issue = [&](int k, int l) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    const int sl = slot_of(k);
+    if (lt >= 32) {
+      asm volatile("bar.arrive %0, 128;" ::"r"(1 + sl) : "memory");
+    } else {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
+      if (lt == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // R-type layers (second conv of a ResBlock, conv2, conv3) accumulate into / create region R, others use T
+        const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
+        const bool acc_first = (MODE == RB4) ? rtype : (MODE == C_RB4 ? (rtype && l > 0) : false);
+        const uint32_t d = tmem_base + sl * 64 + (rtype ? 0 : 32);
+        const uint64_t dA = dA0 + uint64_t((sl * SLOT_BYTES) >> 4), dC = dC0 + uint64_t((sl * SLOT_BYTES) >> 4);
+        const uint64_t dW = dW0 + uint64_t((l * W_LAYER) >> 4);
+        umma_bf16(d, dC, dW + (W_CONV >> 4), acc_first ? 1u : 0u);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + sl))
+                     : "memory");
+      }
+      __syncwarp();
+    }
+  };
+
+  // load the chain input of the slot's tile, build the first A operand / constant operand / residual region
+  auto begin_tile = [&](int k) {
+    const int64_t r = int64_t(tile[k]) * STRIDE - NL + lt;
+    int p = -1;
     int64_t site = 0;
     if (r > 0 && r < a.rows) {
       site = r / Lp1;
-      pos = int(r - site * Lp1) - 1;
+      p = int(r - site * Lp1) - 1;
     }
-    const bool live = pos >= 0;
-    float keep0[32], keep1[32];  // residual stream: x0 (or jump) and the first ResBlock's output
-    // ---------------------------------------------------------------- load the chain's input row
+    row[k] = r;
+    pos[k] = p;
+    const bool live = p >= 0;
+    unsigned char* sA = sA_of(k);
+    uint4 x[4];
     if (MODE == RB4) {
-      if (live) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = __ldg(in4 + q * a.in_rows_alloc + r);
-          keep0[4 * q] = v.x; keep0[4 * q + 1] = v.y; keep0[4 * q + 2] = v.z; keep0[4 * q + 3] = v.w;
+      for (int q = 0; q < 4; ++q) x[q] = live ? __ldg(a.in + q * a.in_rows_alloc + r) : make_uint4(0, 0, 0, 0);
+      // residual region R <- x0 (fp32), first A operand <- relu(x0)
+      uint32_t f[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[8 * q + 2 * j] = w[j] << 16;
+          f[8 * q + 2 * j + 1] = w[j] & 0xFFFF0000u;
         }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) keep0[c] = 0.f;
       }
-    } else {  // MaxPool1d(pk, ps, pp) fused into the load; padding never wins (-inf), model_snv.py:361,371,404,414
-      int lo = pos * a.ps - a.pp, hi = lo + a.pk;
+      TMEM_ST32(tmem_base + lane_off + slot_of(k) * 64, f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = relu_bf16x2(x[q].x); o.y = relu_bf16x2(x[q].y); o.z = relu_bf16x2(x[q].z); o.w = relu_bf16x2(x[q].w);
+        *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = o;
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else {  // MaxPool1d(pk, ps, pp) fused into the load (padding = -inf never wins), model_snv.py:361,371,404,414
+      int lo = p * a.ps - a.pp, hi = lo + a.pk;
       lo = lo < 0 ? 0 : lo;
       hi = hi > a.Lin ? a.Lin : hi;
       if (!live) hi = lo;
       const int64_t base = 1 + site * (a.Lin + 1);
+      const uint32_t ninf = live ? 0xFF80FF80u : 0u;  // bf16 -inf pair; separator rows stay zero
 #pragma unroll
-      for (int c = 0; c < 32; ++c) keep0[c] = live ? -FLT_MAX : 0.f;
+      for (int q = 0; q < 4; ++q) x[q] = make_uint4(ninf, ninf, ninf, ninf);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {  // two channel halves keep 4*7 loads in flight without 8*7 registers
+      for (int u = 0; u < 7; ++u) {  // pk <= 7 for every pool of Network2 (checked on the host)
+        if (lo + u < hi) {
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {         // pk <= 7 for every pool of Network2 (checked on the host)
-          const int p = lo + u;
-          if (p < hi) {
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(a.in + q * a.in_rows_alloc + base + lo + u);
+            x[q].x = max_bf16x2(x[q].x, v.x); x[q].y = max_bf16x2(x[q].y, v.y);
+            x[q].z = max_bf16x2(x[q].z, v.z); x[q].w = max_bf16x2(x[q].w, v.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = x[q];
+    }
+    // constant-column operand row: {1, 1, [pos==0], [pos==0], [pos==L-1], [pos==L-1], 0, 0} in bf16 (1.0 = 0x3F80)
+    const uint32_t one2 = 0x3F803F80u;
+    *reinterpret_cast<uint4*>(sA + A_SLOT + lt * 16) =
+        make_uint4(live ? one2 : 0u, p == 0 ? one2 : 0u, (live && p == a.L - 1) ? one2 : 0u, 0u);
+    layer[k] = 0;
+    sync_and_issue(k, 0);
+  };
+
+#pragma unroll
+  for (int k = 0; k < NINFL; ++k) {
+    tile[k] = (blockIdx.x * NGROUP + g) * NINFL + k;
+    phase[k] = 0;
+    active[k] = tile[k] < a.n_tiles;
+    layer[k] = 0;
+    row[k] = 0;
+    pos[k] = -1;
+  }
+#pragma unroll
+  for (int k = 0; k < NINFL; ++k)
+    if (active[k]) begin_tile(k);
+
+  while (active[0] || active[1]) {
+#pragma unroll
+    for (int k = 0; k < NINFL; ++k) {
+      if (!active[k]) continue;
+      mbar_wait(smem_u32(bars + slot_of(k)), phase[k]);
+      phase[k] ^= 1;
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int l = layer[k];
+      const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
+      const bool live = pos[k] >= 0;
+      const bool valid = live && lt >= NL && lt < TILE - NL;
+      const int64_t r = row[k];
+      uint32_t acc[32];
+      TMEM_LD32(acc, tmem_base + lane_off + slot_of(k) * 64 + (rtype ? 0 : 32));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (l < NL - 1) {
+        uint4 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          o[q].x = pack_bf16(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
+          o[q].y = pack_bf16(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3]));
+          o[q].z = pack_bf16(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
+          o[q].w = pack_bf16(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
+        }
+        if (MODE == C_RB4 && l == 0 && valid) {  // jump = conv2 output: parked (bf16) in the output row, re-read at the end
+          uint4* out4 = reinterpret_cast<uint4*>(a.out);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r] = o[q];
+        }
+        if (live) {  // separator rows were zeroed by begin_tile and are never rewritten
+          unsigned char* sA = sA_of(k);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = relu_bf16x2(o[q].x); w.y = relu_bf16x2(o[q].y); w.z = relu_bf16x2(o[q].z); w.w = relu_bf16x2(o[q].w);
+            *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = w;
+          }
+        }
+        layer[k] = l + 1;
+        sync_and_issue(k, l + 1);
+      } else {
+        if (valid) {
+          if (MODE == SINGLE) {  // conv3 + ReLU -> fp32 planes for the head
+            float4* out4 = reinterpret_cast<float4*>(a.out);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              out4[q * a.out_rows_alloc + r] =
+                  make_float4(fmaxf(__uint_as_float(acc[4 * q]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 1]), 0.f),
+                              fmaxf(__uint_as_float(acc[4 * q + 2]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 3]), 0.f));
+          } else {  // outer skip: + x0 (RB4, re-read from the input) or + jump (C_RB4, parked in the output row)
+            uint4* out4 = reinterpret_cast<uint4*>(a.out);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int qq = half * 4 + q;
-              const float4 v = __ldg(in4 + qq * a.in_rows_alloc + base + p);
-              keep0[4 * qq] = fmaxf(keep0[4 * qq], v.x); keep0[4 * qq + 1] = fmaxf(keep0[4 * qq + 1], v.y);
-              keep0[4 * qq + 2] = fmaxf(keep0[4 * qq + 2], v.z); keep0[4 * qq + 3] = fmaxf(keep0[4 * qq + 3], v.w);
+              const uint4 x = (MODE == RB4) ? __ldg(a.in + q * a.in_rows_alloc + r) : out4[q * a.out_rows_alloc + r];
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(acc[8 * q]) + bf16_lo(x.x), __uint_as_float(acc[8 * q + 1]) + bf16_hi(x.x));
+              o.y = pack_bf16(__uint_as_float(acc[8 * q + 2]) + bf16_lo(x.y), __uint_as_float(acc[8 * q + 3]) + bf16_hi(x.y));
+              o.z = pack_bf16(__uint_as_float(acc[8 * q + 4]) + bf16_lo(x.z), __uint_as_float(acc[8 * q + 5]) + bf16_hi(x.z));
+              o.w = pack_bf16(__uint_as_float(acc[8 * q + 6]) + bf16_lo(x.w), __uint_as_float(acc[8 * q + 7]) + bf16_hi(x.w));
+              out4[q * a.out_rows_alloc + r] = o;
             }
           }
         }
-      }
-    }
-    // constant-column operand row: {1, 1, [pos==0], [pos==0], [pos==L-1], [pos==L-1], 0, 0} in bf16 (1.0 = 0x3F80)
-    {
-      const uint32_t one2 = 0x3F803F80u;
-      uint4 cr = make_uint4(live ? one2 : 0u, pos == 0 ? one2 : 0u, (live && pos == a.L - 1) ? one2 : 0u, 0u);
-      *reinterpret_cast<uint4*>(sC + tid * 16) = cr;
-    }
-    // first A operand: relu(x0) for a ResBlock chain, x itself when the chain starts with BN->Conv (conv2/conv3);
-    // separator rows are written as zeros here and never touched again during the chain
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 pk4;
-      uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        w[k] = (MODE == RB4) ? pack_bf16_relu(keep0[8 * q + 2 * k], keep0[8 * q + 2 * k + 1])
-                             : pack_bf16(keep0[8 * q + 2 * k], keep0[8 * q + 2 * k + 1]);
-      *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
-    }
-
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-      // make the generic-proxy smem writes visible to the tensor core (async proxy), order prior tcgen05.ld
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        umma_bf16(tmem_base, umma_desc(sC_u, AC_PLANE, 128), umma_desc(sW_u + l * W_LAYER + W_CONV, 512, 128), 0u);
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t da = umma_desc(sA_u + (2 * h) * A_PLANE + t * 16, A_PLANE, 128);
-            const uint64_t db = umma_desc(sW_u + l * W_LAYER + (t * 4 + 2 * h) * 512, 512, 128);
-            umma_bf16(tmem_base, da, db, 1u);
-          }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_u) : "memory");
-      }
-      mbar_wait(bar_u, phase);
-      phase ^= 1;
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t acc[32];
-      TMEM_LD32(acc, tmem_row);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float v[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
-      // residual wiring of the chain
-      const bool is_last = (l == NL - 1);
-      if (MODE == RB4) {
-        if (l == 1) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { v[c] += keep0[c]; keep1[c] = v[c]; }      // y1 = x0 + f1(x0)
-        } else if (l == 3) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] += keep1[c] + keep0[c];                 // y2 + jump
-        }
-      } else if (MODE == C_RB4) {
-        if (l == 0) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) keep0[c] = v[c];                             // jump = conv2(x)
-        } else if (l == 2) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { v[c] += keep0[c]; keep1[c] = v[c]; }
-        } else if (l == 4) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] += keep1[c] + keep0[c];
-        }
-      }
-      if (!is_last) {
-        // next layer's A operand: every non-final layer feeds a ReLU->BN->Conv
-        if (live) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 pk4;
-            uint32_t* w = reinterpret_cast<uint32_t*>(&pk4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = pack_bf16_relu(v[8 * q + 2 * k], v[8 * q + 2 * k + 1]);
-            *reinterpret_cast<uint4*>(sA + q * A_PLANE + (tid + 1) * 16) = pk4;
-          }
-        }
-      } else {
-        const bool valid = live && tid >= NL && tid < TILE - NL;
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (MODE == SINGLE) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *(reinterpret_cast<float4*>(a.out) + q * a.out_rows_alloc + r) = o;
-          }
-        }
+        tile[k] += tile_step;
+        active[k] = tile[k] < a.n_tiles;
+        if (active[k]) begin_tile(k);
       }
     }
   }
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // head for the plane layout: global max over the site's L3 rows of both branches, folded BN+Linear, combine
@@ -344,17 +432,29 @@ struct TcState {
 static inline int64_t rows_of(int64_t ns, int L) { return ns * (L + 1) + 1; }
 static inline int64_t rows_alloc(int64_t ns, int L) { return (rows_of(ns, L) + 7 + 8) & ~int64_t(7); }
 
+static int m_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int MODE>
 static int launch_stage(const StageArgs& a, cudaStream_t st) {
   constexpr int NL = n_layers(MODE);
-  const size_t smem = ((A_BYTES + 127) & ~127) + AC_BYTES + NL * W_LAYER + 16;
+  const size_t smem = size_t(NL) * W_LAYER + size_t(NSLOT) * SLOT_BYTES + NSLOT * 8 + 16;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(k_stage_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  int grid = a.n_tiles < 148 * 4 ? a.n_tiles : 148 * 4;
-  LAUNCH(k_stage_tc<MODE>, grid, 128, smem, st, a);
+  int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
+  if (grid > m_sm_count()) grid = m_sm_count();
+  LAUNCH(k_stage_tc<MODE>, grid, THREADS, smem, st, a);
   return 0;
 }
 
@@ -437,18 +537,29 @@ void snv_tc_destroy(mural_snv_model* m) {
   m->tc = nullptr;
 }
 
-// de-plane a [8][rows_alloc][4] buffer into host [site][L][32] for the parity taps
-static int save_tap_planes(mural_snv_model* m, const char* name, const float* d, int64_t ralloc, int64_t ns, int L,
+// de-plane a bf16 [4][rows_alloc][8] (or fp32 [8][rows_alloc][4]) buffer into host [site][L][32] for the parity taps
+static int save_tap_planes(mural_snv_model* m, const char* name, const void* d, bool is_bf16, int64_t ralloc, int64_t ns, int L,
                            cudaStream_t st) {
   if (!m->debug) return 0;
-  std::vector<float> raw(size_t(8) * ralloc * 4);
+  std::vector<uint8_t> raw(size_t(ralloc) * (is_bf16 ? 64 : 128));
   CUDA_TRY(cudaStreamSynchronize(st));
-  CUDA_TRY(cudaMemcpy(raw.data(), d, raw.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(raw.data(), d, raw.size(), cudaMemcpyDeviceToHost));
   std::vector<float>& v = m->tap_store[name];
   v.resize(size_t(ns) * L * 32);
   for (int64_t s = 0; s < ns; ++s)
     for (int p = 0; p < L; ++p)
-      for (int c = 0; c < 32; ++c) v[(s * L + p) * 32 + c] = raw[((c / 4) * ralloc + 1 + s * (L + 1) + p) * 4 + (c % 4)];
+      for (int c = 0; c < 32; ++c) {
+        const int64_t r = 1 + s * (L + 1) + p;
+        float x;
+        if (is_bf16) {
+          const uint16_t h = reinterpret_cast<const uint16_t*>(raw.data())[((c / 8) * ralloc + r) * 8 + (c % 8)];
+          const uint32_t u = uint32_t(h) << 16;
+          memcpy(&x, &u, 4);
+        } else {
+          x = reinterpret_cast<const float*>(raw.data())[((c / 4) * ralloc + r) * 4 + (c % 4)];
+        }
+        v[(s * L + p) * 32 + c] = x;
+      }
   return 0;
 }
 
@@ -469,14 +580,14 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     ra[br][1] = ra[br][0];
     ra[br][2] = rows_alloc(chunk, B.L2);
     ra[br][3] = rows_alloc(chunk, B.L3);
-    for (int k = 0; k < 4; ++k) floats += 32 * ra[br][k];
+    for (int k = 0; k < 4; ++k) floats += (k < 3 ? 16 : 32) * ra[br][k];   // X0, Z1, Z2 are bf16 planes, H is fp32 planes
   }
   floats += chunk * (3 * NC + 64 + m->n_cat) + 64;
   if (int rc = snv_ensure_workspace(m, floats * 4 + 256)) return rc;
   float* w = (float*)m->d_ws;
   float* bufs[2][4];
   for (int br = 0; br < 2; ++br)
-    for (int k = 0; k < 4; ++k) { bufs[br][k] = w; w += 32 * ra[br][k]; }
+    for (int k = 0; k < 4; ++k) { bufs[br][k] = w; w += (k < 3 ? 16 : 32) * ra[br][k]; }
   float* llog = w; w += chunk * NC;
   float* tl0 = w; w += chunk * NC;
   float* tl1 = w; w += chunk * NC;
@@ -490,31 +601,31 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                        d_cat ? nullptr : cat32, st))
+                                        d_cat ? nullptr : cat32, st, /*out_bf16=*/true))
       return rc;
     if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, ns, llog, err_flag, st))
       return rc;
     for (int br = 1; br >= 0; --br) {
       const BranchDev& B = m->br[br];
       const char* sfx = br ? "_2" : "";
-      if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], ra[br][0], ns, B.L1, st)) return rc;
+      if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], true, ra[br][0], ns, B.L1, st)) return rc;
       StageArgs a{};
       // stage 1: two ResBlocks + outer skip at length L1
-      a.in = bufs[br][0]; a.out = bufs[br][1]; a.wblob = S->blob[br][0];
+      a.in = reinterpret_cast<const uint4*>(bufs[br][0]); a.out = bufs[br][1]; a.wblob = S->blob[br][0];
       a.in_rows_alloc = ra[br][0]; a.out_rows_alloc = ra[br][1];
       a.rows = rows_of(ns, B.L1); a.L = B.L1; a.Lin = B.L1; a.pk = 0; a.ps = 1; a.pp = 0;
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 4);
       if (int rc = launch_stage<RB4>(a, st)) return rc;
-      if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], ra[br][1], ns, B.L1, st)) return rc;
+      if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
       // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
-      a.in = bufs[br][1]; a.out = bufs[br][2]; a.wblob = S->blob[br][1];
+      a.in = reinterpret_cast<const uint4*>(bufs[br][1]); a.out = bufs[br][2]; a.wblob = S->blob[br][1];
       a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
       a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 5);
       if (int rc = launch_stage<C_RB4>(a, st)) return rc;
-      if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], ra[br][2], ns, B.L2, st)) return rc;
+      if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
       // stage 3: pool3 + conv3 + ReLU at length L3
-      a.in = bufs[br][2]; a.out = bufs[br][3]; a.wblob = S->blob[br][2];
+      a.in = reinterpret_cast<const uint4*>(bufs[br][2]); a.out = bufs[br][3]; a.wblob = S->blob[br][2];
       a.in_rows_alloc = ra[br][2]; a.out_rows_alloc = ra[br][3];
       a.rows = rows_of(ns, B.L3); a.L = B.L3; a.Lin = B.L2; a.pk = B.pool[2][0]; a.ps = B.pool[2][1]; a.pp = B.pool[2][2];
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 1);

@@ -30,7 +30,7 @@ def test_bf16_taps_close_to_reference(kat, cuda_genome):
         got = m.debug_tap(name).reshape(len(z["start"]), -1)[:16]
         report[name] = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
     print("bf16 tap relative errors:", report)
-    assert report["pool1_2"] < 1e-5 and report["logit_local"] < 1e-4     # fp32 parts of the path
+    assert report["pool1_2"] < 5e-3 and report["logit_local"] < 1e-4     # stem output is stored as bf16; local branch is fp32
     for k, v in report.items():
         assert v < 3e-2, (k, v, report)
     m.set_debug(False)
