@@ -40,6 +40,26 @@ __global__ void k_encode_local(GenomeView G, const int32_t* __restrict__ pos, co
   out[t] = bad ? (int64_t(1) << (2 * order)) : idx;  // 4**order (preprocessing.py:722)
 }
 
+// same k-mer indices as k_encode_local but int32, feeding the local-branch MLP pre-pass of the network
+__global__ void k_local_idx32(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta, int64_t n,
+                              int radius, int order, int W, int n_k, int32_t* __restrict__ out) {
+  const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t >= n * n_k) return;
+  const int64_t site = t / n_k;
+  const int j = int(t - site * n_k);
+  const int m = meta[site];
+  const int strand = m & 1, chrom = int(uint32_t(m) >> 8);
+  const int64_t wstart = int64_t(pos[site]) - radius;
+  int idx = 0;
+  bool bad = false;
+  for (int d = 0; d < order; ++d) {
+    const int s = site_symbol(G, chrom, wstart, W, strand, j + d);
+    bad |= (s > 3);
+    idx = idx * 4 + (s & 3);
+  }
+  out[t] = bad ? (1 << (2 * order)) : idx;
+}
+
 __global__ void k_encode_onehot(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
                                 int64_t n, int radius, int W, int w_shift, float* __restrict__ out) {
   const int64_t site = blockIdx.y;
@@ -71,6 +91,15 @@ __global__ void k_onehot_to_symbols(const float* __restrict__ x, int64_t n, int 
 }
 
 static inline int window_len(int radius, int model_type) { return 2 * radius + (model_type == MURAL_MODEL_SNV ? 1 : 0); }
+
+int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
+                         int32_t* cat32, cudaStream_t st) {
+  const int W = 2 * m->cfg.local_radius + 1;
+  const int64_t total = n * m->n_cat;
+  LAUNCH(k_local_idx32, (unsigned)cdiv(total, 256), 256, 0, st, *G, d_pos, d_meta, n, m->cfg.local_radius, m->cfg.local_order, W,
+         m->n_cat, cat32);
+  return 0;
+}
 
 int onehot_to_symbols_checked(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, int* d_flag, cudaStream_t st) {
   LAUNCH(k_onehot_to_symbols, (unsigned)cdiv(n * W, 256), 256, 0, st, d_onehot, n, W, d_sym, d_flag);

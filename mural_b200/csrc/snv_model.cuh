@@ -93,6 +93,8 @@ int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_po
 int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                            const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
                            int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16 = false);
+int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
+                         int32_t* cat32, cudaStream_t st);
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
                      cudaStream_t st);
 int snv_head_launch(mural_snv_model* m, const float* h_mid, const float* h_large, const float* local_logits, int64_t ns,

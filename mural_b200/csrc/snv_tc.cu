@@ -569,7 +569,12 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   MURAL_CHECK(m->tc != nullptr, "MURAL_MODE_BF16 needs CNN_out_channels == 32 and CNN_kernel_size == 3");
   TcState* S = (TcState*)m->tc;
   const int NC = m->cfg.n_class;
-  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 4096;
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 8192;
+  if (m->chunk_sites <= 0 || (int64_t(1) << 20) % chunk != 0) {  // keep chunks aligned inside super-chunks
+    int64_t c2 = 1;
+    while (c2 * 2 <= chunk) c2 *= 2;
+    chunk = c2;
+  }
   if (chunk > n) chunk = n;
   // workspace: per branch X0 (stem out), Z1, Z2, H as fp32 planes; + local logits, taps, k-mer indices
   int64_t floats = 0;
@@ -582,28 +587,36 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     ra[br][3] = rows_alloc(chunk, B.L3);
     for (int k = 0; k < 4; ++k) floats += (k < 3 ? 16 : 32) * ra[br][k];   // X0, Z1, Z2 are bf16 planes, H is fp32 planes
   }
-  floats += chunk * (3 * NC + 64 + m->n_cat) + 64;
+  // local branch runs as a pre-pass over super-chunks (one launch fills the GPU; per 4096-site chunk it cannot)
+  const int64_t super = n < (int64_t(1) << 20) ? n : (int64_t(1) << 20);
+  floats += chunk * (2 * NC + 64) + super * (NC + m->n_cat) + 64;
   if (int rc = snv_ensure_workspace(m, floats * 4 + 256)) return rc;
   float* w = (float*)m->d_ws;
   float* bufs[2][4];
   for (int br = 0; br < 2; ++br)
     for (int k = 0; k < 4; ++k) { bufs[br][k] = w; w += (k < 3 ? 16 : 32) * ra[br][k]; }
-  float* llog = w; w += chunk * NC;
+  float* llog = w; w += super * NC;
   float* tl0 = w; w += chunk * NC;
   float* tl1 = w; w += chunk * NC;
   float* tg0 = w; w += chunk * 32;
   float* tg1 = w; w += chunk * 32;
-  int32_t* cat32 = (int32_t*)w; w += chunk * m->n_cat;
+  int32_t* cat32 = (int32_t*)w; w += super * m->n_cat;
   int* err_flag = (int*)w;
   CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
 
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
+    if (s0 % super == 0) {  // (chunk divides 2^20 or n <= 2^20, so chunks never straddle a super-chunk)
+      const int64_t nsup = (n - s0 < super) ? (n - s0) : super;
+      if (!d_cat)
+        if (int rc = snv_local_idx_launch(m, G, d_pos + s0, d_meta + s0, nsup, cat32, st)) return rc;
+      if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st))
+        return rc;
+    }
+    const float* llog_c = llog + (s0 % super) * NC;
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                        d_cat ? nullptr : cat32, st, /*out_bf16=*/true))
-      return rc;
-    if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, ns, llog, err_flag, st))
+                                        nullptr, st, /*out_bf16=*/true))
       return rc;
     for (int br = 1; br >= 0; --br) {
       const BranchDev& B = m->br[br];
@@ -633,7 +646,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     }
     HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
                     {bufs[1][3], ra[1][3], m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
-    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 32, 128), 128, 0, st, hb[0], hb[1], llog, ns, NC, d_logp + s0 * NC,
+    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 32, 128), 128, 0, st, hb[0], hb[1], llog_c, ns, NC, d_logp + s0 * NC,
            m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr);
     if (m->debug) {
       auto flat = [&](const char* nm, const float* d, int64_t k) -> int {
@@ -647,7 +660,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       if (int rc = flat("gmax_2", tg1, ns * 32)) return rc;
       if (int rc = flat("logit_mid", tl0, ns * NC)) return rc;
       if (int rc = flat("logit_large", tl1, ns * NC)) return rc;
-      if (int rc = flat("logit_local", llog, ns * NC)) return rc;
+      if (int rc = flat("logit_local", llog_c, ns * NC)) return rc;
     }
   }
   CUDA_TRY(cudaGetLastError());
