@@ -1,0 +1,124 @@
+"""Genome-wide prediction pipeline: BED + FASTA + checkpoint -> calibrated per-site probabilities (TSV).
+
+Mirrors MuRaL/scripts/run_predict.py:34-239 (`run_predict_pipline`): same inputs (model, model.config.pkl,
+model.fdiri_cal.pkl), same sample order, same output columns / sort order / '%.4g' formatting.  Differences:
+windows are gathered on the GPU from the packed genome, and with WORLD_SIZE > 1 (torchrun) the site list is
+split into contiguous genomic intervals, one per rank, with a single final gather (no collective on the data
+path).
+"""
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+import torch
+
+from .calibration import calibrate, load_calibrator_weights
+from .data import PackedSiteDataset, SiteBatch, SiteTable
+from .genome import PackedGenome
+from .nn_utils import model_choice
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous, balanced split of n sites (in emission order = genomic order per strand batch)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_rows(local, n_total, world, rank, group=None):
+    """Concatenate per-rank [n_r, k] CPU tensors on rank 0 in rank order (the only collective of predict)."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(local, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = torch.cat(parts, dim=0)
+    assert out.shape[0] == n_total
+    return out
+
+
+def load_config(path):
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def build_model_from_files(model_path, config, device, n_cont=0):
+    common = {"emb_dims": config["emb_dims"], "n_cont": n_cont, "n_class": config["n_class"], "distal_order": 1,
+              "in_channels": 4 + n_cont}
+    model = model_choice(config["model_no"], config, common, "snv")
+    state = torch.load(model_path, map_location="cpu")
+    model.load_state_dict(state)
+    return model.to(device).eval()
+
+
+def predict_sites(model, dataset, lo, hi, batch_sites=1 << 20):
+    """log-probs [hi-lo, n_class] (CUDA) for the dataset's sites [lo, hi) in emission order."""
+    dev = dataset.genome.device
+    outs = []
+    with torch.no_grad():
+        for a in range(lo, hi, batch_sites):
+            b = min(hi, a + batch_sites)
+            sb = SiteBatch(torch.from_numpy(dataset.pos[a:b]).to(dev), torch.from_numpy(dataset.meta[a:b]).to(dev), dataset.genome)
+            outs.append(model.forward(None, sb))
+    return torch.cat(outs) if outs else torch.empty((0, model.n_class), device=dev)
+
+
+def format_predictions(chrom, start, end, strand, mut_type, prob):
+    """DataFrame in the reference's output shape (run_predict.py:228-238): sorted by (chrom, start)."""
+    import pandas as pd
+    cols = {"chrom": chrom, "start": start, "end": end, "strand": strand, "mut_type": np.asarray(mut_type, dtype=np.float64)}
+    for i in range(prob.shape[1]):
+        cols["prob%d" % i] = prob[:, i]
+    df = pd.DataFrame(cols)
+    df.sort_values(["chrom", "start"], inplace=True)
+    df.reset_index(drop=True, inplace=True)
+    return df
+
+
+def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator_path="", pred_file=None, segment_center=None,
+                poisson_calib=False, compute_mode="bf16", genome=None):
+    """Returns the prediction DataFrame on rank 0 (None elsewhere); writes `pred_file` when given."""
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+    rank = torch.distributed.get_rank() if dist_on else 0
+    world = torch.distributed.get_world_size() if dist_on else 1
+    t0 = time.time()
+    config = load_config(model_config_path)
+    if not segment_center:
+        segment_center = config.get("segment_center", 300000)          # run_predict.py:88-92 / commands/predict.py:84
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if genome is None:
+        genome = PackedGenome.from_fasta(ref_genome, dev)
+    sites = SiteTable.from_bed(test_data)
+    ds = PackedSiteDataset(sites, genome, segment_center, config["local_radius"], config["local_order"], config["distal_radius"])
+    model = build_model_from_files(model_path, config, dev)
+    model.compute_mode = compute_mode
+    n = len(ds.pos)
+    lo, hi = shard_bounds(n, world, rank)
+    logp = predict_sites(model, ds, lo, hi)
+    weights = load_calibrator_weights(calibrator_path) if calibrator_path else None
+    prob = calibrate(logp, weights, poisson_calib).cpu()
+    prob = gather_rows(prob, n, world, rank)
+    if rank != 0:
+        return None
+    names, start, end, strand = ds.position_info()
+    df = format_predictions(names, start, end, strand, ds.label, prob.numpy())
+    if pred_file:
+        df.to_csv(pred_file, sep="\t", float_format="%.4g", index=False)   # run_predict.py:239
+    print("predicted %d sites in %.2f s (%d rank(s))" % (n, time.time() - t0, world))
+    sys.stdout.flush()
+    return df
+
+
+def run_predict_pipline(args, model_type="snv"):
+    """Same entry point / argument names as the reference CLI dispatcher expects (run_predict.py:34)."""
+    if model_type != "snv":
+        raise NotImplementedError("mural_b200.predict: indel prediction is not wired into the pipeline yet")
+    if getattr(args, "cpu_only", False):
+        raise RuntimeError("mural_b200 has no CPU path; drop --cpu_only")
+    return run_predict(args.test_data, args.ref_genome, args.model_path, args.model_config_path,
+                       getattr(args, "calibrator_path", ""), args.pred_file, getattr(args, "segment_center", None),
+                       getattr(args, "poisson_calib", False))

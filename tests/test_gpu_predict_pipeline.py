@@ -1,0 +1,97 @@
+"""GPU: BED + FASTA + checkpoint files -> calibrated TSV, vs the oracle pipeline (run_predict.py:214-239 restated)."""
+import pickle
+import sys
+import types
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import load_snv_golden
+from oracle import encode_np as E
+from oracle import network_t as NT
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_inputs(tmp_path, genome, z, cfg, state):
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as f:
+        for n, s in genome.items():
+            f.write(">%s test\n" % n)
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + "\n")
+    names = list(genome)
+    order = np.lexsort((z["start"], z["chrom"]))            # BED sorted by chrom, start
+    bed = tmp_path / "sites.bed"
+    with open(bed, "w") as f:
+        for i in order:
+            f.write("%s\t%d\t%d\t.\t%d\t%s\n" % (names[z["chrom"][i]], z["start"][i], z["start"][i] + 1, z["start"][i] % 4, "+-"[z["strand"][i]]))
+    from test_gpu_snv_forward import build_model
+    m = build_model(cfg, state, int(z["n_cat"]))
+    torch.save({k: v.cpu() for k, v in m.state_dict().items()}, tmp_path / "model")
+    full_cfg = dict(cfg); full_cfg["emb_dims"] = [(65, 2)] * int(z["n_cat"]); full_cfg["segment_center"] = 5000
+    pickle.dump(full_cfg, open(tmp_path / "model.config.pkl", "wb"))
+    # a pickle shaped like the reference's model.fdiri_cal.pkl (FullDirichletCalibrator -> calibrator_.weights_)
+    mod = types.ModuleType("dirichletcal.calib.fulldirichlet")
+    FullDirichletCalibrator = type("FullDirichletCalibrator", (), {"__module__": "dirichletcal.calib.fulldirichlet"})
+    MultinomialRegression = type("MultinomialRegression", (), {"__module__": "dirichletcal.calib.fulldirichlet"})
+    FullDirichletCalibrator.__qualname__ = "FullDirichletCalibrator"; MultinomialRegression.__qualname__ = "MultinomialRegression"
+    mod.FullDirichletCalibrator, mod.MultinomialRegression = FullDirichletCalibrator, MultinomialRegression
+    for k in ("dirichletcal", "dirichletcal.calib"):
+        sys.modules.setdefault(k, types.ModuleType(k))
+    sys.modules["dirichletcal.calib.fulldirichlet"] = mod
+    cal = FullDirichletCalibrator(); cal.calibrator_ = MultinomialRegression(); cal.calibrator_.weights_ = z["cal_weights"]
+    pickle.dump(cal, open(tmp_path / "model.fdiri_cal.pkl", "wb"))
+    for k in ("dirichletcal.calib.fulldirichlet", "dirichletcal.calib", "dirichletcal"):
+        sys.modules.pop(k, None)
+    return fa, bed, order
+
+
+@pytest.mark.parametrize("poisson", [False, True])
+def test_tsv_matches_oracle_pipeline(tmp_path, kat, poisson):
+    from mural_b200.predict import run_predict
+    z, cfg, state = load_snv_golden("hs_AT")
+    _, genome = kat
+    fa, bed, order = _write_inputs(tmp_path, genome, z, cfg, state)
+    out = tmp_path / "pred.tsv"
+    df = run_predict(str(bed), str(fa), str(tmp_path / "model"), str(tmp_path / "model.config.pkl"),
+                     str(tmp_path / "model.fdiri_cal.pkl"), str(out), poisson_calib=poisson, compute_mode="fp32")
+    # ---- oracle: reference order (bed_reader), network, softmax, calibrator, poisson, sort, %.4g
+    names = list(genome)
+    ch, st, sd = z["chrom"][order], z["start"][order], z["strand"][order]
+    perm, _ = E.order_sites(ch, st, sd, 5000)
+    ch, st, sd = ch[perm], st[perm], sd[perm]
+    cat = np.empty((len(st), int(z["n_cat"])), np.int64); oh = np.empty((len(st), 4, 2 * cfg["distal_radius"] + 1), np.float32)
+    for c in range(len(names)):
+        msk = ch == c
+        sym = E.seq_to_symbols(genome[names[c]])
+        cat[msk] = E.kmer_windows(sym, st[msk], sd[msk], cfg["local_radius"], cfg["local_order"])
+        oh[msk] = E.onehot_windows(sym, st[msk], sd[msk], cfg["distal_radius"])
+    with torch.no_grad():
+        lp = NT.network2_forward(state, cat, oh, torch.float32)
+    prob = NT.dirichlet_apply(z["cal_weights"], torch.softmax(lp, 1).numpy())
+    if poisson:
+        prob = NT.poisson_calibrate(prob)
+    exp = pd.DataFrame({"chrom": np.array(names, dtype=object)[ch], "start": st, "end": st + 1, "strand": np.where(sd == 0, "+", "-"),
+                        "mut_type": (st % 4).astype(np.float64)})
+    for i in range(4):
+        exp["prob%d" % i] = prob[:, i]
+    exp.sort_values(["chrom", "start"], inplace=True); exp.reset_index(drop=True, inplace=True)
+    assert list(df.columns) == list(exp.columns)
+    for c in ("chrom", "start", "end", "strand", "mut_type"):
+        assert (df[c].values == exp[c].values).all(), c
+    got_p, exp_p = df[["prob%d" % i for i in range(4)]].values, exp[["prob%d" % i for i in range(4)]].values
+    assert np.abs(got_p - exp_p).max() <= 1e-3                  # fp32-equivalent gate on calibrated probabilities
+    # file: same header / non-float columns; floats agree at the printed precision up to the gate
+    exp_file = tmp_path / "exp.tsv"
+    exp.to_csv(exp_file, sep="\t", float_format="%.4g", index=False)
+    a, b = open(out).read().splitlines(), open(exp_file).read().splitlines()
+    assert a[0] == b[0] and len(a) == len(b)
+    same = sum(x == y for x, y in zip(a, b))
+    assert same >= 0.97 * len(a), "only %d of %d lines are textually identical" % (same, len(a))
+    for x, y in zip(a[1:], b[1:]):
+        fx, fy = x.split("\t"), y.split("\t")
+        assert fx[:5] == fy[:5]
+        assert np.abs(np.array(fx[5:], float) - np.array(fy[5:], float)).max() <= 1e-3
