@@ -144,6 +144,37 @@ int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, in
                         int64_t* n_written);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training step (MuRaL/training.py:404-452): train-mode forward (batch-statistic BatchNorm with running-stat
+ * update, dropout), backward, and the fused gradient-clip + optimizer update.
+ *
+ * d_blob   : the model's flat fp32 buffer on the device, layout of mural_snv_model_tensor() (trainable part first,
+ *            BatchNorm running statistics after; the forward updates the running statistics in place).
+ * d_grads  : flat fp32 gradient buffer, n_trainable floats, same offsets; overwritten by backward.  In data-parallel
+ *            training this is the single buffer to all-reduce (sum) between backward and mural_optimizer_step.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_snv_train mural_snv_train_t;
+int mural_snv_train_create(mural_snv_model_t* m, mural_snv_train_t** out);
+void mural_snv_train_destroy(mural_snv_train_t* t);
+/* dropout probabilities (config emb_dropout, local_dropout, distal_fc_dropout; model_snv.py:338-339,385,427) */
+int mural_snv_train_set_dropout(mural_snv_train_t* t, float p_emb, float p_local, float p_fc, uint64_t seed);
+/* forward of one batch (n >= 2 sites); d_logp float32 [n, n_class] = what Network2.forward returns in train() mode */
+int mural_snv_train_forward(mural_snv_train_t* t, const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta,
+                            int64_t n, float* d_blob, float* d_logp, void* stream);
+/* backward of the last forward given dLoss/dlogp [n, n_class] */
+int mural_snv_train_backward(mural_snv_train_t* t, const float* d_blob, const float* d_dlogp, float* d_grads, void* stream);
+/* CrossEntropyLoss(reduction='sum') on log-probs (training.py:327,425): adds the loss into *d_loss (may be NULL) and
+ * writes dLoss/dlogp */
+int mural_ce_sum_grad(const float* d_logp, const int32_t* d_meta, int64_t n, int32_t n_class, double* d_loss, float* d_dlogp,
+                      void* stream);
+/* clip_grad_norm_(max_norm) + optimizer.step() (training.py:434-436, 346-357) over a flat buffer, no host sync.
+ * kind 0 Adam (coupled L2 weight decay), 1 AdamW(amsgrad=True), 2 SGD(momentum 0.98, nesterov).  Gradients are
+ * multiplied by grad_scale first (1/world_size to average a summed all-reduce, or 1).  step counts from 1.
+ * d_scratch: >= 8 bytes of device scratch (receives the squared gradient norm). */
+int mural_optimizer_step(int32_t kind, float* d_params, const float* d_grads, float* d_m, float* d_v, float* d_vmax, int64_t n,
+                         float lr, float weight_decay, int64_t step, float max_norm, float grad_scale, double* d_scratch,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Calibration epilogue (run_predict.py:214-225): softmax(logp) -> FullDirichlet apply
  * (dirichletcal/calib/fulldirichlet.py:78-80, multinomial.py:60-64,235-244) -> optional Poisson
  * calibration (MuRaL/model/calibration.py:10-23).  h_weights: fp64 [k, k+1] or NULL.  Output fp64 [n,k].

@@ -54,6 +54,13 @@ PROTOTYPES = {
     "mural_snv_set_chunk": (C.c_int, [_vp, _i64]),
     "mural_snv_set_debug": (C.c_int, [_vp, _i32]),
     "mural_snv_debug_tap": (C.c_int, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64)]),
+    "mural_snv_train_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mural_snv_train_destroy": (None, [_vp]),
+    "mural_snv_train_set_dropout": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_uint64]),
+    "mural_snv_train_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mural_snv_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
 }
 

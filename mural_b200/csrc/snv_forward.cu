@@ -496,7 +496,7 @@ static int conv_launch(const float* in, float* out, const float* r1, const float
   return 0;
 }
 
-static int conv_any(int C, const float* in, float* out, const float* r1, const float* r2, int64_t n, int L,
+int conv_any(int C, const float* in, float* out, const float* r1, const float* r2, int64_t n, int L,
                     const ConvLayerDev& P, int relu_out, cudaStream_t st) {
   switch (C) {
     case 16: return conv_launch<16>(in, out, r1, r2, n, L, P, relu_out, st);

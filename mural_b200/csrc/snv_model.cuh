@@ -99,6 +99,8 @@ int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* ca
                      cudaStream_t st);
 int snv_head_launch(mural_snv_model* m, const float* h_mid, const float* h_large, const float* local_logits, int64_t ns,
                     float* logp, float* tg0, float* tg1, float* tl0, float* tl1, cudaStream_t st);
+int conv_any(int C, const float* in, float* out, const float* r1, const float* r2, int64_t n, int L, const ConvLayerDev& P,
+             int relu_out, cudaStream_t st);
 int snv_ensure_workspace(mural_snv_model* m, int64_t bytes);
 int onehot_to_symbols_checked(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, int* d_flag, cudaStream_t st);
 int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,

@@ -157,6 +157,12 @@ class Network2(nn.Module):
         except Exception:
             pass
 
+    def state_dict(self, *args, **kwargs):
+        st = getattr(self, "_train_state", None)
+        if st is not None:
+            st.sync_counters()              # num_batches_tracked follows the kernels' training forwards
+        return super().state_dict(*args, **kwargs)
+
     # ------------------------------------------------------------------ forward
     def forward(self, local_input, distal_input):
         if self.training:

@@ -1,0 +1,206 @@
+"""Training step of MuRaL-snv on the B200 kernels (MuRaL/training.py:404-452).
+
+Two ways in:
+
+* drop-in — `model.train(); preds = model.forward((cont_x, cat_x), site_batch); loss = criterion(preds, y);
+  loss.backward(); clip_grad_norm_(model.parameters(), 10); optimizer.step()` keeps working with torch optimizers:
+  in train mode `Network2.forward` routes here and returns a differentiable tensor (custom autograd.Function around
+  mural_snv_train_forward / mural_snv_train_backward).
+* fused — `TrainState.step(batch)`: forward, CE(sum)+gradient, backward, (NCCL all-reduce of ONE flat gradient buffer
+  when torch.distributed is initialised), global-norm clip + Adam / AdamW(amsgrad) / SGD(nesterov) in one kernel, no
+  host synchronisation inside the step (the reference syncs with loss.item() every batch).
+
+Parameters and BatchNorm buffers of the model are re-pointed at views of one flat device tensor (the C-ABI blob
+layout), so `state_dict()` / checkpoints stay byte-compatible with the reference while the kernels see one buffer.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data import SiteBatch
+
+OPTIMIZERS = {"Adam": 0, "AdamW": 1, "AdamW2": 1, "SGD": 2}     # training.py:346-357
+
+
+class StepLR:
+    """torch.optim.lr_scheduler.StepLR as used by the reference: step_size=(5000*128)//batch_size, gamma=LR_gamma,
+    stepped every batch, with the min_lr -> restart_lr rule (training.py:366, 444-450)."""
+
+    def __init__(self, lr, step_size, gamma, min_lr=None, restart_lr=None):
+        self.base, self.step_size, self.gamma, self.min_lr, self.restart_lr = lr, max(1, int(step_size)), gamma, min_lr, restart_lr
+        self.lr, self.k = lr, 0
+
+    def step(self):
+        self.k += 1
+        if self.k % self.step_size == 0:
+            self.lr *= self.gamma
+        if self.min_lr is not None and self.lr < self.min_lr:
+            self.lr = self.restart_lr
+        return self.lr
+
+
+class TrainState:
+    def __init__(self, model, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False):
+        L = _lib.lib()
+        self.model = model
+        self.device = model.emb_layer.weight.device
+        if self.device.type != "cuda":
+            raise RuntimeError("mural_b200 training runs on CUDA only")
+        if optim not in OPTIMIZERS:
+            raise ValueError("Error: unsupported optimization method %s" % optim)         # training.py:359-361
+        self.kind, self.lr, self.weight_decay, self.max_norm = OPTIMIZERS[optim], float(lr), float(weight_decay), float(max_norm)
+        layout = model.native_layout()
+        self.n_blob = int(L.mural_snv_model_n_params(model._ensure_handle()))
+        self.n_trainable = int(L.mural_snv_model_n_trainable(model._ensure_handle()))
+        self.blob = torch.empty(self.n_blob, dtype=torch.float32, device=self.device)
+        sd = dict(model.named_parameters())
+        sd.update(dict(model.named_buffers()))
+        self.params, self.grad_views, seen = [], [], set()
+        self.grads = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        for name, off, num, is_buf in layout:
+            t = sd[name]
+            view = self.blob[off:off + num].view(t.shape)
+            view.copy_(t.detach())
+            t.data = view                                     # parameter/buffer now lives inside the flat blob
+            if not is_buf and id(t) not in seen:
+                seen.add(id(t))
+                self.params.append(t)
+                self.grad_views.append(self.grads[off:off + num].view(t.shape))
+        self.m = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros_like(self.m) if self.kind != 2 else None
+        self.vmax = torch.zeros_like(self.m) if self.kind == 1 else None
+        self.scratch = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.opt_step = 0
+        self.n_forward = 0
+        self._tracked_synced = 0
+        self.grad_average = grad_average
+        h = C.c_void_p()
+        _lib.check(L.mural_snv_train_create(model._h, C.byref(h)))
+        self._h = h
+        p_emb = float(model.emb_dropout_layer.p)
+        p_loc = float(model.droput_layers[0].p) if len(model.droput_layers) else 0.0
+        p_fc = float(model.distal_fc1[1].p)
+        _lib.check(L.mural_snv_train_set_dropout(self._h, p_emb, p_loc, p_fc, int(seed)))
+        model._train_state = self
+
+    def set_dropout(self, p_emb, p_local, p_fc, seed=0):
+        _lib.check(_lib.lib().mural_snv_train_set_dropout(self._h, float(p_emb), float(p_local), float(p_fc), int(seed)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().mural_snv_train_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- pieces
+    def forward(self, batch):
+        n = len(batch)
+        logp = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_snv_train_forward(self._h, batch.genome.handle, _lib.ptr(batch.pos), _lib.ptr(batch.meta), n,
+                                                          _lib.ptr(self.blob), _lib.ptr(logp), _lib.current_stream()))
+        self.n_forward += 1
+        self.model.mark_dirty()
+        return logp
+
+    def backward(self, dlogp):
+        dlogp = dlogp.contiguous().to(torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_snv_train_backward(self._h, _lib.ptr(self.blob), _lib.ptr(dlogp), _lib.ptr(self.grads),
+                                                           _lib.current_stream()))
+        return self.grads
+
+    def all_reduce_grads(self):
+        """The only collective of a data-parallel step: one flat fp32 all-reduce (sum) over NVLink."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+            return torch.distributed.get_world_size()
+        return 1
+
+    def apply(self, world=1):
+        self.opt_step += 1
+        scale = 1.0 / world if self.grad_average else 1.0   # reference loss is SUM-reduced: summing == one big batch
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_optimizer_step(self.kind, _lib.ptr(self.blob), _lib.ptr(self.grads), _lib.ptr(self.m),
+                                                       _lib.ptr(self.v), _lib.ptr(self.vmax), self.n_trainable, self.lr,
+                                                       self.weight_decay, self.opt_step, self.max_norm, scale, _lib.ptr(self.scratch),
+                                                       _lib.current_stream()))
+        self.model.mark_dirty()
+
+    # ---- fused step
+    def step(self, batch):
+        """forward + CE(sum) + backward + all-reduce + clip + optimizer; returns the log-probs (loss accumulates in
+        self.loss_dev, read it with .item() once per print interval)."""
+        n = len(batch)
+        if n < 2:
+            return None                                      # training.py:415: batches of one site are skipped
+        logp = self.forward(batch)
+        dlogp = torch.empty_like(logp)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(batch.meta), n, self.model.n_class, _lib.ptr(self.loss_dev),
+                                                    _lib.ptr(dlogp), _lib.current_stream()))
+        self.backward(dlogp)
+        world = self.all_reduce_grads()
+        self.apply(world)
+        return logp
+
+    def sync_counters(self):
+        """num_batches_tracked of every BatchNorm follows the number of training forwards (checkpoint contract)."""
+        d = self.n_forward - self._tracked_synced
+        if d:
+            for mod in self.model.modules():
+                if isinstance(mod, torch.nn.BatchNorm1d) and mod.num_batches_tracked is not None:
+                    mod.num_batches_tracked += d
+            self._tracked_synced = self.n_forward
+
+
+class _TrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, batch, *params):
+        ctx.state = state
+        return state.forward(batch)
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        st = ctx.state
+        st.backward(dlogp)
+        return (None, None) + tuple(g.clone() for g in st.grad_views)
+
+
+def network2_train_forward(model, local_input, distal_input):
+    """Network2.forward in train() mode (differentiable)."""
+    if not isinstance(distal_input, SiteBatch):
+        raise NotImplementedError("mural_b200 training consumes SiteBatch-es (site records); tensor inputs are eval-only")
+    st = getattr(model, "_train_state", None)
+    if st is None:
+        st = TrainState(model)
+    return _TrainFn.apply(st, distal_input, *st.params)
+
+
+def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim="Adam", lr=1e-3, weight_decay=0.0, LR_gamma=0.5,
+                 min_lr=1e-6, restart_lr=1e-4, seed=0, print_every=1000, segment_indices=None):
+    """The hot loop of training.py:387-452 on site records; returns per-epoch mean losses.  Evaluation, calibrator
+    fitting and checkpoint bookkeeping stay with the caller (out of scope)."""
+    from .data import generate_site_batches
+    st = getattr(model, "_train_state", None) or TrainState(model, optim, lr, weight_decay, seed=seed)
+    sched = StepLR(lr, (5000 * 128) // batch_size, LR_gamma, min_lr, restart_lr)
+    losses = []
+    for epoch in range(epochs):
+        model.train()
+        st.loss_dev.zero_()
+        n_sites = 0
+        for batch in generate_site_batches(dataset, sampled_segments, batch_size, shuffle=True, seed=seed + epoch,
+                                           segment_indices=segment_indices):
+            if len(batch) < 2:
+                continue
+            st.step(batch)
+            n_sites += len(batch)
+            st.lr = sched.step()
+        losses.append(float(st.loss_dev.item()) / max(1, n_sites))
+        st.sync_counters()
+    return losses

@@ -1,0 +1,182 @@
+"""GPU: Network2 training step (train-mode forward, backward, clip + optimizer) vs torch autograd on the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_snv_golden
+from oracle import encode_np as E
+from oracle import network_t as NT
+from test_gpu_snv_forward import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_inputs(z, cfg, genome, n):
+    names = list(genome)
+    ch, st, sd = z["chrom"][:n], z["start"][:n], z["strand"][:n]
+    cat = np.empty((n, int(z["n_cat"])), np.int64)
+    oh = np.empty((n, 4, 2 * cfg["distal_radius"] + 1), np.float32)
+    for c in range(len(names)):
+        m = ch == c
+        if m.any():
+            sym = E.seq_to_symbols(genome[names[c]])
+            cat[m] = E.kmer_windows(sym, st[m], sd[m], cfg["local_radius"], cfg["local_order"])
+            oh[m] = E.onehot_windows(sym, st[m], sd[m], cfg["distal_radius"])
+    return cat, oh
+
+
+def _batch(z, genome_dev, n, labels):
+    from mural_b200 import SiteBatch, pack_meta
+    pos = torch.from_numpy(z["start"][:n].astype(np.int32)).cuda()
+    meta = torch.from_numpy(pack_meta(z["strand"][:n], labels, z["chrom"][:n])).cuda()
+    return SiteBatch(pos, meta, genome_dev)
+
+
+@pytest.mark.parametrize("tag", ["ex_ckpt6", "hs_AT"])
+def test_train_forward_backward_vs_autograd(kat, cuda_genome, tag):
+    from mural_b200 import _lib
+    from mural_b200.training import TrainState
+    z, cfg, state = load_snv_golden(tag)
+    _, genome = kat
+    n = 48
+    labels = (z["start"][:n] % 4).astype(np.int64)
+    m = build_model(cfg, state, int(z["n_cat"]))
+    st = TrainState(m, "Adam", lr=1e-3)
+    st.set_dropout(0, 0, 0)
+    m.train()
+    sb = _batch(z, cuda_genome, n, labels)
+    logp = st.forward(sb)
+    # ---- oracle: fp64 autograd through the restated network in train mode (batch-stat BN, dropout off)
+    cat, oh = _oracle_inputs(z, cfg, genome, n)
+    sd64 = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=("running" not in k))
+            for k, v in state.items() if "num_batches" not in k}
+    rec = NT._BNStats()
+    ref = NT.network2_forward(sd64, cat, oh, torch.float64, train=True, rec=rec)
+    assert np.abs(logp.cpu().numpy() - ref.detach().numpy()).max() < 2e-4
+    loss = NT.ce_sum(ref, labels)
+    loss.backward()
+    # fused loss + gradient of the loss w.r.t. log-probs, then backward
+    dlogp = torch.empty_like(logp)
+    _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(sb.meta), n, 4, _lib.ptr(st.loss_dev), _lib.ptr(dlogp),
+                                            _lib.current_stream()))
+    assert abs(float(st.loss_dev.item()) - float(loss)) < 1e-3 * max(1.0, abs(float(loss)))
+    g = st.backward(dlogp).cpu().numpy()
+    worst = 0.0
+    for name, off, num, is_buf in m.native_layout():
+        if is_buf:
+            continue
+        ref_g = sd64[name].grad.numpy().reshape(-1)
+        got = g[off:off + num]
+        scale = max(1e-3, np.abs(ref_g).max())
+        err = np.abs(got - ref_g).max() / scale
+        worst = max(worst, err)
+        assert err < 5e-3, (name, err, np.abs(ref_g).max())
+    print(tag, "worst relative gradient error %.2e" % worst)
+    # running statistics after one training forward (momentum 0.1, unbiased variance)
+    sdm = m.state_dict()
+    for bn, (mean, var_unb) in rec.stats.items():
+        exp_m = 0.9 * np.asarray(state[bn + ".running_mean"]) + 0.1 * mean.numpy()
+        exp_v = 0.9 * np.asarray(state[bn + ".running_var"]) + 0.1 * var_unb.numpy()
+        assert np.abs(sdm[bn + ".running_mean"].cpu().numpy() - exp_m).max() < 1e-4 * max(1, np.abs(exp_m).max()), bn
+        assert np.abs(sdm[bn + ".running_var"].cpu().numpy() - exp_v).max() < 1e-3 * max(1, np.abs(exp_v).max()), bn
+    assert int(sdm["conv1.0.num_batches_tracked"]) == int(state["conv1.0.num_batches_tracked"]) + 1
+
+
+@pytest.mark.parametrize("optim", ["Adam", "AdamW", "SGD"])
+def test_fused_optimizer_matches_torch(optim):
+    """clip_grad_norm_(10) + optimizer.step() over the flat buffer == torch.optim on the same gradients, 3 steps."""
+    from mural_b200 import _lib
+    torch.manual_seed(1)
+    n = 10007
+    p0 = torch.randn(n, device="cuda")
+    ref_p = torch.nn.Parameter(p0.clone())
+    if optim == "Adam":
+        opt, kind = torch.optim.Adam([ref_p], lr=1e-2, weight_decay=1e-3), 0
+    elif optim == "AdamW":
+        opt, kind = torch.optim.AdamW([ref_p], lr=1e-2, weight_decay=1e-2, amsgrad=True), 1
+    else:
+        opt, kind = torch.optim.SGD([ref_p], lr=1e-3, weight_decay=1e-3, momentum=0.98, nesterov=True), 2
+    wd = opt.param_groups[0]["weight_decay"]
+    lr = opt.param_groups[0]["lr"]
+    p = p0.clone()
+    m = torch.zeros_like(p); v = torch.zeros_like(p); vm = torch.zeros_like(p)
+    scratch = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda") * (3.0 if step == 2 else 0.05)     # step 2 exceeds max_norm -> clipped
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], max_norm=10, error_if_nonfinite=False)
+        opt.step()
+        _lib.check(_lib.lib().mural_optimizer_step(kind, _lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.ptr(vm), n, lr, wd,
+                                                   step, 10.0, 1.0, _lib.ptr(scratch), _lib.current_stream()))
+        assert (p - ref_p.detach()).abs().max().item() < 2e-6 * max(1.0, ref_p.detach().abs().max().item()), (optim, step)
+
+
+def test_dropin_loop_equals_fused_step(kat, cuda_genome):
+    """The reference's loop body with torch's optimizer (training.py:424-436) == TrainState.step().
+    SGD is used for the comparison because it is linear in the gradient: several biases sit in front of a
+    batch-statistic BatchNorm, their true gradient is exactly zero, and Adam turns the ~1e-7 summation-order noise of
+    such gradients into O(lr) updates in *any* implementation."""
+    from mural_b200.training import TrainState
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    n = 64
+    labels = (z["start"][:n] % 4).astype(np.int64)
+    sb = _batch(z, cuda_genome, n, labels)
+    y = torch.from_numpy(labels).cuda()
+    crit = torch.nn.CrossEntropyLoss(reduction="sum")
+    # (a) drop-in
+    ma = build_model(cfg, state, int(z["n_cat"]))
+    sta = TrainState(ma, "SGD", lr=1e-4, weight_decay=1e-4)
+    sta.set_dropout(0, 0, 0)
+    ma.train()
+    opt = torch.optim.SGD(ma.parameters(), lr=1e-4, weight_decay=1e-4, momentum=0.98, nesterov=True)
+    for _ in range(2):
+        preds = ma.forward(None, sb)
+        loss = crit(preds, y)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), max_norm=10, error_if_nonfinite=False)
+        opt.step()
+    # (b) fused
+    mb = build_model(cfg, state, int(z["n_cat"]))
+    stb = TrainState(mb, "SGD", lr=1e-4, weight_decay=1e-4)
+    stb.set_dropout(0, 0, 0)
+    mb.train()
+    for _ in range(2):
+        stb.step(sb)
+    d = (sta.blob - stb.blob).abs().max().item()
+    assert d < 2e-6 * max(1.0, sta.blob.abs().max().item()), d
+    moved = (stb.blob[:stb.n_trainable] - torch.from_numpy(mb.flat_blob()[:stb.n_trainable]).cuda()).abs().max().item()
+    assert moved == 0.0                      # model parameters ARE the flat buffer (views), nothing to copy back
+    # eval after training re-folds the updated weights; the loss on the training batch went down
+    mb.eval()
+    with torch.no_grad():
+        after = float(crit(mb.forward(None, sb), y))
+    m0 = build_model(cfg, state, int(z["n_cat"]))
+    with torch.no_grad():
+        before = float(crit(m0.forward(None, sb), y))
+    assert after < before, (before, after)
+
+
+def test_dropout_statistics(kat, cuda_genome):
+    from mural_b200.training import TrainState
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    n = 128
+    sb = _batch(z, cuda_genome, n, np.zeros(n, np.int64))
+    m = build_model(cfg, state, int(z["n_cat"]))
+    st = TrainState(m, seed=5)
+    m.train()
+    st.set_dropout(0.0, 0.0, 0.0, 5)
+    base = st.forward(sb)
+    st.set_dropout(0.1, 0.1, 0.25, 5)
+    a = st.forward(sb)
+    b = st.forward(sb)
+    assert not torch.equal(a, b)                       # different step -> different masks
+    assert (a - base).abs().max().item() > 1e-4        # dropout does something
+    assert torch.isfinite(a).all()
+    m2 = build_model(cfg, state, int(z["n_cat"]))       # determinism: same seed, same step counter -> same result
+    st2 = TrainState(m2, seed=5)
+    m2.train()
+    st2.set_dropout(0.0, 0.0, 0.0, 5)
+    st2.forward(sb)
+    st2.set_dropout(0.1, 0.1, 0.25, 5)
+    assert torch.equal(st2.forward(sb), a)
