@@ -144,6 +144,32 @@ int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, in
                         int64_t* n_written);
 
 /* ------------------------------------------------------------------------------------------------
+ * MuRaL-indel network (UNet_Small, MuRaL/model/model_indel.py:21-176), eval forward.
+ * Window of a site: [start - R + 1, start + 1 + R), length 2R (extend_interval, preprocessing.py:559-567).
+ * d_out: float32 [n, n_class] Softplus activations, exactly what UNet_Small.forward returns.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_indel_config {
+  int32_t distal_radius; /* config['distal_radius'] -> L = 2R                     */
+  int32_t channels;      /* config['CNN_out_channels'] (level i has (i+1)*channels) */
+  int32_t kernel_size;   /* config['CNN_kernel_size']                              */
+  int32_t n_class;       /* config['n_class']                                      */
+  int32_t downsize[6];   /* config['down_list']                                    */
+  int32_t use_reverse;   /* config.get('use_reverse', False)                       */
+} mural_indel_config_t;
+typedef struct mural_indel_model mural_indel_model_t;
+int mural_indel_model_create(const mural_indel_config_t* cfg, int device, mural_indel_model_t** out);
+void mural_indel_model_destroy(mural_indel_model_t* m);
+int32_t mural_indel_model_n_tensors(const mural_indel_model_t* m);
+int mural_indel_model_tensor(const mural_indel_model_t* m, int32_t i, const char** name, int64_t* offset, int64_t* numel,
+                             int32_t* is_buffer);
+int64_t mural_indel_model_n_params(const mural_indel_model_t* m);
+int mural_indel_model_load(mural_indel_model_t* m, const float* h_blob, int64_t n);
+int mural_indel_forward(mural_indel_model_t* m, const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
+                        float* d_out, void* stream);
+/* same network on the reference's own input tensor distal_x float32 [n, 4, 2R] */
+int mural_indel_forward_tensors(mural_indel_model_t* m, const float* d_distal, int64_t n, int32_t L, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Training step (MuRaL/training.py:404-452): train-mode forward (batch-statistic BatchNorm with running-stat
  * update, dropout), backward, and the fused gradient-clip + optimizer update.
  *

@@ -19,6 +19,11 @@ class SnvConfig(C.Structure):
                                           "channels", "kernel_size", "n_class")]
 
 
+class IndelConfig(C.Structure):
+    _fields_ = [("distal_radius", C.c_int32), ("channels", C.c_int32), ("kernel_size", C.c_int32), ("n_class", C.c_int32),
+                ("downsize", C.c_int32 * 6), ("use_reverse", C.c_int32)]
+
+
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/mural_b200.h.
 PROTOTYPES = {
@@ -54,6 +59,14 @@ PROTOTYPES = {
     "mural_snv_set_chunk": (C.c_int, [_vp, _i64]),
     "mural_snv_set_debug": (C.c_int, [_vp, _i32]),
     "mural_snv_debug_tap": (C.c_int, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64)]),
+    "mural_indel_model_create": (C.c_int, [C.POINTER(IndelConfig), C.c_int, C.POINTER(_vp)]),
+    "mural_indel_model_destroy": (None, [_vp]),
+    "mural_indel_model_n_tensors": (_i32, [_vp]),
+    "mural_indel_model_tensor": (C.c_int, [_vp, _i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
+    "mural_indel_model_n_params": (_i64, [_vp]),
+    "mural_indel_model_load": (C.c_int, [_vp, _vp, _i64]),
+    "mural_indel_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "mural_indel_forward_tensors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "mural_snv_train_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "mural_snv_train_destroy": (None, [_vp]),
     "mural_snv_train_set_dropout": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_uint64]),
