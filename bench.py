@@ -282,7 +282,7 @@ def main():
     # ---- roofline of the dominant kernel: library-side CUDA-event profile over an identical pass
     roof = None
     if rank == 0:
-        roof = kernel_roofline(L, step, W, K, S, mode, cfg, barrier)
+        roof = kernel_roofline(L, step, W, K, S, mode, cfg, torch.cuda.synchronize)   # rank-local: no collective here
     line = {"metric": "sites/sec (predict)", "value": value, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
@@ -299,6 +299,7 @@ def main():
                                     "sample": "first %d sites of the step-0 batch, batch 1024, numpy encoders + torch CPU fp32 (%.1f s)" % (n_s, dt)}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
