@@ -179,14 +179,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   const uint64_t dA0 = umma_desc(smem_u32(sSlots), A_PLANE, 128);
   const uint64_t dC0 = umma_desc(smem_u32(sSlots) + A_SLOT, AC_PLANE, 128);
 
-  // per in-flight tile state (registers; the k loops below are fully unrolled)
-  int tile[NINFL], layer[NINFL], pos[NINFL];
-  uint32_t phase[NINFL];
-  int64_t row[NINFL];
-  bool active[NINFL];
-
-  auto slot_of = [&](int k) { return g * NINFL + k; };
-  auto sA_of = [&](int k) { return sSlots + slot_of(k) * SLOT_BYTES; };
+  // ---- per-slot constants of this group (slot k of group g = g*NINFL + k)
+  unsigned char* const sA0 = sSlots + (g * NINFL) * SLOT_BYTES;
+  const uint32_t bar0 = smem_u32(bars + g * NINFL);
+  uint32_t phase[NINFL] = {0, 0};
 
   // publish the slot's operands to the tensor core: warps 1-3 of the group arrive and run ahead, warp 0 waits for
   // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
@@ -194,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   auto sync_and_issue = [&](int k, int l) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    const int sl = slot_of(k);
+    const int sl = g * NINFL + k;
     if (lt >= 32) {
       asm volatile("bar.arrive %0, 128;" ::"r"(1 + sl) : "memory");
     } else {
@@ -213,60 +209,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
 #pragma unroll
           for (int h = 0; h < 2; ++h)
             umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bars + sl))
-                     : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * k) : "memory");
       }
       __syncwarp();
     }
   };
 
-  // load the chain input of the slot's tile, build the first A operand / constant operand / residual region
-  auto begin_tile = [&](int k) {
-    const int64_t r = int64_t(tile[k]) * STRIDE - NL + lt;
-    int p = -1;
-    int64_t site = 0;
-    if (r > 0 && r < a.rows) {
+  // row of this thread in tile `tile_idx`, its position inside the site (-1 = separator / outside) and the chain
+  // input of that row (RB4: the row itself; pooled modes: max over the pool window, model_snv.py:361,371,404,414)
+  auto fetch = [&](int tile_idx, int& r, int& p, uint4 (&x)[4]) {
+    r = tile_idx * STRIDE - NL + lt;
+    p = -1;
+    int site = 0;
+    if (r > 0 && r < int(a.rows)) {
       site = r / Lp1;
-      p = int(r - site * Lp1) - 1;
+      p = r - site * Lp1 - 1;
     }
-    row[k] = r;
-    pos[k] = p;
     const bool live = p >= 0;
-    unsigned char* sA = sA_of(k);
-    uint4 x[4];
     if (MODE == RB4) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = live ? __ldg(a.in + q * a.in_rows_alloc + r) : make_uint4(0, 0, 0, 0);
-      // residual region R <- x0 (fp32), first A operand <- relu(x0)
-      uint32_t f[32];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[q]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[8 * q + 2 * j] = w[j] << 16;
-          f[8 * q + 2 * j + 1] = w[j] & 0xFFFF0000u;
-        }
-      }
-      TMEM_ST32(tmem_base + lane_off + slot_of(k) * 64, f);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = relu_bf16x2(x[q].x); o.y = relu_bf16x2(x[q].y); o.z = relu_bf16x2(x[q].z); o.w = relu_bf16x2(x[q].w);
-        *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = o;
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    } else {  // MaxPool1d(pk, ps, pp) fused into the load (padding = -inf never wins), model_snv.py:361,371,404,414
+    } else {
       int lo = p * a.ps - a.pp, hi = lo + a.pk;
       lo = lo < 0 ? 0 : lo;
       hi = hi > a.Lin ? a.Lin : hi;
       if (!live) hi = lo;
-      const int64_t base = 1 + site * (a.Lin + 1);
+      const int base = 1 + site * (a.Lin + 1);
       const uint32_t ninf = live ? 0xFF80FF80u : 0u;  // bf16 -inf pair; separator rows stay zero
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = make_uint4(ninf, ninf, ninf, ninf);
 #pragma unroll
-      for (int u = 0; u < 7; ++u) {  // pk <= 7 for every pool of Network2 (checked on the host)
+      for (int u = 0; u < 7; ++u) {  // pk <= 7 for every pool of Network2
         if (lo + u < hi) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -276,6 +249,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
           }
         }
       }
+    }
+  };
+
+  // first A operand / constant operand / residual region of slot k from the fetched row, then layer 0
+  auto begin_tile = [&](int k, int p, const uint4 (&x)[4]) {
+    unsigned char* sA = sA0 + k * SLOT_BYTES;
+    const bool live = p >= 0;
+    if (MODE == RB4) {
+      uint32_t f[32];  // residual region R <- x0 (fp32)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&x[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[8 * q + 2 * j] = w[j] << 16;
+          f[8 * q + 2 * j + 1] = w[j] & 0xFFFF0000u;
+        }
+      }
+      TMEM_ST32(tmem_base + lane_off + (g * NINFL + k) * 64, f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = relu_bf16x2(x[q].x); o.y = relu_bf16x2(x[q].y); o.z = relu_bf16x2(x[q].z); o.w = relu_bf16x2(x[q].w);
+        *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = o;
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = x[q];
     }
@@ -283,90 +283,96 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     const uint32_t one2 = 0x3F803F80u;
     *reinterpret_cast<uint4*>(sA + A_SLOT + lt * 16) =
         make_uint4(live ? one2 : 0u, p == 0 ? one2 : 0u, (live && p == a.L - 1) ? one2 : 0u, 0u);
-    layer[k] = 0;
     sync_and_issue(k, 0);
   };
 
+  // static schedule: both slots of the group walk the layer chain in lockstep (layer index is a compile-time
+  // constant after unrolling); the NEXT pair of tiles is fetched into registers while the chain runs.
+  int tile0 = blockIdx.x * NSLOT + g * NINFL;
+  int rn[NINFL], pn[NINFL];
+  uint4 xn[NINFL][4];
 #pragma unroll
   for (int k = 0; k < NINFL; ++k) {
-    tile[k] = (blockIdx.x * NGROUP + g) * NINFL + k;
-    phase[k] = 0;
-    active[k] = tile[k] < a.n_tiles;
-    layer[k] = 0;
-    row[k] = 0;
-    pos[k] = -1;
+    rn[k] = 0; pn[k] = -1;
+    if (tile0 + k < a.n_tiles) fetch(tile0 + k, rn[k], pn[k], xn[k]);
   }
-#pragma unroll
-  for (int k = 0; k < NINFL; ++k)
-    if (active[k]) begin_tile(k);
-
-  while (active[0] || active[1]) {
+  for (; tile0 < a.n_tiles; tile0 += tile_step) {
+    bool act[NINFL];
+    int r[NINFL], p[NINFL];
 #pragma unroll
     for (int k = 0; k < NINFL; ++k) {
-      if (!active[k]) continue;
-      mbar_wait(smem_u32(bars + slot_of(k)), phase[k]);
-      phase[k] ^= 1;
-      __syncwarp();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int l = layer[k];
-      const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
-      const bool live = pos[k] >= 0;
-      const bool valid = live && lt >= NL && lt < TILE - NL;
-      const int64_t r = row[k];
-      uint32_t acc[32];
-      TMEM_LD32(acc, tmem_base + lane_off + slot_of(k) * 64 + (rtype ? 0 : 32));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (l < NL - 1) {
-        uint4 o[4];
+      act[k] = tile0 + k < a.n_tiles;
+      r[k] = rn[k];
+      p[k] = pn[k];
+      if (act[k]) begin_tile(k, p[k], xn[k]);
+    }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          o[q].x = pack_bf16(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
-          o[q].y = pack_bf16(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3]));
-          o[q].z = pack_bf16(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
-          o[q].w = pack_bf16(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
-        }
-        if (MODE == C_RB4 && l == 0 && valid) {  // jump = conv2 output: parked (bf16) in the output row, re-read at the end
-          uint4* out4 = reinterpret_cast<uint4*>(a.out);
+    for (int k = 0; k < NINFL; ++k)
+      if (tile0 + tile_step + k < a.n_tiles) fetch(tile0 + tile_step + k, rn[k], pn[k], xn[k]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r] = o[q];
-        }
-        if (live) {  // separator rows were zeroed by begin_tile and are never rewritten
-          unsigned char* sA = sA_of(k);
+    for (int l = 0; l < NL; ++l) {
+#pragma unroll
+      for (int k = 0; k < NINFL; ++k) {
+        if (!act[k]) continue;
+        mbar_wait(bar0 + 8 * k, phase[k]);
+        phase[k] ^= 1;
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
+        const bool live = p[k] >= 0;
+        const bool valid = live && lt >= NL && lt < TILE - NL;
+        uint32_t acc[32];
+        TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (l < NL - 1) {
+          uint4 o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = relu_bf16x2(o[q].x); w.y = relu_bf16x2(o[q].y); w.z = relu_bf16x2(o[q].z); w.w = relu_bf16x2(o[q].w);
-            *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = w;
+            o[q].x = pack_bf16(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
+            o[q].y = pack_bf16(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3]));
+            o[q].z = pack_bf16(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
+            o[q].w = pack_bf16(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
           }
-        }
-        layer[k] = l + 1;
-        sync_and_issue(k, l + 1);
-      } else {
-        if (valid) {
+          if (MODE == C_RB4 && l == 0 && valid) {  // jump = conv2 output: parked (bf16) in the output row, re-read at the end
+            uint4* out4 = reinterpret_cast<uint4*>(a.out);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r[k]] = o[q];
+          }
+          if (live) {  // separator rows were zeroed by begin_tile and are never rewritten
+            unsigned char* sA = sA0 + k * SLOT_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = relu_bf16x2(o[q].x); w.y = relu_bf16x2(o[q].y); w.z = relu_bf16x2(o[q].z); w.w = relu_bf16x2(o[q].w);
+              *reinterpret_cast<uint4*>(sA + q * A_PLANE + (lt + 1) * 16) = w;
+            }
+          }
+          sync_and_issue(k, l + 1);
+        } else if (valid) {
           if (MODE == SINGLE) {  // conv3 + ReLU -> fp32 planes for the head
             float4* out4 = reinterpret_cast<float4*>(a.out);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              out4[q * a.out_rows_alloc + r] =
+              out4[q * a.out_rows_alloc + r[k]] =
                   make_float4(fmaxf(__uint_as_float(acc[4 * q]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 1]), 0.f),
                               fmaxf(__uint_as_float(acc[4 * q + 2]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 3]), 0.f));
           } else {  // outer skip: + x0 (RB4, re-read from the input) or + jump (C_RB4, parked in the output row)
             uint4* out4 = reinterpret_cast<uint4*>(a.out);
+            uint4 xr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              xr[q] = (MODE == RB4) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 x = (MODE == RB4) ? __ldg(a.in + q * a.in_rows_alloc + r) : out4[q * a.out_rows_alloc + r];
               uint4 o;
-              o.x = pack_bf16(__uint_as_float(acc[8 * q]) + bf16_lo(x.x), __uint_as_float(acc[8 * q + 1]) + bf16_hi(x.x));
-              o.y = pack_bf16(__uint_as_float(acc[8 * q + 2]) + bf16_lo(x.y), __uint_as_float(acc[8 * q + 3]) + bf16_hi(x.y));
-              o.z = pack_bf16(__uint_as_float(acc[8 * q + 4]) + bf16_lo(x.z), __uint_as_float(acc[8 * q + 5]) + bf16_hi(x.z));
-              o.w = pack_bf16(__uint_as_float(acc[8 * q + 6]) + bf16_lo(x.w), __uint_as_float(acc[8 * q + 7]) + bf16_hi(x.w));
-              out4[q * a.out_rows_alloc + r] = o;
+              o.x = pack_bf16(__uint_as_float(acc[8 * q]) + bf16_lo(xr[q].x), __uint_as_float(acc[8 * q + 1]) + bf16_hi(xr[q].x));
+              o.y = pack_bf16(__uint_as_float(acc[8 * q + 2]) + bf16_lo(xr[q].y), __uint_as_float(acc[8 * q + 3]) + bf16_hi(xr[q].y));
+              o.z = pack_bf16(__uint_as_float(acc[8 * q + 4]) + bf16_lo(xr[q].z), __uint_as_float(acc[8 * q + 5]) + bf16_hi(xr[q].z));
+              o.w = pack_bf16(__uint_as_float(acc[8 * q + 6]) + bf16_lo(xr[q].w), __uint_as_float(acc[8 * q + 7]) + bf16_hi(xr[q].w));
+              out4[q * a.out_rows_alloc + r[k]] = o;
             }
           }
         }
-        tile[k] += tile_step;
-        active[k] = tile[k] < a.n_tiles;
-        if (active[k]) begin_tile(k);
       }
     }
   }
