@@ -330,7 +330,7 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier):
     achieved = flops_per_launch / (ms / n * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "+".join(sorted(conv)), "launches": n, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,
+            "kernel": "+".join(sorted(conv)), "launches": n, "profile_count": {k: v["count"] for k, v in prof.items()}, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,
             "peak_source": src + " (bf16 sustained, kernel timed inside a long step)",
             "flops_per_launch": flops_per_launch, "profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 

@@ -210,6 +210,139 @@ __global__ void __launch_bounds__(256, 2) k_stem_fast(GenomeView G, const int32_
   }
 }
 
+// Packed fast stem (genome path): the oriented window is kept as 2-bit codes (16 bases per word) in shared
+// memory — '+' strand by a funnel shift of the genome words, '-' strand by reversing the 2-bit groups of the mirrored
+// words and complementing (~) — and the 4-mer index of a position pair is 8 consecutive bits of that stream, so the 8
+// lookups of a 15-wide pool bin need three word loads and eight funnel shifts.  Windows touching a chromosome end
+// or any non-ACGT base fall back to the exact byte path.
+template <int C>
+__global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
+                                                    int64_t ns, int R, int L, StemBranch b0, StemBranch b1, int local_R, int order,
+                                                    int n_cat, int32_t* __restrict__ cat_out) {
+  constexpr int CG = C / 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sT4 = reinterpret_cast<float*>(smem_raw);  // [2][256][C]
+  float* sT = sT4 + 2 * 256 * C;                    // [2][3][16][C]
+  float* sB = sT + 2 * 3 * 16 * C;                  // [2][C]
+  const int nW = (L + 15) / 16 + 3;
+  uint32_t* pk = reinterpret_cast<uint32_t*>(sB + 2 * C);  // [nW]
+  uint8_t* sym = reinterpret_cast<uint8_t*>(pk + nW);      // [L+4], slow path only
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  for (int e = tid * 4; e < 256 * C; e += 256 * 4) {
+    *reinterpret_cast<float4*>(sT4 + e) = *reinterpret_cast<const float4*>(b0.T4 + e);
+    *reinterpret_cast<float4*>(sT4 + 256 * C + e) = *reinterpret_cast<const float4*>(b1.T4 + e);
+  }
+  for (int e = tid; e < 3 * 16 * C; e += 256) { sT[e] = b0.T[e]; sT[3 * 16 * C + e] = b1.T[e]; }
+  for (int e = tid; e < C; e += 256) { sB[e] = b0.bias[e]; sB[C + e] = b1.bias[e]; }
+  for (int64_t site = blockIdx.x; site < ns; site += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) s_bad = 0;
+    const int m = meta[site];
+    const int strand = m & 1, chrom = int(uint32_t(m) >> 8);
+    const int64_t wstart = int64_t(pos[site]) - R;
+    const int64_t len = G.chrom_len[chrom], g0 = G.chrom_off[chrom] + wstart;
+    const bool inside = wstart >= 16 && wstart + L + 16 <= len;
+    __syncthreads();
+    if (inside) {
+      for (int t = tid; t < nW; t += 256) {
+        uint32_t v;
+        if (!strand) {
+          const int64_t a = (g0 >> 4) + t;
+          v = __funnelshift_r(__ldg(G.bits2 + a), __ldg(G.bits2 + a + 1), 2 * int(g0 & 15));
+        } else {
+          const int64_t lo_base = g0 + L - 1 - 16 * int64_t(t) - 15;
+          if (lo_base >= 0) {
+            const int64_t a = lo_base >> 4;
+            const uint32_t w = __funnelshift_r(__ldg(G.bits2 + a), __ldg(G.bits2 + a + 1), 2 * int(lo_base & 15));
+            uint32_t r = __brev(w);
+            r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+            v = ~r;
+          } else {
+            v = 0;
+          }
+        }
+        pk[t] = v;
+      }
+      const int64_t m0 = g0 >> 5, m1 = (g0 + L - 1) >> 5;
+      for (int64_t w = m0 + tid; w <= m1; w += 256) {
+        uint32_t mk = __ldg(G.mask + w);
+        if (w == m0) mk &= 0xFFFFFFFFu << int(g0 & 31);
+        if (w == m1) mk &= 0xFFFFFFFFu >> (31 - int((g0 + L - 1) & 31));
+        if (mk) s_bad = 1;
+      }
+    }
+    __syncthreads();
+    const bool slow = !inside || s_bad != 0;
+    if (slow) {
+      load_window(G, chrom, wstart, L, strand, sym);
+      __syncthreads();
+    }
+    auto sym_at = [&](int i) -> int { return slow ? int(sym[i]) : int((pk[i >> 4] >> (2 * (i & 15))) & 3u); };
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      const StemBranch& B = br ? b1 : b0;
+      const float* T4 = sT4 + br * 256 * C;
+      const float* Tt = sT + br * 3 * 16 * C;
+      const float* bias = sB + br * C;
+      for (int item = tid; item < B.L1 * CG; item += 256) {
+        const int j = item / CG, q = item - j * CG;
+        int lo = j * B.ps - B.pp, hi = lo + B.pk;
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > B.L0 ? B.L0 : hi;
+        float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        if (slow || lo == 0 || hi == B.L0 || hi - lo < 2) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * q);
+          for (int p = lo; p < hi; ++p) {
+            float4 v = bb;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const int x = p + t - 1;
+              const int sy = (x >= 0 && x < B.L0) ? sym_at(B.off0 + x) : SYM_PAD;
+              const float4 w = *reinterpret_cast<const float4*>(Tt + (t * 16 + sy) * C + 4 * q);
+              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+            mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+          }
+        } else {
+          const int i0 = B.off0 + lo - 1;  // stream index of the first base of the first pair's 4-mer
+          const int w = i0 >> 4, sh = 2 * (i0 & 15);
+          const uint32_t w0 = pk[w], w1 = pk[w + 1], w2 = pk[w + 2];
+          const uint32_t xl = __funnelshift_r(w0, w1, sh), xh = __funnelshift_r(w1, w2, sh);
+          for (int p = lo; p < hi; p += 2) {
+            const int pp = (p + 1 < hi) ? p : hi - 2;  // odd tail: overlap the last pair (max is idempotent)
+            const int k4 = __funnelshift_r(xl, xh, 2 * (pp - lo)) & 0xFF;
+            const float4 wv = *reinterpret_cast<const float4*>(T4 + k4 * C + 4 * q);
+            mx.x = fmaxf(mx.x, wv.x); mx.y = fmaxf(mx.y, wv.y); mx.z = fmaxf(mx.z, wv.z); mx.w = fmaxf(mx.w, wv.w);
+          }
+        }
+        if (B.rows_alloc && B.out_bf16) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(mx.x, mx.y), p1 = __floats2bfloat162_rn(mx.z, mx.w);
+          uint2 pk2 = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(B.out) +
+                                    (int64_t(q >> 1) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 16 + (q & 1) * 8) = pk2;
+        } else if (B.rows_alloc) {
+          *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = mx;
+        } else {
+          *reinterpret_cast<float4*>(B.out + (site * B.L1 + j) * int64_t(C) + 4 * q) = mx;
+        }
+      }
+    }
+    if (cat_out) {
+      for (int j = tid; j < n_cat; j += 256) {
+        int idx = 0;
+        bool bad = false;
+        for (int d = 0; d < order; ++d) {
+          const int sy = sym_at(R - local_R + j + d);
+          bad |= sy > 3;
+          idx = idx * 4 + (sy & 3);
+        }
+        cat_out[site * n_cat + j] = bad ? (1 << (2 * order)) : idx;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ local MLP
 constexpr int MLP_TS = 32;       // sites per CTA
 constexpr int MLP_THREADS = 160;
@@ -540,6 +673,27 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
   if (ks == 3 && !m->slow_stem) {
     const size_t smem_f = sizeof(float) * (2 * size_t(256) * C + 2 * 3 * 16 * size_t(C) + 2 * C) + ((size_t(L) + 4 + 15) & ~size_t(15));
     int grid = int(ns < 148 * 2 ? ns : 148 * 2);
+    if (!d_sym) {  // genome path: packed 2-bit stem
+      const size_t smem_p = smem_f + 4 * (size_t(L + 15) / 16 + 3);
+#define STEMP_CASE(CC)                                                                                                     \
+  case CC: {                                                                                                              \
+    static size_t configured = 0;                                                                                         \
+    if (smem_p > configured) {                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(k_stem_pk<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));            \
+      configured = smem_p;                                                                                                \
+    }                                                                                                                     \
+    LAUNCH(k_stem_pk<CC>, grid, 256, smem_p, st, gvf, d_pos, d_meta, ns, R, L, sb[0], sb[1], m->cfg.local_radius,         \
+           m->cfg.local_order, m->n_cat, cat_out);                                                                        \
+  } break;
+      switch (C) {
+        STEMP_CASE(16)
+        STEMP_CASE(32)
+        STEMP_CASE(64)
+        default: MURAL_FAIL("unsupported channel count");
+      }
+#undef STEMP_CASE
+      return 0;
+    }
 #define STEMF_CASE(CC)                                                                                                     \
   case CC: {                                                                                                              \
     static size_t configured = 0;                                                                                         \

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snv_model.cuh"
@@ -54,6 +55,7 @@ struct StageArgs {
   int Lin;               // site length of the input buffer (== L when not pooled)
   int pk, ps, pp;        // max-pool fused into the loader (RB4: none)
   int n_tiles;
+  int dbg;               // timing experiments only (MURAL_TC_DBG): results are wrong when non-zero
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
   // One named barrier per slot so that a warp running one step ahead never double-arrives.
   auto sync_and_issue = [&](int k, int l) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (!(a.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     const int sl = g * NINFL + k;
     if (lt >= 32) {
@@ -204,11 +206,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         const uint64_t dA = dA0 + uint64_t((sl * SLOT_BYTES) >> 4), dC = dC0 + uint64_t((sl * SLOT_BYTES) >> 4);
         const uint64_t dW = dW0 + uint64_t((l * W_LAYER) >> 4);
         umma_bf16(d, dC, dW + (W_CONV >> 4), acc_first ? 1u : 0u);
+        if (!(a.dbg & 4)) {
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+          for (int t = 0; t < 3; ++t)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
+            for (int h = 0; h < 2; ++h)
+              umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * k) : "memory");
       }
       __syncwarp();
@@ -322,10 +326,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         const bool live = p[k] >= 0;
         const bool valid = live && lt >= NL && lt < TILE - NL;
         uint32_t acc[32];
-        TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!(a.dbg & 2)) {
+          TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c] = 0x3f800000u + lt;
+        }
         if (l < NL - 1) {
           uint4 o[4];
+          if (a.dbg & 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_uint4(acc[q], acc[q + 4], acc[q + 8], acc[q + 12]);
+          } else
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             o[q].x = pack_bf16(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
@@ -460,7 +473,13 @@ static int launch_stage(const StageArgs& a, cudaStream_t st) {
   }
   int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
   if (grid > m_sm_count()) grid = m_sm_count();
-  LAUNCH(k_stage_tc<MODE>, grid, THREADS, smem, st, a);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MURAL_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  StageArgs a2 = a;
+  a2.dbg = dbg;
+  if (MODE == RB4) LAUNCH(k_stage_tc<RB4>, grid, THREADS, smem, st, a2);
+  else if (MODE == C_RB4) LAUNCH(k_stage_tc<C_RB4>, grid, THREADS, smem, st, a2);
+  else LAUNCH(k_stage_tc<SINGLE>, grid, THREADS, smem, st, a2);
   return 0;
 }
 
@@ -575,7 +594,9 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   MURAL_CHECK(m->tc != nullptr, "MURAL_MODE_BF16 needs CNN_out_channels == 32 and CNN_kernel_size == 3");
   TcState* S = (TcState*)m->tc;
   const int NC = m->cfg.n_class;
-  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 8192;
+  static int64_t env_chunk = -1;
+  if (env_chunk < 0) { const char* e = getenv("MURAL_TC_CHUNK"); env_chunk = e ? atoll(e) : 0; }
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (env_chunk > 0 ? env_chunk : 32768);
   if (m->chunk_sites <= 0 || (int64_t(1) << 20) % chunk != 0) {  // keep chunks aligned inside super-chunks
     int64_t c2 = 1;
     while (c2 * 2 <= chunk) c2 *= 2;
