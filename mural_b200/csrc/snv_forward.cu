@@ -213,8 +213,25 @@ __global__ void __launch_bounds__(256, 2) k_stem_fast(GenomeView G, const int32_
 // Packed fast stem (genome path): the oriented window is kept as 2-bit codes (16 bases per word) in shared
 // memory — '+' strand by a funnel shift of the genome words, '-' strand by reversing the 2-bit groups of the mirrored
 // words and complementing (~) — and the 4-mer index of a position pair is 8 consecutive bits of that stream, so the 8
-// lookups of a 15-wide pool bin need three word loads and eight funnel shifts.  Windows touching a chromosome end
-// or any non-ACGT base fall back to the exact byte path.
+// lookups of a 15-wide pool bin need three word loads and eight funnel shifts.  The next site's words are fetched
+// into registers while the current site's bins are computed (one __syncthreads per site).  Windows touching a
+// chromosome end or any non-ACGT base fall back to the exact byte path.
+template <int C, int NP>  // NP: lookups of an interior bin (8 for the 15-wide pool, 2 for the 3-wide pool)
+__device__ __forceinline__ float4 stem_bin_packed(const float* __restrict__ T4, const uint32_t* __restrict__ pk, int i0, int q) {
+  const int w = i0 >> 4, sh = 2 * (i0 & 15);
+  const uint32_t w0 = pk[w], w1 = pk[w + 1], w2 = pk[w + 2];
+  const uint32_t xl = __funnelshift_r(w0, w1, sh), xh = __funnelshift_r(w1, w2, sh);
+  float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int rel = (NP == 8) ? (i < 7 ? 4 * i : 26) : 2 * i;  // pairs at +0,+2,..,+12 and the overlapping tail pair at +13
+    const int k4 = __funnelshift_r(xl, xh, rel) & 0xFF;
+    const float4 wv = *reinterpret_cast<const float4*>(T4 + k4 * C + 4 * q);
+    mx.x = fmaxf(mx.x, wv.x); mx.y = fmaxf(mx.y, wv.y); mx.z = fmaxf(mx.z, wv.z); mx.w = fmaxf(mx.w, wv.w);
+  }
+  return mx;
+}
+
 template <int C>
 __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
                                                     int64_t ns, int R, int L, StemBranch b0, StemBranch b1, int local_R, int order,
@@ -225,9 +242,8 @@ __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t*
   float* sT = sT4 + 2 * 256 * C;                    // [2][3][16][C]
   float* sB = sT + 2 * 3 * 16 * C;                  // [2][C]
   const int nW = (L + 15) / 16 + 3;
-  uint32_t* pk = reinterpret_cast<uint32_t*>(sB + 2 * C);  // [nW]
-  uint8_t* sym = reinterpret_cast<uint8_t*>(pk + nW);      // [L+4], slow path only
-  __shared__ int s_bad;
+  uint32_t* pkbuf = reinterpret_cast<uint32_t*>(sB + 2 * C);  // [2][nW]
+  uint8_t* sym = reinterpret_cast<uint8_t*>(pkbuf + 2 * nW);  // [L+4], slow path only
   const int tid = threadIdx.x;
   for (int e = tid * 4; e < 256 * C; e += 256 * 4) {
     *reinterpret_cast<float4*>(sT4 + e) = *reinterpret_cast<const float4*>(b0.T4 + e);
@@ -235,47 +251,95 @@ __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t*
   }
   for (int e = tid; e < 3 * 16 * C; e += 256) { sT[e] = b0.T[e]; sT[3 * 16 * C + e] = b1.T[e]; }
   for (int e = tid; e < C; e += 256) { sB[e] = b0.bias[e]; sB[C + e] = b1.bias[e]; }
-  for (int64_t site = blockIdx.x; site < ns; site += gridDim.x) {
-    __syncthreads();
-    if (tid == 0) s_bad = 0;
+
+  // Window fetch in two halves so the global-load latency overlaps the bin computation of the current site:
+  // issue_fetch() starts the loads into registers, commit_fetch() shifts/reverses them into pk afterwards.
+  // (windows longer than 4080 bp need more than one word per thread and are fetched synchronously in commit_fetch)
+  const bool one_word = nW <= 256;
+  struct Pre { uint32_t wa, wb, mk; int sh, strand; bool ok, bad; int64_t g0; } pre;
+  auto issue_fetch = [&](int64_t site) {
     const int m = meta[site];
-    const int strand = m & 1, chrom = int(uint32_t(m) >> 8);
+    const int chrom = int(uint32_t(m) >> 8);
+    pre.strand = m & 1;
     const int64_t wstart = int64_t(pos[site]) - R;
-    const int64_t len = G.chrom_len[chrom], g0 = G.chrom_off[chrom] + wstart;
-    const bool inside = wstart >= 16 && wstart + L + 16 <= len;
-    __syncthreads();
-    if (inside) {
-      for (int t = tid; t < nW; t += 256) {
-        uint32_t v;
-        if (!strand) {
-          const int64_t a = (g0 >> 4) + t;
-          v = __funnelshift_r(__ldg(G.bits2 + a), __ldg(G.bits2 + a + 1), 2 * int(g0 & 15));
-        } else {
-          const int64_t lo_base = g0 + L - 1 - 16 * int64_t(t) - 15;
-          if (lo_base >= 0) {
-            const int64_t a = lo_base >> 4;
-            const uint32_t w = __funnelshift_r(__ldg(G.bits2 + a), __ldg(G.bits2 + a + 1), 2 * int(lo_base & 15));
-            uint32_t r = __brev(w);
-            r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-            v = ~r;
-          } else {
-            v = 0;
-          }
-        }
-        pk[t] = v;
+    const int64_t len = G.chrom_len[chrom];
+    pre.g0 = G.chrom_off[chrom] + wstart;
+    pre.ok = wstart >= 16 && wstart + L + 16 <= len;  // otherwise: chromosome overhang -> N imputation -> slow path
+    pre.wa = pre.wb = pre.mk = 0;
+    pre.sh = 0;
+    if (!pre.ok) return;
+    const int64_t m0 = pre.g0 >> 5, m1 = (pre.g0 + L - 1) >> 5;
+    if (one_word) {
+      if (m0 + tid <= m1) {
+        uint32_t mk = __ldg(G.mask + m0 + tid);
+        if (tid == 0) mk &= 0xFFFFFFFFu << int(pre.g0 & 31);
+        if (m0 + tid == m1) mk &= 0xFFFFFFFFu >> (31 - int((pre.g0 + L - 1) & 31));
+        pre.mk = mk;
       }
-      const int64_t m0 = g0 >> 5, m1 = (g0 + L - 1) >> 5;
+      if (tid < nW) {
+        const int64_t base = pre.strand ? (pre.g0 + L - 1 - 16 * int64_t(tid) - 15) : (pre.g0 + 16 * int64_t(tid));
+        if (base >= 0) {
+          pre.wa = __ldg(G.bits2 + (base >> 4));
+          pre.wb = __ldg(G.bits2 + (base >> 4) + 1);
+          pre.sh = 2 * int(base & 15);
+        }
+      }
+    }
+  };
+  auto commit_fetch = [&](uint32_t* pk) -> bool {
+    if (!pre.ok) return true;
+    bool bad = false;
+    if (one_word) {
+      bad = pre.mk != 0u;
+      if (tid < nW) {
+        uint32_t v = __funnelshift_r(pre.wa, pre.wb, pre.sh);
+        if (pre.strand) {
+          uint32_t r = __brev(v);
+          r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+          v = ~r;
+        }
+        pk[tid] = v;
+      }
+    } else {
+      const int64_t g0 = pre.g0, m0 = g0 >> 5, m1 = (g0 + L - 1) >> 5;
       for (int64_t w = m0 + tid; w <= m1; w += 256) {
         uint32_t mk = __ldg(G.mask + w);
         if (w == m0) mk &= 0xFFFFFFFFu << int(g0 & 31);
         if (w == m1) mk &= 0xFFFFFFFFu >> (31 - int((g0 + L - 1) & 31));
-        if (mk) s_bad = 1;
+        bad |= mk != 0u;
+      }
+      for (int t = tid; t < nW; t += 256) {
+        const int64_t base = pre.strand ? (g0 + L - 1 - 16 * int64_t(t) - 15) : (g0 + 16 * int64_t(t));
+        uint32_t v = 0;
+        if (base >= 0) {
+          v = __funnelshift_r(__ldg(G.bits2 + (base >> 4)), __ldg(G.bits2 + (base >> 4) + 1), 2 * int(base & 15));
+          if (pre.strand) {
+            uint32_t r = __brev(v);
+            r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+            v = ~r;
+          }
+        }
+        pk[t] = v;
       }
     }
-    __syncthreads();
-    const bool slow = !inside || s_bad != 0;
-    if (slow) {
-      load_window(G, chrom, wstart, L, strand, sym);
+    return bad;
+  };
+
+  int cur = 0;
+  int64_t site = blockIdx.x;
+  bool slow = false;
+  if (site < ns) {
+    issue_fetch(site);
+    slow = commit_fetch(pkbuf);
+  }
+  slow = __syncthreads_or(slow) != 0;  // also publishes the tables and pk[0]
+  for (; site < ns; site += gridDim.x) {
+    const uint32_t* pk = pkbuf + cur * nW;
+    const int64_t nxt = site + gridDim.x;
+    if (nxt < ns) issue_fetch(nxt);    // loads in flight while this site's bins are computed
+    if (slow) {  // block-uniform
+      const int m = meta[site];
+      load_window(G, int(uint32_t(m) >> 8), int64_t(pos[site]) - R, L, m & 1, sym);
       __syncthreads();
     }
     auto sym_at = [&](int i) -> int { return slow ? int(sym[i]) : int((pk[i >> 4] >> (2 * (i & 15))) & 3u); };
@@ -285,15 +349,52 @@ __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t*
       const float* T4 = sT4 + br * 256 * C;
       const float* Tt = sT + br * 3 * 16 * C;
       const float* bias = sB + br * C;
-      for (int item = tid; item < B.L1 * CG; item += 256) {
+      const int n_items = B.L1 * CG;
+      const int row0 = 1 + int(site) * (B.L1 + 1);  // fits int: chunk * (L1+1) < 2^31
+      for (int item = tid; item < n_items; item += 256) {
         const int j = item / CG, q = item - j * CG;
         int lo = j * B.ps - B.pp, hi = lo + B.pk;
         lo = lo < 0 ? 0 : lo;
         hi = hi > B.L0 ? B.L0 : hi;
-        float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-        if (slow || lo == 0 || hi == B.L0 || hi - lo < 2) {
+        float4 mx;
+        if (!slow && lo > 0 && hi < B.L0 && hi - lo == 15) {
+          mx = stem_bin_packed<C, 8>(T4, pk, B.off0 + lo - 1, q);
+        } else if (!slow && lo > 0 && hi < B.L0 && hi - lo == 3) {
+          mx = stem_bin_packed<C, 2>(T4, pk, B.off0 + lo - 1, q);
+        } else {  // window edges (missing tap = zero padding), odd pool shapes, N / IUPAC / overhang windows
+          mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
           const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * q);
-          for (int p = lo; p < hi; ++p) {
+          int glo = lo, ghi = hi;  // positions still to be done with the exact per-tap tables
+          if (!slow) {
+            const int ilo = lo < 1 ? 1 : lo, ihi = hi > B.L0 - 1 ? B.L0 - 1 : hi;  // interior positions [ilo, ihi)
+            if (ihi - ilo >= 2) {
+              for (int p = ilo; p < ihi; p += 2) {
+                const int pp = (p + 1 < ihi) ? p : ihi - 2;
+                const int i0 = B.off0 + pp - 1;
+                const uint32_t w0 = pk[i0 >> 4], w1 = pk[(i0 >> 4) + 1];
+                const int k4 = __funnelshift_r(w0, w1, 2 * (i0 & 15)) & 0xFF;
+                const float4 wv = *reinterpret_cast<const float4*>(T4 + k4 * C + 4 * q);
+                mx.x = fmaxf(mx.x, wv.x); mx.y = fmaxf(mx.y, wv.y); mx.z = fmaxf(mx.z, wv.z); mx.w = fmaxf(mx.w, wv.w);
+              }
+              // what is left: position 0 and/or position L0-1 (if inside the bin)
+              if (lo == 0) { glo = 0; ghi = 1; } else { glo = ghi = 0; }
+              if (hi == B.L0) {
+                if (glo == ghi) { glo = B.L0 - 1; ghi = B.L0; }
+                else if (B.L0 - 1 > 0) {  // both edges in one bin (tiny windows): do the right edge here
+                  float4 v = bb;
+#pragma unroll
+                  for (int t = 0; t < 3; ++t) {
+                    const int x = B.L0 - 1 + t - 1;
+                    const int sy = (x >= 0 && x < B.L0) ? sym_at(B.off0 + x) : SYM_PAD;
+                    const float4 w = *reinterpret_cast<const float4*>(Tt + (t * 16 + sy) * C + 4 * q);
+                    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                  }
+                  mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+                }
+              }
+            }
+          }
+          for (int p = glo; p < ghi; ++p) {
             float4 v = bb;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -304,25 +405,14 @@ __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t*
             }
             mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
           }
-        } else {
-          const int i0 = B.off0 + lo - 1;  // stream index of the first base of the first pair's 4-mer
-          const int w = i0 >> 4, sh = 2 * (i0 & 15);
-          const uint32_t w0 = pk[w], w1 = pk[w + 1], w2 = pk[w + 2];
-          const uint32_t xl = __funnelshift_r(w0, w1, sh), xh = __funnelshift_r(w1, w2, sh);
-          for (int p = lo; p < hi; p += 2) {
-            const int pp = (p + 1 < hi) ? p : hi - 2;  // odd tail: overlap the last pair (max is idempotent)
-            const int k4 = __funnelshift_r(xl, xh, 2 * (pp - lo)) & 0xFF;
-            const float4 wv = *reinterpret_cast<const float4*>(T4 + k4 * C + 4 * q);
-            mx.x = fmaxf(mx.x, wv.x); mx.y = fmaxf(mx.y, wv.y); mx.z = fmaxf(mx.z, wv.z); mx.w = fmaxf(mx.w, wv.w);
-          }
         }
         if (B.rows_alloc && B.out_bf16) {
           __nv_bfloat162 p0 = __floats2bfloat162_rn(mx.x, mx.y), p1 = __floats2bfloat162_rn(mx.z, mx.w);
           uint2 pk2 = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
-          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(B.out) +
-                                    (int64_t(q >> 1) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) * 16 + (q & 1) * 8) = pk2;
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(B.out) + (int64_t(q >> 1) * B.rows_alloc + row0 + j) * 16 +
+                                    (q & 1) * 8) = pk2;
         } else if (B.rows_alloc) {
-          *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = mx;
+          *(reinterpret_cast<float4*>(B.out) + int64_t(q) * B.rows_alloc + row0 + j) = mx;
         } else {
           *reinterpret_cast<float4*>(B.out + (site * B.L1 + j) * int64_t(C) + 4 * q) = mx;
         }
@@ -340,6 +430,11 @@ __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t*
         cat_out[site * n_cat + j] = bad ? (1 << (2 * order)) : idx;
       }
     }
+    // next site's window into the other buffer; one barrier publishes it and retires this site's readers
+    bool nslow = false;
+    if (nxt < ns) nslow = commit_fetch(pkbuf + (cur ^ 1) * nW);
+    slow = __syncthreads_or(nslow) != 0;
+    cur ^= 1;
   }
 }
 
@@ -674,7 +769,7 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
     const size_t smem_f = sizeof(float) * (2 * size_t(256) * C + 2 * 3 * 16 * size_t(C) + 2 * C) + ((size_t(L) + 4 + 15) & ~size_t(15));
     int grid = int(ns < 148 * 2 ? ns : 148 * 2);
     if (!d_sym) {  // genome path: packed 2-bit stem
-      const size_t smem_p = smem_f + 4 * (size_t(L + 15) / 16 + 3);
+      const size_t smem_p = smem_f + 8 * (size_t(L + 15) / 16 + 3);
 #define STEMP_CASE(CC)                                                                                                     \
   case CC: {                                                                                                              \
     static size_t configured = 0;                                                                                         \
