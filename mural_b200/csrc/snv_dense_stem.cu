@@ -1,0 +1,271 @@
+// Dense-site stem for genome-wide prediction.
+//
+// The first Conv1d of a branch (BN(4) + Conv1d(4->C, k=3) on a one-hot window) at window position i depends only on
+// the three genome bases around genomic position g and on the strand, never on the site; only the max-pool bins are
+// anchored at the site.  When the sites of a chunk are dense on one chromosome (genome-wide `predict`: every A/T,
+// ~2 bp apart) the per-site work  L x C x 3 table lookups  collapses to
+//   (1) k_dense_tables : conv output c[g] once per genomic position and strand, and its sliding-window maxima
+//                        W_w[g] = max(c[g .. g+w-1]) for the three bin widths a window has (full bin, clipped first
+//                        bin, clipped last bin), stored as bf16 rows;
+//   (2) k_stem_gather  : per site and bin ONE 64-byte row copy (plus the two window-edge positions whose conv misses a
+//                        tap, evaluated exactly from the per-tap tables).
+// Values are bit-identical to the per-site stem (same fp32 sums in the same order; max and bf16 rounding commute).
+// Sparse chunks (training sets, several chromosomes) keep using the per-site kernel: the decision is taken on the
+// device (k_chunk_span) so no host synchronisation is needed.
+#include <cuda_bf16.h>
+#include <float.h>
+#include <limits.h>
+
+#include "snv_model.cuh"
+
+namespace mural {
+
+struct ChunkInfo {
+  long long g_lo;  // chromosome coordinate of table index 0 (may be negative: overhang is imputed with N)
+  int n_pos;       // table rows in use
+  int dense;       // 1: tables + gather, 0: per-site stem
+  int chrom;
+  int has[2];      // strands present
+};
+
+constexpr int DT_POS = 256;   // table positions per CTA
+constexpr int DT_MAXW = 16;   // widest pool window supported by the table kernel
+
+__device__ __forceinline__ int sym_genomic(const GenomeView& G, int chrom, long long q) {
+  return (q >= 0 && q < G.chrom_len[chrom]) ? genome_symbol(G, G.chrom_off[chrom] + q) : SYM_N;
+}
+
+__global__ void k_chunk_span(const int32_t* __restrict__ pos, const int32_t* __restrict__ meta, int64_t ns, int R, int cap,
+                             ChunkInfo* __restrict__ info) {
+  __shared__ int s_min, s_max, s_mixed, s_has[2];
+  if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; s_mixed = 0; s_has[0] = s_has[1] = 0; }
+  __syncthreads();
+  const int chrom0 = int(uint32_t(meta[0]) >> 8);
+  int mn = INT_MAX, mx = INT_MIN, mixed = 0, h0 = 0, h1 = 0;
+  for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) {
+    const int p = pos[i], m = meta[i];
+    mn = min(mn, p);
+    mx = max(mx, p);
+    mixed |= int(uint32_t(m) >> 8) != chrom0;
+    if (m & 1) h1 = 1; else h0 = 1;
+  }
+  atomicMin(&s_min, mn);
+  atomicMax(&s_max, mx);
+  if (mixed) s_mixed = 1;
+  if (h0) s_has[0] = 1;
+  if (h1) s_has[1] = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long span = (long long)s_max - s_min + 2LL * R + 64;
+    info->g_lo = (long long)s_min - R - 24;
+    info->n_pos = int(span < cap ? span : cap);
+    info->dense = (!s_mixed && span <= cap) ? 1 : 0;
+    info->chrom = chrom0;
+    info->has[0] = s_has[0];
+    info->has[1] = s_has[1];
+  }
+}
+
+struct DenseBranch {
+  const float* T;     // [3][16][C] per-tap table
+  const float* bias;  // [C]
+  int w[3];           // sliding-window widths: full bin, first-bin interior, last-bin interior (0: unused)
+};
+
+// tables: [strand][branch][3 widths][cap][C] bf16
+template <int C>
+__global__ void __launch_bounds__(256) k_dense_tables(GenomeView G, const ChunkInfo* __restrict__ info, DenseBranch b0, DenseBranch b1,
+                                                      int cap, __nv_bfloat16* __restrict__ tables) {
+  if (!info->dense) return;
+  const int p0 = blockIdx.x * DT_POS;
+  if (p0 >= info->n_pos) return;
+  __shared__ uint8_t sym[DT_POS + DT_MAXW + 4];
+  extern __shared__ __align__(16) float dsm[];
+  float* sT = dsm;                       // [2][3][16][C]
+  float* sB = sT + 2 * 3 * 16 * C;       // [2][C]
+  float* cc = sB + 2 * C;                // [DT_POS + DT_MAXW][C]
+  const int tid = threadIdx.x;
+  const int chrom = info->chrom;
+  const long long g0 = info->g_lo + p0;
+  for (int e = tid; e < 3 * 16 * C; e += 256) { sT[e] = b0.T[e]; sT[3 * 16 * C + e] = b1.T[e]; }
+  for (int e = tid; e < C; e += 256) { sB[e] = b0.bias[e]; sB[C + e] = b1.bias[e]; }
+  for (int k = tid; k < DT_POS + DT_MAXW + 2; k += 256) sym[k] = uint8_t(sym_genomic(G, chrom, g0 - 1 + k));  // sym[k] = base g0-1+k
+  __syncthreads();
+#pragma unroll 1
+  for (int strand = 0; strand < 2; ++strand) {
+    if (!info->has[strand]) continue;
+#pragma unroll 1
+    for (int br = 0; br < 2; ++br) {
+      const DenseBranch& B = br ? b1 : b0;
+      const float* T = sT + br * 3 * 16 * C;
+      // conv output of every position in the oriented sequence of this strand (tap order as in the per-site stem)
+      for (int e = tid; e < (DT_POS + DT_MAXW) * C; e += 256) {
+        const int k = e / C, c = e - k * C;
+        float v = sB[br * C + c];
+        if (!strand) {
+          v += T[(0 * 16 + sym[k]) * C + c];
+          v += T[(1 * 16 + sym[k + 1]) * C + c];
+          v += T[(2 * 16 + sym[k + 2]) * C + c];
+        } else {  // oriented neighbours of genomic g are comp(g+1), comp(g), comp(g-1)
+          v += T[(0 * 16 + comp_sym(sym[k + 2])) * C + c];
+          v += T[(1 * 16 + comp_sym(sym[k + 1])) * C + c];
+          v += T[(2 * 16 + comp_sym(sym[k])) * C + c];
+        }
+        cc[e] = v;
+      }
+      __syncthreads();
+      __nv_bfloat16* tb = tables + (size_t(strand * 2 + br) * 3) * size_t(cap) * C;
+      for (int e = tid; e < DT_POS * C; e += 256) {
+        const int k = e / C, c = e - k * C;
+        if (p0 + k >= info->n_pos) continue;
+        float mx = -FLT_MAX;
+        float out[3] = {0.f, 0.f, 0.f};
+        for (int u = 0; u < DT_MAXW; ++u) {
+          if (u < B.w[0] || u < B.w[1] || u < B.w[2]) mx = fmaxf(mx, cc[(k + u) * C + c]);
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            if (u + 1 == B.w[t]) out[t] = mx;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+          if (B.w[t] > 0) tb[(size_t(t) * cap + p0 + k) * C + c] = __float2bfloat16(out[t]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct GatherBranch {
+  void* out;           // bf16 planes [C/8][rows_alloc][8]
+  int64_t rows_alloc;
+  const float* T;      // per-tap table (edge positions)
+  const float* bias;
+  int L0, off0, L1, pk, ps, pp;
+  int w[3];
+};
+
+// one warp-quarter (8 lanes x 16 B... here: C/8 lanes, 16 B each) copies one table row into one output row
+template <int C>
+__global__ void __launch_bounds__(256) k_stem_gather(GenomeView G, const ChunkInfo* __restrict__ info, const int32_t* __restrict__ pos,
+                                                     const int32_t* __restrict__ meta, int64_t ns, int R, GatherBranch b0, GatherBranch b1,
+                                                     int cap, const __nv_bfloat16* __restrict__ tables) {
+  if (!info->dense) return;
+  constexpr int PL = C / 8;  // 16-byte chunks per row
+  const long long g_lo = info->g_lo;
+  const int chrom = info->chrom;
+#pragma unroll 1
+  for (int br = 0; br < 2; ++br) {
+    const GatherBranch& B = br ? b1 : b0;
+    const int64_t total = ns * B.L1 * PL;
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+      const int q = int(e % PL);
+      const int64_t sj = e / PL;
+      const int j = int(sj % B.L1);
+      const int64_t site = sj / B.L1;
+      const int s = pos[site], strand = meta[site] & 1;
+      int lo = j * B.ps - B.pp, hi = lo + B.pk;
+      lo = lo < 0 ? 0 : lo;
+      hi = hi > B.L0 ? B.L0 : hi;
+      const int ilo = lo < 1 ? 1 : lo, ihi = hi > B.L0 - 1 ? B.L0 - 1 : hi;  // interior positions [ilo, ihi)
+      const int wn = ihi - ilo;
+      uint4 v = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf
+      if (wn > 0) {
+        const int t = wn == B.w[0] ? 0 : (wn == B.w[1] ? 1 : 2);
+        // oriented window index i_w = off0 + i  <->  genomic  s - R + i_w ('+')  /  s + R - i_w ('-')
+        const long long gs = strand ? (long long)s + R - (B.off0 + ihi - 1) : (long long)s - R + B.off0 + ilo;
+        const __nv_bfloat16* row = tables + ((size_t(strand * 2 + br) * 3 + t) * size_t(cap) + size_t(gs - g_lo)) * C;
+        v = *reinterpret_cast<const uint4*>(row + 8 * q);
+      }
+      if (lo == 0 || hi == B.L0) {  // window-edge position(s): the tap outside the window contributes 0 (zero padding)
+        float ev[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ev[c] = -FLT_MAX;
+        for (int side = 0; side < 2; ++side) {
+          const int p = side ? B.L0 - 1 : 0;
+          if (side ? (hi != B.L0) : (lo != 0)) continue;
+          if (side && B.L0 - 1 == 0) continue;
+          float a[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = B.bias[8 * q + c];
+          for (int t = 0; t < 3; ++t) {
+            const int x = p + t - 1;
+            if (x < 0 || x >= B.L0) continue;
+            const int iw = B.off0 + x;
+            const long long g = strand ? (long long)s + R - iw : (long long)s - R + iw;
+            int sy = sym_genomic(G, chrom, g);
+            if (strand) sy = comp_sym(sy);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] += B.T[(t * 16 + sy) * C + 8 * q + c];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ev[c] = fmaxf(ev[c], a[c]);
+        }
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          __nv_bfloat162 e2 = __floats2bfloat162_rn(ev[2 * c], ev[2 * c + 1]);
+          __nv_bfloat162 m2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w[c]), e2);
+          w[c] = *reinterpret_cast<uint32_t*>(&m2);
+        }
+      }
+      *(reinterpret_cast<uint4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = v;
+    }
+  }
+}
+
+static void bin_widths(const BranchDev& B, int w[3]) {
+  // interior positions (conv with all three taps inside the window) of a full bin, the first bin and the last bin
+  w[0] = B.pool[0][0];
+  int lo = 0, hi = B.pool[0][0] - B.pool[0][2];
+  hi = hi > B.L0 ? B.L0 : hi;
+  w[1] = (hi > B.L0 - 1 ? B.L0 - 1 : hi) - (lo < 1 ? 1 : lo);
+  lo = (B.L1 - 1) * B.pool[0][1] - B.pool[0][2];
+  hi = lo + B.pool[0][0];
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > B.L0 ? B.L0 : hi;
+  w[2] = (hi > B.L0 - 1 ? B.L0 - 1 : hi) - (lo < 1 ? 1 : lo);
+  for (int t = 1; t < 3; ++t)
+    if (w[t] < 0) w[t] = 0;
+}
+
+size_t snv_dense_bytes(const mural_snv_model* m, int64_t chunk) {
+  const size_t cap = size_t(8) * chunk + 4096;
+  return sizeof(ChunkInfo) + 256 + size_t(12) * cap * m->cfg.channels * 2;
+}
+
+// Enqueues span detection, table build and gather.  d_scratch: snv_dense_bytes() bytes.  Returns the device flag
+// (int*, 1 = the dense path produced the stem output) so that the per-site kernel can skip itself.
+int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
+                          int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
+                          const int** d_flag, cudaStream_t st) {
+  const int C = m->cfg.channels;
+  MURAL_CHECK(C == 32, "dense stem is built for C == 32");
+  const int cap = int(8 * chunk + 4096);
+  ChunkInfo* info = reinterpret_cast<ChunkInfo*>(d_scratch);
+  __nv_bfloat16* tables = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(d_scratch) + 256);
+  DenseBranch db[2];
+  GatherBranch gb[2];
+  for (int br = 0; br < 2; ++br) {
+    const BranchDev& B = m->br[br];
+    db[br].T = B.T;
+    db[br].bias = B.bias1;
+    bin_widths(B, db[br].w);
+    for (int t = 0; t < 3; ++t) MURAL_CHECK(db[br].w[t] <= DT_MAXW, "pool window too wide for the dense stem");
+    gb[br] = GatherBranch{br ? large_out : mid_out, br ? large_ra : mid_ra, B.T, B.bias1, B.L0, br ? 0 : m->L / 2 - 100, B.L1,
+                          B.pool[0][0], B.pool[0][1], B.pool[0][2], {db[br].w[0], db[br].w[1], db[br].w[2]}};
+  }
+  LAUNCH(k_chunk_span, 1, 1024, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, info);
+  const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C + size_t(DT_POS + DT_MAXW) * C);
+  static bool conf = false;
+  if (!conf) {
+    CUDA_TRY(cudaFuncSetAttribute(k_dense_tables<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = true;
+  }
+  LAUNCH(k_dense_tables<32>, (unsigned)cdiv(cap, DT_POS), 256, smem, st, *G, info, db[0], db[1], cap, tables);
+  LAUNCH(k_stem_gather<32>, 148 * 8, 256, 0, st, *G, info, d_pos, d_meta, ns, m->cfg.distal_radius, gb[0], gb[1], cap, tables);
+  *d_flag = &info->dense;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mural

@@ -235,7 +235,8 @@ __device__ __forceinline__ float4 stem_bin_packed(const float* __restrict__ T4, 
 template <int C>
 __global__ void __launch_bounds__(256, 2) k_stem_pk(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
                                                     int64_t ns, int R, int L, StemBranch b0, StemBranch b1, int local_R, int order,
-                                                    int n_cat, int32_t* __restrict__ cat_out) {
+                                                    int n_cat, int32_t* __restrict__ cat_out, const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;  // the dense-site stem (snv_dense_stem.cu) already produced this chunk
   constexpr int CG = C / 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sT4 = reinterpret_cast<float*>(smem_raw);  // [2][256][C]
@@ -756,7 +757,7 @@ int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_po
 
 int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                            const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
-                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16) {
+                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16, const int* skip_flag) {
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, L = m->L, R = m->cfg.distal_radius;
   StemBranch sb[2];
   for (int br = 0; br < 2; ++br) {
@@ -778,7 +779,7 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
       configured = smem_p;                                                                                                \
     }                                                                                                                     \
     LAUNCH(k_stem_pk<CC>, grid, 256, smem_p, st, gvf, d_pos, d_meta, ns, R, L, sb[0], sb[1], m->cfg.local_radius,         \
-           m->cfg.local_order, m->n_cat, cat_out);                                                                        \
+           m->cfg.local_order, m->n_cat, cat_out, skip_flag);                                                             \
   } break;
       switch (C) {
         STEMP_CASE(16)

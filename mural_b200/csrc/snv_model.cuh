@@ -92,7 +92,13 @@ int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_po
                     const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st);
 int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                            const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
-                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16 = false);
+                           int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16 = false,
+                           const int* skip_flag = nullptr);
+// dense-site stem (snv_dense_stem.cu)
+size_t snv_dense_bytes(const mural_snv_model* m, int64_t chunk);
+int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
+                          int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
+                          const int** d_flag, cudaStream_t st);
 int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                          int32_t* cat32, cudaStream_t st);
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,

@@ -617,6 +617,9 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   // local branch runs as a pre-pass over super-chunks (one launch fills the GPU; per 4096-site chunk it cannot)
   const int64_t super = n < (int64_t(1) << 20) ? n : (int64_t(1) << 20);
   floats += chunk * (2 * NC + 64) + super * (NC + m->n_cat) + 64;
+  const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
+  const int64_t dense_floats = use_dense ? int64_t((snv_dense_bytes(m, chunk) + 255) / 4 + 192) : 0;
+  floats += dense_floats;
   if (int rc = snv_ensure_workspace(m, floats * 4 + 256)) return rc;
   float* w = (float*)m->d_ws;
   float* bufs[2][4];
@@ -628,7 +631,8 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   float* tg0 = w; w += chunk * 32;
   float* tg1 = w; w += chunk * 32;
   int32_t* cat32 = (int32_t*)w; w += super * m->n_cat;
-  int* err_flag = (int*)w;
+  int* err_flag = (int*)w; w += 64;
+  void* dense_scratch = use_dense ? (void*)((uintptr_t(w) + 255) & ~uintptr_t(255)) : nullptr;  // uint4 rows / int64 header
   CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
 
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
@@ -641,9 +645,14 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         return rc;
     }
     const float* llog_c = llog + (s0 % super) * NC;
+    const int* dense_flag = nullptr;
+    if (use_dense)
+      if (int rc = snv_dense_stem_launch(m, G, d_pos + s0, d_meta + s0, ns, chunk, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
+                                         dense_scratch, &dense_flag, st))
+        return rc;
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                        nullptr, st, /*out_bf16=*/true))
+                                        nullptr, st, /*out_bf16=*/true, dense_flag))
       return rc;
     for (int br = 1; br >= 0; --br) {
       const BranchDev& B = m->br[br];

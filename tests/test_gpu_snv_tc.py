@@ -81,3 +81,32 @@ def test_bf16_large_batch_matches_fp32_path(kat, cuda_genome):
     d = (torch.softmax(a, 1) - torch.softmax(b, 1)).abs().max().item()
     print("bf16 vs fp32 kernels, 20k sites: max|dp| = %.3e" % d)
     assert d <= 5e-3
+
+
+def test_dense_site_stem_equals_per_site_stem(kat, cuda_genome):
+    """Genome-wide (dense, one chromosome) chunks take the sliding-window stem; its output must be bit-identical to
+    the per-site stem, including chromosome-end overhang, N runs, IUPAC codes and both strands."""
+    import os
+    from mural_b200 import SiteBatch, pack_meta
+    z, cfg, state = load_snv_golden("hs_AT")
+    rng = np.random.default_rng(12)
+    n = 6000
+    st = np.sort(rng.integers(0, 30000, n)).astype(np.int32)          # chrA: N runs at both ends, IUPAC block at 7000
+    sd = rng.integers(0, 2, n)
+    sb = SiteBatch(torch.from_numpy(st).cuda(), torch.from_numpy(pack_meta(sd, 0 * sd, 0 * sd)).cuda(), cuda_genome)
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    res = {}
+    for key, env in (("dense", None), ("site", "1")):
+        if env is None:
+            os.environ.pop("MURAL_NO_DENSE_STEM", None)
+        else:
+            os.environ["MURAL_NO_DENSE_STEM"] = env
+        m.set_debug(1)
+        with torch.no_grad():
+            out = m.forward(None, sb)
+        res[key] = (m.debug_tap("pool1").copy(), m.debug_tap("pool1_2").copy(), out.clone())
+    os.environ.pop("MURAL_NO_DENSE_STEM", None)
+    m.set_debug(0)
+    assert np.array_equal(res["dense"][0].view(np.uint32), res["site"][0].view(np.uint32))
+    assert np.array_equal(res["dense"][1].view(np.uint32), res["site"][1].view(np.uint32))
+    assert torch.equal(res["dense"][2], res["site"][2])
