@@ -143,7 +143,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mural_b200", choices=["mural_b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MURAL_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
-    ap.add_argument("--sites-per-step", type=int, default=262144)
+    ap.add_argument("--sites-per-step", type=int, default=1048576)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
