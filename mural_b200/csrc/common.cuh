@@ -39,6 +39,15 @@ void prof_post(cudaStream_t st);
     ++::mural::g_launches;                                      \
   } while (0)
 
+// same, with an explicit profile name (template kernels launched in several roles)
+#define LAUNCH_N(name, kernel, grid, block, smem, stream, ...)  \
+  do {                                                          \
+    if (::mural::g_prof) ::mural::prof_pre((name), (stream));   \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+    if (::mural::g_prof) ::mural::prof_post((stream));          \
+    ++::mural::g_launches;                                      \
+  } while (0)
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- symbols -------------------------------------------------------------------------------------

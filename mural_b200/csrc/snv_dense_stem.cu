@@ -12,6 +12,14 @@
 // Values are bit-identical to the per-site stem (same fp32 sums in the same order; max and bf16 rounding commute).
 // Sparse chunks (training sets, several chromosomes) keep using the per-site kernel: the decision is taken on the
 // device (k_chunk_span) so no host synchronisation is needed.
+//
+// Stage-1 lattice (same idea one level up).  An interior pooled bin j of a site is W_pk[g0 + j*ps] with g0 fixed by the
+// site, so the first ResBlock pair (4 convs at stride-ps1 spacing) of every row whose receptive field stays clear of the
+// window ends is a function of the genomic position alone: Y1[g] = RB(W[g-4ps], ..., W[g+4ps]).  We evaluate it ONCE
+// per genomic position and strand on 2*ps1 phase-major pseudo-sites (k_lattice_in feeds the ordinary stage kernel),
+// and per site only the LAT_EO rows at each window end, as one 18-row edge pseudo-site (k_stem_gather in edge mode).
+// The stage-2 loader (snv_tc.cu) max-pools across lattice rows and edge rows.  Every row goes through the same
+// tcgen05 arithmetic as in the per-site path, so the result is bit-identical.
 #include <cuda_bf16.h>
 #include <float.h>
 #include <limits.h>
@@ -19,14 +27,6 @@
 #include "snv_model.cuh"
 
 namespace mural {
-
-struct ChunkInfo {
-  long long g_lo;  // chromosome coordinate of table index 0 (may be negative: overhang is imputed with N)
-  int n_pos;       // table rows in use
-  int dense;       // 1: tables + gather, 0: per-site stem
-  int chrom;
-  int has[2];      // strands present
-};
 
 constexpr int DT_POS = 256;   // table positions per CTA
 constexpr int DT_MAXW = 16;   // widest pool window supported by the table kernel
@@ -36,7 +36,7 @@ __device__ __forceinline__ int sym_genomic(const GenomeView& G, int chrom, long 
 }
 
 __global__ void k_chunk_span(const int32_t* __restrict__ pos, const int32_t* __restrict__ meta, int64_t ns, int R, int cap,
-                             ChunkInfo* __restrict__ info) {
+                             int ps_mid, int ps_large, int tile_stride, ChunkInfo* __restrict__ info) {
   __shared__ int s_min, s_max, s_mixed, s_has[2];
   if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; s_mixed = 0; s_has[0] = s_has[1] = 0; }
   __syncthreads();
@@ -63,6 +63,13 @@ __global__ void k_chunk_span(const int32_t* __restrict__ pos, const int32_t* __r
     info->chrom = chrom0;
     info->has[0] = s_has[0];
     info->has[1] = s_has[1];
+    for (int br = 0; br < 2; ++br) {
+      const int ps = br ? ps_large : ps_mid;
+      const int M = (info->n_pos + ps - 1) / ps;
+      info->M[br] = M;
+      info->lat_rows[br] = 2 * ps * (M + 1) + 1;
+      info->lat_tiles[br] = (info->lat_rows[br] + tile_stride - 1) / tile_stride;
+    }
   }
 }
 
@@ -135,6 +142,38 @@ __global__ void __launch_bounds__(256) k_dense_tables(GenomeView G, const ChunkI
   }
 }
 
+// full-bin sliding maxima -> phase-major lattice rows (bf16 planes): pseudo-site u = strand*ps + phase, step mm
+// ('-' strand steps run against the genome so that the oriented conv taps line up with the '+' ones)
+struct LatIn {
+  uint4* out;
+  int64_t ra;
+  int ps;
+};
+template <int C>
+__global__ void __launch_bounds__(256) k_lattice_in(const ChunkInfo* __restrict__ info, LatIn l0, LatIn l1, int cap,
+                                                    const __nv_bfloat16* __restrict__ tables) {
+  if (!info->dense) return;
+  constexpr int PL = C / 8;
+#pragma unroll 1
+  for (int br = 0; br < 2; ++br) {
+    const LatIn& B = br ? l1 : l0;
+    const int M = info->M[br];
+    const int64_t total = int64_t(2) * B.ps * M * PL;
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+      const int q = int(e % PL);
+      const int64_t um = e / PL;
+      const int mm = int(um % M), u = int(um / M);
+      const int strand = u >= B.ps, phase = u - strand * B.ps;
+      const int m = strand ? M - 1 - mm : mm;
+      const int x = m * B.ps + phase;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (x < info->n_pos && info->has[strand])
+        v = *reinterpret_cast<const uint4*>(tables + ((size_t(strand * 2 + br) * 3) * size_t(cap) + size_t(x)) * C + 8 * q);
+      B.out[int64_t(q) * B.ra + 1 + int64_t(u) * (M + 1) + mm] = v;
+    }
+  }
+}
+
 struct GatherBranch {
   void* out;           // bf16 planes [C/8][rows_alloc][8]
   int64_t rows_alloc;
@@ -142,6 +181,7 @@ struct GatherBranch {
   const float* bias;
   int L0, off0, L1, pk, ps, pp;
   int w[3];
+  int edge;            // 1: only the LAT_EI rows at each window end, written as one LAT_EL-row pseudo-site per site
 };
 
 // one warp-quarter (8 lanes x 16 B... here: C/8 lanes, 16 B each) copies one table row into one output row
@@ -156,12 +196,14 @@ __global__ void __launch_bounds__(256) k_stem_gather(GenomeView G, const ChunkIn
 #pragma unroll 1
   for (int br = 0; br < 2; ++br) {
     const GatherBranch& B = br ? b1 : b0;
-    const int64_t total = ns * B.L1 * PL;
+    const int rows_per_site = B.edge ? LAT_EL : B.L1;
+    const int64_t total = ns * rows_per_site * PL;
     for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
       const int q = int(e % PL);
       const int64_t sj = e / PL;
-      const int j = int(sj % B.L1);
-      const int64_t site = sj / B.L1;
+      const int jj = int(sj % rows_per_site);
+      const int j = (B.edge && jj >= LAT_EI) ? B.L1 - LAT_EL + jj : jj;
+      const int64_t site = sj / rows_per_site;
       const int s = pos[site], strand = meta[site] & 1;
       int lo = j * B.ps - B.pp, hi = lo + B.pk;
       lo = lo < 0 ? 0 : lo;
@@ -208,7 +250,7 @@ __global__ void __launch_bounds__(256) k_stem_gather(GenomeView G, const ChunkIn
           w[c] = *reinterpret_cast<uint32_t*>(&m2);
         }
       }
-      *(reinterpret_cast<uint4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(B.L1 + 1) + j) = v;
+      *(reinterpret_cast<uint4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(rows_per_site + 1) + jj) = v;
     }
   }
 }
@@ -228,19 +270,40 @@ static void bin_widths(const BranchDev& B, int w[3]) {
     if (w[t] < 0) w[t] = 0;
 }
 
+int64_t snv_dense_cap(int64_t chunk) { return 8 * chunk + 4096; }
+
 size_t snv_dense_bytes(const mural_snv_model* m, int64_t chunk) {
-  const size_t cap = size_t(8) * chunk + 4096;
-  return sizeof(ChunkInfo) + 256 + size_t(12) * cap * m->cfg.channels * 2;
+  const size_t cap = size_t(snv_dense_cap(chunk));
+  return 256 + size_t(12) * cap * m->cfg.channels * 2;
+}
+
+// The lattice needs: both branches long enough to have interior rows, and the bins of those rows to be full-width
+// bins made only of interior conv positions (so that they equal the full-bin sliding maximum), and the lattice
+// neighbourhood of every interior row to lie inside the table span [s_min - R - 24, s_max + R + 39].
+bool snv_lattice_supported(const mural_snv_model* m) {
+  if (m->cfg.channels != 32 || m->cfg.kernel_size != 3) return false;
+  const int R = m->cfg.distal_radius;
+  for (int br = 0; br < 2; ++br) {
+    const BranchDev& B = m->br[br];
+    const int pk = B.pool[0][0], ps = B.pool[0][1], pp = B.pool[0][2], off0 = br ? 0 : m->L / 2 - 100;
+    if (B.L1 < 2 * LAT_EI + 6 || pk > DT_MAXW) return false;
+    // rows [LAT_EO-4, L1-LAT_EO+3] are read by the lattice chain of the interior rows [LAT_EO, L1-LAT_EO-1]
+    const int r_lo = LAT_EO - 4, r_hi = B.L1 - LAT_EO + 3;
+    if (r_lo * ps - pp < 1 || r_hi * ps - pp + pk > B.L0 - 1) return false;
+    if (off0 + r_lo * ps - pp + 24 < 0 || off0 + r_hi * ps - pp + pk - 1 > 2 * R + 24 + 39) return false;
+    if (2 * R + 24 - off0 - (r_hi * ps - pp) - pk + 1 < 0) return false;
+  }
+  return true;
 }
 
 // Enqueues span detection, table build and gather.  d_scratch: snv_dense_bytes() bytes.  Returns the device flag
 // (int*, 1 = the dense path produced the stem output) so that the per-site kernel can skip itself.
 int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
-                          const int** d_flag, cudaStream_t st) {
+                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice, const ChunkInfo** d_info) {
   const int C = m->cfg.channels;
   MURAL_CHECK(C == 32, "dense stem is built for C == 32");
-  const int cap = int(8 * chunk + 4096);
+  const int cap = int(snv_dense_cap(chunk));
   ChunkInfo* info = reinterpret_cast<ChunkInfo*>(d_scratch);
   __nv_bfloat16* tables = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(d_scratch) + 256);
   DenseBranch db[2];
@@ -252,9 +315,15 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
     bin_widths(B, db[br].w);
     for (int t = 0; t < 3; ++t) MURAL_CHECK(db[br].w[t] <= DT_MAXW, "pool window too wide for the dense stem");
     gb[br] = GatherBranch{br ? large_out : mid_out, br ? large_ra : mid_ra, B.T, B.bias1, B.L0, br ? 0 : m->L / 2 - 100, B.L1,
-                          B.pool[0][0], B.pool[0][1], B.pool[0][2], {db[br].w[0], db[br].w[1], db[br].w[2]}};
+                          B.pool[0][0], B.pool[0][1], B.pool[0][2], {db[br].w[0], db[br].w[1], db[br].w[2]}, 0};
+    if (lattice) {
+      gb[br].out = lattice[br].edge_in;
+      gb[br].rows_alloc = lattice[br].edge_ra;
+      gb[br].edge = 1;
+    }
   }
-  LAUNCH(k_chunk_span, 1, 1024, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, info);
+  LAUNCH(k_chunk_span, 1, 1024, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
+         128 - 2 * 4, info);
   const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C + size_t(DT_POS + DT_MAXW) * C);
   static bool conf = false;
   if (!conf) {
@@ -262,8 +331,14 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
     conf = true;
   }
   LAUNCH(k_dense_tables<32>, (unsigned)cdiv(cap, DT_POS), 256, smem, st, *G, info, db[0], db[1], cap, tables);
+  if (lattice) {
+    LatIn li[2];
+    for (int br = 0; br < 2; ++br) li[br] = LatIn{reinterpret_cast<uint4*>(lattice[br].lat_in), lattice[br].lat_ra, m->br[br].pool[0][1]};
+    LAUNCH(k_lattice_in<32>, 148 * 4, 256, 0, st, info, li[0], li[1], cap, tables);
+  }
   LAUNCH(k_stem_gather<32>, 148 * 8, 256, 0, st, *G, info, d_pos, d_meta, ns, m->cfg.distal_radius, gb[0], gb[1], cap, tables);
   *d_flag = &info->dense;
+  if (d_info) *d_info = info;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -94,11 +94,33 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
                            const uint8_t* d_sym, int64_t ns, float* mid_out, int64_t mid_rows_alloc, float* large_out,
                            int64_t large_rows_alloc, int32_t* cat_out, cudaStream_t st, bool out_bf16 = false,
                            const int* skip_flag = nullptr);
-// dense-site stem (snv_dense_stem.cu)
+// dense-site stem + stage-1 lattice (snv_dense_stem.cu)
+// Device-side description of a chunk (written by k_chunk_span, read by every kernel of the dense path: no host sync).
+struct ChunkInfo {
+  long long g_lo;  // chromosome coordinate of table index 0 (may be negative: overhang is imputed with N)
+  int n_pos;       // table rows in use
+  int dense;       // 1: tables + gather (+ lattice), 0: per-site kernels
+  int chrom;
+  int has[2];      // strands present
+  // stage-1 lattice geometry per branch: 2*ps1 pseudo-sites (strand x phase) of M lattice steps each
+  int M[2];
+  int lat_rows[2];   // 2*ps1*(M+1)+1
+  int lat_tiles[2];  // RB4 tiles covering lat_rows
+};
+constexpr int LAT_EO = 5;   // stage-1 output rows per window end that depend on the site (4 convs + the clipped first/last bin)
+constexpr int LAT_EI = 9;   // stage-1 input rows per window end those outputs read
+constexpr int LAT_EL = 2 * LAT_EI;  // length of a site's edge pseudo-site: [rows 0..8 | rows L1-9..L1-1]
+struct LatticeBufs {        // per branch; all bf16 planes [4][ra][8]
+  void* lat_in; void* lat_out; int64_t lat_ra;
+  void* edge_in; void* edge_out; int64_t edge_ra;
+};
+int64_t snv_dense_cap(int64_t chunk);
+bool snv_lattice_supported(const mural_snv_model* m);
 size_t snv_dense_bytes(const mural_snv_model* m, int64_t chunk);
 int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
-                          const int** d_flag, cudaStream_t st);
+                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice = nullptr,
+                          const ChunkInfo** d_info = nullptr);
 int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                          int32_t* cat32, cudaStream_t st);
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,

@@ -56,6 +56,18 @@ struct StageArgs {
   int pk, ps, pp;        // max-pool fused into the loader (RB4: none)
   int n_tiles;
   int dbg;               // timing experiments only (MURAL_TC_DBG): results are wrong when non-zero
+  // dense-site dispatch (snv_dense_stem.cu): all decided on the device, no host synchronisation
+  const ChunkInfo* info;  // nullptr: unconditional launch
+  int want;               // run only if info->dense == want
+  int lat_branch;         // >= 0: this launch is the stage-1 lattice of that branch; L / rows / n_tiles come from info
+  // LAT loader (C_RB4 only): stage-1 rows of a site come from the lattice (interior) and the edge pseudo-site (ends)
+  const uint4* lat;       // stage-1 lattice output planes [4][lat_ra]
+  int64_t lat_ra;
+  const uint4* edge;      // stage-1 edge output planes [4][edge_ra], LAT_EL rows per site
+  int64_t edge_ra;
+  const int32_t* pos;
+  const int32_t* meta;
+  int ps1, pp1, pk1, off0, R, br;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,8 +142,15 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // TMEM region R (32 columns) is pre-loaded with x0 (tcgen05.st) and the second conv of each ResBlock
 // ACCUMULATES onto it, the first conv of each ResBlock goes to a scratch region T.  The epilogue of a layer is
 // therefore only  tcgen05.ld -> bf16 -> ReLU -> st.shared  (the next layer's A operand).
-template <int MODE>
+template <int MODE, bool LAT>
 __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
+  if (a.info && a.info->dense != a.want) return;  // uniform over the grid; nothing allocated yet
+  // RB4 with LAT: stage-1 lattice launch, geometry known only on the device
+  constexpr bool DYN = (MODE == RB4) && LAT;
+  const int L_ = DYN ? a.info->M[a.lat_branch] : a.L;
+  const int rows_ = DYN ? a.info->lat_rows[a.lat_branch] : int(a.rows);
+  const int n_tiles_ = DYN ? a.info->lat_tiles[a.lat_branch] : a.n_tiles;
+  if (DYN && int(blockIdx.x) * NSLOT >= n_tiles_) return;
   constexpr int NL = n_layers(MODE);
   constexpr int STRIDE = TILE - 2 * NL;  // valid output rows per tile (the chain eats NL rows on each side)
   extern __shared__ __align__(128) unsigned char smem[];
@@ -174,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-  const int Lp1 = a.L + 1;
+  const int Lp1 = L_ + 1;
   const int tile_step = gridDim.x * NSLOT;
   // descriptor bases (start-address field is the low 14 bits: offsets below never carry out of it)
   const uint64_t dW0 = umma_desc(smem_u32(sW), 512, 128);
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     r = tile_idx * STRIDE - NL + lt;
     p = -1;
     int site = 0;
-    if (r > 0 && r < int(a.rows)) {
+    if (r > 0 && r < rows_) {
       site = r / Lp1;
       p = r - site * Lp1 - 1;
     }
@@ -233,23 +252,54 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     if (MODE == RB4) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = live ? __ldg(a.in + q * a.in_rows_alloc + r) : make_uint4(0, 0, 0, 0);
-    } else {
+    } else if (MODE != RB4) {
       int lo = p * a.ps - a.pp, hi = lo + a.pk;
       lo = lo < 0 ? 0 : lo;
       hi = hi > a.Lin ? a.Lin : hi;
       if (!live) hi = lo;
-      const int base = 1 + site * (a.Lin + 1);
       const uint32_t ninf = live ? 0xFF80FF80u : 0u;  // bf16 -inf pair; separator rows stay zero
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = make_uint4(ninf, ninf, ninf, ninf);
+      if (!LAT || MODE != C_RB4) {
+        const int base = 1 + site * (a.Lin + 1);
 #pragma unroll
-      for (int u = 0; u < 7; ++u) {  // pk <= 7 for every pool of Network2
-        if (lo + u < hi) {
+        for (int u = 0; u < 7; ++u) {  // pk <= 7 for every pool of Network2
+          if (lo + u < hi) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 v = __ldg(a.in + q * a.in_rows_alloc + base + lo + u);
-            x[q].x = max_bf16x2(x[q].x, v.x); x[q].y = max_bf16x2(x[q].y, v.y);
-            x[q].z = max_bf16x2(x[q].z, v.z); x[q].w = max_bf16x2(x[q].w, v.w);
+            for (int q = 0; q < 4; ++q) {
+              const uint4 v = __ldg(a.in + q * a.in_rows_alloc + base + lo + u);
+              x[q].x = max_bf16x2(x[q].x, v.x); x[q].y = max_bf16x2(x[q].y, v.y);
+              x[q].z = max_bf16x2(x[q].z, v.z); x[q].w = max_bf16x2(x[q].w, v.w);
+            }
+          }
+        }
+      } else {
+        // stage-1 row rr of this site: rr < LAT_EO / rr >= Lin - LAT_EO -> the site's edge pseudo-site, otherwise the
+        // lattice row of genomic bin start x(rr) = x(0) +- rr*ps1, which is lat_base + rr for either strand
+        int lat_base = 0;
+        const int ebase = 1 + site * (LAT_EL + 1);
+        if (live) {
+          const int s = __ldg(a.pos + site), strand = __ldg(a.meta + site) & 1;
+          const int M = a.info->M[a.br];
+          const int g_lo = int(a.info->g_lo);
+          const int x0 = strand ? s + a.R - a.off0 + a.pp1 - a.pk1 + 1 - g_lo : s - a.R + a.off0 - a.pp1 - g_lo;
+          const int m0 = x0 / a.ps1, phase = x0 - m0 * a.ps1;
+          lat_base = strand ? 1 + (a.ps1 + phase) * (M + 1) + (M - 1 - m0) : 1 + phase * (M + 1) + m0;
+        }
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+          const int rr = lo + u;
+          if (rr < hi) {
+            const bool e_lo = rr < LAT_EO, e_hi = rr >= a.Lin - LAT_EO;
+            const uint4* src = (e_lo || e_hi) ? a.edge : a.lat;
+            const int64_t ra = (e_lo || e_hi) ? a.edge_ra : a.lat_ra;
+            const int64_t idx = e_lo ? ebase + rr : (e_hi ? ebase + rr - a.Lin + LAT_EL : lat_base + rr);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 v = __ldg(src + q * ra + idx);
+              x[q].x = max_bf16x2(x[q].x, v.x); x[q].y = max_bf16x2(x[q].y, v.y);
+              x[q].z = max_bf16x2(x[q].z, v.z); x[q].w = max_bf16x2(x[q].w, v.w);
+            }
           }
         }
       }
@@ -286,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     // constant-column operand row: {1, 1, [pos==0], [pos==0], [pos==L-1], [pos==L-1], 0, 0} in bf16 (1.0 = 0x3F80)
     const uint32_t one2 = 0x3F803F80u;
     *reinterpret_cast<uint4*>(sA + A_SLOT + lt * 16) =
-        make_uint4(live ? one2 : 0u, p == 0 ? one2 : 0u, (live && p == a.L - 1) ? one2 : 0u, 0u);
+        make_uint4(live ? one2 : 0u, p == 0 ? one2 : 0u, (live && p == L_ - 1) ? one2 : 0u, 0u);
     sync_and_issue(k, 0);
   };
 
@@ -298,21 +348,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
 #pragma unroll
   for (int k = 0; k < NINFL; ++k) {
     rn[k] = 0; pn[k] = -1;
-    if (tile0 + k < a.n_tiles) fetch(tile0 + k, rn[k], pn[k], xn[k]);
+    if (tile0 + k < n_tiles_) fetch(tile0 + k, rn[k], pn[k], xn[k]);
   }
-  for (; tile0 < a.n_tiles; tile0 += tile_step) {
+  for (; tile0 < n_tiles_; tile0 += tile_step) {
     bool act[NINFL];
     int r[NINFL], p[NINFL];
 #pragma unroll
     for (int k = 0; k < NINFL; ++k) {
-      act[k] = tile0 + k < a.n_tiles;
+      act[k] = tile0 + k < n_tiles_;
       r[k] = rn[k];
       p[k] = pn[k];
       if (act[k]) begin_tile(k, p[k], xn[k]);
     }
 #pragma unroll
     for (int k = 0; k < NINFL; ++k)
-      if (tile0 + tile_step + k < a.n_tiles) fetch(tile0 + tile_step + k, rn[k], pn[k], xn[k]);
+      if (tile0 + tile_step + k < n_tiles_) fetch(tile0 + tile_step + k, rn[k], pn[k], xn[k]);
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
 #pragma unroll
@@ -462,13 +512,13 @@ static int m_sm_count() {
   return n;
 }
 
-template <int MODE>
-static int launch_stage(const StageArgs& a, cudaStream_t st) {
+template <int MODE, bool LAT = false>
+static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = "") {
   constexpr int NL = n_layers(MODE);
   const size_t smem = size_t(NL) * W_LAYER + size_t(NSLOT) * SLOT_BYTES + NSLOT * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY(cudaFuncSetAttribute(k_stage_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY((cudaFuncSetAttribute(k_stage_tc<MODE, LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     configured = true;
   }
   int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
@@ -477,9 +527,15 @@ static int launch_stage(const StageArgs& a, cudaStream_t st) {
   if (dbg < 0) { const char* e = getenv("MURAL_TC_DBG"); dbg = e ? atoi(e) : 0; }
   StageArgs a2 = a;
   a2.dbg = dbg;
-  if (MODE == RB4) LAUNCH(k_stage_tc<RB4>, grid, THREADS, smem, st, a2);
-  else if (MODE == C_RB4) LAUNCH(k_stage_tc<C_RB4>, grid, THREADS, smem, st, a2);
-  else LAUNCH(k_stage_tc<SINGLE>, grid, THREADS, smem, st, a2);
+  // profile names are interned per (mode, role): prof_pre keeps the pointer
+  static std::map<std::string, std::string> names;
+  const std::string key = std::string(MODE == RB4 ? "k_stage_tc<RB4>" : (MODE == C_RB4 ? "k_stage_tc<C_RB4>" : "k_stage_tc<SINGLE>")) + role;
+  const char* nm = names.emplace(key, key).first->second.c_str();
+  if (MODE == RB4 && LAT) LAUNCH_N(nm, (k_stage_tc<RB4, true>), grid, THREADS, smem, st, a2);
+  else if (MODE == RB4) LAUNCH_N(nm, (k_stage_tc<RB4, false>), grid, THREADS, smem, st, a2);
+  else if (MODE == C_RB4 && LAT) LAUNCH_N(nm, (k_stage_tc<C_RB4, true>), grid, THREADS, smem, st, a2);
+  else if (MODE == C_RB4) LAUNCH_N(nm, (k_stage_tc<C_RB4, false>), grid, THREADS, smem, st, a2);
+  else LAUNCH_N(nm, (k_stage_tc<SINGLE, false>), grid, THREADS, smem, st, a2);
   return 0;
 }
 
@@ -603,12 +659,21 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     chunk = c2;
   }
   if (chunk > n) chunk = n;
-  // workspace: per branch X0 (stem out), Z1, Z2, H as fp32 planes; + local logits, taps, k-mer indices
+  // workspace: per branch X0 (stem out), Z1, Z2 as bf16 planes, H as fp32 planes; + local logits, taps, k-mer indices.
+  // On the dense path X0 / Z1 hold the stage-1 lattice and the edge pseudo-sites instead of per-site rows.
+  const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
+  const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   int64_t floats = 0;
-  int64_t ra[2][4];
+  int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0};
   for (int br = 0; br < 2; ++br) {
     const BranchDev& B = m->br[br];
     ra[br][0] = rows_alloc(chunk, B.L1);
+    if (use_lat) {
+      const int ps = B.pool[0][1];
+      lat_ra[br] = (2 * ps * (cdiv(snv_dense_cap(chunk), ps) + 1) + 1 + 15) & ~int64_t(7);
+      edge_ra[br] = rows_alloc(chunk, LAT_EL);
+      if (lat_ra[br] + edge_ra[br] > ra[br][0]) ra[br][0] = lat_ra[br] + edge_ra[br];
+    }
     ra[br][1] = ra[br][0];
     ra[br][2] = rows_alloc(chunk, B.L2);
     ra[br][3] = rows_alloc(chunk, B.L3);
@@ -617,7 +682,6 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   // local branch runs as a pre-pass over super-chunks (one launch fills the GPU; per 4096-site chunk it cannot)
   const int64_t super = n < (int64_t(1) << 20) ? n : (int64_t(1) << 20);
   floats += chunk * (2 * NC + 64) + super * (NC + m->n_cat) + 64;
-  const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
   const int64_t dense_floats = use_dense ? int64_t((snv_dense_bytes(m, chunk) + 255) / 4 + 192) : 0;
   floats += dense_floats;
   if (int rc = snv_ensure_workspace(m, floats * 4 + 256)) return rc;
@@ -625,6 +689,16 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   float* bufs[2][4];
   for (int br = 0; br < 2; ++br)
     for (int k = 0; k < 4; ++k) { bufs[br][k] = w; w += (k < 3 ? 16 : 32) * ra[br][k]; }
+  // lattice / edge sub-buffers: plane stride is the sub-buffer's own row count, carved out of X0 (inputs) and Z1 (outputs)
+  LatticeBufs lb[2];
+  for (int br = 0; br < 2; ++br) {
+    lb[br].lat_in = bufs[br][0];
+    lb[br].lat_out = bufs[br][1];
+    lb[br].lat_ra = lat_ra[br];
+    lb[br].edge_in = bufs[br][0] + 16 * lat_ra[br];
+    lb[br].edge_out = bufs[br][1] + 16 * lat_ra[br];
+    lb[br].edge_ra = edge_ra[br];
+  }
   float* llog = w; w += super * NC;
   float* tl0 = w; w += chunk * NC;
   float* tl1 = w; w += chunk * NC;
@@ -646,9 +720,10 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     }
     const float* llog_c = llog + (s0 % super) * NC;
     const int* dense_flag = nullptr;
+    const ChunkInfo* info = nullptr;
     if (use_dense)
       if (int rc = snv_dense_stem_launch(m, G, d_pos + s0, d_meta + s0, ns, chunk, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                         dense_scratch, &dense_flag, st))
+                                         dense_scratch, &dense_flag, st, use_lat ? lb : nullptr, &info))
         return rc;
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
@@ -659,21 +734,51 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       const char* sfx = br ? "_2" : "";
       if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], true, ra[br][0], ns, B.L1, st)) return rc;
       StageArgs a{};
-      // stage 1: two ResBlocks + outer skip at length L1
+      a.lat_branch = -1;
+      // stage 1: two ResBlocks + outer skip at length L1 (per-site rows; skipped on the device when the chunk is dense)
       a.in = reinterpret_cast<const uint4*>(bufs[br][0]); a.out = bufs[br][1]; a.wblob = S->blob[br][0];
       a.in_rows_alloc = ra[br][0]; a.out_rows_alloc = ra[br][1];
       a.rows = rows_of(ns, B.L1); a.L = B.L1; a.Lin = B.L1; a.pk = 0; a.ps = 1; a.pp = 0;
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 4);
-      if (int rc = launch_stage<RB4>(a, st)) return rc;
+      if (use_lat) { a.info = info; a.want = 0; }
+      if (int rc = launch_stage<RB4>(a, st, use_lat ? "/site" : "")) return rc;
+      if (use_lat) {
+        // stage 1 on the lattice (geometry read from info on the device; grid sized for the largest lattice) ...
+        StageArgs l = a;
+        l.want = 1; l.lat_branch = br;
+        l.in = reinterpret_cast<const uint4*>(lb[br].lat_in); l.out = lb[br].lat_out;
+        l.in_rows_alloc = l.out_rows_alloc = lb[br].lat_ra;
+        l.n_tiles = (int)cdiv(lb[br].lat_ra, TILE - 2 * 4);
+        if (int rc = (launch_stage<RB4, true>(l, st, "/lattice"))) return rc;
+        // ... and on the per-site edge pseudo-sites
+        StageArgs e = a;
+        e.want = 1;
+        e.in = reinterpret_cast<const uint4*>(lb[br].edge_in); e.out = lb[br].edge_out;
+        e.in_rows_alloc = e.out_rows_alloc = lb[br].edge_ra;
+        e.rows = rows_of(ns, LAT_EL); e.L = e.Lin = LAT_EL;
+        e.n_tiles = (int)cdiv(e.rows, TILE - 2 * 4);
+        if (int rc = launch_stage<RB4>(e, st, "/edge")) return rc;
+      }
       if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
       // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
       a.in = reinterpret_cast<const uint4*>(bufs[br][1]); a.out = bufs[br][2]; a.wblob = S->blob[br][1];
       a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
       a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 5);
-      if (int rc = launch_stage<C_RB4>(a, st)) return rc;
+      if (int rc = launch_stage<C_RB4>(a, st, use_lat ? "/site" : "")) return rc;
+      if (use_lat) {
+        StageArgs l = a;
+        l.want = 1;
+        l.lat = reinterpret_cast<const uint4*>(lb[br].lat_out); l.lat_ra = lb[br].lat_ra;
+        l.edge = reinterpret_cast<const uint4*>(lb[br].edge_out); l.edge_ra = lb[br].edge_ra;
+        l.pos = d_pos + s0; l.meta = d_meta + s0;
+        l.ps1 = B.pool[0][1]; l.pp1 = B.pool[0][2]; l.pk1 = B.pool[0][0];
+        l.off0 = br ? 0 : m->L / 2 - 100; l.R = m->cfg.distal_radius; l.br = br;
+        if (int rc = (launch_stage<C_RB4, true>(l, st, "/lattice"))) return rc;
+      }
       if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
       // stage 3: pool3 + conv3 + ReLU at length L3
+      a.info = nullptr;
       a.in = reinterpret_cast<const uint4*>(bufs[br][2]); a.out = bufs[br][3]; a.wblob = S->blob[br][2];
       a.in_rows_alloc = ra[br][2]; a.out_rows_alloc = ra[br][3];
       a.rows = rows_of(ns, B.L3); a.L = B.L3; a.Lin = B.L2; a.pk = B.pool[2][0]; a.ps = B.pool[2][1]; a.pp = B.pool[2][2];

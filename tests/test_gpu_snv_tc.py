@@ -110,3 +110,35 @@ def test_dense_site_stem_equals_per_site_stem(kat, cuda_genome):
     assert np.array_equal(res["dense"][0].view(np.uint32), res["site"][0].view(np.uint32))
     assert np.array_equal(res["dense"][1].view(np.uint32), res["site"][1].view(np.uint32))
     assert torch.equal(res["dense"][2], res["site"][2])
+
+
+@pytest.mark.parametrize("chunk", [0, 2048])
+def test_dense_lattice_equals_per_site_stages(kat, cuda_genome, chunk):
+    """Dense chunks evaluate the first ResBlock pair once per genomic position (stage-1 lattice) plus an 18-row edge
+    pseudo-site per site; every row takes the same tcgen05 arithmetic as in the per-site row space, so the log-probs
+    must be bit-identical to the per-site stages (MURAL_NO_LATTICE=1), across chunk boundaries, chromosome-end
+    overhang, N runs, IUPAC codes and both strands."""
+    import os
+    from mural_b200 import SiteBatch, pack_meta
+    z, cfg, state = load_snv_golden("hs_AT")
+    rng = np.random.default_rng(13)
+    n = 9000
+    st = np.sort(rng.integers(0, 30000, n)).astype(np.int32)
+    sd = rng.integers(0, 2, n)
+    sb = SiteBatch(torch.from_numpy(st).cuda(), torch.from_numpy(pack_meta(sd, 0 * sd, 0 * sd)).cuda(), cuda_genome)
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    m.set_debug(False, chunk=chunk)
+    res = {}
+    for key, env in (("lattice", None), ("site", "1")):
+        if env is None:
+            os.environ.pop("MURAL_NO_LATTICE", None)
+        else:
+            os.environ["MURAL_NO_LATTICE"] = env
+        with torch.no_grad():
+            res[key] = m.forward(None, sb).clone()
+    os.environ.pop("MURAL_NO_LATTICE", None)
+    m.set_debug(False, chunk=0)
+    assert torch.isfinite(res["lattice"]).all()
+    bad = (res["lattice"] != res["site"]).any(1).nonzero().flatten()
+    assert bad.numel() == 0, (bad[:10].tolist(), st[bad[:10].cpu().numpy()].tolist(),
+                              float((res["lattice"] - res["site"]).abs().max()))
