@@ -29,6 +29,7 @@
 namespace mural {
 
 constexpr int DT_POS = 256;   // table positions per CTA
+constexpr int DT_RUN = 16;    // consecutive positions per thread (16 threads x 2 channels per run)
 constexpr int DT_MAXW = 16;   // widest pool window supported by the table kernel
 
 __device__ __forceinline__ int sym_genomic(const GenomeView& G, int chrom, long long q) {
@@ -79,10 +80,65 @@ struct DenseBranch {
   int w[3];           // sliding-window widths: full bin, first-bin interior, last-bin interior (0: unused)
 };
 
+// o[i] = max(v[i .. i+W-1]) for i < 16 by doubling: m_p[i] = max(m_{p/2}[i], m_{p/2}[i+p/2]), then two overlapping
+// power-of-two windows.  max is exact, so the evaluation order does not matter for bit-identity with the per-site stem.
+template <int W>
+__device__ __forceinline__ void win_max16(const float (&v)[DT_RUN + DT_MAXW - 1], float (&o)[DT_RUN]) {
+  constexpr int P = W >= 16 ? 16 : (W >= 8 ? 8 : (W >= 4 ? 4 : (W >= 2 ? 2 : 1)));
+  float m[DT_RUN + DT_MAXW - 1];
+#pragma unroll
+  for (int i = 0; i < DT_RUN + DT_MAXW - 1; ++i) m[i] = v[i];
+  constexpr int NV = DT_RUN + DT_MAXW - 1;
+  // ascending i: m[i+p] is still the previous level when m[i] is updated
+  if constexpr (P >= 2) {
+#pragma unroll
+    for (int i = 0; i + 1 < NV; ++i) m[i] = fmaxf(m[i], m[i + 1]);
+  }
+  if constexpr (P >= 4) {
+#pragma unroll
+    for (int i = 0; i + 2 < NV; ++i) m[i] = fmaxf(m[i], m[i + 2]);
+  }
+  if constexpr (P >= 8) {
+#pragma unroll
+    for (int i = 0; i + 4 < NV; ++i) m[i] = fmaxf(m[i], m[i + 4]);
+  }
+  if constexpr (P >= 16) {
+#pragma unroll
+    for (int i = 0; i + 8 < NV; ++i) m[i] = fmaxf(m[i], m[i + 8]);
+  }
+#pragma unroll
+  for (int i = 0; i < DT_RUN; ++i) o[i] = fmaxf(m[i], m[i + W - P]);
+}
+
+__device__ __forceinline__ void win_max_any(int w, const float (&v)[DT_RUN + DT_MAXW - 1], float (&o)[DT_RUN]) {
+  switch (w) {
+    case 1: win_max16<1>(v, o); break;
+    case 2: win_max16<2>(v, o); break;
+    case 3: win_max16<3>(v, o); break;
+    case 4: win_max16<4>(v, o); break;
+    case 5: win_max16<5>(v, o); break;
+    case 6: win_max16<6>(v, o); break;
+    case 7: win_max16<7>(v, o); break;
+    case 8: win_max16<8>(v, o); break;
+    case 9: win_max16<9>(v, o); break;
+    case 10: win_max16<10>(v, o); break;
+    case 11: win_max16<11>(v, o); break;
+    case 12: win_max16<12>(v, o); break;
+    case 13: win_max16<13>(v, o); break;
+    case 14: win_max16<14>(v, o); break;
+    case 15: win_max16<15>(v, o); break;
+    default: win_max16<16>(v, o); break;
+  }
+}
+
 // tables: [strand][branch][3 widths][cap][C] bf16
+// One thread owns a channel pair and a run of DT_RUN positions: the DT_RUN + 15 conv values it needs stay in registers
+// (3 table rows summed per position, same order as the per-site stem), the window maxima are computed with static
+// indexing per width, and every store is one packed bf16 pair.
 template <int C>
-__global__ void __launch_bounds__(256) k_dense_tables(GenomeView G, const ChunkInfo* __restrict__ info, DenseBranch b0, DenseBranch b1,
+__global__ void __launch_bounds__(256, 2) k_dense_tables(GenomeView G, const ChunkInfo* __restrict__ info, DenseBranch b0, DenseBranch b1,
                                                       int cap, __nv_bfloat16* __restrict__ tables) {
+  static_assert(C == 32, "channel-pair mapping assumes 16 lanes x 2 channels");
   if (!info->dense) return;
   const int p0 = blockIdx.x * DT_POS;
   if (p0 >= info->n_pos) return;
@@ -90,7 +146,6 @@ __global__ void __launch_bounds__(256) k_dense_tables(GenomeView G, const ChunkI
   extern __shared__ __align__(16) float dsm[];
   float* sT = dsm;                       // [2][3][16][C]
   float* sB = sT + 2 * 3 * 16 * C;       // [2][C]
-  float* cc = sB + 2 * C;                // [DT_POS + DT_MAXW][C]
   const int tid = threadIdx.x;
   const int chrom = info->chrom;
   const long long g0 = info->g_lo + p0;
@@ -98,46 +153,46 @@ __global__ void __launch_bounds__(256) k_dense_tables(GenomeView G, const ChunkI
   for (int e = tid; e < C; e += 256) { sB[e] = b0.bias[e]; sB[C + e] = b1.bias[e]; }
   for (int k = tid; k < DT_POS + DT_MAXW + 2; k += 256) sym[k] = uint8_t(sym_genomic(G, chrom, g0 - 1 + k));  // sym[k] = base g0-1+k
   __syncthreads();
+  const int c2 = (tid & 15) * 2;         // channels c2, c2+1
+  const int k0 = (tid >> 4) * DT_RUN;    // first position of this thread's run (16 runs x DT_RUN = DT_POS)
+  const int n_pos = info->n_pos;
 #pragma unroll 1
   for (int strand = 0; strand < 2; ++strand) {
     if (!info->has[strand]) continue;
 #pragma unroll 1
     for (int br = 0; br < 2; ++br) {
-      const DenseBranch& B = br ? b1 : b0;
-      const float* T = sT + br * 3 * 16 * C;
+      const int bw[3] = {br ? b1.w[0] : b0.w[0], br ? b1.w[1] : b0.w[1], br ? b1.w[2] : b0.w[2]};
+      const float* T = sT + br * 3 * 16 * C + c2;
+      const float2 bias = *reinterpret_cast<const float2*>(sB + br * C + c2);
+      float v0[DT_RUN + DT_MAXW - 1], v1[DT_RUN + DT_MAXW - 1];
       // conv output of every position in the oriented sequence of this strand (tap order as in the per-site stem)
-      for (int e = tid; e < (DT_POS + DT_MAXW) * C; e += 256) {
-        const int k = e / C, c = e - k * C;
-        float v = sB[br * C + c];
-        if (!strand) {
-          v += T[(0 * 16 + sym[k]) * C + c];
-          v += T[(1 * 16 + sym[k + 1]) * C + c];
-          v += T[(2 * 16 + sym[k + 2]) * C + c];
-        } else {  // oriented neighbours of genomic g are comp(g+1), comp(g), comp(g-1)
-          v += T[(0 * 16 + comp_sym(sym[k + 2])) * C + c];
-          v += T[(1 * 16 + comp_sym(sym[k + 1])) * C + c];
-          v += T[(2 * 16 + comp_sym(sym[k])) * C + c];
+#pragma unroll
+      for (int i = 0; i < DT_RUN + DT_MAXW - 1; ++i) {
+        const int k = k0 + i;
+        int s0 = sym[k], s1 = sym[k + 1], s2 = sym[k + 2];
+        if (strand) {  // oriented neighbours of genomic g are comp(g+1), comp(g), comp(g-1)
+          const int t = comp_sym(s0);
+          s0 = comp_sym(s2); s1 = comp_sym(s1); s2 = t;
         }
-        cc[e] = v;
+        const float2 t0 = *reinterpret_cast<const float2*>(T + (0 * 16 + s0) * C);
+        const float2 t1 = *reinterpret_cast<const float2*>(T + (1 * 16 + s1) * C);
+        const float2 t2 = *reinterpret_cast<const float2*>(T + (2 * 16 + s2) * C);
+        v0[i] = ((bias.x + t0.x) + t1.x) + t2.x;
+        v1[i] = ((bias.y + t0.y) + t1.y) + t2.y;
       }
-      __syncthreads();
       __nv_bfloat16* tb = tables + (size_t(strand * 2 + br) * 3) * size_t(cap) * C;
-      for (int e = tid; e < DT_POS * C; e += 256) {
-        const int k = e / C, c = e - k * C;
-        if (p0 + k >= info->n_pos) continue;
-        float mx = -FLT_MAX;
-        float out[3] = {0.f, 0.f, 0.f};
-        for (int u = 0; u < DT_MAXW; ++u) {
-          if (u < B.w[0] || u < B.w[1] || u < B.w[2]) mx = fmaxf(mx, cc[(k + u) * C + c]);
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-            if (u + 1 == B.w[t]) out[t] = mx;
-        }
+      for (int t = 0; t < 3; ++t) {
+        const int w = bw[t];
+        if (w <= 0) continue;
+        float o0[DT_RUN], o1[DT_RUN];
+        win_max_any(w, v0, o0);
+        win_max_any(w, v1, o1);
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
-          if (B.w[t] > 0) tb[(size_t(t) * cap + p0 + k) * C + c] = __float2bfloat16(out[t]);
+        for (int i = 0; i < DT_RUN; ++i)
+          if (p0 + k0 + i < n_pos)
+            *reinterpret_cast<__nv_bfloat162*>(tb + (size_t(t) * cap + p0 + k0 + i) * C + c2) = __floats2bfloat162_rn(o0[i], o1[i]);
       }
-      __syncthreads();
     }
   }
 }
@@ -324,7 +379,7 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
   }
   LAUNCH(k_chunk_span, 1, 1024, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
          128 - 2 * 4, info);
-  const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C + size_t(DT_POS + DT_MAXW) * C);
+  const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C);
   static bool conf = false;
   if (!conf) {
     CUDA_TRY(cudaFuncSetAttribute(k_dense_tables<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -43,6 +43,21 @@ constexpr int THREADS = NGROUP * 128;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 enum Mode { RB4 = 0, C_RB4 = 1, SINGLE = 2 };
+
+// Optional in-kernel phase timing (-DMURAL_TC_TIMING, scratch builds only): per-thread clock() deltas accumulated
+// per phase, dumped for lane 0 of warps 0 (issuer) and 1 of every group by mural_tc_timing_dump().
+enum { T_WAIT = 0, T_LD, T_EPI, T_FENCE, T_BAR, T_ISSUE, T_BEGIN, T_FETCH, T_FINAL, T_OTHER, T_N };
+#ifdef MURAL_TC_TIMING
+__device__ unsigned long long g_tc_timing[3][148][NGROUP][2][T_N + 2];
+#define TT(cat)                         \
+  do {                                  \
+    const uint32_t _n = clock();        \
+    tacc[cat] += _n - tlast;            \
+    tlast = _n;                         \
+  } while (0)
+#else
+#define TT(cat) do { } while (0)
+#endif
 __host__ __device__ constexpr int n_layers(int mode) { return mode == RB4 ? 4 : (mode == C_RB4 ? 5 : 1); }
 
 struct StageArgs {
@@ -55,7 +70,6 @@ struct StageArgs {
   int Lin;               // site length of the input buffer (== L when not pooled)
   int pk, ps, pp;        // max-pool fused into the loader (RB4: none)
   int n_tiles;
-  int dbg;               // timing experiments only (MURAL_TC_DBG): results are wrong when non-zero
   // dense-site dispatch (snv_dense_stem.cu): all decided on the device, no host synchronisation
   const ChunkInfo* info;  // nullptr: unconditional launch
   int want;               // run only if info->dense == want
@@ -160,6 +174,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = tid >> 7, lt = tid & 127;
+#ifdef MURAL_TC_TIMING
+  uint32_t tacc[T_N] = {0};
+  uint32_t tlast = clock(), tlayers = 0;
+  const uint32_t tstart = tlast;
+#endif
 
   // ---- one-time setup
   {
@@ -209,13 +228,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
   // One named barrier per slot so that a warp running one step ahead never double-arrives.
   auto sync_and_issue = [&](int k, int l) {
-    if (!(a.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    TT(T_EPI);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    TT(T_FENCE);
     const int sl = g * NINFL + k;
     if (lt >= 32) {
       asm volatile("bar.arrive %0, 128;" ::"r"(1 + sl) : "memory");
+      TT(T_BAR);
     } else {
       asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
+      TT(T_BAR);
       if (lt == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // R-type layers (second conv of a ResBlock, conv2, conv3) accumulate into / create region R, others use T
@@ -225,16 +248,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         const uint64_t dA = dA0 + uint64_t((sl * SLOT_BYTES) >> 4), dC = dC0 + uint64_t((sl * SLOT_BYTES) >> 4);
         const uint64_t dW = dW0 + uint64_t((l * W_LAYER) >> 4);
         umma_bf16(d, dC, dW + (W_CONV >> 4), acc_first ? 1u : 0u);
-        if (!(a.dbg & 4)) {
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
+        for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-              umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
-        }
+          for (int h = 0; h < 2; ++h)
+            umma_bf16(d, dA + uint64_t((2 * h * A_PLANE + t * 16) >> 4), dW + uint64_t(((t * 4 + 2 * h) * 512) >> 4), 1u);
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * k) : "memory");
       }
       __syncwarp();
+      TT(T_ISSUE);
     }
   };
 
@@ -337,6 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     const uint32_t one2 = 0x3F803F80u;
     *reinterpret_cast<uint4*>(sA + A_SLOT + lt * 16) =
         make_uint4(live ? one2 : 0u, p == 0 ? one2 : 0u, (live && p == L_ - 1) ? one2 : 0u, 0u);
+    TT(T_BEGIN);
     sync_and_issue(k, 0);
   };
 
@@ -358,16 +381,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
       act[k] = tile0 + k < n_tiles_;
       r[k] = rn[k];
       p[k] = pn[k];
+      TT(T_OTHER);
       if (act[k]) begin_tile(k, p[k], xn[k]);
     }
 #pragma unroll
     for (int k = 0; k < NINFL; ++k)
       if (tile0 + tile_step + k < n_tiles_) fetch(tile0 + tile_step + k, rn[k], pn[k], xn[k]);
+    TT(T_FETCH);
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
 #pragma unroll
       for (int k = 0; k < NINFL; ++k) {
         if (!act[k]) continue;
+#ifdef MURAL_TC_TIMING
+        ++tlayers;
+#endif
+        TT(T_OTHER);
         mbar_wait(bar0 + 8 * k, phase[k]);
         phase[k] ^= 1;
         __syncwarp();
@@ -376,19 +405,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         const bool live = p[k] >= 0;
         const bool valid = live && lt >= NL && lt < TILE - NL;
         uint32_t acc[32];
-        if (!(a.dbg & 2)) {
-          TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c] = 0x3f800000u + lt;
-        }
+        TT(T_WAIT);
+        TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        TT(T_LD);
         if (l < NL - 1) {
           uint4 o[4];
-          if (a.dbg & 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_uint4(acc[q], acc[q + 4], acc[q + 8], acc[q + 12]);
-          } else
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             o[q].x = pack_bf16(__uint_as_float(acc[8 * q]), __uint_as_float(acc[8 * q + 1]));
@@ -436,9 +458,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
             }
           }
         }
+        if (l == NL - 1) TT(T_FINAL);
       }
     }
   }
+#ifdef MURAL_TC_TIMING
+  if ((lt & 31) == 0 && (lt >> 5) < 2) {
+    unsigned long long* o = g_tc_timing[MODE][blockIdx.x % 148][g][lt >> 5];
+    for (int i = 0; i < T_N; ++i) atomicAdd(&o[i], (unsigned long long)tacc[i]);
+    atomicAdd(&o[T_N], (unsigned long long)tlayers);
+    atomicAdd(&o[T_N + 1], (unsigned long long)(clock() - tstart));
+  }
+#endif
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -523,10 +554,7 @@ static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = 
   }
   int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
   if (grid > m_sm_count()) grid = m_sm_count();
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("MURAL_TC_DBG"); dbg = e ? atoi(e) : 0; }
-  StageArgs a2 = a;
-  a2.dbg = dbg;
+  const StageArgs& a2 = a;
   // profile names are interned per (mode, role): prof_pre keeps the pointer
   static std::map<std::string, std::string> names;
   const std::string key = std::string(MODE == RB4 ? "k_stage_tc<RB4>" : (MODE == C_RB4 ? "k_stage_tc<C_RB4>" : "k_stage_tc<SINGLE>")) + role;
@@ -815,5 +843,32 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
 }
 
 }  // namespace mural
+
+// scratch builds with -DMURAL_TC_TIMING: prints the per-phase cycle breakdown of the stage kernels and clears it
+extern "C" int mural_tc_timing_dump(void) {
+#ifdef MURAL_TC_TIMING
+  using namespace mural::tc;
+  static unsigned long long h[3][148][NGROUP][2][T_N + 2];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+  const char* nm[T_N] = {"wait", "ld", "epi", "fence", "bar", "issue", "begin", "fetch", "final", "other"};
+  for (int mode = 0; mode < 3; ++mode)
+    for (int w = 0; w < 2; ++w) {
+      double tot[T_N + 2] = {0};
+      for (int b = 0; b < 148; ++b)
+        for (int g = 0; g < NGROUP; ++g)
+          for (int i = 0; i < T_N + 2; ++i) tot[i] += double(h[mode][b][g][w][i]);
+      if (tot[T_N] == 0) continue;
+      fprintf(stderr, "mode %d warp %d: layers/thread-sum %.0f, cycles per tile-layer (per group):", mode, w, tot[T_N]);
+      for (int i = 0; i < T_N; ++i) fprintf(stderr, " %s=%.0f", nm[i], tot[i] / tot[T_N]);
+      fprintf(stderr, " | total=%.0f\n", tot[T_N + 1] / tot[T_N]);
+    }
+  static unsigned long long z[3][148][NGROUP][2][T_N + 2];
+  cudaMemcpyToSymbol(g_tc_timing, z, sizeof(z));
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 extern "C" int mural_snv_tc_available(const mural_snv_model_t* m) { return (m && m->tc) ? 1 : 0; }

@@ -276,7 +276,102 @@ __global__ void __launch_bounds__(512, 1) k_mb(Out* o) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
+
+// ---------------- clean tensor-pipe timing: one issuing lane, its warp-mates parked at __syncwarp, everyone else on the mbarrier
+__global__ void __launch_bounds__(256, 1) k_t3(long long* cyc, int variant, int reps) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + 16384 * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int e = tid; e < 65536 / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem)[e] = 0x3C003C00u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tslot;
+  const uint32_t barA = smem_u32(&bar);
+  const uint64_t dA = umma_desc(smem_u32(sA), 130 * 16, 128);
+  const uint64_t dA2 = umma_desc(smem_u32(sA) + 16384, 130 * 16, 128);
+  const uint64_t dB = umma_desc(smem_u32(sB), 96 * 16, 128);
+  long long t0 = 0;
+  if (warp == 1) {
+    if ((tid & 31) == 0) {
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        const uint32_t d = tb + (r & 7) * 32;
+        switch (variant) {
+          case 0:  // 7 dependent N=32 (current kernel's batch), D rotates over 8 regions per batch
+            for (int i = 0; i < 7; ++i) mma_ss(d, dA + (i % 3), dB, idesc(32), i > 0);
+            break;
+          case 1:  // 7 independent N=32 (7 different D)
+            for (int i = 0; i < 7; ++i) mma_ss(tb + i * 32, dA + (i % 3), dB, idesc(32), 0);
+            break;
+          case 2:  // two interleaved dependent chains of 7 (2 batches)
+            for (int i = 0; i < 7; ++i) { mma_ss(d, dA + (i % 3), dB, idesc(32), i > 0); mma_ss(d + 256, dA2 + (i % 3), dB, idesc(32), i > 0); }
+            break;
+          case 3:  // 1 x N=32
+            mma_ss(d, dA, dB, idesc(32), 0);
+            break;
+          case 4:  // 2 dependent N=96
+            mma_ss(tb + (r & 3) * 96, dA, dB, idesc(96), 0); mma_ss(tb + (r & 3) * 96, dA + 1, dB, idesc(96), 1);
+            break;
+          case 5:  // 7 dependent, A from TMEM
+            for (int i = 0; i < 7; ++i) mma_ts(d, tb + 256 + (i & 1) * 8, dB, idesc(32), i > 0);
+            break;
+          case 6:  // 7 independent, A from TMEM
+            for (int i = 0; i < 7; ++i) mma_ts(tb + i * 32, tb + 256 + (i & 1) * 8, dB, idesc(32), 0);
+            break;
+          case 7:  // 1 x N=256
+            mma_ss(tb, dA, dB, idesc(256), 0);
+            break;
+          case 8:  // 1 x N=64
+            mma_ss(d, dA, dB, idesc(64), 0);
+            break;
+          case 9:  // 1 x N=128
+            mma_ss(tb + (r & 3) * 128, dA, dB, idesc(128), 0);
+            break;
+          case 10:  // 4 dependent N=64 (row-pair formulation: K=64 per 2 taps...) 
+            for (int i = 0; i < 4; ++i) mma_ss(tb + (r & 3) * 64, dA + i, dB, idesc(64), i > 0);
+            break;
+          case 11:  // 4 shifts
+            tshift(tb + 256); tshift(tb + 264); tshift(tb + 256); tshift(tb + 264);
+            break;
+          case 12:  // 7 dependent N=32 + commit per batch (as the real kernel does)
+            for (int i = 0; i < 7; ++i) mma_ss(d, dA + (i % 3), dB, idesc(32), i > 0);
+            if (r + 1 < reps) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar) + 0) : "memory");
+            break;
+        }
+      }
+      if (variant != 12) commit(barA);
+      else commit(barA);
+    }
+    __syncwarp();
+  }
+  if (variant == 12) {
+    // the barrier completes reps times; wait for each phase
+    uint32_t ph = 0;
+    for (int r = 0; r < reps; ++r) { mbar_wait(barA, ph); ph ^= 1; }
+  } else {
+    mbar_wait(barA, 0);
+  }
+  if (tid == 32) cyc[variant] = clock64() - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
 int main() {
+  setvbuf(stdout, NULL, _IONBF, 0);
   Out* d;
   CK(cudaMalloc(&d, sizeof(Out)));
   CK(cudaMemset(d, 0xEE, sizeof(Out)));
@@ -313,6 +408,15 @@ int main() {
   const char* names[] = {"7x mma_ss N32", "7x mma_ts N32", "7 mma_ts + 4 shift", "2x mma_ss N96", "4 shifts", "2x mma_ts N96", "1 mma_ss N32", "1 mma_ts N32", "1 mma_ss N256", "1 shift"};
   for (int v = 0; v < 10; ++v) printf("T3 %-20s %8.1f cyc/layer (256 layers, incl. ~issue+commit latency)\n", names[v], h.cyc[v] / 256.0);
   for (int c = 0; c < 3; ++c) printf("T4 ld x32 nw=%2d: %6.1f cyc per load-round; st: %6.1f\n", c == 0 ? 4 : (c == 1 ? 8 : 16), h.cyc[10 + c] / 256.0, h.cyc[13 + c] / 256.0);
+  {
+    long long* dc; CK(cudaMalloc(&dc, 64 * 8)); CK(cudaMemset(dc, 0, 64 * 8));
+    CK(cudaFuncSetAttribute(k_t3, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const char* nm[] = {"7 dep N32 ss", "7 indep N32 ss", "2x7 interleaved dep N32", "1 N32", "2 dep N96", "7 dep N32 ts", "7 indep N32 ts", "1 N256", "1 N64", "1 N128", "4 dep N64", "4 shifts", "7 dep N32 + commit each"};
+    for (int rep = 0; rep < 2; ++rep)
+      for (int v = 0; v < 12; ++v) { k_t3<<<1, 256, 65536>>>(dc, v, rep ? 512 : 256); CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, dc + v, 8, cudaMemcpyDeviceToHost));
+        printf("T3v2 reps=%d %-28s total %8lld cyc  = %7.1f cyc/batch\n", rep ? 512 : 256, nm[v], c, double(c) / (rep ? 512 : 256)); }
+  }
   printf("T5 shfl dependent chain, 16 warps: %.2f cyc per shfl round; independent: %.2f cyc per 16-warp round\n", h.cyc[16] / 1024.0, h.cyc[17] / 1024.0);
   return 0;
 }
