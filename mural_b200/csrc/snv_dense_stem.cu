@@ -36,41 +36,67 @@ __device__ __forceinline__ int sym_genomic(const GenomeView& G, int chrom, long 
   return (q >= 0 && q < G.chrom_len[chrom]) ? genome_symbol(G, G.chrom_off[chrom] + q) : SYM_N;
 }
 
-__global__ void k_chunk_span(const int32_t* __restrict__ pos, const int32_t* __restrict__ meta, int64_t ns, int R, int cap,
-                             int ps_mid, int ps_large, int tile_stride, ChunkInfo* __restrict__ info) {
-  __shared__ int s_min, s_max, s_mixed, s_has[2];
+// Multi-CTA span detection; the last CTA to finish writes ChunkInfo and re-zeroes the scratch words (self-cleaning:
+// scr[] must be zero before the first launch).  scr: [0] max(INT_MAX - pos), [1] max(pos + 1), [2] mixed, [3] has '+',
+// [4] has '-', [5] finished-CTA counter.
+__global__ void __launch_bounds__(256) k_chunk_span(const int32_t* __restrict__ pos, const int32_t* __restrict__ meta, int64_t ns, int R,
+                                                    int cap, int ps_mid, int ps_large, int tile_stride, ChunkInfo* __restrict__ info,
+                                                    int* __restrict__ scr) {
+  __shared__ int s_min, s_max, s_mixed, s_has[2], s_last;
   if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; s_mixed = 0; s_has[0] = s_has[1] = 0; }
   __syncthreads();
   const int chrom0 = int(uint32_t(meta[0]) >> 8);
   int mn = INT_MAX, mx = INT_MIN, mixed = 0, h0 = 0, h1 = 0;
-  for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < ns; i += int64_t(gridDim.x) * blockDim.x) {
     const int p = pos[i], m = meta[i];
     mn = min(mn, p);
     mx = max(mx, p);
     mixed |= int(uint32_t(m) >> 8) != chrom0;
     if (m & 1) h1 = 1; else h0 = 1;
   }
-  atomicMin(&s_min, mn);
-  atomicMax(&s_max, mx);
-  if (mixed) s_mixed = 1;
-  if (h0) s_has[0] = 1;
-  if (h1) s_has[1] = 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mixed |= __shfl_xor_sync(0xffffffffu, mixed, o);
+    h0 |= __shfl_xor_sync(0xffffffffu, h0, o);
+    h1 |= __shfl_xor_sync(0xffffffffu, h1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_min, mn);
+    atomicMax(&s_max, mx);
+    if (mixed) s_mixed = 1;
+    if (h0) s_has[0] = 1;
+    if (h1) s_has[1] = 1;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const long long span = (long long)s_max - s_min + 2LL * R + 64;
-    info->g_lo = (long long)s_min - R - 24;
-    info->n_pos = int(span < cap ? span : cap);
-    info->dense = (!s_mixed && span <= cap) ? 1 : 0;
-    info->chrom = chrom0;
-    info->has[0] = s_has[0];
-    info->has[1] = s_has[1];
-    for (int br = 0; br < 2; ++br) {
-      const int ps = br ? ps_large : ps_mid;
-      const int M = (info->n_pos + ps - 1) / ps;
-      info->M[br] = M;
-      info->lat_rows[br] = 2 * ps * (M + 1) + 1;
-      info->lat_tiles[br] = (info->lat_rows[br] + tile_stride - 1) / tile_stride;
-    }
+    if (s_min != INT_MAX) { atomicMax(&scr[0], INT_MAX - s_min); atomicMax(&scr[1], s_max + 1); }
+    if (s_mixed) atomicOr(&scr[2], 1);
+    if (s_has[0]) atomicOr(&scr[3], 1);
+    if (s_has[1]) atomicOr(&scr[4], 1);
+    __threadfence();
+    s_last = atomicAdd(&scr[5], 1) == int(gridDim.x) - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  const int g_min = INT_MAX - atomicExch(&scr[0], 0), g_max = atomicExch(&scr[1], 0) - 1;
+  const int g_mixed = atomicExch(&scr[2], 0), g_h0 = atomicExch(&scr[3], 0), g_h1 = atomicExch(&scr[4], 0);
+  atomicExch(&scr[5], 0);
+  const long long span = (long long)g_max - g_min + 2LL * R + 64;
+  info->g_lo = (long long)g_min - R - 24;
+  info->n_pos = int(span < cap ? span : cap);
+  info->dense = (!g_mixed && span <= cap) ? 1 : 0;
+  info->chrom = chrom0;
+  info->has[0] = g_h0;
+  info->has[1] = g_h1;
+  for (int br = 0; br < 2; ++br) {
+    const int ps = br ? ps_large : ps_mid;
+    const int M = (info->n_pos + ps - 1) / ps;
+    info->M[br] = M;
+    info->lat_rows[br] = 2 * ps * (M + 1) + 1;
+    info->lat_tiles[br] = (info->lat_rows[br] + tile_stride - 1) / tile_stride;
   }
 }
 
@@ -377,8 +403,9 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
       gb[br].edge = 1;
     }
   }
-  LAUNCH(k_chunk_span, 1, 1024, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
-         128 - 2 * 4, info);
+  int* scr = reinterpret_cast<int*>(reinterpret_cast<char*>(d_scratch) + 128);  // zeroed once per forward call by the caller
+  LAUNCH(k_chunk_span, 32, 256, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
+         128 - 2 * 4, info, scr);
   const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C);
   static bool conf = false;
   if (!conf) {

@@ -76,6 +76,7 @@ struct StageArgs {
   int lat_branch;         // >= 0: this launch is the stage-1 lattice of that branch; L / rows / n_tiles come from info
   // LAT loader (C_RB4 only): stage-1 rows of a site come from the lattice (interior) and the edge pseudo-site (ends)
   const uint4* lat;       // stage-1 lattice output planes [4][lat_ra]
+  const uint4* lat2;      // the same max-pooled along the lattice: lat2[row] = max(lat[row .. row+pk-1]) (k_lattice_pool)
   int64_t lat_ra;
   const uint4* edge;      // stage-1 edge output planes [4][edge_ra], LAT_EL rows per site
   int64_t edge_ra;
@@ -149,9 +150,9 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 
 // One stage of one branch, persistent: one CTA per SM, 4 thread groups x 2 tiles in flight.
 //
-// A group's 128 threads own the 128 rows of a tile (thread = row = TMEM lane).  Per layer the group's warp 0
+// A group's 128 threads own the 128 rows of a tile (thread = row = TMEM lane).  Per layer one warp of the group (rotating)
 // issues 7 tcgen05.mma (constant-column MMA for bias + site-edge corrections, then 3 taps x 2 K-halves) and
-// commits to the slot's mbarrier; while those run, the group serves its other in-flight tile.  Warps 1-3 only
+// commits to the slot's mbarrier; while those run, the group serves its other in-flight tile.  The other three warps only
 // bar.arrive on the slot's named barrier and run ahead.  The residual stream never leaves the tensor core:
 // TMEM region R (32 columns) is pre-loaded with x0 (tcgen05.st) and the second conv of each ResBlock
 // ACCUMULATES onto it, the first conv of each ResBlock goes to a scratch region T.  The epilogue of a layer is
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   const uint32_t bar0 = smem_u32(bars + g * NINFL);
   uint32_t phase[NINFL] = {0, 0};
 
-  // publish the slot's operands to the tensor core: warps 1-3 of the group arrive and run ahead, warp 0 waits for
+  // publish the slot's operands to the tensor core: three warps of the group arrive and run ahead, the issuing warp waits for
   // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
   // One named barrier per slot so that a warp running one step ahead never double-arrives.
   auto sync_and_issue = [&](int k, int l) {
@@ -233,13 +234,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     TT(T_FENCE);
     const int sl = g * NINFL + k;
-    if (lt >= 32) {
+    // the issuing warp rotates with (layer, slot): UTCHMMA issue blocks while the tensor pipe's queue is full, and no
+    // single warp should carry all of that back-pressure
+    if ((lt >> 5) != ((l + k) & 3)) {
       asm volatile("bar.arrive %0, 128;" ::"r"(1 + sl) : "memory");
       TT(T_BAR);
     } else {
       asm volatile("bar.sync %0, 128;" ::"r"(1 + sl) : "memory");
       TT(T_BAR);
-      if (lt == 0) {
+      if ((lt & 31) == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // R-type layers (second conv of a ResBlock, conv2, conv3) accumulate into / create region R, others use T
         const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
@@ -307,6 +310,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
           const int x0 = strand ? s + a.R - a.off0 + a.pp1 - a.pk1 + 1 - g_lo : s - a.R + a.off0 - a.pp1 - g_lo;
           const int m0 = x0 / a.ps1, phase = x0 - m0 * a.ps1;
           lat_base = strand ? 1 + (a.ps1 + phase) * (M + 1) + (M - 1 - m0) : 1 + phase * (M + 1) + m0;
+        }
+        if (live && lo >= LAT_EO && hi <= a.Lin - LAT_EO && hi - lo == a.pk) {  // whole pool window on the lattice: pre-pooled row
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = __ldg(a.lat2 + q * a.lat_ra + lat_base + lo);
+          hi = lo;
         }
 #pragma unroll
         for (int u = 0; u < 7; ++u) {
@@ -476,6 +484,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+// second-level reuse on the lattice: the stage-2 pool window of an interior bin covers pk consecutive lattice rows of
+// one pseudo-site, so its maximum is again a function of the genomic position only
+__global__ void __launch_bounds__(256) k_lattice_pool(const ChunkInfo* __restrict__ info, int br, int pk, const uint4* __restrict__ y1,
+                                                      uint4* __restrict__ p2, int64_t ra) {
+  if (!info->dense) return;
+  const int M = info->M[br], rows = info->lat_rows[br];
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < int64_t(rows) * 4; e += int64_t(gridDim.x) * blockDim.x) {
+    const int q = int(e & 3), row = int(e >> 2);
+    if (row < 1) continue;
+    const int mm = (row - 1) % (M + 1);
+    if (mm == M) continue;  // separator
+    const int n = pk < M - mm ? pk : M - mm;
+    uint4 v = __ldg(y1 + q * ra + row);
+    for (int k = 1; k < n; ++k) {
+      const uint4 w = __ldg(y1 + q * ra + row + k);
+      v.x = max_bf16x2(v.x, w.x); v.y = max_bf16x2(v.y, w.y); v.z = max_bf16x2(v.z, w.z); v.w = max_bf16x2(v.w, w.w);
+    }
+    p2[q * ra + row] = v;
+  }
+}
+
 // head for the plane layout: global max over the site's L3 rows of both branches, folded BN+Linear, combine
 struct HeadTc {
   const float* x;  // fp32 planes [8][rows_alloc][4], conv3 output after ReLU
@@ -485,43 +514,69 @@ struct HeadTc {
   int L3;
 };
 
-__global__ void __launch_bounds__(128) k_head_tc(HeadTc b0, HeadTc b1, const float* __restrict__ local_logits, int64_t n, int NC,
+// 8 threads per site, one per 4-channel plane: each reads its plane's L3 consecutive float4 rows (coalesced across the
+// sites of a warp), reduces the max, multiplies its 4 channels into the folded BN+Linear and the 8 partial sums are
+// combined with three xor-shuffles.
+__global__ void __launch_bounds__(256) k_head_tc(HeadTc b0, HeadTc b1, const float* __restrict__ local_logits, int64_t n, int NC,
                                                  float* __restrict__ logp, float* __restrict__ tg0, float* __restrict__ tg1,
                                                  float* __restrict__ tl0, float* __restrict__ tl1) {
-  const int lane = threadIdx.x & 31;
-  const int64_t site = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
-  if (site >= n) return;
+  const int64_t gt = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t site = gt >> 3;
+  const int q = int(gt & 7);
+  const bool ok = site < n;  // out-of-range lanes stay for the shuffles
   float lg[2][16];
 #pragma unroll 1
   for (int br = 0; br < 2; ++br) {
     const HeadTc& B = br ? b1 : b0;
-    const int64_t base = 1 + site * (B.L3 + 1);
-    float mx = -FLT_MAX;  // lane = channel (C == 32)
-    for (int p = 0; p < B.L3; ++p) mx = fmaxf(mx, B.x[((lane >> 2) * B.rows_alloc + base + p) * 4 + (lane & 3)]);
-    float* tg = br ? tg1 : tg0;
-    if (tg) tg[site * 32 + lane] = mx;
+    float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    if (ok) {
+      const float4* x = reinterpret_cast<const float4*>(B.x) + int64_t(q) * B.rows_alloc + 1 + site * (B.L3 + 1);
+      for (int p = 0; p < B.L3; ++p) {
+        const float4 v = __ldg(x + p);
+        mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+      }
+      float* tg = br ? tg1 : tg0;
+      if (tg) *reinterpret_cast<float4*>(tg + site * 32 + 4 * q) = mx;
+    }
+    const float* W = B.Wfc + 4 * q * NC;
 #pragma unroll
     for (int o = 0; o < 16; ++o)
-      if (o < NC) lg[br][o] = warp_sum(mx * B.Wfc[lane * NC + o]) + B.bfc[o];
+      if (o < NC) {
+        float part = mx.x * W[o] + mx.y * W[NC + o] + mx.z * W[2 * NC + o] + mx.w * W[3 * NC + o];
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        lg[br][o] = part + B.bfc[o];
+      }
   }
-  if (lane != 0) return;
-  float sm[3][16];
-#pragma unroll 1
+  if (q != 0 || !ok) return;
+  // combine (model_snv.py:515-523); static indexing keeps everything in registers
+  float pr[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) pr[o] = 0.f;
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    float mx = -FLT_MAX, sum = 0.f;
-    for (int o = 0; o < NC; ++o) {
-      const float v = k == 2 ? local_logits[site * NC + o] : lg[k][o];
-      sm[k][o] = v;
-      mx = fmaxf(mx, v);
+    float v[16], mx = -FLT_MAX, sum = 0.f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < NC) {
+        v[o] = k == 2 ? local_logits[site * NC + o] : lg[k][o];
+        mx = fmaxf(mx, v[o]);
+      }
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < NC) { v[o] = expf(v[o] - mx); sum += v[o]; }
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+      if (o < NC) pr[o] += (k == 2 ? 1.f : 0.5f) * (v[o] / sum);
+  }
+#pragma unroll
+  for (int o = 0; o < 16; ++o)
+    if (o < NC) {
+      if (tl0) tl0[site * NC + o] = lg[0][o];
+      if (tl1) tl1[site * NC + o] = lg[1][o];
+      logp[site * NC + o] = logf(fmaxf(pr[o] / 2.f, 1e-9f));
     }
-    for (int o = 0; o < NC; ++o) { sm[k][o] = expf(sm[k][o] - mx); sum += sm[k][o]; }
-    for (int o = 0; o < NC; ++o) sm[k][o] /= sum;
-  }
-  for (int o = 0; o < NC; ++o) {
-    if (tl0) tl0[site * NC + o] = lg[0][o];
-    if (tl1) tl1[site * NC + o] = lg[1][o];
-    logp[site * NC + o] = logf(fmaxf((sm[2][o] + (sm[0][o] + sm[1][o]) / 2.f) / 2.f, 1e-9f));
-  }
 }
 
 struct TcState {
@@ -680,7 +735,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const int NC = m->cfg.n_class;
   static int64_t env_chunk = -1;
   if (env_chunk < 0) { const char* e = getenv("MURAL_TC_CHUNK"); env_chunk = e ? atoll(e) : 0; }
-  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (env_chunk > 0 ? env_chunk : 32768);
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (env_chunk > 0 ? env_chunk : 131072);
   if (m->chunk_sites <= 0 || (int64_t(1) << 20) % chunk != 0) {  // keep chunks aligned inside super-chunks
     int64_t c2 = 1;
     while (c2 * 2 <= chunk) c2 *= 2;
@@ -736,6 +791,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   int* err_flag = (int*)w; w += 64;
   void* dense_scratch = use_dense ? (void*)((uintptr_t(w) + 255) & ~uintptr_t(255)) : nullptr;  // uint4 rows / int64 header
   CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
+  if (use_dense) CUDA_TRY(cudaMemsetAsync(dense_scratch, 0, 256, st));  // ChunkInfo + k_chunk_span scratch words
 
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
@@ -795,9 +851,13 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 5);
       if (int rc = launch_stage<C_RB4>(a, st, use_lat ? "/site" : "")) return rc;
       if (use_lat) {
+        // pooled lattice rows overwrite the (now dead) lattice input
+        LAUNCH(k_lattice_pool, 148 * 4, 256, 0, st, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
+               reinterpret_cast<uint4*>(lb[br].lat_in), lb[br].lat_ra);
         StageArgs l = a;
         l.want = 1;
         l.lat = reinterpret_cast<const uint4*>(lb[br].lat_out); l.lat_ra = lb[br].lat_ra;
+        l.lat2 = reinterpret_cast<const uint4*>(lb[br].lat_in);
         l.edge = reinterpret_cast<const uint4*>(lb[br].edge_out); l.edge_ra = lb[br].edge_ra;
         l.pos = d_pos + s0; l.meta = d_meta + s0;
         l.ps1 = B.pool[0][1]; l.pp1 = B.pool[0][2]; l.pk1 = B.pool[0][0];
@@ -815,7 +875,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     }
     HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
                     {bufs[1][3], ra[1][3], m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
-    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 32, 128), 128, 0, st, hb[0], hb[1], llog_c, ns, NC, d_logp + s0 * NC,
+    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 8, 256), 256, 0, st, hb[0], hb[1], llog_c, ns, NC, d_logp + s0 * NC,
            m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr);
     if (m->debug) {
       auto flat = [&](const char* nm, const float* d, int64_t k) -> int {
