@@ -96,6 +96,58 @@ def build_model(cfg, state, n_cat, mode):
     return m
 
 
+# ------------------------------------------------------------------------------------------ train leg
+def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5):
+    """BASELINE configs[2] on the same genome: MuRaL-snv training from scratch (local 10 bp 3-mers, expanded 1 Kb,
+    Adam lr 1e-3), fused step = forward + CE(sum) + backward + flat-gradient all-reduce (NCCL, world > 1) + global-norm
+    clip + Adam, one batch per GPU per step.  Sites: a seeded random subset of this rank's A/T sites (sorted), labels
+    iid Categorical(0.952381, 0.0140095, 0.0198, 0.0138095) (training.py:332).  Returns sites/s per batch size."""
+    import torch
+    from mural_b200 import SiteBatch, model_choice, pack_meta, weights_init
+    from mural_b200.training import TrainState
+    cfg = {"local_radius": 10, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": 1000,
+           "emb_dropout": .1, "local_dropout": .1, "CNN_kernel_size": 3, "CNN_out_channels": 32, "distal_fc_dropout": .25,
+           "n_class": 4, "model_no": 2}
+    n_cat = 2 * 10 + 1 - 2
+    torch.manual_seed(0)
+    model = model_choice(2, cfg, dict(emb_dims=[(65, 2)] * n_cat, n_cont=0, n_class=4, distal_order=1, in_channels=4), "snv")
+    model.apply(weights_init)
+    model.to("cuda").train()
+    ts = TrainState(model, "Adam", lr=1e-3, weight_decay=1e-5, seed=rank)
+    rng = np.random.default_rng(4321 + rank)
+    out = {}
+    for B in (128, 4096):
+        need = B * (steps + warmup)
+        sel = np.sort(rng.choice(len(pos), size=min(need, len(pos)), replace=False))
+        lab = rng.choice(4, size=len(sel), p=[0.952381, 0.0140095, 0.0198, 0.0138095])
+        mt = pack_meta(meta[sel] & 1, lab, meta[sel] >> 8)
+        order = rng.permutation(len(sel))                      # batches are drawn from a shuffled pool (training.py:241)
+        d_pos = torch.from_numpy(pos[sel][order]).cuda(); d_meta = torch.from_numpy(mt[order]).cuda()
+        k_tot = len(sel) // B
+        w = min(warmup, k_tot - 1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(k_tot):
+            if i == w:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                ev0.record()
+            ts.step(SiteBatch(d_pos[i * B:(i + 1) * B], d_meta[i * B:(i + 1) * B], genome))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out["batch_%d" % B] = {"sites_per_s": world * B * (k_tot - w) / (ms * 1e-3), "ms_per_step": ms / (k_tot - w), "steps": k_tot - w}
+    loss = float(ts.loss_dev.item())
+    return {"metric": "sites/sec (train: fwd+bwd+clip+Adam, fused step)", "value": out["batch_128"]["sites_per_s"], "unit": "sites/s",
+            "batch_per_gpu": 128, "large_batch": out["batch_4096"], "small_batch": out["batch_128"], "dtype": "f32",
+            "config": "MuRaL-snv from scratch, local 10bp 3-mers + expanded 1Kb, Adam lr 1e-3, batch per GPU as stated; "
+                      "gradient all-reduce over NCCL when n_gpus > 1", "loss_sum_finite": bool(np.isfinite(loss))}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
     """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
@@ -167,6 +219,7 @@ def main():
     ap.add_argument("--sites-per-step", type=int, default=1048576)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -279,10 +332,18 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * S * K / float(te.item())
 
+    # ---- training leg (fwd + bwd + optimizer), all ranks (it contains the gradient all-reduce)
+    train = None
+    if not a.no_train:
+        try:
+            train = train_leg(genome, pos, meta, world, rank, dist)
+        except Exception as e:  # the predict line must survive a failure here
+            train = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- roofline of the dominant kernel: library-side CUDA-event profile over an identical pass
     roof = None
     if rank == 0:
-        roof = kernel_roofline(L, step, W, K, S, mode, cfg, torch.cuda.synchronize)   # rank-local: no collective here
+        roof = kernel_roofline(L, step, W, K, S, mode, cfg, torch.cuda.synchronize, pos)   # rank-local: no collective here
     line = {"metric": "sites/sec (predict)", "value": value, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
@@ -290,7 +351,7 @@ def main():
                            "per-step activation workspace > L2", wall_s_timed_region=t_wall),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof}
+            "roofline": roof, "train": train}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample
@@ -304,7 +365,30 @@ def main():
     return 0
 
 
-def kernel_roofline(L, step, W, K, S, mode, cfg, barrier):
+def executed_conv_flops(pos, S, K, W, R):
+    """FLOPs the stage kernels actually execute on the dense-site path (bf16 mode): stage 1 runs once per genomic
+    position and strand on the lattice plus a 19-row edge pseudo-site per site; stages 2 and 3 run per site."""
+    chunk = int(os.environ.get("MURAL_TC_CHUNK", "131072"))
+    pools = {0: ((3, 3, 1), (3, 3, 1), (3, 3, 1)), 1: ((15, 15, 7), (7, 7, 3), (3, 3, 1))}
+    L0 = {0: 201, 1: 2 * R + 1}
+    rl = 0
+    for i in range(W, W + K):
+        p = pos[i * S:(i + 1) * S]
+        for c0 in range(0, S, chunk):
+            pc = p[c0:c0 + chunk]
+            ns = len(pc)
+            n_pos = int(pc.max()) - int(pc.min()) + 2 * R + 64
+            for br in (0, 1):
+                Ls = [L0[br]]
+                for (k, s_, pd) in pools[br]:
+                    Ls.append((Ls[-1] + 2 * pd - k) // s_ + 1)
+                ps = pools[br][0][1]
+                M = -(-n_pos // ps)
+                rl += 4 * (2 * ps * (M + 1) + 1) + 4 * (ns * 19 + 1) + 5 * (ns * (Ls[2] + 1) + 1) + (ns * (Ls[3] + 1) + 1)
+    return rl * 2.0 * 32 * 32 * 3
+
+
+def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
     if not hasattr(L, "mural_profile_begin"):
         return None
     peaks = {}
@@ -329,7 +413,15 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier):
     flops_per_launch = FLOP_CONV_ONLY * S * K / n
     achieved = flops_per_launch / (ms / n * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    executed = None
+    if pos is not None and mode == "bf16" and any("lattice" in k for k in conv):
+        ex = executed_conv_flops(pos, S, K, W, cfg["distal_radius"])
+        executed = {"flops_per_launch": ex / n, "tflops": ex / (ms * 1e-3) / 1e12, "frac_of_peak": ex / (ms * 1e-3) / 1e12 / peak,
+                    "share_of_algorithmic": ex / (FLOP_CONV_ONLY * S * K),
+                    "note": "dense-site reuse: stage 1 is evaluated once per genomic position and strand (lattice) plus 19 edge rows per "
+                            "site, so fewer FLOPs are executed than the per-site algorithmic count that `achieved` uses (SURVEY 8d)"}
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "executed": executed,
             "kernel": "+".join(sorted(conv)), "launches": n, "profile_count": {k: v["count"] for k, v in prof.items()}, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,
             "peak_source": src + " (bf16 sustained, kernel timed inside a long step)",
             "flops_per_launch": flops_per_launch, "profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}

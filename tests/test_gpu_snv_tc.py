@@ -142,3 +142,46 @@ def test_dense_lattice_equals_per_site_stages(kat, cuda_genome, chunk):
     bad = (res["lattice"] != res["site"]).any(1).nonzero().flatten()
     assert bad.numel() == 0, (bad[:10].tolist(), st[bad[:10].cpu().numpy()].tolist(),
                               float((res["lattice"] - res["site"]).abs().max()))
+
+
+@pytest.mark.parametrize("R_d", [100, 200, 500, 2000])
+def test_bf16_window_sweep_dense_sites(kat, cuda_genome, R_d):
+    """Config-5 window sweep on the tcgen05 path with random-init weights and dense sorted sites: the lattice path
+    (where the window is long enough for it) equals the per-site stages bit for bit, and both stay within 5e-3 of the
+    fp32 kernels."""
+    import os
+    from mural_b200 import SiteBatch, model_choice, pack_meta, weights_init
+    torch.manual_seed(R_d)
+    cfg = {"local_radius": 7, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": R_d,
+           "emb_dropout": .1, "local_dropout": .1, "CNN_kernel_size": 3, "CNN_out_channels": 32, "distal_fc_dropout": .25,
+           "n_class": 4, "model_no": 2}
+    common = dict(emb_dims=[(65, 2)] * 13, n_cat=13, n_cont=0, n_class=4, distal_order=1, in_channels=4)
+    common.pop("n_cat")
+    m = model_choice(2, cfg, common, "snv")
+    m.apply(weights_init)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d) and mod.num_features > 0:
+            mod.running_mean.normal_(0, .3); mod.running_var.uniform_(.5, 1.5)
+            mod.weight.data.uniform_(.5, 1.5); mod.bias.data.normal_(0, .2)
+    m.to("cuda").eval()
+    rng = np.random.default_rng(R_d)
+    n = 3000
+    st = np.sort(rng.integers(0, 30000, n)).astype(np.int32)
+    sd = rng.integers(0, 2, n)
+    sb = SiteBatch(torch.from_numpy(st).cuda(), torch.from_numpy(pack_meta(sd, 0 * sd, 0 * sd)).cuda(), cuda_genome)
+    res = {}
+    with torch.no_grad():
+        m.compute_mode = "fp32"
+        res["fp32"] = m.forward(None, sb).clone()
+        m.compute_mode = "bf16"
+        for key, env in (("lattice", None), ("site", "1")):
+            if env is None:
+                os.environ.pop("MURAL_NO_LATTICE", None)
+            else:
+                os.environ["MURAL_NO_LATTICE"] = env
+            res[key] = m.forward(None, sb).clone()
+    os.environ.pop("MURAL_NO_LATTICE", None)
+    assert torch.equal(res["lattice"], res["site"]), float((res["lattice"] - res["site"]).abs().max())
+    d = (torch.softmax(res["lattice"], 1) - torch.softmax(res["fp32"], 1)).abs().max().item()
+    print("R_d=%d bf16 vs fp32 kernels max|dp| = %.3e" % (R_d, d))
+    assert d <= 5e-3
