@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--impl", default="mural_b200", choices=["mural_b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MURAL_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
     ap.add_argument("--sites-per-step", type=int, default=1048576)
-    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     a = ap.parse_args()
@@ -420,7 +420,13 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
                     "share_of_algorithmic": ex / (FLOP_CONV_ONLY * S * K),
                     "note": "dense-site reuse: stage 1 is evaluated once per genomic position and strand (lattice) plus 19 edge rows per "
                             "site, so fewer FLOPs are executed than the per-site algorithmic count that `achieved` uses (SURVEY 8d)"}
-    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and mode == "bf16":
+        tj = json.load(open(tp))      # dram__bytes_read+write of the stage kernels from the committed ncu --set full capture
+        if tj.get("chunk_sites") == int(os.environ.get("MURAL_TC_CHUNK", "131072")):
+            traffic = tj["dram_bytes_per_launch"]
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "executed": executed,
             "kernel": "+".join(sorted(conv)), "launches": n, "profile_count": {k: v["count"] for k, v in prof.items()}, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,
             "peak_source": src + " (bf16 sustained, kernel timed inside a long step)",
