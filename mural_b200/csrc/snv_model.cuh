@@ -66,8 +66,9 @@ struct mural_snv_model {
   mural::LocalDev local;
   mural::BranchDev br[2];  // 0 = middle-scale (201 bp), 1 = large-scale (full window)
   bool loaded = false;
-  // bf16 tcgen05 path (snv_tc.cu)
+  // bf16 tcgen05 path (snv_tc.cu) and the tensor-core local branch (snv_mlp_tc.cu)
   void* tc = nullptr;
+  void* mlp_tc = nullptr;
   // forward workspace (grown on demand)
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
@@ -87,6 +88,11 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob);
 void snv_tc_destroy(mural_snv_model* m);
 int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                    const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st);
+// tensor-core local branch (snv_mlp_tc.cu); launch returns -1 when unavailable for this model
+int snv_mlp_tc_prepare(mural_snv_model* m);
+void snv_mlp_tc_destroy(mural_snv_model* m);
+int snv_local_launch_tc(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
+                        cudaStream_t st);
 // shared launch helpers (snv_forward.cu)
 int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                     const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st);

@@ -690,10 +690,11 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
   for (int br = 0; br < 2; ++br)
     for (int stg = 0; stg < 3; ++stg) S->blob[br][stg] = S->d_w + offs[br][stg];
   m->tc = S;
-  return 0;
+  return snv_mlp_tc_prepare(m);
 }
 
 void snv_tc_destroy(mural_snv_model* m) {
+  snv_mlp_tc_destroy(m);
   if (!m->tc) return;
   tc::TcState* S = (tc::TcState*)m->tc;
   cudaFree(S->d_w);
@@ -745,6 +746,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   // workspace: per branch X0 (stem out), Z1, Z2 as bf16 planes, H as fp32 planes; + local logits, taps, k-mer indices.
   // On the dense path X0 / Z1 hold the stage-1 lattice and the edge pseudo-sites instead of per-site rows.
   const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
+  const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   int64_t floats = 0;
   int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0};
@@ -799,8 +801,9 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       const int64_t nsup = (n - s0 < super) ? (n - s0) : super;
       if (!d_cat)
         if (int rc = snv_local_idx_launch(m, G, d_pos + s0, d_meta + s0, nsup, cat32, st)) return rc;
-      if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st))
-        return rc;
+      int rc = use_mlp_tc ? snv_local_launch_tc(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st) : -1;
+      if (rc < 0) rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st);
+      if (rc) return rc;
     }
     const float* llog_c = llog + (s0 % super) * NC;
     const int* dense_flag = nullptr;

@@ -144,19 +144,18 @@ def test_dense_lattice_equals_per_site_stages(kat, cuda_genome, chunk):
                               float((res["lattice"] - res["site"]).abs().max()))
 
 
-@pytest.mark.parametrize("R_d", [100, 200, 500, 2000])
-def test_bf16_window_sweep_dense_sites(kat, cuda_genome, R_d):
+@pytest.mark.parametrize("R_d,R_l", [(100, 7), (200, 10), (500, 7), (2000, 10)])
+def test_bf16_window_sweep_dense_sites(kat, cuda_genome, R_d, R_l):
     """Config-5 window sweep on the tcgen05 path with random-init weights and dense sorted sites: the lattice path
     (where the window is long enough for it) equals the per-site stages bit for bit, and both stay within 5e-3 of the
     fp32 kernels."""
     import os
     from mural_b200 import SiteBatch, model_choice, pack_meta, weights_init
     torch.manual_seed(R_d)
-    cfg = {"local_radius": 7, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": R_d,
+    cfg = {"local_radius": R_l, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": R_d,
            "emb_dropout": .1, "local_dropout": .1, "CNN_kernel_size": 3, "CNN_out_channels": 32, "distal_fc_dropout": .25,
            "n_class": 4, "model_no": 2}
-    common = dict(emb_dims=[(65, 2)] * 13, n_cat=13, n_cont=0, n_class=4, distal_order=1, in_channels=4)
-    common.pop("n_cat")
+    common = dict(emb_dims=[(65, 2)] * (2 * R_l - 1), n_cont=0, n_class=4, distal_order=1, in_channels=4)
     m = model_choice(2, cfg, common, "snv")
     m.apply(weights_init)
     for mod in m.modules():
@@ -185,3 +184,26 @@ def test_bf16_window_sweep_dense_sites(kat, cuda_genome, R_d):
     d = (torch.softmax(res["lattice"], 1) - torch.softmax(res["fp32"], 1)).abs().max().item()
     print("R_d=%d bf16 vs fp32 kernels max|dp| = %.3e" % (R_d, d))
     assert d <= 5e-3
+
+
+def test_local_branch_tensor_core_equals_fp32_kernel(kat, cuda_genome):
+    """Split-bf16 tcgen05 local branch (snv_mlp_tc.cu) vs the fp32 CUDA-core kernel: same folded weights, logits to 1e-5."""
+    import os
+    z, cfg, state = load_snv_golden("hs_AT")
+    m = build_model(cfg, state, int(z["n_cat"]), mode="bf16")
+    sb = site_batch(z, cuda_genome)
+    taps = {}
+    for key, env in (("tc", None), ("fp32", "1")):
+        if env is None:
+            os.environ.pop("MURAL_NO_MLP_TC", None)
+        else:
+            os.environ["MURAL_NO_MLP_TC"] = env
+        m.set_debug(True, chunk=0)
+        with torch.no_grad():
+            m.forward(None, sb)
+        taps[key] = m.debug_tap("logit_local").copy()
+    os.environ.pop("MURAL_NO_MLP_TC", None)
+    m.set_debug(False)
+    d = np.abs(taps["tc"] - taps["fp32"]).max()
+    print("local logits tensor-core vs fp32 kernel: max|d| = %.3e (|logit| max %.2f)" % (d, np.abs(taps["fp32"]).max()))
+    assert d < 1e-5 * max(1.0, np.abs(taps["fp32"]).max())
