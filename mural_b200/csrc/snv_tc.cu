@@ -80,6 +80,9 @@ struct StageArgs {
   int64_t lat_ra;
   const uint4* edge;      // stage-1 edge output planes [4][edge_ra], LAT_EL rows per site
   int64_t edge_ra;
+  const uint4* epool;     // pooled rows of the bins that touch edge rows (k_edge_pool): planes [4][epool_ra], row = site*(nlo+nhi) + b
+  int64_t epool_ra;
+  int nlo, nhi;           // such bins at the low / high end of a site
   const int32_t* pos;
   const int32_t* meta;
   int ps1, pp1, pk1, off0, R, br;
@@ -147,6 +150,15 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),    \
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                                 \
       : "memory")
+
+// lattice row of stage-1 row 0 of a site (row rr is lat_base + rr for either strand; see snv_dense_stem.cu)
+__device__ __forceinline__ int lattice_base(const ChunkInfo* info, int br, int s, int strand, int R, int off0, int ps1, int pp1, int pk1) {
+  const int M = info->M[br];
+  const int g_lo = int(info->g_lo);
+  const int x0 = strand ? s + R - off0 + pp1 - pk1 + 1 - g_lo : s - R + off0 - pp1 - g_lo;
+  const int m0 = x0 / ps1, phase = x0 - m0 * ps1;
+  return strand ? 1 + (ps1 + phase) * (M + 1) + (M - 1 - m0) : 1 + phase * (M + 1) + m0;
+}
 
 // One stage of one branch, persistent: one CTA per SM, 4 thread groups x 2 tiles in flight.
 //
@@ -299,37 +311,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
           }
         }
       } else {
-        // stage-1 row rr of this site: rr < LAT_EO / rr >= Lin - LAT_EO -> the site's edge pseudo-site, otherwise the
-        // lattice row of genomic bin start x(rr) = x(0) +- rr*ps1, which is lat_base + rr for either strand
-        int lat_base = 0;
-        const int ebase = 1 + site * (LAT_EL + 1);
+        // every stage-2 input row is ONE pre-pooled row: bins whose pool window lies on the stage-1 lattice read the pooled
+        // lattice (k_lattice_pool) at genomic bin start x(rr) = x(0) +- rr*ps1, i.e. row lat_base + rr for either strand;
+        // the nlo + nhi bins per site that touch edge rows read the per-site pooled rows of k_edge_pool.  Plain loads
+        // into the prefetch registers: nothing here waits for memory.
         if (live) {
-          const int s = __ldg(a.pos + site), strand = __ldg(a.meta + site) & 1;
-          const int M = a.info->M[a.br];
-          const int g_lo = int(a.info->g_lo);
-          const int x0 = strand ? s + a.R - a.off0 + a.pp1 - a.pk1 + 1 - g_lo : s - a.R + a.off0 - a.pp1 - g_lo;
-          const int m0 = x0 / a.ps1, phase = x0 - m0 * a.ps1;
-          lat_base = strand ? 1 + (a.ps1 + phase) * (M + 1) + (M - 1 - m0) : 1 + phase * (M + 1) + m0;
-        }
-        if (live && lo >= LAT_EO && hi <= a.Lin - LAT_EO && hi - lo == a.pk) {  // whole pool window on the lattice: pre-pooled row
+          if (p >= a.nlo && p < L_ - a.nhi) {
+            const int s = __ldg(a.pos + site), strand = __ldg(a.meta + site) & 1;
+            const int lat_base = lattice_base(a.info, a.br, s, strand, a.R, a.off0, a.ps1, a.pp1, a.pk1);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) x[q] = __ldg(a.lat2 + q * a.lat_ra + lat_base + lo);
-          hi = lo;
-        }
+            for (int q = 0; q < 4; ++q) x[q] = __ldg(a.lat2 + q * a.lat_ra + lat_base + lo);
+          } else {
+            const int64_t idx = int64_t(site) * (a.nlo + a.nhi) + (p < a.nlo ? p : p - (L_ - a.nhi) + a.nlo);
 #pragma unroll
-        for (int u = 0; u < 7; ++u) {
-          const int rr = lo + u;
-          if (rr < hi) {
-            const bool e_lo = rr < LAT_EO, e_hi = rr >= a.Lin - LAT_EO;
-            const uint4* src = (e_lo || e_hi) ? a.edge : a.lat;
-            const int64_t ra = (e_lo || e_hi) ? a.edge_ra : a.lat_ra;
-            const int64_t idx = e_lo ? ebase + rr : (e_hi ? ebase + rr - a.Lin + LAT_EL : lat_base + rr);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 v = __ldg(src + q * ra + idx);
-              x[q].x = max_bf16x2(x[q].x, v.x); x[q].y = max_bf16x2(x[q].y, v.y);
-              x[q].z = max_bf16x2(x[q].z, v.z); x[q].w = max_bf16x2(x[q].w, v.w);
-            }
+            for (int q = 0; q < 4; ++q) x[q] = __ldg(a.epool + q * a.epool_ra + idx);
           }
         }
       }
@@ -502,6 +497,51 @@ __global__ void __launch_bounds__(256) k_lattice_pool(const ChunkInfo* __restric
       v.x = max_bf16x2(v.x, w.x); v.y = max_bf16x2(v.y, w.y); v.z = max_bf16x2(v.z, w.z); v.w = max_bf16x2(v.w, w.w);
     }
     p2[q * ra + row] = v;
+  }
+}
+
+// pool-2 bins of a site that touch its edge rows (the first nlo and last nhi bins): max over the window's stage-1 rows,
+// each taken from the site's edge pseudo-site (rr < LAT_EO or rr >= L1 - LAT_EO) or from the lattice
+struct EdgePool {
+  const uint4* lat; int64_t lat_ra;
+  const uint4* edge; int64_t edge_ra;
+  uint4* out; int64_t out_ra;
+  const int32_t* pos; const int32_t* meta;
+  int64_t ns;
+  int br, L1, L2, pk, ps, pp, nlo, nhi, ps1, pp1, pk1, off0, R;
+};
+__global__ void __launch_bounds__(256) k_edge_pool(const ChunkInfo* __restrict__ info, EdgePool a) {
+  if (!info->dense) return;
+  const int neb = a.nlo + a.nhi;
+  const int64_t total = a.ns * neb * 4;
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int q = int(e & 3);
+    const int64_t sb = e >> 2;
+    const int64_t site = sb / neb;
+    const int b = int(sb - site * neb);
+    const int p = b < a.nlo ? b : a.L2 - a.nhi + (b - a.nlo);
+    int lo = p * a.ps - a.pp, hi = lo + a.pk;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > a.L1 ? a.L1 : hi;
+    const int s = a.pos[site], strand = a.meta[site] & 1;
+    const int lat_base = lattice_base(info, a.br, s, strand, a.R, a.off0, a.ps1, a.pp1, a.pk1);
+    const int64_t ebase = 1 + site * (LAT_EL + 1);
+    const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // bf16 -inf
+    uint4 w[7];  // pk <= 7 for every pool of Network2; all loads are issued before the first max
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int rr = lo + u;
+      const bool e_lo = rr < LAT_EO, e_hi = rr >= a.L1 - LAT_EO;
+      const uint4* src = (e_lo || e_hi) ? a.edge + q * a.edge_ra + (e_lo ? ebase + rr : ebase + rr - a.L1 + LAT_EL)
+                                        : a.lat + q * a.lat_ra + lat_base + rr;
+      w[u] = rr < hi ? __ldg(src) : ninf;
+    }
+    uint4 v = w[0];
+#pragma unroll
+    for (int u = 1; u < 7; ++u) {
+      v.x = max_bf16x2(v.x, w[u].x); v.y = max_bf16x2(v.y, w[u].y); v.z = max_bf16x2(v.z, w[u].z); v.w = max_bf16x2(v.w, w[u].w);
+    }
+    a.out[q * a.out_ra + sb] = v;
   }
 }
 
@@ -749,7 +789,8 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   int64_t floats = 0;
-  int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0};
+  int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0}, epool_ra[2] = {0, 0};
+  int nlo[2] = {0, 0}, nhi[2] = {0, 0};
   for (int br = 0; br < 2; ++br) {
     const BranchDev& B = m->br[br];
     ra[br][0] = rows_alloc(chunk, B.L1);
@@ -758,6 +799,15 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       lat_ra[br] = (2 * ps * (cdiv(snv_dense_cap(chunk), ps) + 1) + 1 + 15) & ~int64_t(7);
       edge_ra[br] = rows_alloc(chunk, LAT_EL);
       if (lat_ra[br] + edge_ra[br] > ra[br][0]) ra[br][0] = lat_ra[br] + edge_ra[br];
+      // pool-2 bins that touch edge rows: p < nlo or p >= L2 - nhi (a bin is lattice-only iff its unclipped window lies
+      // inside stage-1 rows [LAT_EO, L1 - LAT_EO))
+      const int pk2 = B.pool[1][0], ps2 = B.pool[1][1], pp2 = B.pool[1][2];
+      nlo[br] = 0;
+      while (nlo[br] < B.L2 && nlo[br] * ps2 - pp2 < LAT_EO) ++nlo[br];
+      nhi[br] = 0;
+      while (nhi[br] < B.L2 - nlo[br] && (B.L2 - 1 - nhi[br]) * ps2 - pp2 + pk2 > B.L1 - LAT_EO) ++nhi[br];
+      epool_ra[br] = (chunk * (nlo[br] + nhi[br]) + 15) & ~int64_t(7);
+      floats += 16 * epool_ra[br];
     }
     ra[br][1] = ra[br][0];
     ra[br][2] = rows_alloc(chunk, B.L2);
@@ -784,6 +834,8 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     lb[br].edge_out = bufs[br][1] + 16 * lat_ra[br];
     lb[br].edge_ra = edge_ra[br];
   }
+  float* epool[2];
+  for (int br = 0; br < 2; ++br) { epool[br] = w; w += 16 * epool_ra[br]; }
   float* llog = w; w += super * NC;
   float* tl0 = w; w += chunk * NC;
   float* tl1 = w; w += chunk * NC;
@@ -865,6 +917,10 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         l.pos = d_pos + s0; l.meta = d_meta + s0;
         l.ps1 = B.pool[0][1]; l.pp1 = B.pool[0][2]; l.pk1 = B.pool[0][0];
         l.off0 = br ? 0 : m->L / 2 - 100; l.R = m->cfg.distal_radius; l.br = br;
+        l.epool = reinterpret_cast<const uint4*>(epool[br]); l.epool_ra = epool_ra[br]; l.nlo = nlo[br]; l.nhi = nhi[br];
+        EdgePool ep{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
+                    br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
+        LAUNCH(k_edge_pool, 148 * 4, 256, 0, st, info, ep);
         if (int rc = (launch_stage<C_RB4, true>(l, st, "/lattice"))) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
