@@ -69,6 +69,7 @@ struct mural_snv_model {
   // bf16 tcgen05 path (snv_tc.cu) and the tensor-core local branch (snv_mlp_tc.cu)
   void* tc = nullptr;
   void* mlp_tc = nullptr;
+  void* tail = nullptr;  // warp-level tail kernel (snv_tail.cu)
   // forward workspace (grown on demand)
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
@@ -93,6 +94,11 @@ int snv_mlp_tc_prepare(mural_snv_model* m);
 void snv_mlp_tc_destroy(mural_snv_model* m);
 int snv_local_launch_tc(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
                         cudaStream_t st);
+// warp-level tail: pool 3 + conv3 + global max + heads + combine (snv_tail.cu); launch returns -1 when unavailable
+int snv_tail_prepare(mural_snv_model* m, const float* h_blob);
+void snv_tail_destroy(mural_snv_model* m);
+int snv_tail_launch(mural_snv_model* m, const void* z2_mid, int64_t ra_mid, const void* z2_large, int64_t ra_large,
+                    const float* local_logits, int64_t ns, float* logp, float* tg0, float* tg1, float* tl0, float* tl1, cudaStream_t st);
 // shared launch helpers (snv_forward.cu)
 int snv_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
                     const uint8_t* d_sym, int64_t ns, float* mid_out, float* large_out, int32_t* cat_out, cudaStream_t st);

@@ -730,11 +730,13 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
   for (int br = 0; br < 2; ++br)
     for (int stg = 0; stg < 3; ++stg) S->blob[br][stg] = S->d_w + offs[br][stg];
   m->tc = S;
-  return snv_mlp_tc_prepare(m);
+  if (int rc = snv_mlp_tc_prepare(m)) return rc;
+  return snv_tail_prepare(m, h_blob);
 }
 
 void snv_tc_destroy(mural_snv_model* m) {
   snv_mlp_tc_destroy(m);
+  snv_tail_destroy(m);
   if (!m->tc) return;
   tc::TcState* S = (tc::TcState*)m->tc;
   cudaFree(S->d_w);
@@ -787,6 +789,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   // On the dense path X0 / Z1 hold the stage-1 lattice and the edge pseudo-sites instead of per-site rows.
   const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
   const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
+  const bool use_tail = m->tail != nullptr && getenv("MURAL_NO_TAIL") == nullptr;
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   int64_t floats = 0;
   int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0}, epool_ra[2] = {0, 0};
@@ -924,6 +927,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         if (int rc = (launch_stage<C_RB4, true>(l, st, "/lattice"))) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
+      if (use_tail) continue;  // stage 3 and the heads run in the warp-level tail kernel below
       // stage 3: pool3 + conv3 + ReLU at length L3
       a.info = nullptr;
       a.in = reinterpret_cast<const uint4*>(bufs[br][2]); a.out = bufs[br][3]; a.wblob = S->blob[br][2];
@@ -932,10 +936,16 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 1);
       if (int rc = launch_stage<SINGLE>(a, st)) return rc;
     }
-    HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
-                    {bufs[1][3], ra[1][3], m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
-    LAUNCH(k_head_tc, (unsigned)cdiv(ns * 8, 256), 256, 0, st, hb[0], hb[1], llog_c, ns, NC, d_logp + s0 * NC,
-           m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr);
+    if (use_tail) {
+      if (int rc = snv_tail_launch(m, bufs[0][2], ra[0][2], bufs[1][2], ra[1][2], llog_c, ns, d_logp + s0 * NC, m->debug ? tg0 : nullptr,
+                                   m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr, st))
+        return rc;
+    } else {
+      HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
+                      {bufs[1][3], ra[1][3], m->br[1].Wfc, m->br[1].bfc, m->br[1].L3}};
+      LAUNCH(k_head_tc, (unsigned)cdiv(ns * 8, 256), 256, 0, st, hb[0], hb[1], llog_c, ns, NC, d_logp + s0 * NC,
+             m->debug ? tg0 : nullptr, m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr);
+    }
     if (m->debug) {
       auto flat = [&](const char* nm, const float* d, int64_t k) -> int {
         std::vector<float>& v = m->tap_store[nm];
