@@ -147,17 +147,24 @@ template <int C>
 __global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ x, const float* __restrict__ dy, int64_t rows, int L,
                                                int ks, int relu, const float* __restrict__ a, const float* __restrict__ b,
                                                float* __restrict__ G, int64_t w_off, int64_t b_off) {
+  // dW[co][ci][t] = sum_r dy[r][co] * u[r + t - half][ci] over rows whose tap stays inside the site (u = BN(act(x))).
+  // A thread owns a 4(ci) x 4(co) block of one tap: per row two LDS.128 feed 16 FMAs.  Tiles of TR rows are staged in
+  // shared memory; the per-(row, tap) validity is folded into a masked copy of dy per tap.
   constexpr int TR = 64;
-  extern __shared__ float shf[];
-  float* us = shf;                         // [(TR + ks - 1)][C + 1]
-  float* ds = us + (TR + ks - 1) * (C + 1);  // [TR][C + 1]
-  int* ps = reinterpret_cast<int*>(ds + TR * (C + 1));  // [TR] position of the row inside its site (-1: beyond rows)
+  constexpr int CS = C + 4;  // row stride (floats), keeps float4 alignment and spreads banks
+  extern __shared__ __align__(16) float shf[];
+  float* us = shf;                           // [(TR + ks - 1)][CS]
+  float* ds = us + (TR + ks - 1) * CS;       // [TR][CS]
+  int* ps = reinterpret_cast<int*>(ds + TR * CS);  // [TR] position of the row inside its site (very negative: beyond rows)
   const int half = ks / 2, tid = threadIdx.x;
-  const int n_out = ks * C * C;
-  constexpr int MAXO = 3 * 64 * 64 / 256 > 7 * 32 * 32 / 256 ? 3 * 64 * 64 / 256 : 7 * 32 * 32 / 256;  // outputs per thread bound
-  float acc[MAXO];
+  constexpr int NB = (C / 4) * (C / 4);      // 4x4 blocks per tap
+  const int n_blocks = ks * NB;
+  constexpr int MAXB = (7 * NB + 255) / 256;  // blocks per thread bound (ks <= 7)
+  float acc[MAXB][16];
 #pragma unroll
-  for (int k = 0; k < MAXO; ++k) acc[k] = 0.f;
+  for (int k = 0; k < MAXB; ++k)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[k][e] = 0.f;
   float accb = 0.f;
   const int64_t n_tiles = (rows + TR - 1) / TR;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -172,40 +179,49 @@ __global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ x, cons
         if (relu) v = fmaxf(v, 0.f);
         v = fmaf(v, a[ci], b[ci]);
       }
-      us[k * (C + 1) + ci] = v;
+      us[k * CS + ci] = v;
     }
     for (int e = tid; e < TR * C; e += 256) {
       const int k = e / C, co = e - k * C;
       const int64_t r = r0 + k;
-      ds[k * (C + 1) + co] = r < rows ? dy[r * C + co] : 0.f;
+      ds[k * CS + co] = r < rows ? dy[r * C + co] : 0.f;
     }
     if (tid < TR) ps[tid] = (r0 + tid < rows) ? int((r0 + tid) % L) : -1000000;
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < MAXO; ++k) {
-      const int o = tid + k * 256;
-      if (o < n_out) {
-        const int t = o / (C * C), ci = (o / C) % C, co = o % C;
-        float s = 0.f;
+    for (int k = 0; k < MAXB; ++k) {
+      const int blk = tid + k * 256;
+      if (blk < n_blocks) {
+        const int t = blk / NB, ci4 = ((blk % NB) / (C / 4)) * 4, co4 = (blk % (C / 4)) * 4;
+#pragma unroll 4
         for (int r = 0; r < TR; ++r) {
           const int q = ps[r] + t - half;
-          if (q >= 0 && q < L) s = fmaf(ds[r * (C + 1) + co], us[(r + t) * (C + 1) + ci], s);
+          if (q < 0 || q >= L) continue;  // tap falls on the zero padding of this row's site (warp-uniform: same t per warp mostly)
+          const float4 d4 = *reinterpret_cast<const float4*>(ds + r * CS + co4);
+          const float4 u4 = *reinterpret_cast<const float4*>(us + (r + t) * CS + ci4);
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[k][i * 4 + o] = fmaf(dv[o], uv[i], acc[k][i * 4 + o]);
         }
-        acc[k] += s;
       }
     }
     if (tid < C) {
       float s = 0.f;
-      for (int r = 0; r < TR; ++r) s += ds[r * (C + 1) + tid];
+      for (int r = 0; r < TR; ++r) s += ds[r * CS + tid];
       accb += s;
     }
   }
 #pragma unroll
-  for (int k = 0; k < MAXO; ++k) {
-    const int o = tid + k * 256;
-    if (o < n_out) {
-      const int t = o / (C * C), ci = (o / C) % C, co = o % C;
-      atomicAdd(G + w_off + (int64_t(co) * C + ci) * ks + t, acc[k]);
+  for (int k = 0; k < MAXB; ++k) {
+    const int blk = tid + k * 256;
+    if (blk < n_blocks) {
+      const int t = blk / NB, ci4 = ((blk % NB) / (C / 4)) * 4, co4 = (blk % (C / 4)) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) atomicAdd(G + w_off + (int64_t(co4 + o) * C + ci4 + i) * ks + t, acc[k][i * 4 + o]);
     }
   }
   if (tid < C) atomicAdd(G + b_off + tid, accb);
@@ -290,19 +306,68 @@ __global__ void k_linear_fwd(const float* __restrict__ x, const float* __restric
   y[e] = relu ? fmaxf(acc, 0.f) : acc;
 }
 // dy <- dy * (y > 0) when relu; dW[o][k] += sum_i dy[i][o] x[i][k]; db[o] += sum_i dy[i][o]
-__global__ void k_linear_bwd_w(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x, int64_t n,
-                               int K, int N, int relu, float* __restrict__ gW, float* __restrict__ gb) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N * (K + 1)) return;
-  const int o = e / (K + 1), k = e % (K + 1);
-  float acc = 0.f;
-  for (int64_t i = 0; i < n; ++i) {
-    float d = dy[i * N + o];
-    if (relu && y[i * N + o] <= 0.f) d = 0.f;
-    acc = fmaf(d, k < K ? x[i * K + k] : 1.f, acc);
+// gW[o][k] += sum_i dy'[i][o] * x[i][k],  gb[o] += sum_i dy'[i][o]   (dy' = dy masked by the ReLU of the layer's output).
+// One CTA per chunk of LBW_TS samples (staged in shared memory), threads own 4(o) x 4(k) blocks, atomicAdd at the end.
+constexpr int LBW_TS = 64;
+__global__ void __launch_bounds__(256) k_linear_bwd_w(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                                                      int64_t n, int K, int N, int relu, float* __restrict__ gW, float* __restrict__ gb) {
+  extern __shared__ __align__(16) float lsm[];
+  const int Np = (N + 3) & ~3, Kp = (K + 1 + 3) & ~3;  // column K of x is the constant 1 (bias gradient)
+  float* sd = lsm;                 // [TS][Np]
+  float* sx = sd + LBW_TS * Np;    // [TS][Kp]
+  const int tid = threadIdx.x;
+  const int64_t i0 = int64_t(blockIdx.x) * LBW_TS;
+  for (int e = tid; e < LBW_TS * Np; e += 256) {
+    const int i = e / Np, o = e - i * Np;
+    float d = 0.f;
+    if (o < N && i0 + i < n) {
+      d = dy[(i0 + i) * N + o];
+      if (relu && y[(i0 + i) * N + o] <= 0.f) d = 0.f;
+    }
+    sd[e] = d;
   }
-  if (k < K) gW[o * K + k] += acc;
-  else gb[o] += acc;
+  for (int e = tid; e < LBW_TS * Kp; e += 256) {
+    const int i = e / Kp, k = e - i * Kp;
+    float v = 0.f;
+    if (i0 + i < n) v = k < K ? x[(i0 + i) * K + k] : (k == K ? 1.f : 0.f);
+    sx[e] = v;
+  }
+  __syncthreads();
+  const int nbo = Np / 4, nbk = Kp / 4;
+  for (int blk = tid; blk < nbo * nbk; blk += 256) {
+    const int o4 = (blk / nbk) * 4, k4 = (blk % nbk) * 4;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < LBW_TS; ++i) {
+      const float4 d4 = *reinterpret_cast<const float4*>(sd + i * Np + o4);
+      const float4 x4 = *reinterpret_cast<const float4*>(sx + i * Kp + k4);
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a * 4 + c] = fmaf(dv[a], xv[c], acc[a * 4 + c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int o = o4 + a, k = k4 + c;
+        if (o < N && k < K) atomicAdd(gW + o * K + k, acc[a * 4 + c]);
+        else if (o < N && k == K) atomicAdd(gb + o, acc[a * 4 + c]);
+      }
+  }
+}
+static inline unsigned lbw_grid(int64_t n) { return (unsigned)((n + LBW_TS - 1) / LBW_TS); }
+static inline size_t lbw_smem(int K, int N) {
+  const size_t bytes = sizeof(float) * LBW_TS * size_t(((N + 3) & ~3) + ((K + 1 + 3) & ~3));
+  static size_t conf = 48 * 1024;
+  if (bytes > conf) {
+    cudaFuncSetAttribute(k_linear_bwd_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    conf = bytes;
+  }
+  return bytes;
 }
 __global__ void k_linear_bwd_x(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ W, int64_t n,
                                int K, int N, int relu, float* __restrict__ dx) {
@@ -927,7 +992,7 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   const ConvDesc& d = T->h_conv[li];
   float* bn = T->d_bn + int64_t(li) * 4 * C;
   const int64_t rows = n * L;
-  const size_t smem = sizeof(float) * (size_t(64 + d.ks - 1) * (C + 1) + size_t(64) * (C + 1)) + sizeof(int) * 64;
+  const size_t smem = sizeof(float) * (size_t(64 + d.ks - 1) * (C + 4) + size_t(64) * (C + 4)) + sizeof(int) * 64;
   int wg = (int)cdiv(rows, 64);
   if (wg > 296) wg = 296;
 #define WG(CC)                                                                                                  \
@@ -969,15 +1034,15 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
   // ---- local branch
   {
     const int64_t W3 = off_of(m, "local_fc.0.weight"), W2 = off_of(m, "lin_layers.1.weight"), W1 = off_of(m, "lin_layers.0.weight");
-    LAUNCH(k_linear_bwd_w, gridn(NC * (H2 + 1)), 256, 0, st, dl, nullptr, T->d2, n, H2, NC, 0, G + W3, G + off_of(m, "local_fc.0.bias"));
+    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(H2, NC), st, dl, nullptr, T->d2, n, H2, NC, 0, G + W3, G + off_of(m, "local_fc.0.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * H2), 256, 0, st, dl, nullptr, P + W3, n, H2, NC, 0, ga);
     LAUNCH(k_bn1d_bwd, H2, 256, 0, st, ga, T->r2, n, H2, P, off_of(m, "bn_layers.1.weight"), T->mu2, T->is2, T->p_local, T->seed, T->step, 2u, gb,
            G, off_of(m, "bn_layers.1.weight"), off_of(m, "bn_layers.1.bias"));
-    LAUNCH(k_linear_bwd_w, gridn(H2 * (H1 + 1)), 256, 0, st, gb, T->r2, T->d1, n, H1, H2, 1, G + W2, G + off_of(m, "lin_layers.1.bias"));
+    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(H1, H2), st, gb, T->r2, T->d1, n, H1, H2, 1, G + W2, G + off_of(m, "lin_layers.1.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * H1), 256, 0, st, gb, T->r2, P + W2, n, H1, H2, 1, ga);
     LAUNCH(k_bn1d_bwd, H1, 256, 0, st, ga, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), T->mu1, T->is1, T->p_local, T->seed, T->step, 1u, gb,
            G, off_of(m, "bn_layers.0.weight"), off_of(m, "bn_layers.0.bias"));
-    LAUNCH(k_linear_bwd_w, gridn(H1 * (K1 + 1)), 256, 0, st, gb, T->r1, T->e0, n, K1, H1, 1, G + W1, G + off_of(m, "lin_layers.0.bias"));
+    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(K1, H1), st, gb, T->r1, T->e0, n, K1, H1, 1, G + W1, G + off_of(m, "lin_layers.0.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * K1), 256, 0, st, gb, T->r1, P + W1, n, K1, H1, 1, ga);
     LAUNCH(k_emb_bwd, gridn(n * K1), 256, 0, st, ga, T->cat, n, m->n_cat, T->p_emb, T->seed, T->step, G + off_of(m, "emb_layer.weight"));
   }
@@ -989,7 +1054,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     const std::string fc = br ? "distal_fc2" : "distal_fc1";
     const float* dlogit = br ? dg : dm;
     float *G0 = T->gbuf[0], *G1 = T->gbuf[1], *G2 = T->gbuf[2], *G3 = T->gbuf[3], *D = T->gbuf[4];
-    LAUNCH(k_linear_bwd_w, gridn(NC * (C + 1)), 256, 0, st, dlogit, nullptr, b.gmn, n, C, NC, 0, G + off_of(m, fc + ".2.weight"),
+    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(C, NC), st, dlogit, nullptr, b.gmn, n, C, NC, 0, G + off_of(m, fc + ".2.weight"),
            G + off_of(m, fc + ".2.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * C), 256, 0, st, dlogit, nullptr, P + off_of(m, fc + ".2.weight"), n, C, NC, 0, ga);
     LAUNCH(k_bn1d_bwd, C, 256, 0, st, ga, b.gm, n, C, P, off_of(m, fc + ".0.weight"), b.mu, b.is, T->p_fc, T->seed, T->step, 10u + br, gb, G,
