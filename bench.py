@@ -148,6 +148,46 @@ def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5):
                       "gradient all-reduce over NCCL when n_gpus > 1", "loss_sum_finite": bool(np.isfinite(loss))}
 
 
+# ------------------------------------------------------------------------------------------ indel leg
+def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2):
+    """BASELINE configs[3] (predict half): MuRaL-indel UNet_Small with the shipped Homo_sapiens/INDEL/insertion weights
+    (tests/golden/indel_hs_ins.npz), one site every 50 bp on the '+' strand of this rank's interval, expanded radius as
+    in the checkpoint's config.  fp32 kernels (the indel network has no tcgen05 path yet)."""
+    import torch
+    from mural_b200 import SiteBatch, model_choice, pack_meta
+    z = np.load(os.path.join(ROOT, "tests", "golden", "indel_hs_ins.npz"))
+    state = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    cfg = {"CNN_out_channels": state["uplblocks.0.0.weight"].shape[0], "CNN_kernel_size": state["uplblocks.0.0.weight"].shape[2],
+           "down_list": [int(v) for v in z["down"]], "use_reverse": bool(z["use_reverse"]), "n_class": state["out_fc.2.weight"].shape[0]}
+    m = model_choice(0, cfg, {"n_class": cfg["n_class"]}, "indel")
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
+    m.to("cuda").eval()
+    Rd = int(z["distal_radius"])
+    n = batch * (steps + warmup)
+    lo = 20_000 + (CHROM_LEN - 40_000) * rank // max(world, 1) // 50 * 50
+    pos = (lo + 50 * np.arange(n)) % (CHROM_LEN - 40_000) + 20_000
+    d_pos = torch.from_numpy(pos.astype(np.int32)).cuda()
+    d_meta = torch.from_numpy(pack_meta(np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64))).cuda()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(steps + warmup):
+            if i == warmup:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                ev0.record()
+            out = m.forward(SiteBatch(d_pos[i * batch:(i + 1) * batch], d_meta[i * batch:(i + 1) * batch], genome), distal_radius=Rd)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"metric": "sites/sec (MuRaL-indel predict)", "value": world * batch * steps / (ms * 1e-3), "unit": "sites/s", "batch_per_gpu": batch,
+            "ms_per_step": ms / steps, "dtype": "f32", "finite": bool(torch.isfinite(out).all().item()),
+            "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), sites every 50 bp" % (Rd, 2 * Rd)}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
     """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
@@ -220,6 +260,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
+    ap.add_argument("--no-indel", action="store_true", help="skip the MuRaL-indel predict leg (BASELINE configs[3])")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,6 +381,13 @@ def main():
         except Exception as e:  # the predict line must survive a failure here
             train = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    indel = None
+    if not a.no_indel:
+        try:
+            indel = indel_leg(genome, world, rank, dist)
+        except Exception as e:
+            indel = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- roofline of the dominant kernel: library-side CUDA-event profile over an identical pass
     roof = None
     if rank == 0:
@@ -351,7 +399,7 @@ def main():
                            "per-step activation workspace > L2", wall_s_timed_region=t_wall),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof, "train": train}
+            "roofline": roof, "train": train, "indel": indel}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample

@@ -17,7 +17,8 @@
 // site, so the first ResBlock pair (4 convs at stride-ps1 spacing) of every row whose receptive field stays clear of the
 // window ends is a function of the genomic position alone: Y1[g] = RB(W[g-4ps], ..., W[g+4ps]).  We evaluate it ONCE
 // per genomic position and strand on 2*ps1 phase-major pseudo-sites (k_lattice_in feeds the ordinary stage kernel),
-// and per site only the LAT_EO rows at each window end, as one 18-row edge pseudo-site (k_stem_gather in edge mode).
+// and per site only the LAT_EO rows at each window end, as one 18-row edge pseudo-site whose rows 1..16 are table rows
+// read in place by the stage kernel and whose rows 0 and 17 are written by k_stem_gather in edge mode.
 // The stage-2 loader (snv_tc.cu) max-pools across lattice rows and edge rows.  Every row goes through the same
 // tcgen05 arithmetic as in the per-site path, so the result is bit-identical.
 #include <cuda_bf16.h>
@@ -262,7 +263,8 @@ struct GatherBranch {
   const float* bias;
   int L0, off0, L1, pk, ps, pp;
   int w[3];
-  int edge;            // 1: only the LAT_EI rows at each window end, written as one LAT_EL-row pseudo-site per site
+  int edge;            // 1: only the first and last row of a site's edge pseudo-site (the stage kernel reads the 16 rows in
+                       //    between straight from the tables), written as row 2*site + (last ? 1 : 0)
 };
 
 // one warp-quarter (8 lanes x 16 B... here: C/8 lanes, 16 B each) copies one table row into one output row
@@ -278,13 +280,20 @@ __global__ void __launch_bounds__(256) k_stem_gather(GenomeView G, const ChunkIn
   for (int br = 0; br < 2; ++br) {
     const GatherBranch& B = br ? b1 : b0;
     const int rows_per_site = B.edge ? LAT_EL : B.L1;
-    const int64_t total = ns * rows_per_site * PL;
-    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    // two passes so that the lanes of a warp do the same kind of work: pass 0 = the rows strictly inside the (pseudo-)site,
+    // plain 64-byte row copies; pass 1 = its first and last row, which carry the exactly evaluated window-edge positions
+    // (symbol lookups + 3 table rows per channel, ~10x the work of a copy)
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+    const int rows_pass = pass ? (rows_per_site > 1 ? 2 : 1) : ((rows_per_site > 2 && !B.edge) ? rows_per_site - 2 : 0);
+    const uint32_t total = uint32_t(ns) * uint32_t(rows_pass) * PL;  // < 2^31 (host-checked): 32-bit index arithmetic only
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
       const int q = int(e % PL);
-      const int64_t sj = e / PL;
-      const int jj = int(sj % rows_per_site);
+      const uint32_t sj = e / PL;
+      const uint32_t site = sj / uint32_t(rows_pass);
+      const int jr = int(sj - site * uint32_t(rows_pass));
+      const int jj = pass ? (jr ? rows_per_site - 1 : 0) : jr + 1;
       const int j = (B.edge && jj >= LAT_EI) ? B.L1 - LAT_EL + jj : jj;
-      const int64_t site = sj / rows_per_site;
       const int s = pos[site], strand = meta[site] & 1;
       int lo = j * B.ps - B.pp, hi = lo + B.pk;
       lo = lo < 0 ? 0 : lo;
@@ -331,7 +340,9 @@ __global__ void __launch_bounds__(256) k_stem_gather(GenomeView G, const ChunkIn
           w[c] = *reinterpret_cast<uint32_t*>(&m2);
         }
       }
-      *(reinterpret_cast<uint4*>(B.out) + int64_t(q) * B.rows_alloc + 1 + site * int64_t(rows_per_site + 1) + jj) = v;
+      const int64_t orow = B.edge ? 2 * int64_t(site) + (jj ? 1 : 0) : 1 + site * int64_t(rows_per_site + 1) + jj;
+      *(reinterpret_cast<uint4*>(B.out) + int64_t(q) * B.rows_alloc + orow) = v;
+    }
     }
   }
 }
@@ -418,6 +429,7 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
     for (int br = 0; br < 2; ++br) li[br] = LatIn{reinterpret_cast<uint4*>(lattice[br].lat_in), lattice[br].lat_ra, m->br[br].pool[0][1]};
     LAUNCH(k_lattice_in<32>, 148 * 4, 256, 0, st, info, li[0], li[1], cap, tables);
   }
+  MURAL_CHECK(ns * int64_t(m->br[1].L1 > LAT_EL ? m->br[1].L1 : LAT_EL) * 4 < (int64_t(1) << 31), "chunk too large for the stem gather's 32-bit indices");
   LAUNCH(k_stem_gather<32>, 148 * 8, 256, 0, st, *G, info, d_pos, d_meta, ns, m->cfg.distal_radius, gb[0], gb[1], cap, tables);
   *d_flag = &info->dense;
   if (d_info) *d_info = info;

@@ -83,6 +83,12 @@ struct StageArgs {
   const uint4* epool;     // pooled rows of the bins that touch edge rows (k_edge_pool): planes [4][epool_ra], row = site*(nlo+nhi) + b
   int64_t epool_ra;
   int nlo, nhi;           // such bins at the low / high end of a site
+  // EDGE loader (RB4 on the edge pseudo-sites): rows 1..16 of a pseudo-site are full-bin table rows read in place
+  // (snv_dense_stem.cu tables, width-0 table of this branch per strand), rows 0 and 17 come from the special-row buffer
+  const uint4* tab[2];    // [strand]: rows of 4 uint4 (32 bf16) per genomic position
+  const uint4* special;   // planes [4][special_ra], row = 2*site + (last ? 1 : 0)
+  int64_t special_ra;
+  int L1real;             // stage-1 length of a real site (pseudo-site row jj >= LAT_EI is real row L1real - LAT_EL + jj)
   const int32_t* pos;
   const int32_t* meta;
   int ps1, pp1, pk1, off0, R, br;
@@ -169,8 +175,10 @@ __device__ __forceinline__ int lattice_base(const ChunkInfo* info, int br, int s
 // TMEM region R (32 columns) is pre-loaded with x0 (tcgen05.st) and the second conv of each ResBlock
 // ACCUMULATES onto it, the first conv of each ResBlock goes to a scratch region T.  The epilogue of a layer is
 // therefore only  tcgen05.ld -> bf16 -> ReLU -> st.shared  (the next layer's A operand).
-template <int MODE, bool LAT>
+template <int MODE, int FM>  // FM: 0 plain rows, 1 lattice (RB4: device-side geometry; C_RB4: pre-pooled single rows), 2 edge gather (RB4)
 __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
+  constexpr bool LAT = FM == 1;
+  constexpr bool EDGE = (MODE == RB4) && FM == 2;
   if (a.info && a.info->dense != a.want) return;  // uniform over the grid; nothing allocated yet
   // RB4 with LAT: stage-1 lattice launch, geometry known only on the device
   constexpr bool DYN = (MODE == RB4) && LAT;
@@ -286,7 +294,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
       p = r - site * Lp1 - 1;
     }
     const bool live = p >= 0;
-    if (MODE == RB4) {
+    if (EDGE) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = make_uint4(0, 0, 0, 0);
+      if (live) {
+        if (p == 0 || p == LAT_EL - 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = __ldg(a.special + q * a.special_ra + 2 * int64_t(site) + (p ? 1 : 0));
+        } else {
+          const int s = __ldg(a.pos + site), strand = __ldg(a.meta + site) & 1;
+          const int j = p < LAT_EI ? p : a.L1real - LAT_EL + p;
+          const int lo = j * a.ps1 - a.pp1, g_lo = int(a.info->g_lo);
+          const int idx = strand ? s + a.R - a.off0 - lo - a.pk1 + 1 - g_lo : s - a.R + a.off0 + lo - g_lo;
+          const uint4* row = a.tab[strand] + int64_t(idx) * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = __ldg(row + q);
+        }
+      }
+    } else if (MODE == RB4) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = live ? __ldg(a.in + q * a.in_rows_alloc + r) : make_uint4(0, 0, 0, 0);
     } else if (MODE != RB4) {
@@ -332,9 +357,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   };
 
   // first A operand / constant operand / residual region of slot k from the fetched row, then layer 0
-  auto begin_tile = [&](int k, int p, const uint4 (&x)[4]) {
+  auto begin_tile = [&](int k, int r, int p, const uint4 (&x)[4]) {
     unsigned char* sA = sA0 + k * SLOT_BYTES;
     const bool live = p >= 0;
+    if (EDGE && live && lt >= NL && lt < TILE - NL) {  // the gathered input row is needed again for the outer skip: parked in
+      // the output row like C_RB4's jump — only the rows this tile owns, a halo row belongs to (and is written by) a neighbour
+      uint4* out4 = reinterpret_cast<uint4*>(a.out);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r] = x[q];
+    }
     if (MODE == RB4) {
       uint32_t f[32];  // residual region R <- x0 (fp32)
 #pragma unroll
@@ -385,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
       r[k] = rn[k];
       p[k] = pn[k];
       TT(T_OTHER);
-      if (act[k]) begin_tile(k, p[k], xn[k]);
+      if (act[k]) begin_tile(k, r[k], p[k], xn[k]);
     }
 #pragma unroll
     for (int k = 0; k < NINFL; ++k)
@@ -449,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
             uint4 xr[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              xr[q] = (MODE == RB4) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
+              xr[q] = (MODE == RB4 && !EDGE) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
@@ -638,13 +669,13 @@ static int m_sm_count() {
   return n;
 }
 
-template <int MODE, bool LAT = false>
+template <int MODE, int FM = 0>
 static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = "") {
   constexpr int NL = n_layers(MODE);
   const size_t smem = size_t(NL) * W_LAYER + size_t(NSLOT) * SLOT_BYTES + NSLOT * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    CUDA_TRY((cudaFuncSetAttribute(k_stage_tc<MODE, LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    CUDA_TRY((cudaFuncSetAttribute(k_stage_tc<MODE, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     configured = true;
   }
   int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
@@ -654,11 +685,12 @@ static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = 
   static std::map<std::string, std::string> names;
   const std::string key = std::string(MODE == RB4 ? "k_stage_tc<RB4>" : (MODE == C_RB4 ? "k_stage_tc<C_RB4>" : "k_stage_tc<SINGLE>")) + role;
   const char* nm = names.emplace(key, key).first->second.c_str();
-  if (MODE == RB4 && LAT) LAUNCH_N(nm, (k_stage_tc<RB4, true>), grid, THREADS, smem, st, a2);
-  else if (MODE == RB4) LAUNCH_N(nm, (k_stage_tc<RB4, false>), grid, THREADS, smem, st, a2);
-  else if (MODE == C_RB4 && LAT) LAUNCH_N(nm, (k_stage_tc<C_RB4, true>), grid, THREADS, smem, st, a2);
-  else if (MODE == C_RB4) LAUNCH_N(nm, (k_stage_tc<C_RB4, false>), grid, THREADS, smem, st, a2);
-  else LAUNCH_N(nm, (k_stage_tc<SINGLE, false>), grid, THREADS, smem, st, a2);
+  if (MODE == RB4 && FM == 2) LAUNCH_N(nm, (k_stage_tc<RB4, 2>), grid, THREADS, smem, st, a2);
+  else if (MODE == RB4 && FM == 1) LAUNCH_N(nm, (k_stage_tc<RB4, 1>), grid, THREADS, smem, st, a2);
+  else if (MODE == RB4) LAUNCH_N(nm, (k_stage_tc<RB4, 0>), grid, THREADS, smem, st, a2);
+  else if (MODE == C_RB4 && FM == 1) LAUNCH_N(nm, (k_stage_tc<C_RB4, 1>), grid, THREADS, smem, st, a2);
+  else if (MODE == C_RB4) LAUNCH_N(nm, (k_stage_tc<C_RB4, 0>), grid, THREADS, smem, st, a2);
+  else LAUNCH_N(nm, (k_stage_tc<SINGLE, 0>), grid, THREADS, smem, st, a2);
   return 0;
 }
 
@@ -891,15 +923,22 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         l.in = reinterpret_cast<const uint4*>(lb[br].lat_in); l.out = lb[br].lat_out;
         l.in_rows_alloc = l.out_rows_alloc = lb[br].lat_ra;
         l.n_tiles = (int)cdiv(lb[br].lat_ra, TILE - 2 * 4);
-        if (int rc = (launch_stage<RB4, true>(l, st, "/lattice"))) return rc;
+        if (int rc = (launch_stage<RB4, 1>(l, st, "/lattice"))) return rc;
         // ... and on the per-site edge pseudo-sites
         StageArgs e = a;
         e.want = 1;
-        e.in = reinterpret_cast<const uint4*>(lb[br].edge_in); e.out = lb[br].edge_out;
+        e.in = nullptr; e.out = lb[br].edge_out;
         e.in_rows_alloc = e.out_rows_alloc = lb[br].edge_ra;
         e.rows = rows_of(ns, LAT_EL); e.L = e.Lin = LAT_EL;
         e.n_tiles = (int)cdiv(e.rows, TILE - 2 * 4);
-        if (int rc = launch_stage<RB4>(e, st, "/edge")) return rc;
+        const uint4* tab0 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dense_scratch) + 256);
+        for (int sd = 0; sd < 2; ++sd) e.tab[sd] = tab0 + int64_t((sd * 2 + br) * 3) * snv_dense_cap(chunk) * 4;
+        e.special = reinterpret_cast<const uint4*>(lb[br].edge_in); e.special_ra = lb[br].edge_ra;
+        e.L1real = B.L1;
+        e.pos = d_pos + s0; e.meta = d_meta + s0;
+        e.ps1 = B.pool[0][1]; e.pp1 = B.pool[0][2]; e.pk1 = B.pool[0][0];
+        e.off0 = br ? 0 : m->L / 2 - 100; e.R = m->cfg.distal_radius; e.br = br;
+        if (int rc = (launch_stage<RB4, 2>(e, st, "/edge"))) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
       // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
@@ -924,7 +963,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         EdgePool ep{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
                     br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
         LAUNCH(k_edge_pool, 148 * 4, 256, 0, st, info, ep);
-        if (int rc = (launch_stage<C_RB4, true>(l, st, "/lattice"))) return rc;
+        if (int rc = (launch_stage<C_RB4, 1>(l, st, "/lattice"))) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
       if (use_tail) continue;  // stage 3 and the heads run in the warp-level tail kernel below
