@@ -431,13 +431,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         ++tlayers;
 #endif
         TT(T_OTHER);
+        const bool live = p[k] >= 0;
+        const bool valid = live && lt >= NL && lt < TILE - NL;
+        // outer-skip operand of the last layer (x0 re-read / parked jump): requested before the wait on the MMAs so that
+        // its L2 round trip is hidden behind them
+        uint4 xr[4];
+        if (MODE != SINGLE && l == NL - 1 && valid) {
+          const uint4* out4 = reinterpret_cast<const uint4*>(a.out);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            xr[q] = (MODE == RB4 && !EDGE) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
+        }
         mbar_wait(bar0 + 8 * k, phase[k]);
         phase[k] ^= 1;
         __syncwarp();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const bool rtype = (MODE == RB4) ? (l & 1) : (MODE == C_RB4 ? !(l & 1) : true);
-        const bool live = p[k] >= 0;
-        const bool valid = live && lt >= NL && lt < TILE - NL;
         uint32_t acc[32];
         TT(T_WAIT);
         TMEM_LD32(acc, tmem_base + lane_off + (g * NINFL + k) * 64 + (rtype ? 0 : 32));
@@ -477,10 +486,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
                               fmaxf(__uint_as_float(acc[4 * q + 2]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 3]), 0.f));
           } else {  // outer skip: + x0 (RB4, re-read from the input) or + jump (C_RB4, parked in the output row)
             uint4* out4 = reinterpret_cast<uint4*>(a.out);
-            uint4 xr[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              xr[q] = (MODE == RB4 && !EDGE) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;

@@ -24,14 +24,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // NI issuing warps (warps 4..4+NI-1, lane 0); each issues ITER x 8 MMAs (N, K=16), accumulate chain per 8; TS: A from TMEM
-template <int N, int NI, bool TS, bool DEP>
+template <int N, int NI, bool TS, bool DEP, bool CE = false>
 __global__ void __launch_bounds__(256, 1) k_issue(long long* out, int iters) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar[4];
+  __shared__ uint64_t dummy[4];
   __shared__ uint32_t tslot;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256, 1) k_issue(long long* out, int iters) {
           if (TS) mma_ts<N>(d, tb + 480 + (i & 1) * 8, dB, (DEP && i > 0) ? 1u : 0u);
           else mma_ss<N>(d, dA + (i % 3), dB, (DEP && i > 0) ? 1u : 0u);
         }
+        if (CE) commit(smem_u32(&dummy[w]));  // one commit per batch of 8 MMAs, as the stage kernel does per layer
       }
       commit(smem_u32(&bar[w]));
     }
@@ -71,13 +74,13 @@ __global__ void __launch_bounds__(256, 1) k_issue(long long* out, int iters) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
-template <int N, int NI, bool TS, bool DEP>
+template <int N, int NI, bool TS, bool DEP, bool CE = false>
 void run(long long* d, const char* name) {
-  CK(cudaFuncSetAttribute(k_issue<N, NI, TS, DEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+  CK(cudaFuncSetAttribute(k_issue<N, NI, TS, DEP, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
   long long c[2];
   for (int r = 0; r < 2; ++r) {
     const int iters = r ? 128 : 64;
-    k_issue<N, NI, TS, DEP><<<1, 256, 98304>>>(d, iters);
+    k_issue<N, NI, TS, DEP, CE><<<1, 256, 98304>>>(d, iters);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(&c[r], d, 8, cudaMemcpyDeviceToHost));
   }
@@ -89,6 +92,9 @@ void run(long long* d, const char* name) {
 int main() {
   setvbuf(stdout, NULL, _IONBF, 0);
   long long* d; CK(cudaMalloc(&d, 64));
+  run<32, 4, false, true, true>(d, "ss dependent + commit per 8");
+  run<32, 2, false, true, true>(d, "ss dependent + commit per 8");
+  run<32, 1, false, true, true>(d, "ss dependent + commit per 8");
   run<32, 1, false, true>(d, "ss dependent");
   run<32, 1, false, false>(d, "ss independent");
   run<32, 2, false, true>(d, "ss dependent");
