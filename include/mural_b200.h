@@ -208,6 +208,15 @@ int mural_optimizer_step(int32_t kind, float* d_params, const float* d_grads, fl
 int mural_calibrate(const float* d_logp, int64_t n, int32_t n_class, const double* h_weights,
                     int32_t poisson, double* d_prob, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Prediction TSV (run_predict.py:228-239): pred_df.to_csv(pred_file, sep='\t', float_format='%.4g', index=False) with
+ * columns chrom, start, end, strand, mut_type, prob0..prob{k-1}.  Host arrays, rows already in output order
+ * (sorted by chrom name, start); strand is one char per row; formatted by n_threads host threads.
+ * ---------------------------------------------------------------------------------------------- */
+int mural_write_tsv(const char* path, int64_t n, int32_t n_class, const char* const* chrom_names, const int32_t* chrom_idx,
+                    const int64_t* start, const int64_t* end, const char* strand, const double* mut_type, const double* prob,
+                    int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

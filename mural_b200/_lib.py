@@ -75,6 +75,7 @@ PROTOTYPES = {
     "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "mural_write_tsv": (C.c_int, [C.c_char_p, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
 }
 
 _lib = None

@@ -46,10 +46,10 @@ def load_config(path):
         return pickle.load(f)
 
 
-def build_model_from_files(model_path, config, device, n_cont=0):
-    common = {"emb_dims": config["emb_dims"], "n_cont": n_cont, "n_class": config["n_class"], "distal_order": 1,
+def build_model_from_files(model_path, config, device, n_cont=0, model_type="snv"):
+    common = {"emb_dims": config.get("emb_dims"), "n_cont": n_cont, "n_class": config["n_class"], "distal_order": 1,
               "in_channels": 4 + n_cont}
-    model = model_choice(config["model_no"], config, common, "snv")
+    model = model_choice(config["model_no"], config, common, model_type)
     state = torch.load(model_path, map_location="cpu")
     model.load_state_dict(state)
     return model.to(device).eval()
@@ -63,7 +63,11 @@ def predict_sites(model, dataset, lo, hi, batch_sites=1 << 20):
         for a in range(lo, hi, batch_sites):
             b = min(hi, a + batch_sites)
             sb = SiteBatch(torch.from_numpy(dataset.pos[a:b]).to(dev), torch.from_numpy(dataset.meta[a:b]).to(dev), dataset.genome)
-            outs.append(model.forward(None, sb))
+            if dataset.model_type == "indel":        # UNet_Small.forward(distal) (model_indel.py:151); batches bound the U-Net workspace
+                outs.extend(model.forward(SiteBatch(sb.pos[c:c + 4096], sb.meta[c:c + 4096], sb.genome), distal_radius=dataset.distal_radius)
+                            for c in range(0, b - a, 4096))
+            else:
+                outs.append(model.forward(None, sb))
     return torch.cat(outs) if outs else torch.empty((0, model.n_class), device=dev)
 
 
@@ -79,8 +83,28 @@ def format_predictions(chrom, start, end, strand, mut_type, prob):
     return df
 
 
+def write_tsv(path, chrom_names, start, end, strand, mut_type, prob, n_threads=None):
+    """`pred_df.sort_values(['chrom','start']).to_csv(path, sep='\\t', float_format='%.4g', index=False)` (run_predict.py:237-239)
+    without pandas: stable sort by (chromosome name, start) here, formatting + writing in the C library (threaded)."""
+    import ctypes as C
+    import os
+    from . import _lib
+    names = np.asarray(chrom_names, dtype=object)
+    uniq, inv = np.unique(names.astype(str), return_inverse=True)          # lexicographic, like pandas on strings
+    order = np.lexsort((np.asarray(start), inv))                            # stable: ties keep emission order
+    idx = np.ascontiguousarray(inv[order].astype(np.int32))
+    st = np.ascontiguousarray(np.asarray(start, dtype=np.int64)[order])
+    en = np.ascontiguousarray(np.asarray(end, dtype=np.int64)[order])
+    sd = np.ascontiguousarray(np.asarray([ord(c[0]) for c in ("+", "-")], dtype=np.uint8)[(np.asarray(strand) != "+").astype(np.int64)][order])
+    mt = np.ascontiguousarray(np.asarray(mut_type, dtype=np.float64)[order])
+    pr = np.ascontiguousarray(np.asarray(prob, dtype=np.float64)[order])
+    arr = (C.c_char_p * len(uniq))(*[u.encode() for u in uniq])
+    _lib.check(_lib.lib().mural_write_tsv(str(path).encode(), len(st), pr.shape[1], C.cast(arr, C.c_void_p), _lib.ptr(idx), _lib.ptr(st),
+                                          _lib.ptr(en), _lib.ptr(sd), _lib.ptr(mt), _lib.ptr(pr), n_threads or min(32, os.cpu_count() or 1)))
+
+
 def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator_path="", pred_file=None, segment_center=None,
-                poisson_calib=False, compute_mode="bf16", genome=None):
+                poisson_calib=False, compute_mode="bf16", genome=None, model_type="snv", return_frame=True):
     """Returns the prediction DataFrame on rank 0 (None elsewhere); writes `pred_file` when given."""
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     rank = torch.distributed.get_rank() if dist_on else 0
@@ -93,9 +117,12 @@ def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator
     if genome is None:
         genome = PackedGenome.from_fasta(ref_genome, dev)
     sites = SiteTable.from_bed(test_data)
-    ds = PackedSiteDataset(sites, genome, segment_center, config["local_radius"], config["local_order"], config["distal_radius"])
-    model = build_model_from_files(model_path, config, dev)
-    model.compute_mode = compute_mode
+    ds = PackedSiteDataset(sites, genome, segment_center, config["local_radius"], config["local_order"], config["distal_radius"],
+                           model_type=model_type)
+    model = build_model_from_files(model_path, config, dev, model_type=model_type)
+    if model_type == "snv":
+        model.compute_mode = compute_mode
+    poisson_calib = bool(poisson_calib) or model_type == "indel"          # run_predict.py:224
     n = len(ds.pos)
     lo, hi = shard_bounds(n, world, rank)
     logp = predict_sites(model, ds, lo, hi)
@@ -105,9 +132,9 @@ def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator
     if rank != 0:
         return None
     names, start, end, strand = ds.position_info()
-    df = format_predictions(names, start, end, strand, ds.label, prob.numpy())
     if pred_file:
-        df.to_csv(pred_file, sep="\t", float_format="%.4g", index=False)   # run_predict.py:239
+        write_tsv(pred_file, names, start, end, strand, ds.label, prob.numpy())   # run_predict.py:237-239
+    df = format_predictions(names, start, end, strand, ds.label, prob.numpy()) if return_frame else None
     print("predicted %d sites in %.2f s (%d rank(s))" % (n, time.time() - t0, world))
     sys.stdout.flush()
     return df
@@ -115,10 +142,10 @@ def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator
 
 def run_predict_pipline(args, model_type="snv"):
     """Same entry point / argument names as the reference CLI dispatcher expects (run_predict.py:34)."""
-    if model_type != "snv":
-        raise NotImplementedError("mural_b200.predict: indel prediction is not wired into the pipeline yet")
+    if model_type not in ("snv", "indel"):
+        raise ValueError("model_type must be 'snv' or 'indel'")
     if getattr(args, "cpu_only", False):
         raise RuntimeError("mural_b200 has no CPU path; drop --cpu_only")
     return run_predict(args.test_data, args.ref_genome, args.model_path, args.model_config_path,
                        getattr(args, "calibrator_path", ""), args.pred_file, getattr(args, "segment_center", None),
-                       getattr(args, "poisson_calib", False))
+                       getattr(args, "poisson_calib", False), model_type=model_type)

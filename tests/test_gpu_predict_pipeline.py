@@ -95,3 +95,56 @@ def test_tsv_matches_oracle_pipeline(tmp_path, kat, poisson):
         fx, fy = x.split("\t"), y.split("\t")
         assert fx[:5] == fy[:5]
         assert np.abs(np.array(fx[5:], float) - np.array(fy[5:], float)).max() <= 1e-3
+
+
+def test_indel_tsv_matches_oracle_pipeline(tmp_path, kat):
+    """MuRaL-indel through the same pipeline (run_predict.py with model_type='indel'): UNet_Small outputs -> softmax ->
+    Poisson calibration (always on for indel, run_predict.py:224) -> sorted %.4g TSV."""
+    import os
+    from conftest import GOLD
+    from mural_b200 import model_choice
+    from mural_b200.predict import run_predict
+    z = np.load(os.path.join(GOLD, "indel_ex_indel9.npz"))
+    _, genome = kat
+    names = list(genome)
+    state = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    cfg = {"CNN_out_channels": int(state["uplblocks.0.0.weight"].shape[0]), "CNN_kernel_size": int(state["uplblocks.0.0.weight"].shape[2]),
+           "down_list": [int(v) for v in z["down"]], "use_reverse": bool(z["use_reverse"]), "n_class": int(state["out_fc.2.weight"].shape[0]),
+           "model_no": 0, "local_radius": 5, "local_order": 3, "distal_radius": int(z["distal_radius"]), "segment_center": 5000}
+    m = model_choice(0, cfg, {"n_class": cfg["n_class"]}, "indel")
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
+    torch.save(m.state_dict(), tmp_path / "model")
+    pickle.dump(cfg, open(tmp_path / "model.config.pkl", "wb"))
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as f:
+        for n, s in genome.items():
+            f.write(">%s\n%s\n" % (n, s))
+    order = np.lexsort((z["start"], z["chrom"]))
+    bed = tmp_path / "sites.bed"
+    with open(bed, "w") as f:
+        for i in order:
+            f.write("%s\t%d\t%d\t.\t%d\t%s\n" % (names[z["chrom"][i]], z["start"][i], z["start"][i] + 1, z["start"][i] % 8, "+-"[z["strand"][i]]))
+    out = tmp_path / "pred.tsv"
+    df = run_predict(str(bed), str(fa), str(tmp_path / "model"), str(tmp_path / "model.config.pkl"), "", str(out), model_type="indel")
+    ch, st, sd = z["chrom"][order], z["start"][order], z["strand"][order]
+    perm, _ = E.order_sites(ch, st, sd, 5000)
+    ch, st, sd = ch[perm], st[perm], sd[perm]
+    oh = np.empty((len(st), 4, 2 * cfg["distal_radius"]), np.float32)
+    for c in range(len(names)):
+        msk = ch == c
+        if msk.any():
+            oh[msk] = E.onehot_windows(E.seq_to_symbols(genome[names[c]]), st[msk], sd[msk], cfg["distal_radius"], "indel")
+    with torch.no_grad():
+        y = NT.unet_small_forward(state, oh, cfg["down_list"], cfg["use_reverse"], torch.float32)
+    prob = NT.poisson_calibrate(torch.softmax(y, 1).numpy().astype(np.float64))
+    exp = pd.DataFrame({"chrom": np.array(names, dtype=object)[ch], "start": st, "end": st + 1, "strand": np.where(sd == 0, "+", "-"),
+                        "mut_type": (st % 8).astype(np.float64)})
+    for i in range(cfg["n_class"]):
+        exp["prob%d" % i] = prob[:, i]
+    exp.sort_values(["chrom", "start"], inplace=True); exp.reset_index(drop=True, inplace=True)
+    cols = ["prob%d" % i for i in range(cfg["n_class"])]
+    assert (df[["chrom", "start", "strand"]].values == exp[["chrom", "start", "strand"]].values).all()
+    assert np.abs(df[cols].values - exp[cols].values).max() <= 1e-3
+    got = pd.read_csv(out, sep="\t")
+    assert list(got.columns) == list(exp.columns) and len(got) == len(exp)
+    assert np.abs(got[cols].values - exp[cols].values).max() <= 1e-3 + 5e-4 * np.abs(exp[cols].values).max()

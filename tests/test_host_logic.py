@@ -86,3 +86,25 @@ def test_state_dict_contract(manifest):
     assert sum(p.numel() for p in m.parameters()) == 86904
     with pytest.raises(ValueError):
         model_choice(1, cfg, common, "snv")
+
+
+def test_native_tsv_writer_equals_pandas(tmp_path):
+    """mural_write_tsv (threaded C formatter) == DataFrame.sort_values(['chrom','start']).to_csv(sep='\\t',
+    float_format='%.4g', index=False) byte for byte (run_predict.py:237-239), incl. ties, tiny / huge / exact values."""
+    from mural_b200.predict import format_predictions, write_tsv
+    rng = np.random.default_rng(0)
+    n = 30000
+    names = np.array(["chr10", "chr2", "chrX", "chr1"], dtype=object)[rng.integers(0, 4, n)]
+    start = rng.integers(0, 50_000, n)            # many (chrom, start) ties: the sort must be stable
+    end = start + 1
+    strand = np.where(rng.integers(0, 2, n) == 0, "+", "-")
+    mt = rng.integers(0, 4, n)
+    prob = np.c_[rng.random(n), rng.random(n) * 1e-3, rng.random(n) * 1e-7, 10 ** rng.uniform(-12, 0, n)]
+    prob[:5] = [[1, 0, 0.5, 1e-5], [0.99995, 1e-4, 123456.7, 1e-300], [0.1, 0.25, 1e-5, 9.9995e-5], [0, 0, 0, 0],
+                [1e-4, 99999, 100000, 0.00012345]]
+    a, b = tmp_path / "native.tsv", tmp_path / "pandas.tsv"
+    write_tsv(a, names, start, end, strand, mt, prob, n_threads=3)
+    format_predictions(names, start, end, strand, mt, prob).to_csv(b, sep="\t", float_format="%.4g", index=False)
+    assert a.read_bytes() == b.read_bytes()
+    write_tsv(a, names[:0], start[:0], end[:0], strand[:0], mt[:0], prob[:0])      # empty input: header only
+    assert a.read_text() == "chrom\tstart\tend\tstrand\tmut_type\tprob0\tprob1\tprob2\tprob3\n"
