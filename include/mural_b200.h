@@ -209,6 +209,31 @@ int mural_calibrate(const float* d_logp, int64_t n, int32_t n_class, const doubl
                     int32_t poisson, double* d_prob, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Host ingest (no GPU involved): streaming BED / FASTA readers, plain or gzip.
+ * mural_bed_read   replaces iterating `BedTool(file)` for .chrom/.start/.stop/.score/.strand
+ *                  (MuRaL/data/preprocessing.py:39-106, 752-754): BED6, score = label, strand '+' -> 0 else 1;
+ *                  chromosome indices in order of first appearance.
+ * mural_fasta_read replaces `SeqIO.to_dict(SeqIO.parse(open(ref_genome), 'fasta'))` (preprocessing.py:836): records in
+ *                  file order, id = first word of the header; a duplicate id is an error ("ValueError: Duplicate key").
+ *                  mural_fasta_seq pointers stay valid until mural_fasta_destroy and can be passed to
+ *                  mural_genome_create directly.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_bed mural_bed_t;
+typedef struct mural_fasta mural_fasta_t;
+int mural_bed_read(const char* path, mural_bed_t** out);
+int64_t mural_bed_n(const mural_bed_t* b);
+int32_t mural_bed_n_chrom(const mural_bed_t* b);
+const char* mural_bed_chrom_name(const mural_bed_t* b, int32_t i);
+int mural_bed_columns(const mural_bed_t* b, int32_t* chrom, int64_t* start, int64_t* end, int8_t* strand, int64_t* label);
+void mural_bed_destroy(mural_bed_t* b);
+int mural_fasta_read(const char* path, mural_fasta_t** out);
+int32_t mural_fasta_n(const mural_fasta_t* f);
+const char* mural_fasta_name(const mural_fasta_t* f, int32_t i);
+const char* mural_fasta_seq(const mural_fasta_t* f, int32_t i);
+int64_t mural_fasta_len(const mural_fasta_t* f, int32_t i);
+void mural_fasta_destroy(mural_fasta_t* f);
+
+/* ------------------------------------------------------------------------------------------------
  * Prediction TSV (run_predict.py:228-239): pred_df.to_csv(pred_file, sep='\t', float_format='%.4g', index=False) with
  * columns chrom, start, end, strand, mut_type, prob0..prob{k-1}.  Host arrays, rows already in output order
  * (sorted by chrom name, start); strand is one char per row; formatted by n_threads host threads.

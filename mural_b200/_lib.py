@@ -75,6 +75,18 @@ PROTOTYPES = {
     "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "mural_bed_read": (C.c_int, [C.c_char_p, _vp]),
+    "mural_bed_n": (_i64, [_vp]),
+    "mural_bed_n_chrom": (_i32, [_vp]),
+    "mural_bed_chrom_name": (C.c_char_p, [_vp, _i32]),
+    "mural_bed_columns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mural_bed_destroy": (None, [_vp]),
+    "mural_fasta_read": (C.c_int, [C.c_char_p, _vp]),
+    "mural_fasta_n": (_i32, [_vp]),
+    "mural_fasta_name": (C.c_char_p, [_vp, _i32]),
+    "mural_fasta_seq": (_vp, [_vp, _i32]),
+    "mural_fasta_len": (_i64, [_vp, _i32]),
+    "mural_fasta_destroy": (None, [_vp]),
     "mural_write_tsv": (C.c_int, [C.c_char_p, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
 }
 
@@ -101,6 +113,8 @@ def check(rc):
         msg = lib().mural_last_error().decode("utf-8", "replace")
         if "KeyError" in msg:
             raise KeyError(msg)
+        if "ValueError" in msg:
+            raise ValueError(msg)
         if "IndexError" in msg:
             raise IndexError(msg)
         raise RuntimeError("mural_b200: " + msg)

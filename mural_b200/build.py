@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out.decode())
     if rebuilt or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

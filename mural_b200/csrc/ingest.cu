@@ -1,0 +1,210 @@
+// Host-side ingest: streaming BED and FASTA readers replacing `BedTool(test_file)` iteration
+// (MuRaL/data/preprocessing.py:39-106 reads .chrom/.start/.stop/.score/.strand per record through pybedtools) and
+// `SeqIO.to_dict(SeqIO.parse(open(ref_genome), 'fasta'))` (preprocessing.py:836).  Plain or gzip files (zlib).
+// At genome-wide scale (5e7 sites, 3e9 bases) the Python readers take minutes while the network takes a second.
+#include <ctype.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct mural_bed {
+  std::vector<std::string> names;  // chromosome index -> name, order of first appearance
+  std::vector<int32_t> chrom;
+  std::vector<int64_t> start, end, label;
+  std::vector<int8_t> strand;      // 0 '+', 1 anything else (bed_reader :97-101)
+};
+struct mural_fasta {
+  std::vector<std::string> names;  // record id = first word of the header (Bio.SeqIO record.id)
+  std::vector<std::string> seqs;
+};
+
+namespace {
+
+// calls fn(line, len) for every line of a (possibly gzip-compressed) file; the trailing '\n' / '\r\n' is removed
+template <class F>
+int for_each_line(const char* path, F&& fn) {
+  gzFile f = gzopen(path, "rb");
+  if (!f) return 1;
+  gzbuffer(f, 1 << 20);
+  std::vector<char> buf(1 << 22);
+  std::string carry;
+  int n;
+  while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) {
+    const char* p = buf.data();
+    const char* e = p + n;
+    while (p < e) {
+      const char* nl = (const char*)memchr(p, '\n', size_t(e - p));
+      if (!nl) {
+        carry.append(p, size_t(e - p));
+        break;
+      }
+      if (!carry.empty()) {
+        carry.append(p, size_t(nl - p));
+        size_t len = carry.size();
+        if (len && carry[len - 1] == '\r') --len;
+        fn(carry.data(), len);
+        carry.clear();
+      } else {
+        size_t len = size_t(nl - p);
+        if (len && p[len - 1] == '\r') --len;
+        fn(p, len);
+      }
+      p = nl + 1;
+    }
+  }
+  if (!carry.empty()) {
+    size_t len = carry.size();
+    if (len && carry[len - 1] == '\r') --len;
+    fn(carry.data(), len);
+  }
+  const bool bad = n < 0;
+  gzclose(f);
+  return bad ? 2 : 0;
+}
+
+}  // namespace
+
+// BED6: chrom start end name score strand; score = label (preprocessing.py:752-754).  Same rules as
+// mural_b200.data.SiteTable.from_bed: blank lines and '#', 'track', 'browser' lines are skipped; fields split on tabs,
+// or on any whitespace when a line has fewer than three tab-separated fields; label = int(float(score)), '.'/'' -> 0.
+extern "C" int mural_bed_read(const char* path, mural_bed_t** out) {
+  MURAL_CHECK(path && out, "NULL argument");
+  mural_bed* b = new mural_bed();
+  std::map<std::string, int32_t> index;
+  std::string err;
+  int64_t lineno = 0;
+  const int rc = for_each_line(path, [&](const char* s, size_t len) {
+    ++lineno;
+    if (!err.empty()) return;
+    size_t i = 0;
+    while (i < len && isspace((unsigned char)s[i])) ++i;
+    if (i == len) return;                                    // blank
+    if (s[0] == '#' || (len >= 5 && !memcmp(s, "track", 5)) || (len >= 7 && !memcmp(s, "browser", 7))) return;
+    const char* f[6];
+    size_t fl[6];
+    int nf = 0;
+    {
+      size_t a = 0;
+      for (size_t k = 0; k <= len && nf < 6; ++k)
+        if (k == len || s[k] == '\t') { f[nf] = s + a; fl[nf] = k - a; ++nf; a = k + 1; }
+    }
+    if (nf < 3) {                                            // whitespace-separated
+      nf = 0;
+      size_t k = 0;
+      while (k < len && nf < 6) {
+        while (k < len && isspace((unsigned char)s[k])) ++k;
+        if (k == len) break;
+        const size_t a = k;
+        while (k < len && !isspace((unsigned char)s[k])) ++k;
+        f[nf] = s + a; fl[nf] = k - a; ++nf;
+      }
+    }
+    if (nf < 3) { err = "line " + std::to_string(lineno) + ": fewer than 3 fields"; return; }
+    char tmp[64];
+    auto to_ll = [&](int j, long long& v) {
+      if (fl[j] == 0 || fl[j] >= sizeof tmp) return false;
+      memcpy(tmp, f[j], fl[j]); tmp[fl[j]] = 0;
+      char* endp = nullptr;
+      v = strtoll(tmp, &endp, 10);
+      return endp && *endp == 0;
+    };
+    long long st, en;
+    if (!to_ll(1, st) || !to_ll(2, en)) { err = "line " + std::to_string(lineno) + ": start/end are not integers"; return; }
+    long long lab = 0;
+    if (nf > 4 && !(fl[4] == 0 || (fl[4] == 1 && f[4][0] == '.'))) {
+      if (fl[4] >= sizeof tmp) { err = "line " + std::to_string(lineno) + ": bad score"; return; }
+      memcpy(tmp, f[4], fl[4]); tmp[fl[4]] = 0;
+      char* endp = nullptr;
+      const double d = strtod(tmp, &endp);
+      if (!endp || *endp != 0) { err = "line " + std::to_string(lineno) + ": bad score"; return; }
+      lab = (long long)d;                                    // int(float(score)) truncates toward zero
+    }
+    const std::string name(f[0], fl[0]);
+    auto it = index.find(name);
+    if (it == index.end()) {
+      it = index.emplace(name, (int32_t)b->names.size()).first;
+      b->names.push_back(name);
+    }
+    b->chrom.push_back(it->second);
+    b->start.push_back(st);
+    b->end.push_back(en);
+    b->label.push_back(lab);
+    b->strand.push_back((nf > 5 && fl[5] == 1 && f[5][0] == '+') ? 0 : 1);
+  });
+  if (rc || !err.empty()) {
+    delete b;
+    MURAL_FAIL(rc == 1 ? std::string("cannot open ") + path : (rc == 2 ? std::string("read error on ") + path : "ValueError: " + std::string(path) + " " + err));
+  }
+  *out = b;
+  return 0;
+}
+extern "C" int64_t mural_bed_n(const mural_bed_t* b) { return b ? (int64_t)b->start.size() : 0; }
+extern "C" int32_t mural_bed_n_chrom(const mural_bed_t* b) { return b ? (int32_t)b->names.size() : 0; }
+extern "C" const char* mural_bed_chrom_name(const mural_bed_t* b, int32_t i) {
+  return (b && i >= 0 && i < (int32_t)b->names.size()) ? b->names[i].c_str() : nullptr;
+}
+extern "C" int mural_bed_columns(const mural_bed_t* b, int32_t* chrom, int64_t* start, int64_t* end, int8_t* strand, int64_t* label) {
+  MURAL_CHECK(b && chrom && start && end && strand && label, "NULL argument");
+  const size_t n = b->start.size();
+  if (n) {
+    memcpy(chrom, b->chrom.data(), n * sizeof(int32_t));
+    memcpy(start, b->start.data(), n * sizeof(int64_t));
+    memcpy(end, b->end.data(), n * sizeof(int64_t));
+    memcpy(strand, b->strand.data(), n);
+    memcpy(label, b->label.data(), n * sizeof(int64_t));
+  }
+  return 0;
+}
+extern "C" void mural_bed_destroy(mural_bed_t* b) { delete b; }
+
+// FASTA -> records in file order; sequence lines are stripped of surrounding whitespace and concatenated; a repeated
+// record id is an error (SeqIO.to_dict raises ValueError("Duplicate key ...")).
+extern "C" int mural_fasta_read(const char* path, mural_fasta_t** out) {
+  MURAL_CHECK(path && out, "NULL argument");
+  mural_fasta* fa = new mural_fasta();
+  std::map<std::string, int> seen;
+  std::string err;
+  const int rc = for_each_line(path, [&](const char* s, size_t len) {
+    if (!err.empty()) return;
+    if (len && s[0] == '>') {
+      size_t a = 1;
+      while (a < len && isspace((unsigned char)s[a])) ++a;
+      size_t e = a;
+      while (e < len && !isspace((unsigned char)s[e])) ++e;
+      std::string name(s + a, e - a);
+      if (seen.count(name)) { err = "ValueError: Duplicate key '" + name + "'"; return; }
+      seen[name] = 1;
+      fa->names.push_back(name);
+      fa->seqs.emplace_back();
+      return;
+    }
+    if (fa->seqs.empty()) return;                            // text before the first header is ignored
+    size_t a = 0, e = len;
+    while (a < e && isspace((unsigned char)s[a])) ++a;
+    while (e > a && isspace((unsigned char)s[e - 1])) --e;
+    fa->seqs.back().append(s + a, e - a);
+  });
+  if (rc || !err.empty()) {
+    delete fa;
+    MURAL_FAIL(rc == 1 ? std::string("cannot open ") + path : (rc == 2 ? std::string("read error on ") + path : err));
+  }
+  *out = fa;
+  return 0;
+}
+extern "C" int32_t mural_fasta_n(const mural_fasta_t* f) { return f ? (int32_t)f->names.size() : 0; }
+extern "C" const char* mural_fasta_name(const mural_fasta_t* f, int32_t i) {
+  return (f && i >= 0 && i < (int32_t)f->names.size()) ? f->names[i].c_str() : nullptr;
+}
+extern "C" const char* mural_fasta_seq(const mural_fasta_t* f, int32_t i) {
+  return (f && i >= 0 && i < (int32_t)f->seqs.size()) ? f->seqs[i].data() : nullptr;
+}
+extern "C" int64_t mural_fasta_len(const mural_fasta_t* f, int32_t i) {
+  return (f && i >= 0 && i < (int32_t)f->seqs.size()) ? (int64_t)f->seqs[i].size() : -1;
+}
+extern "C" void mural_fasta_destroy(mural_fasta_t* f) { delete f; }

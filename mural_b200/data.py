@@ -32,24 +32,21 @@ class SiteTable:
 
     @classmethod
     def from_bed(cls, path):
-        """chrom start end name score strand (BED6; score = label, preprocessing.py:752-754)."""
-        opener = gzip.open if str(path).endswith(".gz") else open
-        names, index = [], {}
-        chrom, start, end, strand, label = [], [], [], [], []
-        with opener(path, "rt") as f:
-            for line in f:
-                if not line.strip() or line.startswith(("#", "track", "browser")):
-                    continue
-                p = line.rstrip("\n").split("\t")
-                if len(p) < 3:
-                    p = line.split()
-                c = p[0]
-                if c not in index:
-                    index[c] = len(names)
-                    names.append(c)
-                chrom.append(index[c]); start.append(int(p[1])); end.append(int(p[2]))
-                label.append(int(float(p[4])) if len(p) > 4 and p[4] not in (".", "") else 0)
-                strand.append(0 if (len(p) > 5 and p[5] == "+") else 1)
+        """chrom start end name score strand (BED6; score = label, preprocessing.py:752-754), plain or .gz — parsed by the
+        C library's streaming reader (mural_bed_read; replaces iterating BedTool(file), preprocessing.py:39-106)."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.mural_bed_read(str(path).encode(), C.byref(h)))
+        try:
+            n = int(L.mural_bed_n(h))
+            names = [L.mural_bed_chrom_name(h, i).decode() for i in range(L.mural_bed_n_chrom(h))]
+            chrom, strand = np.empty(n, np.int32), np.empty(n, np.int8)
+            start, end, label = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int64)
+            _lib.check(L.mural_bed_columns(h, _lib.ptr(chrom), _lib.ptr(start), _lib.ptr(end), _lib.ptr(strand), _lib.ptr(label)))
+        finally:
+            L.mural_bed_destroy(h)
         return cls(names, chrom, start, end, strand, label)
 
 

@@ -53,7 +53,28 @@ class PackedGenome:
 
     @classmethod
     def from_fasta(cls, path, device=None):
-        return cls(read_fasta(path), device)
+        """FASTA (plain or .gz) -> packed genome without a Python copy of the sequences: the C library's reader
+        (mural_fasta_read) hands its buffers straight to mural_genome_create."""
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mural_b200.PackedGenome needs a CUDA device (no CPU fallback)")
+        f = C.c_void_p()
+        _lib.check(L.mural_fasta_read(str(path).encode(), C.byref(f)))
+        try:
+            self = cls.__new__(cls)
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            n = int(L.mural_fasta_n(f))
+            self.names = [L.mural_fasta_name(f, i).decode() for i in range(n)]
+            self.chrom_index = {nm: i for i, nm in enumerate(self.names)}
+            self.lengths = np.array([L.mural_fasta_len(f, i) for i in range(n)], dtype=np.int64)
+            arr = (C.c_void_p * n)(*[L.mural_fasta_seq(f, i) for i in range(n)])
+            lens = (C.c_int64 * n)(*[int(x) for x in self.lengths])
+            h = C.c_void_p()
+            _lib.check(L.mural_genome_create(n, C.cast(arr, C.POINTER(C.c_char_p)), lens, self.device.index or 0, C.byref(h)))
+            self._h = h
+        finally:
+            L.mural_fasta_destroy(f)
+        return self
 
     @property
     def handle(self):

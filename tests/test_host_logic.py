@@ -108,3 +108,74 @@ def test_native_tsv_writer_equals_pandas(tmp_path):
     assert a.read_bytes() == b.read_bytes()
     write_tsv(a, names[:0], start[:0], end[:0], strand[:0], mt[:0], prob[:0])      # empty input: header only
     assert a.read_text() == "chrom\tstart\tend\tstrand\tmut_type\tprob0\tprob1\tprob2\tprob3\n"
+
+
+def _bed_py(path):
+    """The reader the C library replaced (kept here as the parity reference)."""
+    import gzip
+    opener = gzip.open if str(path).endswith(".gz") else open
+    names, index, rows = [], {}, []
+    with opener(path, "rt") as f:
+        for line in f:
+            if not line.strip() or line.startswith(("#", "track", "browser")):
+                continue
+            p = line.rstrip("\n").split("\t")
+            if len(p) < 3:
+                p = line.split()
+            if p[0] not in index:
+                index[p[0]] = len(names); names.append(p[0])
+            rows.append((index[p[0]], int(p[1]), int(p[2]), 0 if (len(p) > 5 and p[5] == "+") else 1,
+                         int(float(p[4])) if len(p) > 4 and p[4] not in (".", "") else 0))
+    return names, np.array(rows, dtype=np.int64).reshape(-1, 5)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_native_bed_reader(tmp_path, gz):
+    import gzip
+    from mural_b200.data import SiteTable
+    rng = np.random.default_rng(5)
+    lines = ["# comment", "track name=x", "browser position chr1", "", "chr2\t10\t11\t.\t3\t+", "chr1\t5\t6\tn\t1.0\t-",
+             "chr2 7 8 . 2 +", "chr10\t1\t2", "chr1\t9\t10\t.\t.\t+", "chr3\t4\t5\tx\t0\t*\textra\tcols", "chrX\t100\t101\t.\t\t+\r"]
+    for _ in range(5000):
+        lines.append("chr%d\t%d\t%d\t.\t%d\t%s" % (rng.integers(1, 6), rng.integers(0, 10**8), rng.integers(0, 10**8), rng.integers(0, 4), "+-"[rng.integers(0, 2)]))
+    path = tmp_path / ("s.bed.gz" if gz else "s.bed")
+    (gzip.open if gz else open)(path, "wt").write("\n".join(lines) + "\n")
+    names, rows = _bed_py(path)
+    t = SiteTable.from_bed(path)
+    assert t.chrom_names == names and len(t) == len(rows)
+    assert (t.chrom == rows[:, 0]).all() and (t.start == rows[:, 1]).all() and (t.end == rows[:, 2]).all()
+    assert (t.strand == rows[:, 3]).all() and (t.label == rows[:, 4]).all()
+    bad = tmp_path / "bad.bed"
+    bad.write_text("chr1\tx\t2\n")
+    with pytest.raises(ValueError):
+        SiteTable.from_bed(bad)
+    with pytest.raises(RuntimeError):
+        SiteTable.from_bed(tmp_path / "missing.bed")
+
+
+def test_native_fasta_reader(tmp_path):
+    import ctypes as C
+    import gzip
+    from mural_b200 import _lib
+    from mural_b200.genome import read_fasta
+    rng = np.random.default_rng(6)
+    recs = {"chrA desc": "ACGTNRYacgtn" * 50, "chrB": "".join("ACGT"[i] for i in rng.integers(0, 4, 12345)), "empty": "", "chrC\tx": "GATTACA"}
+    txt = "; junk before the first header\n"
+    for k, v in recs.items():
+        txt += ">" + k + "\n" + "".join(v[i:i + 60] + ("  \r\n" if i % 120 else "\n") for i in range(0, len(v), 60))
+    for gz in (False, True):
+        path = tmp_path / ("g.fa.gz" if gz else "g.fa")
+        (gzip.open if gz else open)(path, "wt", newline="").write(txt)
+        exp = read_fasta(path)
+        L = _lib.lib()
+        f = C.c_void_p()
+        _lib.check(L.mural_fasta_read(str(path).encode(), C.byref(f)))
+        got = {L.mural_fasta_name(f, i).decode(): C.string_at(L.mural_fasta_seq(f, i), L.mural_fasta_len(f, i)) for i in range(L.mural_fasta_n(f))}
+        L.mural_fasta_destroy(f)
+        assert list(got) == list(exp) == ["chrA", "chrB", "empty", "chrC"]
+        assert got == exp
+    dup = tmp_path / "dup.fa"
+    dup.write_text(">a\nAC\n>a\nGT\n")
+    f = C.c_void_p()
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib().mural_fasta_read(str(dup).encode(), C.byref(f)))
