@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "snv_model.cuh"
+#include "snv_tc_args.cuh"
 
 namespace mural {
 namespace tc {
@@ -35,14 +36,15 @@ constexpr int SLOT_BYTES = A_SLOT + AC_BYTES;
 constexpr int W_CONV = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
 constexpr int W_BIAS = 2 * 32 * 16;      // bf16 [k/8][co][8]: bias / edge-correction rows of the 7th MMA = 1024 bytes
 constexpr int W_LAYER = W_CONV + W_BIAS;
-constexpr int NGROUP = 4;                // thread groups (128 threads = one tile's rows) per CTA
-constexpr int NINFL = 2;                 // tiles in flight per group
+#ifndef MURAL_TC_NGROUP
+#define MURAL_TC_NGROUP 4
+#endif
+constexpr int NGROUP = MURAL_TC_NGROUP;  // thread groups (128 threads = one tile's rows) per CTA
+constexpr int NINFL = 8 / NGROUP;        // tiles in flight per group
 constexpr int NSLOT = NGROUP * NINFL;    // 8 slots x 64 TMEM columns = all 512 columns of the SM
 constexpr int THREADS = NGROUP * 128;
 // instruction descriptor, kind::f16: D=F32 (bit4), A=BF16 (bit7), B=BF16 (bit10), K-major A and B, N=32, M=128
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-
-enum Mode { RB4 = 0, C_RB4 = 1, SINGLE = 2 };
 
 // Optional in-kernel phase timing (-DMURAL_TC_TIMING, scratch builds only): per-thread clock() deltas accumulated
 // per phase, dumped for lane 0 of warps 0 (issuer) and 1 of every group by mural_tc_timing_dump().
@@ -58,42 +60,6 @@ __device__ unsigned long long g_tc_timing[3][148][NGROUP][2][T_N + 2];
 #else
 #define TT(cat) do { } while (0)
 #endif
-__host__ __device__ constexpr int n_layers(int mode) { return mode == RB4 ? 4 : (mode == C_RB4 ? 5 : 1); }
-
-struct StageArgs {
-  const uint4* in;       // bf16 planes [4][in_rows_alloc] (one uint4 = 8 channels of one row)
-  void* out;             // bf16 planes [4][out_rows_alloc] (RB4, C_RB4) or fp32 planes [8][out_rows_alloc] float4 (SINGLE)
-  const uint8_t* wblob;  // n_layers * W_LAYER bytes
-  int64_t in_rows_alloc, out_rows_alloc;
-  int64_t rows;          // n_sites*(L+1)+1 rows of this stage
-  int L;                 // site length at this stage
-  int Lin;               // site length of the input buffer (== L when not pooled)
-  int pk, ps, pp;        // max-pool fused into the loader (RB4: none)
-  int n_tiles;
-  // dense-site dispatch (snv_dense_stem.cu): all decided on the device, no host synchronisation
-  const ChunkInfo* info;  // nullptr: unconditional launch
-  int want;               // run only if info->dense == want
-  int lat_branch;         // >= 0: this launch is the stage-1 lattice of that branch; L / rows / n_tiles come from info
-  // LAT loader (C_RB4 only): stage-1 rows of a site come from the lattice (interior) and the edge pseudo-site (ends)
-  const uint4* lat;       // stage-1 lattice output planes [4][lat_ra]
-  const uint4* lat2;      // the same max-pooled along the lattice: lat2[row] = max(lat[row .. row+pk-1]) (k_lattice_pool)
-  int64_t lat_ra;
-  const uint4* edge;      // stage-1 edge output planes [4][edge_ra], LAT_EL rows per site
-  int64_t edge_ra;
-  const uint4* epool;     // pooled rows of the bins that touch edge rows (k_edge_pool): planes [4][epool_ra], row = site*(nlo+nhi) + b
-  int64_t epool_ra;
-  int nlo, nhi;           // such bins at the low / high end of a site
-  // EDGE loader (RB4 on the edge pseudo-sites): rows 1..16 of a pseudo-site are full-bin table rows read in place
-  // (snv_dense_stem.cu tables, width-0 table of this branch per strand), rows 0 and 17 come from the special-row buffer
-  const uint4* tab[2];    // [strand]: rows of 4 uint4 (32 bf16) per genomic position
-  const uint4* special;   // planes [4][special_ra], row = 2*site + (last ? 1 : 0)
-  int64_t special_ra;
-  int L1real;             // stage-1 length of a real site (pseudo-site row jj >= LAT_EI is real row L1real - LAT_EL + jj)
-  const int32_t* pos;
-  const int32_t* meta;
-  int ps1, pp1, pk1, off0, R, br;
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // SWIZZLE_NONE, K-major UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout)
@@ -243,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   // ---- per-slot constants of this group (slot k of group g = g*NINFL + k)
   unsigned char* const sA0 = sSlots + (g * NINFL) * SLOT_BYTES;
   const uint32_t bar0 = smem_u32(bars + g * NINFL);
-  uint32_t phase[NINFL] = {0, 0};
+  uint32_t phase[NINFL] = {};
 
   // publish the slot's operands to the tensor core: three warps of the group arrive and run ahead, the issuing warp waits for
   // all 128 threads and its elected lane issues the 7 MMAs of layer l, then commits to the slot's mbarrier.
@@ -768,12 +734,14 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
     for (int stg = 0; stg < 3; ++stg) S->blob[br][stg] = S->d_w + offs[br][stg];
   m->tc = S;
   if (int rc = snv_mlp_tc_prepare(m)) return rc;
+  if (int rc = snv_tc2_prepare(m, h_blob)) return rc;
   return snv_tail_prepare(m, h_blob);
 }
 
 void snv_tc_destroy(mural_snv_model* m) {
   snv_mlp_tc_destroy(m);
   snv_tail_destroy(m);
+  snv_tc2_destroy(m);
   if (!m->tc) return;
   tc::TcState* S = (tc::TcState*)m->tc;
   cudaFree(S->d_w);
@@ -827,6 +795,19 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
   const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
   const bool use_tail = m->tail != nullptr && getenv("MURAL_NO_TAIL") == nullptr;
+  // two-rows-per-lane stage kernels (snv_tc2.cu): bit-identical, measured ~15 % slower than the one-row kernels on B200
+  // (profiles/r01_stage_tc_variants.txt), so they are opt-in
+  const bool use_v2 = m->tc2 != nullptr && getenv("MURAL_TC_V2") != nullptr;
+  const int stride_rb4 = use_v2 ? snv_tc2_stride(RB4) : TILE - 2 * 4, stride_crb4 = use_v2 ? snv_tc2_stride(C_RB4) : TILE - 2 * 5;
+  // one stage launch: v2 kernels take their own weight blob; SINGLE exists only in the first generation
+  auto stage = [&](int mode, int fm, StageArgs sa, int br, int stg, const char* role) -> int {
+    if (use_v2) {
+      sa.wblob = snv_tc2_blob(m, br, stg);
+      return snv_tc2_launch(mode, fm, sa, st, role);
+    }
+    if (mode == RB4) return fm == 2 ? launch_stage<RB4, 2>(sa, st, role) : (fm == 1 ? launch_stage<RB4, 1>(sa, st, role) : launch_stage<RB4, 0>(sa, st, role));
+    return fm == 1 ? launch_stage<C_RB4, 1>(sa, st, role) : launch_stage<C_RB4, 0>(sa, st, role);
+  };
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   int64_t floats = 0;
   int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0}, epool_ra[2] = {0, 0};
@@ -918,24 +899,24 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       a.in = reinterpret_cast<const uint4*>(bufs[br][0]); a.out = bufs[br][1]; a.wblob = S->blob[br][0];
       a.in_rows_alloc = ra[br][0]; a.out_rows_alloc = ra[br][1];
       a.rows = rows_of(ns, B.L1); a.L = B.L1; a.Lin = B.L1; a.pk = 0; a.ps = 1; a.pp = 0;
-      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 4);
+      a.n_tiles = (int)cdiv(a.rows, stride_rb4);
       if (use_lat) { a.info = info; a.want = 0; }
-      if (int rc = launch_stage<RB4>(a, st, use_lat ? "/site" : "")) return rc;
+      if (int rc = stage(RB4, 0, a, br, 0, use_lat ? "/site" : "")) return rc;
       if (use_lat) {
         // stage 1 on the lattice (geometry read from info on the device; grid sized for the largest lattice) ...
         StageArgs l = a;
         l.want = 1; l.lat_branch = br;
         l.in = reinterpret_cast<const uint4*>(lb[br].lat_in); l.out = lb[br].lat_out;
         l.in_rows_alloc = l.out_rows_alloc = lb[br].lat_ra;
-        l.n_tiles = (int)cdiv(lb[br].lat_ra, TILE - 2 * 4);
-        if (int rc = (launch_stage<RB4, 1>(l, st, "/lattice"))) return rc;
+        l.n_tiles = (int)cdiv(lb[br].lat_ra, stride_rb4);
+        if (int rc = stage(RB4, 1, l, br, 0, "/lattice")) return rc;
         // ... and on the per-site edge pseudo-sites
         StageArgs e = a;
         e.want = 1;
         e.in = nullptr; e.out = lb[br].edge_out;
         e.in_rows_alloc = e.out_rows_alloc = lb[br].edge_ra;
         e.rows = rows_of(ns, LAT_EL); e.L = e.Lin = LAT_EL;
-        e.n_tiles = (int)cdiv(e.rows, TILE - 2 * 4);
+        e.n_tiles = (int)cdiv(e.rows, stride_rb4);
         const uint4* tab0 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dense_scratch) + 256);
         for (int sd = 0; sd < 2; ++sd) e.tab[sd] = tab0 + int64_t((sd * 2 + br) * 3) * snv_dense_cap(chunk) * 4;
         e.special = reinterpret_cast<const uint4*>(lb[br].edge_in); e.special_ra = lb[br].edge_ra;
@@ -943,15 +924,15 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         e.pos = d_pos + s0; e.meta = d_meta + s0;
         e.ps1 = B.pool[0][1]; e.pp1 = B.pool[0][2]; e.pk1 = B.pool[0][0];
         e.off0 = br ? 0 : m->L / 2 - 100; e.R = m->cfg.distal_radius; e.br = br;
-        if (int rc = (launch_stage<RB4, 2>(e, st, "/edge"))) return rc;
+        if (int rc = stage(RB4, 2, e, br, 0, "/edge")) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
       // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
       a.in = reinterpret_cast<const uint4*>(bufs[br][1]); a.out = bufs[br][2]; a.wblob = S->blob[br][1];
       a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
       a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
-      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 5);
-      if (int rc = launch_stage<C_RB4>(a, st, use_lat ? "/site" : "")) return rc;
+      a.n_tiles = (int)cdiv(a.rows, stride_crb4);
+      if (int rc = stage(C_RB4, 0, a, br, 1, use_lat ? "/site" : "")) return rc;
       if (use_lat) {
         // pooled lattice rows overwrite the (now dead) lattice input
         LAUNCH(k_lattice_pool, 148 * 4, 256, 0, st, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
@@ -968,7 +949,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         EdgePool ep{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
                     br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
         LAUNCH(k_edge_pool, 148 * 4, 256, 0, st, info, ep);
-        if (int rc = (launch_stage<C_RB4, 1>(l, st, "/lattice"))) return rc;
+        if (int rc = stage(C_RB4, 1, l, br, 1, "/lattice")) return rc;
       }
       if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
       if (use_tail) continue;  // stage 3 and the heads run in the warp-level tail kernel below
