@@ -276,7 +276,7 @@ def main():
         if rank != 0:
             return 0
         chroms = [synth_chromosome(0)]                # the bounded sample lives on the first chromosome
-        per_step = min(a.cpu_sample, a.sites_per_step)
+        per_step = min(a.cpu_sample, a.sites_per_step, 32768)      # bounded: K steps of this stay within a few minutes on 8-16 cores
         pos, meta = rank_sites(chroms, 0, 1, per_step * (a.steps + a.warmup))
         for w in range(a.warmup):
             cpu_port_sites_per_sec(chroms, pos[w * per_step:(w + 1) * per_step][:2048], meta[w * per_step:(w + 1) * per_step][:2048], cfg, state)
@@ -345,7 +345,6 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = int(L.mural_launch_count())
-    clocks = sampler.stop()
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -369,6 +368,7 @@ def main():
         step_host(W + i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()          # sampled during the timed region and the end-to-end region (same kernels under load)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
