@@ -41,6 +41,48 @@ class StepLR:
         return self.lr
 
 
+class ReduceLROnPlateau:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(mode='min', factor=0.2, patience=1, threshold=1e-4 (rel), min_lr=1e-7) as the
+    reference configures it (training.py:370); stepped once per epoch with the validation loss."""
+
+    def __init__(self, lr, factor=0.2, patience=1, threshold=1e-4, min_lr=1e-7, eps=1e-8):
+        self.lr, self.factor, self.patience, self.threshold, self.min_lr, self.eps = lr, factor, patience, threshold, min_lr, eps
+        self.best, self.bad = float("inf"), 0
+
+    def step(self, metric):
+        if metric < self.best * (1.0 - self.threshold):
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+        if self.bad > self.patience:
+            new = max(self.lr * self.factor, self.min_lr)
+            if self.lr - new > self.eps:
+                self.lr = new
+            self.bad = 0
+        return self.lr
+
+
+def auto_weight_decay(weight_decay_auto, batch_size, epochs, train_size):
+    """--weight_decay_auto (training.py:339-344): weight_decay = 1 - wda ** (batch_size / (epochs * train_size))."""
+    if not 0 < weight_decay_auto < 1:
+        raise ValueError("Please set a value smaller than 1 for --weight_decay_auto.")
+    return 1 - weight_decay_auto ** (batch_size / (epochs * train_size))
+
+
+def make_scheduler(config, train_size):
+    """The three schedulers of training.py:364-371.  StepLR / StepLR2 are stepped every batch (with the min_lr -> restart_lr
+    rule, :444-450), ROP once per epoch on the validation loss."""
+    kind, lr = config["lr_scheduler"], config["learning_rate"]
+    if kind == "StepLR":
+        return StepLR(lr, (5000 * 128) // config["batch_size"], config["LR_gamma"], config.get("min_lr"), config.get("restart_lr"))
+    if kind == "StepLR2":
+        gamma = (config["min_lr"] / config["restart_lr"]) ** (1 / (train_size // config["batch_size"]))
+        return StepLR(lr, 1, gamma, config.get("min_lr"), config.get("restart_lr"))
+    if kind == "ROP":
+        return ReduceLROnPlateau(lr)
+    raise ValueError("unsupported lr_scheduler %s" % kind)
+
+
 class TrainState:
     def __init__(self, model, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False):
         L = _lib.lib()

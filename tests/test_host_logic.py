@@ -179,3 +179,36 @@ def test_native_fasta_reader(tmp_path):
     f = C.c_void_p()
     with pytest.raises(ValueError):
         _lib.check(_lib.lib().mural_fasta_read(str(dup).encode(), C.byref(f)))
+
+
+def test_lr_schedulers_match_torch():
+    """StepLR / StepLR2 (per batch, with the min_lr -> restart_lr rule) and ReduceLROnPlateau (per epoch) vs torch on a dummy
+    optimizer (training.py:364-371, 444-450)."""
+    from mural_b200.training import auto_weight_decay, make_scheduler
+    rng = np.random.default_rng(3)
+    for kind in ("StepLR", "StepLR2"):
+        cfg = {"lr_scheduler": kind, "learning_rate": 1e-3, "batch_size": 4096, "LR_gamma": 0.5, "min_lr": 1e-5, "restart_lr": 2e-4}
+        train_size = 4096 * 40
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=cfg["learning_rate"])
+        if kind == "StepLR":
+            ref = torch.optim.lr_scheduler.StepLR(opt, step_size=(5000 * 128) // cfg["batch_size"], gamma=cfg["LR_gamma"])
+        else:
+            ref = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=(cfg["min_lr"] / cfg["restart_lr"]) ** (1 / (train_size // cfg["batch_size"])))
+        mine = make_scheduler(cfg, train_size)
+        for _ in range(1500):
+            opt.step(); ref.step()
+            if opt.param_groups[0]["lr"] < cfg["min_lr"]:
+                for g in opt.param_groups:
+                    g["lr"] = cfg["restart_lr"]
+            lr = mine.step()
+            assert abs(lr - opt.param_groups[0]["lr"]) <= 1e-12 + 1e-9 * lr, kind
+    cfg = {"lr_scheduler": "ROP", "learning_rate": 1e-3, "batch_size": 128}
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+    ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", factor=0.2, patience=1, threshold=0.0001, min_lr=1e-7)
+    mine = make_scheduler(cfg, 1000)
+    for loss in np.r_[np.linspace(5, 4, 6), 4 + 0.01 * rng.random(12), np.linspace(3.9, 3.0, 4), 3.0 * np.ones(10)]:
+        ref.step(float(loss))
+        assert abs(mine.step(float(loss)) - opt.param_groups[0]["lr"]) < 1e-15
+    assert abs(auto_weight_decay(0.1, 128, 20, 10_000_000) - (1 - 0.1 ** (128 / (20 * 10_000_000)))) < 1e-18
+    with pytest.raises(ValueError):
+        auto_weight_decay(1.5, 128, 20, 1000)
