@@ -319,10 +319,17 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
 
+    # a batch that straddles two chromosomes is issued as one call per chromosome (as mural_b200.predict.predict_sites does):
+    # the dense-site path works on single-chromosome chunks
+    chrom_of = meta >> 8
+    cuts = [[0] + [int(c) + 1 for c in np.flatnonzero(np.diff(chrom_of[i * S:(i + 1) * S]))] + [S] for i in range(K + W)]
+    NCb = cfg["n_class"]
+
     def step(i):
-        _lib.check(L.mural_snv_forward(model._h, genome.handle, C.c_void_p(d_pos.data_ptr() + 4 * i * S),
-                                       C.c_void_p(d_meta.data_ptr() + 4 * i * S), S, _lib.MODES[mode], _lib.ptr(out),
-                                       C.c_void_p(stream.cuda_stream)))
+        for a0, a1 in zip(cuts[i][:-1], cuts[i][1:]):
+            _lib.check(L.mural_snv_forward(model._h, genome.handle, C.c_void_p(d_pos.data_ptr() + 4 * (i * S + a0)),
+                                           C.c_void_p(d_meta.data_ptr() + 4 * (i * S + a0)), a1 - a0, _lib.MODES[mode],
+                                           C.c_void_p(out.data_ptr() + 4 * NCb * a0), C.c_void_p(stream.cuda_stream)))
 
     def barrier():
         if world > 1:
@@ -357,9 +364,10 @@ def main():
     h_out = torch.empty((S, cfg["n_class"]), dtype=torch.float32).pin_memory()
 
     def step_host(i):
-        _lib.check(L.mural_snv_predict_host(model._h, genome.handle, C.c_void_p(h_pos.data_ptr() + 4 * i * S),
-                                            C.c_void_p(h_meta.data_ptr() + 4 * i * S), S, _lib.MODES[mode], _lib.ptr(h_out),
-                                            C.c_void_p(stream.cuda_stream)))
+        for a0, a1 in zip(cuts[i][:-1], cuts[i][1:]):
+            _lib.check(L.mural_snv_predict_host(model._h, genome.handle, C.c_void_p(h_pos.data_ptr() + 4 * (i * S + a0)),
+                                                C.c_void_p(h_meta.data_ptr() + 4 * (i * S + a0)), a1 - a0, _lib.MODES[mode],
+                                                C.c_void_p(h_out.data_ptr() + 4 * NCb * a0), C.c_void_p(stream.cuda_stream)))
     for i in range(min(W, 2)):
         step_host(i)
     barrier()
@@ -417,7 +425,7 @@ def main():
 def executed_conv_flops(pos, S, K, W, R):
     """FLOPs the stage kernels actually execute on the dense-site path (bf16 mode): stage 1 runs once per genomic
     position and strand on the lattice plus a 19-row edge pseudo-site per site; stages 2 and 3 run per site."""
-    chunk = int(os.environ.get("MURAL_TC_CHUNK", "131072"))
+    chunk = int(os.environ.get("MURAL_TC_CHUNK", "524288"))
     pools = {0: ((3, 3, 1), (3, 3, 1), (3, 3, 1)), 1: ((15, 15, 7), (7, 7, 3), (3, 3, 1))}
     L0 = {0: 201, 1: 2 * R + 1}
     rl = 0
@@ -473,9 +481,8 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp) and mode == "bf16":
-        tj = json.load(open(tp))      # dram__bytes_read+write of the stage kernels from the committed ncu --set full capture
-        if tj.get("chunk_sites") == int(os.environ.get("MURAL_TC_CHUNK", "131072")):
-            traffic = tj["dram_bytes_per_launch"]
+        tj = json.load(open(tp))      # dram__bytes_read+write of the stage kernels from the committed ncu --set full capture,
+        traffic = tj["dram_bytes_per_site"] * S * K / n     # per site of a dense chunk, scaled to this run's launches
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "executed": executed,
             "kernel": "+".join(sorted(conv)), "launches": n, "profile_count": {k: v["count"] for k, v in prof.items()}, "mean_launch_ms": ms / n, "share_of_step": ms / total_ms,

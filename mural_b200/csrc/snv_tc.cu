@@ -783,7 +783,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const int NC = m->cfg.n_class;
   static int64_t env_chunk = -1;
   if (env_chunk < 0) { const char* e = getenv("MURAL_TC_CHUNK"); env_chunk = e ? atoll(e) : 0; }
-  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (env_chunk > 0 ? env_chunk : 131072);
+  int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : (env_chunk > 0 ? env_chunk : 524288);
   if (m->chunk_sites <= 0 || (int64_t(1) << 20) % chunk != 0) {  // keep chunks aligned inside super-chunks
     int64_t c2 = 1;
     while (c2 * 2 <= chunk) c2 *= 2;

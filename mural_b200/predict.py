@@ -59,9 +59,11 @@ def predict_sites(model, dataset, lo, hi, batch_sites=1 << 20):
     """log-probs [hi-lo, n_class] (CUDA) for the dataset's sites [lo, hi) in emission order."""
     dev = dataset.genome.device
     outs = []
+    # batches never straddle two chromosomes: the dense-site path (stem tables, stage-1 lattice) works on single-chromosome chunks
+    cuts = [lo] + [lo + int(c) + 1 for c in np.flatnonzero(np.diff(dataset.chrom[lo:hi]))] + [hi]
+    spans = [(a, min(b0, a + batch_sites)) for a0, b0 in zip(cuts[:-1], cuts[1:]) for a in range(a0, b0, batch_sites)]
     with torch.no_grad():
-        for a in range(lo, hi, batch_sites):
-            b = min(hi, a + batch_sites)
+        for a, b in spans:
             sb = SiteBatch(torch.from_numpy(dataset.pos[a:b]).to(dev), torch.from_numpy(dataset.meta[a:b]).to(dev), dataset.genome)
             if dataset.model_type == "indel":        # UNet_Small.forward(distal) (model_indel.py:151); batches bound the U-Net workspace
                 outs.extend(model.forward(SiteBatch(sb.pos[c:c + 4096], sb.meta[c:c + 4096], sb.genome), distal_radius=dataset.distal_radius)
