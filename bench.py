@@ -215,6 +215,7 @@ def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
                 oh[m] = E.onehot_windows(syms[c], p[m], mt[m] & 1, cfg["distal_radius"])
             out.append(NT.network2_forward(state, cat, oh, torch.float32))
     dt = time.perf_counter() - t0
+    cpu_port_sites_per_sec.last_logp = torch.cat(out).numpy() if out else None   # kept for the GPU-vs-oracle spot check
     return n / dt, dt
 
 
@@ -415,6 +416,16 @@ def main():
             v, dt = cpu_port_sites_per_sec(chroms, pos[:n_s], meta[:n_s], cfg, state)
             line["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "first %d sites of the step-0 batch, batch 1024, numpy encoders + torch CPU fp32 (%.1f s)" % (n_s, dt)}
+            # parity at bench scale: the same sites through the GPU path (as part of a full-size call) vs the oracle's log-probs
+            ref_lp = getattr(cpu_port_sites_per_sec, "last_logp", None)
+            if ref_lp is not None:
+                step(0)
+                torch.cuda.synchronize()
+                got = out[:n_s].cpu().numpy()
+                pg = np.exp(got - got.max(1, keepdims=True)); pg /= pg.sum(1, keepdims=True)
+                pr = np.exp(ref_lp - ref_lp.max(1, keepdims=True)); pr /= pr.sum(1, keepdims=True)
+                line["parity_spot_check"] = {"sites": int(n_s), "max_abs_dp": float(np.abs(pg - pr).max()), "tolerance": 5e-3 if mode == "bf16" else 1e-3,
+                                             "what": "GPU probabilities of the first sites of a full-size step vs the CPU oracle"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
