@@ -32,7 +32,8 @@ constexpr int A_BYTES = 4 * A_PLANE;     // 8320
 constexpr int A_SLOT = (A_BYTES + 127) & ~127;
 constexpr int AC_PLANE = TILE * 16;      // constant-column operand: [2 planes][128 rows][16 B]
 constexpr int AC_BYTES = 2 * AC_PLANE;
-constexpr int SLOT_BYTES = A_SLOT + AC_BYTES;
+constexpr int PARK_BYTES = 4 * TILE * 16;  // outer-skip operand of the tile (x0 / conv2 output), bf16 planes, private to its thread
+constexpr int SLOT_BYTES = A_SLOT + AC_BYTES + PARK_BYTES;
 constexpr int W_CONV = 3 * 4 * 32 * 16;  // bf16 [tap][ci/8][co][8] = 6144 bytes
 constexpr int W_BIAS = 2 * 32 * 16;      // bf16 [k/8][co][8]: bias / edge-correction rows of the 7th MMA = 1024 bytes
 constexpr int W_LAYER = W_CONV + W_BIAS;
@@ -326,11 +327,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   auto begin_tile = [&](int k, int r, int p, const uint4 (&x)[4]) {
     unsigned char* sA = sA0 + k * SLOT_BYTES;
     const bool live = p >= 0;
-    if (EDGE && live && lt >= NL && lt < TILE - NL) {  // the gathered input row is needed again for the outer skip: parked in
-      // the output row like C_RB4's jump — only the rows this tile owns, a halo row belongs to (and is written by) a neighbour
-      uint4* out4 = reinterpret_cast<uint4*>(a.out);
+    if (MODE == RB4) {  // x0 is needed again for the outer skip after the last layer: parked in the slot (same thread reads it back)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r] = x[q];
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(sA + A_SLOT + AC_BYTES + q * (TILE * 16) + lt * 16) = x[q];
     }
     if (MODE == RB4) {
       uint32_t f[32];  // residual region R <- x0 (fp32)
@@ -399,15 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
         TT(T_OTHER);
         const bool live = p[k] >= 0;
         const bool valid = live && lt >= NL && lt < TILE - NL;
-        // outer-skip operand of the last layer (x0 re-read / parked jump): requested before the wait on the MMAs so that
-        // its L2 round trip is hidden behind them
         uint4 xr[4];
-        if (MODE != SINGLE && l == NL - 1 && valid) {
-          const uint4* out4 = reinterpret_cast<const uint4*>(a.out);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            xr[q] = (MODE == RB4 && !EDGE) ? __ldg(a.in + q * a.in_rows_alloc + r[k]) : out4[q * a.out_rows_alloc + r[k]];
-        }
         mbar_wait(bar0 + 8 * k, phase[k]);
         phase[k] ^= 1;
         __syncwarp();
@@ -427,10 +418,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
             o[q].z = pack_bf16(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
             o[q].w = pack_bf16(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
           }
-          if (MODE == C_RB4 && l == 0 && valid) {  // jump = conv2 output: parked (bf16) in the output row, re-read at the end
-            uint4* out4 = reinterpret_cast<uint4*>(a.out);
+          if (MODE == C_RB4 && l == 0) {  // jump = conv2 output: parked (bf16) in the slot, re-read by the same thread at the end
+            unsigned char* pk = sA0 + k * SLOT_BYTES + A_SLOT + AC_BYTES + lt * 16;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) out4[q * a.out_rows_alloc + r[k]] = o[q];
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(pk + q * (TILE * 16)) = o[q];
           }
           if (live) {  // separator rows were zeroed by begin_tile and are never rewritten
             unsigned char* sA = sA0 + k * SLOT_BYTES;
@@ -452,6 +443,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
                               fmaxf(__uint_as_float(acc[4 * q + 2]), 0.f), fmaxf(__uint_as_float(acc[4 * q + 3]), 0.f));
           } else {  // outer skip: + x0 (RB4, re-read from the input) or + jump (C_RB4, parked in the output row)
             uint4* out4 = reinterpret_cast<uint4*>(a.out);
+            {
+              const unsigned char* pk = sA0 + k * SLOT_BYTES + A_SLOT + AC_BYTES + lt * 16;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) xr[q] = *reinterpret_cast<const uint4*>(pk + q * (TILE * 16));
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 o;
