@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
       site = r / Lp1;
       p = r - site * Lp1 - 1;
     }
-    const bool live = p >= 0;
+    bool live = p >= 0;
+#ifdef MURAL_TC_TIMING
+    if (a.ablate & 1) live = false;  // ablation (scratch timing builds only): no loads at all
+#endif
     if (EDGE) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = make_uint4(0, 0, 0, 0);
@@ -647,7 +650,12 @@ static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = 
   }
   int grid = (a.n_tiles + NSLOT - 1) / NSLOT;
   if (grid > m_sm_count()) grid = m_sm_count();
+#ifdef MURAL_TC_TIMING
+  StageArgs a2 = a;
+  { const char* e = getenv("MURAL_TC_ABLATE"); a2.ablate = e ? atoi(e) : 0; }
+#else
   const StageArgs& a2 = a;
+#endif
   // profile names are interned per (mode, role): prof_pre keeps the pointer
   static std::map<std::string, std::string> names;
   const std::string key = std::string(MODE == RB4 ? "k_stage_tc<RB4>" : (MODE == C_RB4 ? "k_stage_tc<C_RB4>" : "k_stage_tc<SINGLE>")) + role;

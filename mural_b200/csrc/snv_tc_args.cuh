@@ -41,6 +41,7 @@ struct StageArgs {
   const int32_t* pos;
   const int32_t* meta;
   int ps1, pp1, pk1, off0, R, br;
+  int ablate;             // scratch timing builds only (-DMURAL_TC_TIMING): bit 0 = loaders fetch nothing
 };
 
 
