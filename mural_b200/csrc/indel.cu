@@ -26,7 +26,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-constexpr int TP = 64;  // output positions per CTA
+constexpr int TP_MIN = 64;  // output positions per CTA for wide layers; narrow layers take more so that all 128 threads have an item
 
 struct ConvOp {
   const float* W;     // [ks][Cin][Cout], BatchNorm folded in
@@ -38,13 +38,13 @@ struct ConvOp {
 // positions are taken in the (virtually) upsampled input of length Lin*up; outside it the input is zero.
 __global__ void __launch_bounds__(128) k_conv_gen(const float* __restrict__ in, float* __restrict__ out,
                                                   const float* __restrict__ res1, const float* __restrict__ res2, int Lin, int Lout,
-                                                  ConvOp P) {
+                                                  ConvOp P, int TP) {
   extern __shared__ __align__(16) float sm[];
   const int Cin = P.Cin, Cout = P.Cout, ks = P.ks, half = ks / 2;
   float* ws = sm;                                 // [ks*Cin*Cout]
   const int xrows = (TP - 1) * P.stride + ks;
-  const int xs_stride = Cin + 1;
-  float* xs = ws + ((ks * Cin * Cout + 3) & ~3);  // [xrows][Cin+1]
+  const int xs_stride = Cin + 4;                  // Cin % 4 == 0: rows stay 16-byte aligned for float4 loads
+  float* xs = ws + ((ks * Cin * Cout + 3) & ~3);  // [xrows][Cin+4]
   const int tid = threadIdx.x;
   const int64_t site = blockIdx.y;
   const int p0 = blockIdx.x * TP;
@@ -70,15 +70,22 @@ __global__ void __launch_bounds__(128) k_conv_gen(const float* __restrict__ in, 
     for (int t = 0; t < ks; ++t) {
       const float* wt = ws + t * Cin * Cout + 4 * cg;
       const float* xt = xs + (pg * 4 * P.stride + t) * xs_stride;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float4 w = *reinterpret_cast<const float4*>(wt + ci * Cout);
+      for (int ci = 0; ci < Cin; ci += 4) {  // 4 input channels per step: 8 LDS.128 feed 64 FMAs (same summation order as ci = 0, 1, 2, ...)
+        const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * Cout);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + (ci + 1) * Cout);
+        const float4 w2 = *reinterpret_cast<const float4*>(wt + (ci + 2) * Cout);
+        const float4 w3 = *reinterpret_cast<const float4*>(wt + (ci + 3) * Cout);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float x = xt[i * P.stride * xs_stride + ci];
-          acc[i][0] = fmaf(x, w.x, acc[i][0]);
-          acc[i][1] = fmaf(x, w.y, acc[i][1]);
-          acc[i][2] = fmaf(x, w.z, acc[i][2]);
-          acc[i][3] = fmaf(x, w.w, acc[i][3]);
+          const float4 x = *reinterpret_cast<const float4*>(xt + i * P.stride * xs_stride + ci);
+          acc[i][0] = fmaf(x.x, w0.x, acc[i][0]); acc[i][1] = fmaf(x.x, w0.y, acc[i][1]);
+          acc[i][2] = fmaf(x.x, w0.z, acc[i][2]); acc[i][3] = fmaf(x.x, w0.w, acc[i][3]);
+          acc[i][0] = fmaf(x.y, w1.x, acc[i][0]); acc[i][1] = fmaf(x.y, w1.y, acc[i][1]);
+          acc[i][2] = fmaf(x.y, w1.z, acc[i][2]); acc[i][3] = fmaf(x.y, w1.w, acc[i][3]);
+          acc[i][0] = fmaf(x.z, w2.x, acc[i][0]); acc[i][1] = fmaf(x.z, w2.y, acc[i][1]);
+          acc[i][2] = fmaf(x.z, w2.z, acc[i][2]); acc[i][3] = fmaf(x.z, w2.w, acc[i][3]);
+          acc[i][0] = fmaf(x.w, w3.x, acc[i][0]); acc[i][1] = fmaf(x.w, w3.y, acc[i][1]);
+          acc[i][2] = fmaf(x.w, w3.z, acc[i][2]); acc[i][3] = fmaf(x.w, w3.w, acc[i][3]);
         }
       }
     }
@@ -371,15 +378,20 @@ static int run_conv(const mural_indel_model* m, int oi, const float* in, float* 
                     int Lin, int Lout, cudaStream_t st) {
   const mural_indel_model::Op& o = m->ops[oi];
   ConvOp P{m->d_prep + o.W, m->d_prep + o.b, o.Cin, o.Cout, o.ks, o.stride, o.up, o.act};
+  // items per CTA = (TP/4) position groups x (Cout/4) channel groups: keep >= 128 of them (the U-Net's widest levels are
+  // also its narrowest in channels: Cout = 8 / 16 at L = 8000 / 2000)
+  int TP = TP_MIN;
+  while ((TP / 4) * (o.Cout / 4) < 128 && TP < 512) TP *= 2;
   const int xrows = (TP - 1) * o.stride + o.ks;
-  const size_t smem = sizeof(float) * (((size_t(o.ks) * o.Cin * o.Cout + 3) & ~size_t(3)) + size_t(xrows) * (o.Cin + 1));
+  MURAL_CHECK(o.Cin % 4 == 0 && o.Cout % 4 == 0, "indel conv: channel counts must be multiples of 4");
+  const size_t smem = sizeof(float) * (((size_t(o.ks) * o.Cin * o.Cout + 3) & ~size_t(3)) + size_t(xrows) * (o.Cin + 4));
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     CUDA_TRY(cudaFuncSetAttribute(k_conv_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid((unsigned)cdiv(Lout, TP), (unsigned)ns);
-  LAUNCH(k_conv_gen, grid, 128, smem, st, in, out, r1, r2, Lin, Lout, P);
+  LAUNCH(k_conv_gen, grid, 128, smem, st, in, out, r1, r2, Lin, Lout, P, TP);
   return 0;
 }
 
