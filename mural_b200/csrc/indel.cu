@@ -51,12 +51,17 @@ __global__ void __launch_bounds__(128) k_conv_gen(const float* __restrict__ in, 
   for (int e = tid; e < ks * Cin * Cout; e += 128) ws[e] = P.W[e];
   const int Lv = Lin * P.up;  // virtual (upsampled) input length
   const float* ins = in + site * int64_t(Lin) * Cin;
-  for (int e = tid; e < xrows * Cin; e += 128) {
-    const int k = e / Cin, ci = e - k * Cin;
-    const int q = p0 * P.stride - half + k;
-    float v = 0.f;
-    if (q >= 0 && q < Lv) v = ins[int64_t(q / P.up) * Cin + ci];
-    xs[k * xs_stride + ci] = v;
+  {  // (k, ci) advance by 128 elements per step without a division per element
+    const int dk = 128 / Cin, dci = 128 - dk * Cin;
+    int k = tid / Cin, ci = tid - k * Cin;
+    for (int e = tid; e < xrows * Cin; e += 128) {
+      const int q = p0 * P.stride - half + k;
+      float v = 0.f;
+      if (q >= 0 && q < Lv) v = ins[int64_t(P.up == 1 ? q : q / P.up) * Cin + ci];
+      xs[k * xs_stride + ci] = v;
+      k += dk; ci += dci;
+      if (ci >= Cin) { ci -= Cin; ++k; }
+    }
   }
   __syncthreads();
   const int CG = Cout >> 2;
