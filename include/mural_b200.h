@@ -66,6 +66,9 @@ int32_t mural_genome_n_chrom(const mural_genome_t* g);
 int64_t mural_genome_chrom_len(const mural_genome_t* g, int32_t chrom);
 int64_t mural_genome_device_bytes(const mural_genome_t* g);
 int64_t mural_genome_n_exception_runs(const mural_genome_t* g);
+/* host copy of the non-ACGT runs (R Y M S W K B D H V N) as chromosome index / start / end (end exclusive), sorted; arrays
+ * of mural_genome_n_exception_runs() elements.  Lets a caller tell which site windows contain such symbols. */
+int mural_genome_exception_runs(const mural_genome_t* g, int32_t* h_chrom, int64_t* h_start, int64_t* h_end);
 
 /* ------------------------------------------------------------------------------------------------
  * Encoders (bit-exact with the reference; exposed for parity tests and for callers that still want

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmural_b200.so")
 
 MODEL_SNV, MODEL_INDEL = 0, 1
 MODE_FP32, MODE_BF16 = 0, 1
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "auto_bf16": 1}
 
 
 class SnvConfig(C.Structure):
@@ -75,6 +75,7 @@ PROTOTYPES = {
     "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "mural_genome_exception_runs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mural_bed_read": (C.c_int, [C.c_char_p, _vp]),
     "mural_bed_n": (_i64, [_vp]),
     "mural_bed_n_chrom": (_i32, [_vp]),

@@ -188,3 +188,21 @@ extern "C" int64_t mural_genome_chrom_len(const mural_genome_t* g, int32_t c) {
 }
 extern "C" int64_t mural_genome_device_bytes(const mural_genome_t* g) { return g ? g->device_bytes : 0; }
 extern "C" int64_t mural_genome_n_exception_runs(const mural_genome_t* g) { return g ? g->view.n_exc : 0; }
+
+// Host copy of the non-ACGT run table as (chromosome, start, end) in chromosome coordinates, end exclusive, sorted.
+extern "C" int mural_genome_exception_runs(const mural_genome_t* g, int32_t* h_chrom, int64_t* h_start, int64_t* h_end) {
+  MURAL_CHECK(g && (g->view.n_exc == 0 || (h_chrom && h_start && h_end)), "NULL argument");
+  const int64_t n = g->view.n_exc;
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaMemcpy(h_start, g->view.exc_start, n * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(h_end, g->view.exc_end, n * 8, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {  // global -> chromosome coordinates (runs never span chromosomes)
+    int c = 0;
+    while (c + 1 < (int)g->h_off.size() && g->h_off[c + 1] <= h_start[i]) ++c;
+    h_chrom[i] = c;
+    h_start[i] -= g->h_off[c];
+    h_end[i] -= g->h_off[c];
+  }
+  return 0;
+}

@@ -88,6 +88,33 @@ class PackedGenome:
     def n_exception_runs(self):
         return int(_lib.lib().mural_genome_n_exception_runs(self._h))
 
+    def exception_runs(self):
+        """(chrom index, start, end) numpy arrays of the non-ACGT runs (end exclusive), sorted by chromosome then start."""
+        L = _lib.lib()
+        n = int(L.mural_genome_n_exception_runs(self._h))
+        ch, st, en = np.empty(n, np.int32), np.empty(n, np.int64), np.empty(n, np.int64)
+        _lib.check(L.mural_genome_exception_runs(self._h, _lib.ptr(ch), _lib.ptr(st), _lib.ptr(en)))
+        return ch, st, en
+
+    def windows_with_exceptions(self, chrom, pos, radius, model_type="snv"):
+        """Boolean mask: the expanded window of the site contains a non-ACGT symbol or overhangs its chromosome (the reference
+        imputes N there, preprocessing.py:791-800).  chrom: genome chromosome index per site; pos: BED start."""
+        chrom, pos = np.asarray(chrom, dtype=np.int64), np.asarray(pos, dtype=np.int64)
+        lo = pos - radius + (1 if model_type == "indel" else 0)
+        hi = pos + radius + (0 if model_type == "indel" else 1)                     # exclusive
+        out = (lo < 0) | (hi > self.lengths[chrom])
+        ech, est, een = self.exception_runs()
+        if len(est):
+            # per chromosome: first run that ends after the window start; it intersects iff it starts before the window end
+            big = int(self.lengths.max()) + 2 * int(radius) + 8
+            key_runs_end = ech.astype(np.int64) * big + een
+            key_lo = chrom * big + np.maximum(lo, 0)
+            i = np.searchsorted(key_runs_end, key_lo, side="right")
+            ok = i < len(est)
+            ii = np.minimum(i, len(est) - 1)
+            out |= ok & (ech[ii] == chrom) & (est[ii] < hi)
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().mural_genome_destroy(self._h)

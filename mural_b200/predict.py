@@ -70,7 +70,25 @@ def predict_sites(model, dataset, lo, hi, batch_sites=1 << 20):
                             for c in range(0, b - a, 4096))
             else:
                 outs.append(model.forward(None, sb))
-    return torch.cat(outs) if outs else torch.empty((0, model.n_class), device=dev)
+    logp = torch.cat(outs) if outs else torch.empty((0, model.n_class), device=dev)
+    if dataset.model_type == "snv" and getattr(model, "compute_mode", "fp32") == "auto_bf16":
+        # precision policy of compute_mode="auto": the bf16 tensor-core path everywhere, and the fp32 kernels again for the
+        # (rare) sites whose expanded window contains N / IUPAC symbols or overhangs the chromosome — inputs far from what
+        # the network was trained on can drive activations (and logits) an order of magnitude up, where bf16's relative
+        # rounding no longer stays inside the 5e-3 gate on probabilities
+        mask = dataset.genome.windows_with_exceptions(dataset.chrom[lo:hi], dataset.pos[lo:hi], dataset.distal_radius)
+        idx = np.flatnonzero(mask)
+        if len(idx):
+            model.compute_mode = "fp32"
+            try:
+                with torch.no_grad():
+                    for c in range(0, len(idx), 1 << 16):
+                        sel = idx[c:c + (1 << 16)] + lo
+                        sb = SiteBatch(torch.from_numpy(dataset.pos[sel]).to(dev), torch.from_numpy(dataset.meta[sel]).to(dev), dataset.genome)
+                        logp[torch.from_numpy(sel - lo).to(dev)] = model.forward(None, sb)
+            finally:
+                model.compute_mode = "auto_bf16"
+    return logp
 
 
 def format_predictions(chrom, start, end, strand, mut_type, prob):
@@ -106,7 +124,7 @@ def write_tsv(path, chrom_names, start, end, strand, mut_type, prob, n_threads=N
 
 
 def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator_path="", pred_file=None, segment_center=None,
-                poisson_calib=False, compute_mode="bf16", genome=None, model_type="snv", return_frame=True):
+                poisson_calib=False, compute_mode="auto", genome=None, model_type="snv", return_frame=True):
     """Returns the prediction DataFrame on rank 0 (None elsewhere); writes `pred_file` when given."""
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     rank = torch.distributed.get_rank() if dist_on else 0
@@ -123,7 +141,7 @@ def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator
                            model_type=model_type)
     model = build_model_from_files(model_path, config, dev, model_type=model_type)
     if model_type == "snv":
-        model.compute_mode = compute_mode
+        model.compute_mode = "auto_bf16" if compute_mode == "auto" else compute_mode
     poisson_calib = bool(poisson_calib) or model_type == "indel"          # run_predict.py:224
     n = len(ds.pos)
     lo, hi = shard_bounds(n, world, rank)

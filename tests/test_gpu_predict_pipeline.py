@@ -148,3 +148,35 @@ def test_indel_tsv_matches_oracle_pipeline(tmp_path, kat):
     got = pd.read_csv(out, sep="\t")
     assert list(got.columns) == list(exp.columns) and len(got) == len(exp)
     assert np.abs(got[cols].values - exp[cols].values).max() <= 1e-3 + 5e-4 * np.abs(exp[cols].values).max()
+
+
+def test_auto_mode_routes_exception_windows_to_fp32(kat, cuda_genome):
+    """compute_mode='auto': bf16 everywhere, fp32 kernels for sites whose window has N / IUPAC symbols or overhangs the
+    chromosome.  The mask equals a brute-force scan of the windows; masked rows equal the fp32 path bit for bit, the
+    others the bf16 path."""
+    from mural_b200 import PackedSiteDataset, SiteTable
+    from mural_b200.predict import predict_sites
+    from test_gpu_snv_forward import build_model
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    _, genome = kat
+    names = list(genome)
+    rng = np.random.default_rng(31)
+    n = 4000
+    ch = rng.integers(0, len(names), n)
+    st = np.array([rng.integers(0, len(genome[names[c]])) for c in ch])
+    order = np.lexsort((st, ch)); ch, st = ch[order], st[order]
+    sd = rng.integers(0, 2, n)
+    sites = SiteTable(names, ch, st, st + 1, sd, st % 4)
+    R = cfg["distal_radius"]
+    ds = PackedSiteDataset(sites, cuda_genome, 5000, cfg["local_radius"], cfg["local_order"], R)
+    mask = cuda_genome.windows_with_exceptions(ds.chrom, ds.pos, R)
+    brute = np.array([(p - R < 0) or (p + R + 1 > len(genome[names[c]])) or any(b not in "ACGTacgt" for b in genome[names[c]][max(0, p - R):p + R + 1])
+                      for c, p in zip(ds.chrom, ds.pos)])
+    assert (mask == brute).all() and 0 < mask.sum() < n
+    m = build_model(cfg, state, int(z["n_cat"]))
+    out = {}
+    for mode in ("fp32", "bf16", "auto_bf16"):
+        m.compute_mode = mode
+        out[mode] = predict_sites(m, ds, 0, n).cpu().numpy()
+    assert np.array_equal(out["auto_bf16"][mask], out["fp32"][mask])
+    assert np.array_equal(out["auto_bf16"][~mask], out["bf16"][~mask])
