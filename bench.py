@@ -189,6 +189,54 @@ def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2):
             "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), sites every 50 bp" % (Rd, 2 * Rd)}
 
 
+def eval_leg(genome, pos, meta, logp, cfg, n=1_000_000, reps=5):
+    """Per-epoch validation metrics of the reference's Evaluator (training.py:488-520) on the first n sites of a
+    step: 3/5/7-mer correlations, the regional score (3- and 5-mer tables per 10 000-site region) and the 100 kb / 500 kb window
+    correlations — device reductions (csrc/metrics.cu) + host Pearson over the small tables.  Rank-local, no collective."""
+    import torch
+    from mural_b200.calibration import calibrate
+    from mural_b200.evaluation import EvalData, Evaluator
+    n = int(min(n, len(pos), logp.shape[0]))
+    rng = np.random.default_rng(99)
+    labels = rng.choice(4, n, p=[0.952381, 0.0140095, 0.0198, 0.0138095])
+    m = (np.asarray(meta[:n]).astype(np.int64) & ~0xfe) | (labels << 1)
+    d_meta = torch.from_numpy(m.astype(np.int32)).cuda()
+    d_pos = torch.from_numpy(np.asarray(pos[:n]).astype(np.int32)).cuda()
+    flank = genome.encode_local(d_pos, d_meta, cfg["local_radius"], 1)
+    prob = calibrate(logp[:n].contiguous())
+    ed = EvalData(flank, d_meta, prob, f32=True, start=d_pos)
+    lines = []
+
+    def epoch_metrics():
+        E = Evaluator(ed, None, cfg["n_class"], printer=lambda *a: lines.append(a))
+        E.evaluate_kmer([3, 5, 7])
+        E.evaluate_regional_score(n, [3, 5])
+        return E
+    epoch_metrics()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        E = epoch_metrics()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    # device time of the k-mer reduction alone (one pass over the sites): algorithmic bytes = codes of the 2d flank columns
+    # (int64) + meta + n_class fp64 probabilities
+    from mural_b200.evaluation import kmer_group_table
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kmer_group_table(ed, 5)
+    ev0.record()
+    for _ in range(reps):
+        kmer_group_table(ed, 5)
+    ev1.record()
+    torch.cuda.synchronize()
+    k_ms = ev0.elapsed_time(ev1) / reps
+    bytes_site = 4 * 8 + 4 + 8 * cfg["n_class"]
+    return {"metric": "validation sites/sec (Evaluator: 3/5/7-mer correlations + regional score)", "value": n / dt, "unit": "sites/s",
+            "sites": n, "ms_per_epoch_metrics": dt * 1e3, "kmer5_table_ms": k_ms, "kmer5_algorithmic_GBps": n * bytes_site / (k_ms * 1e-3) / 1e9,
+            "kmer3_corr": [round(float(c), 4) for c in E.metrics["kmer3"]], "regional_score": float(E.metrics["score"]),
+            "note": "includes the host sync + table copy of every launch; labels synthetic (class proportions of training.py:332)"}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
     """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
@@ -263,6 +311,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     ap.add_argument("--no-indel", action="store_true", help="skip the MuRaL-indel predict leg (BASELINE configs[3])")
+    ap.add_argument("--no-eval", action="store_true", help="skip the validation-metrics leg (Evaluator, SURVEY 8f N3)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -398,6 +447,14 @@ def main():
         except Exception as e:
             indel = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    evalm = None
+    if rank == 0 and not a.no_eval:
+        try:
+            step(0)
+            evalm = eval_leg(genome, pos, meta, out, cfg)
+        except Exception as e:
+            evalm = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- roofline of the dominant kernel: library-side CUDA-event profile over an identical pass
     roof = None
     if rank == 0:
@@ -409,7 +466,7 @@ def main():
                            "per-step activation workspace > L2", wall_s_timed_region=t_wall),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof, "train": train, "indel": indel}
+            "roofline": roof, "train": train, "indel": indel, "eval_metrics": evalm}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample

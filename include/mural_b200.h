@@ -212,6 +212,28 @@ int mural_calibrate(const float* d_logp, int64_t n, int32_t n_class, const doubl
                     int32_t poisson, double* d_prob, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Validation metrics of the reference's Evaluator (MuRaL/evaluation/evaluation.py, called every epoch from
+ * MuRaL/training.py:488-520) as device-side grouped reductions.  Labels are read from d_meta (MURAL_META), probabilities
+ * are fp64 [n, n_class] (mural_calibrate output).  All sums are 64-bit integers: counts exactly, probabilities in fixed
+ * point with MURAL_METRIC_SCALE units per 1.0, so tables are reproducible bit for bit; n <= 2^27 per call.
+ * mural_kmer_group_stats  the groupby(...).mean() of freq_kmer_comp_multi (:48-67) and, with region_size > 0, of every
+ *                   region of evaluate_regional_score (:545-566; calc_avg_prob :196-203 is the sum over a region's groups).
+ *                   d_flank: int64 [n, n_cols] order-1 local codes 0..4 (columns us_R..us1, mid, ds1..ds_R of data_local);
+ *                   group index = codes of us_d..us1, ds1..ds_d (d = k/2) as a base-5 number, first column most significant
+ *                   (= pandas group order).  region_size 0: one region of n sites; otherwise n / region_size regions of
+ *                   consecutive sites (the remainder is ignored, as the reference's iloc slices do).
+ *                   d_table: int64 [n_regions, 5^(2d), 1 + 2*n_class] = sites, sites per label, fixed-point prob sums.
+ * mural_window_runs corr_calc_sub (:124-193): runs of consecutive sites (in d_order if given, else as stored) that share
+ *                   (chrom, start // window).  *h_n_runs receives the number of runs (host sync).  With d_rows == NULL only
+ *                   counts; otherwise fills int64 [n_runs, 1 + 2*n_class] (same columns as above; n_runs <= max_runs).
+ * ---------------------------------------------------------------------------------------------- */
+#define MURAL_METRIC_SCALE 68719476736.0 /* 2^36 */
+int mural_kmer_group_stats(const int64_t* d_flank, int64_t n, int32_t n_cols, int32_t k, const int32_t* d_meta,
+                           const double* d_prob, int32_t n_class, int64_t region_size, int64_t* d_table, void* stream);
+int mural_window_runs(const int32_t* d_meta, const int32_t* d_start, const int64_t* d_order, const double* d_prob, int64_t n,
+                      int32_t n_class, int32_t window, int64_t* h_n_runs, int64_t* d_rows, int64_t max_runs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host ingest (no GPU involved): streaming BED / FASTA readers, plain or gzip.
  * mural_bed_read   replaces iterating `BedTool(file)` for .chrom/.start/.stop/.score/.strand
  *                  (MuRaL/data/preprocessing.py:39-106, 752-754): BED6, score = label, strand '+' -> 0 else 1;

@@ -75,6 +75,8 @@ PROTOTYPES = {
     "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "mural_kmer_group_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "mural_window_runs": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mural_genome_exception_runs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "mural_bed_read": (C.c_int, [C.c_char_p, _vp]),
     "mural_bed_n": (_i64, [_vp]),

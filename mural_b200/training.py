@@ -224,6 +224,39 @@ def network2_train_forward(model, local_input, distal_input):
     return _TrainFn.apply(st, distal_input, *st.params)
 
 
+def load_pretrained(model, model_state, train_all=True, init_fc_with_pretrained=True, model_type="snv"):
+    """Transfer-learning initialisation, training.py:289-320: load the pretrained state dict on the CPU copy (strict keys,
+    `.layer.N` aliases included), move back, then the two switches.  As in the reference both switches only work when
+    True for Network2 / UNet_Small: the partial-freeze and fc re-initialisation branches address `model.distal_fc`, which
+    neither model defines (the SNV CLI forces train_all, mural_snv.py:103-106), so they end in the same AttributeError
+    here; INDEL exits with the reference's messages (training.py:307,318)."""
+    from .nn_utils import weights_init
+    device = next(model.parameters()).device
+    model.to(torch.device("cpu"))
+    model.load_state_dict(model_state)
+    model.to(device)
+    if train_all:
+        for param in model.parameters():
+            param.requires_grad = True
+    else:
+        if model_type == "indel":
+            raise SystemExit("Error: --train_all need used in commend line for INDEL, transfer learning for INDEL model need fine tune "
+                             "all parameters !")
+        for param in model.parameters():
+            param.requires_grad = False
+        model.local_fc[-1].weight.requires_grad = True
+        model.local_fc[-1].bias.requires_grad = True
+        model.distal_fc[-1].weight.requires_grad = True
+        model.distal_fc[-1].bias.requires_grad = True
+    if not init_fc_with_pretrained:
+        if model_type == "indel":
+            raise SystemExit("Error: --init_fc_with_pretrained need used in commend line for INDEL, transfer learning for INDEL model "
+                             "need fine tune all parameters !")
+        model.local_fc[-1].apply(weights_init)
+        model.distal_fc[-1].apply(weights_init)
+    return model
+
+
 def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim="Adam", lr=1e-3, weight_decay=0.0, LR_gamma=0.5,
                  min_lr=1e-6, restart_lr=1e-4, seed=0, print_every=1000, segment_indices=None):
     """The hot loop of training.py:387-452 on site records; returns per-epoch mean losses.  Evaluation, calibrator

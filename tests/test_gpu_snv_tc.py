@@ -144,7 +144,7 @@ def test_dense_lattice_equals_per_site_stages(kat, cuda_genome, chunk):
                               float((res["lattice"] - res["site"]).abs().max()))
 
 
-@pytest.mark.parametrize("R_d,R_l", [(100, 7), (200, 10), (500, 7), (2000, 10)])
+@pytest.mark.parametrize("R_d,R_l", [(100, 7), (200, 10), (500, 7), (2000, 10), (5000, 7)])
 def test_bf16_window_sweep_dense_sites(kat, cuda_genome, R_d, R_l):
     """Config-5 window sweep on the tcgen05 path with random-init weights and dense sorted sites: the lattice path
     (where the window is long enough for it) equals the per-site stages bit for bit, and both stay within 5e-3 of the

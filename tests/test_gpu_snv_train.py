@@ -82,6 +82,48 @@ def test_train_forward_backward_vs_autograd(kat, cuda_genome, tag):
     assert int(sdm["conv1.0.num_batches_tracked"]) == int(state["conv1.0.num_batches_tracked"]) + 1
 
 
+@pytest.mark.parametrize("R_d", [100, 5000])
+def test_transfer_window_sweep_train_step(kat, cuda_genome, R_d):
+    """a checkpoint trained at R_d=1000 fine-tuned at another distal radius (the network is fully
+    convolutional; run_train_TL_raytune.py:138-170 copies every other hyper-parameter from the pretrained config).
+    Train-mode forward and all gradients at L=201 and L=10001 vs fp64 autograd on the oracle."""
+    from mural_b200 import _lib
+    from mural_b200.training import TrainState, load_pretrained
+    z, cfg, state = load_snv_golden("hs_AT")
+    cfg = dict(cfg, distal_radius=R_d)
+    _, genome = kat
+    n = 12
+    labels = (z["start"][:n] % 4).astype(np.int64)
+    pretrained = {k: v.cpu().clone() for k, v in build_model(dict(cfg, distal_radius=1000), state, int(z["n_cat"])).state_dict().items()}
+    from mural_b200 import model_choice, weights_init
+    common = dict(emb_dims=[(65, 2)] * int(z["n_cat"]), n_cont=0, n_class=cfg["n_class"], distal_order=1, in_channels=4)
+    m = model_choice(2, cfg, common, "snv").to("cuda")
+    m.apply(weights_init)
+    load_pretrained(m, pretrained, train_all=True, init_fc_with_pretrained=True)
+    assert all(p.requires_grad for p in m.parameters())
+    st = TrainState(m, "Adam", lr=1e-3)
+    st.set_dropout(0, 0, 0)
+    m.train()
+    sb = _batch(z, cuda_genome, n, labels)
+    logp = st.forward(sb)
+    cat, oh = _oracle_inputs(z, cfg, genome, n)
+    sd64 = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=("running" not in k))
+            for k, v in state.items() if "num_batches" not in k}
+    ref = NT.network2_forward(sd64, cat, oh, torch.float64, train=True)
+    assert np.abs(logp.cpu().numpy() - ref.detach().numpy()).max() < 2e-4
+    NT.ce_sum(ref, labels).backward()
+    dlogp = torch.empty_like(logp)
+    _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(sb.meta), n, 4, _lib.ptr(st.loss_dev), _lib.ptr(dlogp),
+                                            _lib.current_stream()))
+    g = st.backward(dlogp).cpu().numpy()
+    for name, off, num, is_buf in m.native_layout():
+        if is_buf:
+            continue
+        ref_g = sd64[name].grad.numpy().reshape(-1)
+        err = np.abs(g[off:off + num] - ref_g).max() / max(1e-3, np.abs(ref_g).max())
+        assert err < 5e-3, (R_d, name, err)
+
+
 @pytest.mark.parametrize("optim", ["Adam", "AdamW", "SGD"])
 def test_fused_optimizer_matches_torch(optim):
     """clip_grad_norm_(10) + optimizer.step() over the flat buffer == torch.optim on the same gradients, 3 steps."""

@@ -88,6 +88,38 @@ def test_state_dict_contract(manifest):
         model_choice(1, cfg, common, "snv")
 
 
+def test_transfer_initialisation_mirrors_reference():
+    """training.py:289-320: pretrained state loaded at another distal radius (all tensors are radius-independent); the two
+    switches behave as in the reference, including its dead partial-freeze / fc re-init branches (AttributeError)."""
+    import torch
+    from mural_b200 import model_choice, weights_init
+    from mural_b200.training import load_pretrained
+    cfg = {"local_radius": 7, "local_order": 3, "local_hidden1_size": 150, "local_hidden2_size": 75, "distal_radius": 1000,
+           "emb_dropout": .1, "local_dropout": .1, "CNN_kernel_size": 3, "CNN_out_channels": 32, "distal_fc_dropout": .25,
+           "n_class": 4, "model_no": 2}
+    common = dict(emb_dims=[(65, 2)] * 13, n_cont=0, n_class=4, distal_order=1, in_channels=4)
+    torch.manual_seed(0)
+    src = model_choice(2, cfg, common, "snv")
+    src.apply(weights_init)
+    state = {k: v.clone() for k, v in src.state_dict().items()}
+    dst = model_choice(2, dict(cfg, distal_radius=200), common, "snv")
+    dst.apply(weights_init)
+    for p in dst.parameters():
+        p.requires_grad = False
+    load_pretrained(dst, state, train_all=True, init_fc_with_pretrained=True)
+    assert all(p.requires_grad for p in dst.parameters())
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, state[k]), k
+    with pytest.raises(AttributeError):
+        load_pretrained(dst, state, train_all=False, init_fc_with_pretrained=True)
+    with pytest.raises(AttributeError):
+        load_pretrained(dst, state, train_all=True, init_fc_with_pretrained=False)
+    with pytest.raises(RuntimeError):          # strict load: a state dict of another architecture is refused
+        load_pretrained(dst, {k: v for k, v in state.items() if "conv3" not in k})
+    with pytest.raises(SystemExit):
+        load_pretrained(dst, state, train_all=False, model_type="indel")
+
+
 def test_native_tsv_writer_equals_pandas(tmp_path):
     """mural_write_tsv (threaded C formatter) == DataFrame.sort_values(['chrom','start']).to_csv(sep='\\t',
     float_format='%.4g', index=False) byte for byte (run_predict.py:237-239), incl. ties, tiny / huge / exact values."""

@@ -1,4 +1,5 @@
 """CPU: the oracle (oracle/) against the fixtures generated from the real reference."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -107,3 +108,25 @@ def test_poisson_calibrate_properties():
     lam = -np.log(p[:, 0])
     assert np.allclose(q[:, 0], 1 - lam)
     assert np.allclose(q[:, 1:].sum(1), lam)          # non-reference classes re-scaled to sum to lambda
+
+
+def test_evaluation_oracle_matches_reference_goldens():
+    """oracle/evaluation_np.py vs the outputs of the reference's own evaluation.py (tests/golden/eval_kat.npz)."""
+    from oracle import evaluation_np as EN
+    z = np.load(os.path.join(GOLD, "eval_kat.npz"))
+    for tag, K, kmers in (("snv_f32", 4, [3, 5, 7]), ("snv_f64", 4, [3, 5, 7]), ("indel_f32", 8, [2, 4, 6])):
+        flank, labels, prob = z[tag + ":flank"].astype(np.int64), z[tag + ":labels"].astype(np.int64), z[tag + ":prob"]
+        f32 = prob.dtype == np.float32
+        for k in kmers:
+            assert np.allclose(EN.freq_kmer_comp_multi(flank, labels, prob, k, K, f32), z["%s:kmer%d" % (tag, k)], rtol=0, atol=1e-12, equal_nan=True)
+        assert np.allclose(EN.calc_avg_prob(labels, prob, K, f32), z[tag + ":avg_prob"], rtol=0, atol=1e-15)
+        if tag != "snv_f32":     # the float32 python loops are slow; one float32 case is covered by the indel fixture
+            score, corr_list, n_regions = EN.regional_score(flank, labels, prob, len(prob), kmers, K, f32)
+            assert n_regions == int(z[tag + ":regional_score"][1])
+            assert abs(score - z[tag + ":regional_score"][0]) < 1e-9 * max(1.0, score)
+            assert np.allclose(corr_list, z[tag + ":regional_corr_list"], rtol=0, atol=1e-10, equal_nan=True)
+        names, chrom, start = z[tag + ":chrom_names"], z[tag + ":chrom"].astype(np.int64), z[tag + ":start"].astype(np.int64)
+        order = np.lexsort((start, names[chrom]))
+        for w in (100000, 500000):
+            got = EN.corr_calc_sub(chrom[order], start[order], labels[order], prob[order], w, K, f32)
+            assert np.allclose(got, z["%s:window%d" % (tag, w)], rtol=0, atol=1e-9, equal_nan=True)
