@@ -202,6 +202,11 @@ int mural_ce_sum_grad(const float* d_logp, const int32_t* d_meta, int64_t n, int
 int mural_optimizer_step(int32_t kind, float* d_params, const float* d_grads, float* d_m, float* d_v, float* d_vmax, int64_t n,
                          float lr, float weight_decay, int64_t step, float max_norm, float grad_scale, double* d_scratch,
                          void* stream);
+/* Same step with the per-step hyper-parameters on the device, so that the whole training step can be captured once in a
+ * CUDA graph and replayed: *d_lr is read by the kernel, *d_step (int64, starts at 0) is incremented by the call before use. */
+int mural_optimizer_step_dev(int32_t kind, float* d_params, const float* d_grads, float* d_m, float* d_v, float* d_vmax, int64_t n,
+                             const float* d_lr, float weight_decay, int64_t* d_step, float max_norm, float grad_scale,
+                             double* d_scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Calibration epilogue (run_predict.py:214-225): softmax(logp) -> FullDirichlet apply

@@ -386,8 +386,9 @@ __global__ void k_linear_bwd_x(const float* __restrict__ dy, const float* __rest
 // BatchNorm1d over the batch of an [n][F] tensor + dropout; one block per feature
 __global__ void k_bn1d_fwd(const float* __restrict__ x, int64_t n, int F, float* __restrict__ P, int64_t g, int64_t be, int64_t rm,
                            int64_t rv, float* __restrict__ mu, float* __restrict__ invstd, float p_drop, uint64_t seed,
-                           uint32_t step, uint32_t layer, float* __restrict__ y) {
+                           const uint32_t* __restrict__ step_p, uint32_t layer, float* __restrict__ y) {
   __shared__ double sh[2][256];
+  const uint32_t step = __ldg(step_p);
   const int f = blockIdx.x;
   double s = 0, q = 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -422,9 +423,10 @@ __global__ void k_bn1d_fwd(const float* __restrict__ x, int64_t n, int F, float*
 // backward of dropout(BN1d(x)): dx, dgamma, dbeta
 __global__ void k_bn1d_bwd(const float* __restrict__ dy, const float* __restrict__ x, int64_t n, int F, const float* __restrict__ P,
                            int64_t g, const float* __restrict__ mu, const float* __restrict__ invstd, float p_drop, uint64_t seed,
-                           uint32_t step, uint32_t layer, float* __restrict__ dx, float* __restrict__ G, int64_t g_off,
+                           const uint32_t* __restrict__ step_p, uint32_t layer, float* __restrict__ dx, float* __restrict__ G, int64_t g_off,
                            int64_t be_off) {
   __shared__ double sh[2][256];
+  const uint32_t step = __ldg(step_p);
   const int f = blockIdx.x;
   const float m = mu[f], is = invstd[f], ga = P[g + f];
   double s = 0, q = 0;
@@ -452,7 +454,8 @@ __global__ void k_bn1d_bwd(const float* __restrict__ dy, const float* __restrict
   }
 }
 __global__ void k_emb_fwd(const float* __restrict__ E, const int32_t* __restrict__ cat, int64_t n, int n_cat, float p_drop,
-                          uint64_t seed, uint32_t step, float* __restrict__ y) {
+                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ y) {
+  const uint32_t step = __ldg(step_p);
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int K1 = n_cat * 5;
   if (e >= n * K1) return;
@@ -461,7 +464,8 @@ __global__ void k_emb_fwd(const float* __restrict__ E, const int32_t* __restrict
   y[e] = E[cat[i * n_cat + k / 5] * 5 + k % 5] * drop_scale(p_drop, seed, step, 100, uint64_t(e));
 }
 __global__ void k_emb_bwd(const float* __restrict__ dy, const int32_t* __restrict__ cat, int64_t n, int n_cat, float p_drop,
-                          uint64_t seed, uint32_t step, float* __restrict__ gE) {
+                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ gE) {
+  const uint32_t step = __ldg(step_p);
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int K1 = n_cat * 5;
   if (e >= n * K1) return;
@@ -708,13 +712,17 @@ __global__ void k_sumsq(const float* __restrict__ g, int64_t n, float scale, dou
   }
   if (threadIdx.x == 0) atomicAdd(out, sh[0]);
 }
+__global__ void k_bump_u32(uint32_t* c) { *c += 1u; }
+__global__ void k_bump_i64(int64_t* c) { *c += 1; }
 // kind 0: Adam (coupled L2), 1: AdamW + amsgrad, 2: SGD momentum 0.98 nesterov  (training.py:346-357);
 // gradient first scaled by grad_scale, then by the clip_grad_norm_ coefficient min(1, max_norm/(norm+1e-6))
 __global__ void k_opt_step(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                            float* __restrict__ vmax, int64_t n, float lr, float wd, int64_t step, float max_norm, float grad_scale,
-                           const double* __restrict__ sumsq) {
+                           const double* __restrict__ sumsq, const float* __restrict__ lr_p, const int64_t* __restrict__ step_p) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
+  if (lr_p) lr = __ldg(lr_p);          // graph-captured steps: hyper-parameters that change per step live on the device
+  if (step_p) step = __ldg(step_p);
   float clip = 1.f;
   if (max_norm > 0.f) {
     const float norm = float(sqrt(*sumsq));
@@ -767,7 +775,8 @@ struct mural_snv_train {
   // dropout
   float p_emb = 0.f, p_local = 0.f, p_fc = 0.f;
   uint64_t seed = 0;
-  uint32_t step = 0;
+  uint32_t* d_step = nullptr;  // forward counter on the device (dropout stream position): bumped by a kernel, so that a
+                               // captured CUDA graph of the step draws new masks at every replay
   // tape pointers (valid after forward)
   int64_t n = 0;
   uint8_t* sym = nullptr;
@@ -818,6 +827,8 @@ extern "C" int mural_snv_train_create(mural_snv_model_t* m, mural_snv_train_t** 
   CUDA_TRY(cudaMalloc((void**)&T->d_stat, sizeof(double) * (2 * 1024 + 8)));
   CUDA_TRY(cudaMalloc((void**)&T->d_stem, sizeof(float) * 2 * (16 + 2 * int64_t(ks) * 16 * C)));
   CUDA_TRY(cudaMalloc((void**)&T->d_cnt, sizeof(unsigned long long) * 32));
+  CUDA_TRY(cudaMalloc((void**)&T->d_step, 4));
+  CUDA_TRY(cudaMemset(T->d_step, 0, 4));
   *out = T;
   return 0;
 }
@@ -825,7 +836,7 @@ extern "C" int mural_snv_train_create(mural_snv_model_t* m, mural_snv_train_t** 
 extern "C" void mural_snv_train_destroy(mural_snv_train_t* T) {
   if (!T) return;
   cudaFree(T->d_conv); cudaFree(T->d_Wt); cudaFree(T->d_Wf); cudaFree(T->d_bn); cudaFree(T->d_const);
-  cudaFree(T->d_stat); cudaFree(T->d_stem); cudaFree(T->d_cnt); cudaFree(T->d_tape);
+  cudaFree(T->d_stat); cudaFree(T->d_stem); cudaFree(T->d_cnt); cudaFree(T->d_tape); cudaFree(T->d_step);
   delete T;
 }
 
@@ -917,7 +928,7 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
   MURAL_CHECK(ks * C * C <= 48 * 256, "unsupported conv shape for training (CNN_kernel_size * C^2 must be <= 12288)");
   if (int rc = ensure_tape(T, n)) return rc;
   T->n = n;
-  T->step += 1;
+  LAUNCH(k_bump_u32, 1, 1, 0, st, T->d_step);
   float* P = d_blob;
   const int64_t wsz = int64_t(7) * C * C;
   LAUNCH(k_prep_conv, N_CONV, 256, 0, st, P, T->d_conv, C, T->d_Wt, T->d_Wf, wsz);
@@ -963,20 +974,20 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
     LAUNCH(k_gmax_fwd, gridn(n * C), 256, 0, st, b.h, b.gm, b.ig, n, B.L3, C);
     const std::string fc = br ? "distal_fc2" : "distal_fc1";
     LAUNCH(k_bn1d_fwd, C, 256, 0, st, b.gm, n, C, P, off_of(m, fc + ".0.weight"), off_of(m, fc + ".0.bias"),
-           off_of(m, fc + ".0.running_mean"), off_of(m, fc + ".0.running_var"), b.mu, b.is, T->p_fc, T->seed, T->step, 10u + br, b.gmn);
+           off_of(m, fc + ".0.running_mean"), off_of(m, fc + ".0.running_var"), b.mu, b.is, T->p_fc, T->seed, T->d_step, 10u + br, b.gmn);
     LAUNCH(k_linear_fwd, gridn(n * NC), 256, 0, st, b.gmn, P + off_of(m, fc + ".2.weight"), P + off_of(m, fc + ".2.bias"), n, C, NC, 0,
            b.logit);
   }
   // local branch (model_snv.py:452-468, 492)
-  LAUNCH(k_emb_fwd, gridn(n * K1), 256, 0, st, P + off_of(m, "emb_layer.weight"), T->cat, n, m->n_cat, T->p_emb, T->seed, T->step, T->e0);
+  LAUNCH(k_emb_fwd, gridn(n * K1), 256, 0, st, P + off_of(m, "emb_layer.weight"), T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, T->e0);
   LAUNCH(k_linear_fwd, gridn(n * H1), 256, 0, st, T->e0, P + off_of(m, "lin_layers.0.weight"), P + off_of(m, "lin_layers.0.bias"), n, K1, H1,
          1, T->r1);
   LAUNCH(k_bn1d_fwd, H1, 256, 0, st, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), off_of(m, "bn_layers.0.bias"),
-         off_of(m, "bn_layers.0.running_mean"), off_of(m, "bn_layers.0.running_var"), T->mu1, T->is1, T->p_local, T->seed, T->step, 1u, T->d1);
+         off_of(m, "bn_layers.0.running_mean"), off_of(m, "bn_layers.0.running_var"), T->mu1, T->is1, T->p_local, T->seed, T->d_step, 1u, T->d1);
   LAUNCH(k_linear_fwd, gridn(n * H2), 256, 0, st, T->d1, P + off_of(m, "lin_layers.1.weight"), P + off_of(m, "lin_layers.1.bias"), n, H1, H2,
          1, T->r2);
   LAUNCH(k_bn1d_fwd, H2, 256, 0, st, T->r2, n, H2, P, off_of(m, "bn_layers.1.weight"), off_of(m, "bn_layers.1.bias"),
-         off_of(m, "bn_layers.1.running_mean"), off_of(m, "bn_layers.1.running_var"), T->mu2, T->is2, T->p_local, T->seed, T->step, 2u, T->d2);
+         off_of(m, "bn_layers.1.running_mean"), off_of(m, "bn_layers.1.running_var"), T->mu2, T->is2, T->p_local, T->seed, T->d_step, 2u, T->d2);
   LAUNCH(k_linear_fwd, gridn(n * NC), 256, 0, st, T->d2, P + off_of(m, "local_fc.0.weight"), P + off_of(m, "local_fc.0.bias"), n, H2, NC, 0,
          T->ll);
   LAUNCH(k_combine_fwd, gridn(n, 128), 128, 0, st, T->ll, T->br[0].logit, T->br[1].logit, n, NC, T->smx, d_logp);
@@ -1036,15 +1047,15 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     const int64_t W3 = off_of(m, "local_fc.0.weight"), W2 = off_of(m, "lin_layers.1.weight"), W1 = off_of(m, "lin_layers.0.weight");
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(H2, NC), st, dl, nullptr, T->d2, n, H2, NC, 0, G + W3, G + off_of(m, "local_fc.0.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * H2), 256, 0, st, dl, nullptr, P + W3, n, H2, NC, 0, ga);
-    LAUNCH(k_bn1d_bwd, H2, 256, 0, st, ga, T->r2, n, H2, P, off_of(m, "bn_layers.1.weight"), T->mu2, T->is2, T->p_local, T->seed, T->step, 2u, gb,
+    LAUNCH(k_bn1d_bwd, H2, 256, 0, st, ga, T->r2, n, H2, P, off_of(m, "bn_layers.1.weight"), T->mu2, T->is2, T->p_local, T->seed, T->d_step, 2u, gb,
            G, off_of(m, "bn_layers.1.weight"), off_of(m, "bn_layers.1.bias"));
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(H1, H2), st, gb, T->r2, T->d1, n, H1, H2, 1, G + W2, G + off_of(m, "lin_layers.1.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * H1), 256, 0, st, gb, T->r2, P + W2, n, H1, H2, 1, ga);
-    LAUNCH(k_bn1d_bwd, H1, 256, 0, st, ga, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), T->mu1, T->is1, T->p_local, T->seed, T->step, 1u, gb,
+    LAUNCH(k_bn1d_bwd, H1, 256, 0, st, ga, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), T->mu1, T->is1, T->p_local, T->seed, T->d_step, 1u, gb,
            G, off_of(m, "bn_layers.0.weight"), off_of(m, "bn_layers.0.bias"));
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(K1, H1), st, gb, T->r1, T->e0, n, K1, H1, 1, G + W1, G + off_of(m, "lin_layers.0.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * K1), 256, 0, st, gb, T->r1, P + W1, n, K1, H1, 1, ga);
-    LAUNCH(k_emb_bwd, gridn(n * K1), 256, 0, st, ga, T->cat, n, m->n_cat, T->p_emb, T->seed, T->step, G + off_of(m, "emb_layer.weight"));
+    LAUNCH(k_emb_bwd, gridn(n * K1), 256, 0, st, ga, T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, G + off_of(m, "emb_layer.weight"));
   }
   // ---- CNN branches
   for (int br = 0; br < 2; ++br) {
@@ -1057,7 +1068,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(C, NC), st, dlogit, nullptr, b.gmn, n, C, NC, 0, G + off_of(m, fc + ".2.weight"),
            G + off_of(m, fc + ".2.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * C), 256, 0, st, dlogit, nullptr, P + off_of(m, fc + ".2.weight"), n, C, NC, 0, ga);
-    LAUNCH(k_bn1d_bwd, C, 256, 0, st, ga, b.gm, n, C, P, off_of(m, fc + ".0.weight"), b.mu, b.is, T->p_fc, T->seed, T->step, 10u + br, gb, G,
+    LAUNCH(k_bn1d_bwd, C, 256, 0, st, ga, b.gm, n, C, P, off_of(m, fc + ".0.weight"), b.mu, b.is, T->p_fc, T->seed, T->d_step, 10u + br, gb, G,
            off_of(m, fc + ".0.weight"), off_of(m, fc + ".0.bias"));
     LAUNCH(k_gmax_bwd, gridn(n * B.L3 * C), 256, 0, st, gb, b.ig, b.h, G0, n, B.L3, C);  // G0 = d(conv3 out)
     const int base = br * 10;
@@ -1115,7 +1126,23 @@ extern "C" int mural_optimizer_step(int32_t kind, float* d_params, const float* 
   CUDA_TRY(cudaMemsetAsync(d_scratch, 0, sizeof(double), st));
   if (max_norm > 0.f) LAUNCH(k_sumsq, 296, 256, 0, st, d_grads, n, grad_scale, d_scratch);
   LAUNCH(k_opt_step, gridn(n), 256, 0, st, kind, d_params, d_grads, d_m, d_v, d_vmax, n, lr, weight_decay, step, max_norm, grad_scale,
-         d_scratch);
+         d_scratch, (const float*)nullptr, (const int64_t*)nullptr);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mural_optimizer_step_dev(int32_t kind, float* d_params, const float* d_grads, float* d_m, float* d_v, float* d_vmax,
+                                        int64_t n, const float* d_lr, float weight_decay, int64_t* d_step, float max_norm,
+                                        float grad_scale, double* d_scratch, void* stream) {
+  MURAL_CHECK(d_params && d_grads && d_scratch && d_lr && d_step && n > 0, "bad argument");
+  MURAL_CHECK(kind >= 0 && kind <= 2, "optimizer kind must be 0 (Adam), 1 (AdamW/amsgrad) or 2 (SGD nesterov)");
+  MURAL_CHECK(d_m && (kind == 2 || d_v) && (kind != 1 || d_vmax), "optimizer state buffer missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(d_scratch, 0, sizeof(double), st));
+  LAUNCH(k_bump_i64, 1, 1, 0, st, d_step);
+  if (max_norm > 0.f) LAUNCH(k_sumsq, 296, 256, 0, st, d_grads, n, grad_scale, d_scratch);
+  LAUNCH(k_opt_step, gridn(n), 256, 0, st, kind, d_params, d_grads, d_m, d_v, d_vmax, n, 0.f, weight_decay, int64_t(1), max_norm,
+         grad_scale, d_scratch, d_lr, (const int64_t*)d_step);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

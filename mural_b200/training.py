@@ -84,7 +84,9 @@ def make_scheduler(config, train_size):
 
 
 class TrainState:
-    def __init__(self, model, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False):
+    def __init__(self, model, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False, use_graph=True):
+        """use_graph: capture the step of the first full-size batch in CUDA graphs and replay them for every batch of that size
+        (the step is ~200 small launches and launch-bound at the reference's batch of 128); other batch sizes run eagerly."""
         L = _lib.lib()
         self.model = model
         self.device = model.emb_layer.weight.device
@@ -116,6 +118,13 @@ class TrainState:
         self.scratch = torch.zeros(4, dtype=torch.float64, device=self.device)
         self.loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.opt_step = 0
+        # per-step hyper-parameters on the device (read by the optimizer kernel) so that a captured graph never goes stale
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+        self._lr_on_dev = float(lr)
+        self._opt_step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.use_graph = bool(use_graph)
+        self._graph = None            # dict(n, genome, pos, meta, logp, dlogp, fb, opt)
+        self._graph_warm = {}         # batch size -> eager steps seen (one eager step sizes the tape before capture)
         self.n_forward = 0
         self._tracked_synced = 0
         self.grad_average = grad_average
@@ -166,13 +175,50 @@ class TrainState:
 
     def apply(self, world=1):
         self.opt_step += 1
+        if self._lr_on_dev != self.lr:
+            self._lr_dev.fill_(self.lr)
+            self._lr_on_dev = self.lr
+        self._launch_optimizer(world)
+        self.model.mark_dirty()
+
+    def _launch_optimizer(self, world):
         scale = 1.0 / world if self.grad_average else 1.0   # reference loss is SUM-reduced: summing == one big batch
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().mural_optimizer_step(self.kind, _lib.ptr(self.blob), _lib.ptr(self.grads), _lib.ptr(self.m),
-                                                       _lib.ptr(self.v), _lib.ptr(self.vmax), self.n_trainable, self.lr,
-                                                       self.weight_decay, self.opt_step, self.max_norm, scale, _lib.ptr(self.scratch),
-                                                       _lib.current_stream()))
-        self.model.mark_dirty()
+            _lib.check(_lib.lib().mural_optimizer_step_dev(self.kind, _lib.ptr(self.blob), _lib.ptr(self.grads), _lib.ptr(self.m),
+                                                           _lib.ptr(self.v), _lib.ptr(self.vmax), self.n_trainable, _lib.ptr(self._lr_dev),
+                                                           self.weight_decay, _lib.ptr(self._opt_step_dev), self.max_norm, scale,
+                                                           _lib.ptr(self.scratch), _lib.current_stream()))
+
+    def _launch_forward_backward(self, genome, pos, meta, n, logp, dlogp):
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(L.mural_snv_train_forward(self._h, genome.handle, _lib.ptr(pos), _lib.ptr(meta), n, _lib.ptr(self.blob),
+                                                 _lib.ptr(logp), _lib.current_stream()))
+            _lib.check(L.mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(meta), n, self.model.n_class, _lib.ptr(self.loss_dev), _lib.ptr(dlogp),
+                                           _lib.current_stream()))
+            _lib.check(L.mural_snv_train_backward(self._h, _lib.ptr(self.blob), _lib.ptr(dlogp), _lib.ptr(self.grads),
+                                                  _lib.current_stream()))
+
+    def _world(self):
+        d = torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+    def _capture(self, batch):
+        """Two graphs: forward + CE + backward, and clip + optimizer.  The gradient all-reduce of a data-parallel step runs
+        between them on the same stream (eagerly: NCCL stays outside the capture); with one rank the two replays are back to
+        back.  Static buffers hold the batch; dropout position, lr and the optimizer step are read from device memory."""
+        n = len(batch)
+        g = {"n": n, "genome": batch.genome, "pos": batch.pos.clone(), "meta": batch.meta.clone(),
+             "logp": torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device),
+             "world": self._world()}
+        g["dlogp"] = torch.empty_like(g["logp"])
+        torch.cuda.synchronize(self.device)
+        g["fb"], g["opt"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g["fb"]):
+            self._launch_forward_backward(g["genome"], g["pos"], g["meta"], n, g["logp"], g["dlogp"])
+        with torch.cuda.graph(g["opt"]):
+            self._launch_optimizer(g["world"])
+        return g
 
     # ---- fused step
     def step(self, batch):
@@ -181,6 +227,25 @@ class TrainState:
         n = len(batch)
         if n < 2:
             return None                                      # training.py:415: batches of one site are skipped
+        if self.use_graph:
+            g = self._graph
+            if g is None and self._graph_warm.get(n, 0) >= 1:
+                # capture does not execute: the captured step runs at the replay below
+                g = self._graph = self._capture(batch)
+            if g is not None and g["n"] == n and g["genome"] is batch.genome and g["world"] == self._world():
+                g["pos"].copy_(batch.pos)
+                g["meta"].copy_(batch.meta)
+                if self._lr_on_dev != self.lr:
+                    self._lr_dev.fill_(self.lr)
+                    self._lr_on_dev = self.lr
+                g["fb"].replay()
+                self.n_forward += 1
+                self.all_reduce_grads()
+                g["opt"].replay()
+                self.opt_step += 1
+                self.model.mark_dirty()
+                return g["logp"]
+            self._graph_warm[n] = self._graph_warm.get(n, 0) + 1
         logp = self.forward(batch)
         dlogp = torch.empty_like(logp)
         with torch.cuda.device(self.device):

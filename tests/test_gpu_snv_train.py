@@ -222,3 +222,37 @@ def test_dropout_statistics(kat, cuda_genome):
     st2.forward(sb)
     st2.set_dropout(0.1, 0.1, 0.25, 5)
     assert torch.equal(st2.forward(sb), a)
+
+
+def test_graph_step_equals_eager_step(kat, cuda_genome):
+    """TrainState.step replays CUDA graphs from the second batch of a size on.  With dropout ON the masks are a function of
+    (seed, forward counter, layer, element): the counter lives on the device and is bumped inside the graph, so graph and
+    eager runs draw the same masks step by step and stay equal — a stale counter, lr or optimizer step would show up here.
+    lr changes between steps (StepLR) and reaches the captured optimizer through device memory."""
+    from mural_b200.training import TrainState
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    n = 64
+    labels = (z["start"][:n] % 4).astype(np.int64)
+    sb = _batch(z, cuda_genome, n, labels)
+    runs = {}
+    for key, use_graph in (("eager", False), ("graph", True)):
+        m = build_model(cfg, state, int(z["n_cat"]))
+        st = TrainState(m, "SGD", lr=1e-4, weight_decay=1e-4, seed=5, use_graph=use_graph)
+        m.train()
+        traj = []
+        for i in range(5):
+            st.lr = 1e-4 * (0.5 ** (i // 2))
+            traj.append(st.step(sb).clone())
+        assert (st._graph is not None) == use_graph
+        assert int(st._opt_step_dev.item()) == 5 == st.opt_step and st.n_forward == 5
+        runs[key] = (traj, st.blob.clone(), float(st.loss_dev.item()))
+    for a, b in zip(runs["eager"][0], runs["graph"][0]):
+        assert (a - b).abs().max().item() < 1e-4
+    assert not torch.equal(runs["graph"][0][2], runs["graph"][0][3])
+    d = (runs["eager"][1] - runs["graph"][1]).abs().max().item()
+    assert d < 5e-6 * max(1.0, runs["eager"][1].abs().max().item()), d
+    assert abs(runs["eager"][2] - runs["graph"][2]) < 1e-3 * abs(runs["eager"][2])
+    # a batch of another size falls back to the eager path and keeps the counters in step
+    sb2 = _batch(z, cuda_genome, 40, labels[:40])
+    st.step(sb2)
+    assert int(st._opt_step_dev.item()) == 6 == st.opt_step
