@@ -214,9 +214,10 @@ class TrainState:
         g["dlogp"] = torch.empty_like(g["logp"])
         torch.cuda.synchronize(self.device)
         g["fb"], g["opt"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g["fb"]):
+        # thread-local capture mode: CUDA calls of other threads (NCCL watchdog, clock sampler) must not invalidate the capture
+        with torch.cuda.graph(g["fb"], capture_error_mode="thread_local"):
             self._launch_forward_backward(g["genome"], g["pos"], g["meta"], n, g["logp"], g["dlogp"])
-        with torch.cuda.graph(g["opt"]):
+        with torch.cuda.graph(g["opt"], capture_error_mode="thread_local"):
             self._launch_optimizer(g["world"])
         return g
 

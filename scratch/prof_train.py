@@ -14,7 +14,7 @@ cfg = {"local_radius": 10, "local_order": 3, "local_hidden1_size": 150, "local_h
 torch.manual_seed(0)
 model = model_choice(2, cfg, dict(emb_dims=[(65, 2)] * 19, n_cont=0, n_class=4, distal_order=1, in_channels=4), "snv")
 model.apply(weights_init); model.to("cuda").train()
-ts = TrainState(model, "Adam", lr=1e-3, weight_decay=1e-5)
+ts = TrainState(model, "Adam", lr=1e-3, weight_decay=1e-5, use_graph=False)   # eager: the event profiler hooks the launches
 rng = np.random.default_rng(0)
 for B in (128, 4096):
     sel = np.sort(rng.choice(len(pos), size=B * 8, replace=False))
