@@ -219,20 +219,31 @@ def eval_leg(genome, pos, meta, logp, cfg, n=1_000_000, reps=5):
         E = epoch_metrics()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    # device time of the k-mer reduction alone (one pass over the sites): algorithmic bytes = codes of the 2d flank columns
-    # (int64) + meta + n_class fp64 probabilities
-    from mural_b200.evaluation import kmer_group_table
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kmer_group_table(ed, 5)
-    ev0.record()
-    for _ in range(reps):
-        kmer_group_table(ed, 5)
-    ev1.record()
-    torch.cuda.synchronize()
-    k_ms = ev0.elapsed_time(ev1) / reps
-    bytes_site = 4 * 8 + 4 + 8 * cfg["n_class"]
+    # device time of each reduction kernel alone (library CUDA-event profile); algorithmic bytes per site: the 2d flank codes
+    # (int64) + meta + n_class fp64 probabilities for the k-mer tables; pos + meta (read twice) + probabilities for the windows
+    from mural_b200 import _lib
+    from mural_b200.evaluation import kmer_group_table, window_table
+    L = _lib.lib()
+    kern = {}
+    for name, fn, bytes_site in (("kmer3", lambda: kmer_group_table(ed, 3), 2 * 8 + 4 + 8 * cfg["n_class"]),
+                                 ("kmer5", lambda: kmer_group_table(ed, 5), 4 * 8 + 4 + 8 * cfg["n_class"]),
+                                 ("kmer7", lambda: kmer_group_table(ed, 7), 6 * 8 + 4 + 8 * cfg["n_class"]),
+                                 ("kmer5_regions", lambda: kmer_group_table(ed, 5, 10000), 4 * 8 + 4 + 8 * cfg["n_class"]),
+                                 ("window100k", lambda: window_table(ed, 100000), 2 * 8 + 8 * cfg["n_class"])):
+        fn()
+        torch.cuda.synchronize()
+        L.mural_profile_begin()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        buf = C.create_string_buffer(1 << 16)
+        L.mural_profile_end(buf, len(buf))
+        prof = json.loads(buf.value.decode())
+        us = sum(v["ms"] for v in prof.values()) * 1e3 / reps
+        kern[name] = {"us": round(us, 1), "algorithmic_GBps": round(n * bytes_site / (us * 1e-6) / 1e9, 1),
+                      "kernels": sorted(prof)}
     return {"metric": "validation sites/sec (Evaluator: 3/5/7-mer correlations + regional score)", "value": n / dt, "unit": "sites/s",
-            "sites": n, "ms_per_epoch_metrics": dt * 1e3, "kmer5_table_ms": k_ms, "kmer5_algorithmic_GBps": n * bytes_site / (k_ms * 1e-3) / 1e9,
+            "sites": n, "ms_per_epoch_metrics": dt * 1e3, "kernels": kern, "bound": "hbm",
             "kmer3_corr": [round(float(c), 4) for c in E.metrics["kmer3"]], "regional_score": float(E.metrics["score"]),
             "note": "includes the host sync + table copy of every launch; labels synthetic (class proportions of training.py:332)"}
 

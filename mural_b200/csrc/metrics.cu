@@ -20,19 +20,22 @@ __device__ __forceinline__ long long to_fixed(double p) { return __double2ll_rn(
 
 // ---- k-mer context groups ---------------------------------------------------------------------------------------------
 // table[region][group][0] = sites, [1 + c] = sites with label c, [1 + K + c] = fixed-point sum of prob c
+// SMEM: the CTA accumulates in shared memory, in `copies` private replicas of the table (warp w uses replica w % copies) so that
+// the few hot groups of a short k-mer do not serialise every warp on the same addresses; replicas are summed at the flush.
 template <bool SMEM>
 __global__ void __launch_bounds__(MET_THREADS) k_kmer_groups(const int64_t* __restrict__ flank, int n_cols, int d, const int32_t* __restrict__ meta,
-                                                           const double* __restrict__ prob, int K, int64_t region_size, int G,
+                                                           const double* __restrict__ prob, int K, int64_t region_size, int G, int copies,
                                                            unsigned long long* __restrict__ table, int* __restrict__ err) {
   extern __shared__ unsigned long long s_tab[];
   const int W = 1 + 2 * K;
+  const int GW = G * W;
   const int64_t r = blockIdx.y;
-  unsigned long long* out = table + r * int64_t(G) * W;
+  unsigned long long* out = table + r * int64_t(GW);
   if (SMEM) {
-    for (int e = threadIdx.x; e < G * W; e += blockDim.x) s_tab[e] = 0ull;
+    for (int e = threadIdx.x; e < GW * copies; e += blockDim.x) s_tab[e] = 0ull;
     __syncthreads();
   }
-  unsigned long long* acc = SMEM ? s_tab : out;
+  unsigned long long* acc = SMEM ? s_tab + ((threadIdx.x >> 5) % copies) * GW : out;
   const int mid = n_cols / 2;
   const int64_t lo = r * region_size, per = cdiv_dev(region_size, gridDim.x);
   const int64_t b = lo + blockIdx.x * per, e_ = (b + per < lo + region_size) ? b + per : lo + region_size;
@@ -60,8 +63,11 @@ __global__ void __launch_bounds__(MET_THREADS) k_kmer_groups(const int64_t* __re
   if (bad) atomicOr(err, 1);
   if (SMEM) {
     __syncthreads();
-    for (int e = threadIdx.x; e < G * W; e += blockDim.x)
-      if (s_tab[e]) atomicAdd(out + e, s_tab[e]);
+    for (int e = threadIdx.x; e < GW; e += blockDim.x) {
+      unsigned long long v = 0ull;
+      for (int c = 0; c < copies; ++c) v += s_tab[c * GW + e];
+      if (v) atomicAdd(out + e, v);
+    }
   }
 }
 
@@ -219,22 +225,30 @@ extern "C" int mural_kmer_group_stats(const int64_t* d_flank, int64_t n, int32_t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  int64_t per_region = cdiv(int64_t(2) * sms, n_regions);
-  const int64_t cap = cdiv(region_size, 4096);
+  // the pass is latency-bound (one dependent load chain per site): many small CTAs keep enough loads in flight
+  int64_t per_region = cdiv(int64_t(8) * sms, n_regions);
+  const int64_t cap = cdiv(region_size, 1024);
   if (per_region > cap) per_region = cap;
+  // every CTA zeroes and flushes a whole table: keep that below the work of accumulating its sites
+  const int64_t cap_flush = region_size * 4 / (int64_t(G) * (1 + 2 * n_class));
+  if (G * (1 + 2 * n_class) <= MET_SMEM_WORDS && per_region > cap_flush) per_region = cap_flush;
   if (per_region < 1) per_region = 1;
   const dim3 grid((unsigned)per_region, (unsigned)n_regions);
   auto* tab = reinterpret_cast<unsigned long long*>(d_table);
   if (G * W <= MET_SMEM_WORDS) {
-    const size_t smem = size_t(G) * W * 8;
+    int copies = (MET_SMEM_WORDS / 2) / (G * W);  // replicas within 48 KB so that four CTAs fit an SM
+    if (copies > MET_THREADS / 32) copies = MET_THREADS / 32;
+    if (copies < 1) copies = 1;
+    const size_t smem = size_t(G) * W * 8 * copies;
     static bool configured = false;
     if (!configured) {
       CUDA_TRY(cudaFuncSetAttribute(k_kmer_groups<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MET_SMEM_WORDS * 8));
       configured = true;
     }
-    LAUNCH(k_kmer_groups<true>, grid, MET_THREADS, smem, st, d_flank, n_cols, d, d_meta, d_prob, n_class, region_size, G, tab, d_err);
+    LAUNCH(k_kmer_groups<true>, grid, MET_THREADS, smem, st, d_flank, n_cols, d, d_meta, d_prob, n_class, region_size, G, copies, tab,
+           d_err);
   } else {
-    LAUNCH(k_kmer_groups<false>, grid, MET_THREADS, 0, st, d_flank, n_cols, d, d_meta, d_prob, n_class, region_size, G, tab, d_err);
+    LAUNCH(k_kmer_groups<false>, grid, MET_THREADS, 0, st, d_flank, n_cols, d, d_meta, d_prob, n_class, region_size, G, 1, tab, d_err);
   }
   CUDA_TRY(cudaGetLastError());
   int h_err = 0;

@@ -83,16 +83,27 @@ def kmer_group_table(ed, k, region_size=0):
     return table.cpu().numpy()
 
 
-def _kmer_corr(tab, n_class, f32):
-    """Correlation of observed and predicted group means over the OBSERVED groups of one region (evaluation.py:58-65)."""
-    seen = tab[:, 0] > 0
-    cnt = tab[seen, 0].astype(np.float64)
-    out = []
-    for i in range(n_class):
-        obs = tab[seen, 1 + i] / cnt
-        pred = _means(tab[seen, 1 + n_class + i], cnt, f32)
-        out.append(_pearson(obs, pred))
+def _kmer_corr_regions(tabs, n_class, f32):
+    """Correlation of observed and predicted group means over the OBSERVED groups (evaluation.py:58-65) of every region of
+    `tabs` [R, G, W] at once: float64 [R, n_class]; NaN where a region has fewer than two groups or a constant column."""
+    cnt = tabs[:, :, 0].astype(np.float64)
+    seen = cnt > 0
+    safe = np.where(seen, cnt, 1.0)
+    m = seen.sum(1).astype(np.float64)
+    out = np.full((tabs.shape[0], n_class), np.nan)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(n_class):
+            obs = tabs[:, :, 1 + i] / safe
+            pred = _means(tabs[:, :, 1 + n_class + i], safe, f32)
+            xm = np.where(seen, obs - (obs * seen).sum(1, keepdims=True) / m[:, None], 0.0)
+            ym = np.where(seen, pred - (pred * seen).sum(1, keepdims=True) / m[:, None], 0.0)
+            den = np.sqrt((xm * xm).sum(1) * (ym * ym).sum(1))
+            out[:, i] = np.where((m >= 2) & (den > 0), (xm * ym).sum(1) / den, np.nan)
     return out
+
+
+def _kmer_corr(tab, n_class, f32):
+    return [float(c) for c in _kmer_corr_regions(tab[None], n_class, f32)[0]]
 
 
 def _as_eval_data(data, n_class):
@@ -244,16 +255,13 @@ class Evaluator:
         sub = self.ed if valid_size >= self.ed.n else EvalData(self.ed.flank[:valid_size], self.ed.meta[:valid_size],
                                                                self.ed.prob[:valid_size], f32=self.ed.f32)
         tabs = [kmer_group_table(sub, k, region_size)[:n_regions] for k in kmer_list[:2]]
-        score = 0
-        region_avg = []
         K = self.n_class
-        for r in range(n_regions):
-            for t in tabs:
-                score += np.sum([(1 - corr) ** 2 for corr in _kmer_corr(t[r], K, self.ed.f32)])
-            tot = tabs[0][r].sum(0)
-            cnt = float(tot[0])
-            region_avg.append([tot[1 + i] / cnt for i in range(K)] + [float(_means(tot[1 + K + i], cnt, self.ed.f32)) for i in range(K)])
-        region_avg = np.asarray(region_avg, np.float64).reshape(n_regions, 2 * K)
+        score = 0
+        for t in tabs:      # the reference adds (1 - corr)^2 of every class, k-mer length and region; NaN propagates as it does there
+            score += float(np.sum((1 - _kmer_corr_regions(t, K, self.ed.f32)) ** 2))
+        tot = tabs[0].sum(1).astype(np.float64)                 # [n_regions, W]: calc_avg_prob of every region
+        cnt = tot[:, :1]
+        region_avg = np.concatenate([tot[:, 1:1 + K] / cnt, _means(tabs[0].sum(1)[:, 1 + K:], cnt, self.ed.f32)], 1).reshape(n_regions, 2 * K)
         corr_list = [_pearson(region_avg[:, i], region_avg[:, i + K]) for i in range(K)]
         corr_list_perfix = {'no_calibra': 'corr_list: ', 'FullDiri': 'corr_list(after fdiri_cal)', 'Poisson': 'corr_list(after Poisson_cal)'}
         regional_score_perfix = {'no_calibra': 'regional score: ', 'FullDiri': 'regional score(after fdiri_cal)',

@@ -244,3 +244,43 @@ def test_lr_schedulers_match_torch():
     assert abs(auto_weight_decay(0.1, 128, 20, 10_000_000) - (1 - 0.1 ** (128 / (20 * 10_000_000)))) < 1e-18
     with pytest.raises(ValueError):
         auto_weight_decay(1.5, 128, 20, 1000)
+
+
+def test_evaluator_host_math_on_numpy_tables():
+    """The host half of mural_b200.evaluation (means from the integer tables, Pearson over observed groups, regional score)
+    on tables built with numpy in the kernel's layout, against the reference's outputs (tests/golden/eval_kat.npz)."""
+    import os
+    import numpy as np
+    from conftest import GOLD
+    from mural_b200 import evaluation as EV
+    z = np.load(os.path.join(GOLD, "eval_kat.npz"))
+    tag, K = "snv_f64", 4
+    flank, labels, prob = z[tag + ":flank"].astype(np.int64), z[tag + ":labels"].astype(np.int64), z[tag + ":prob"]
+    n = len(labels)
+
+    def table(k, region_size):
+        d, mid = k // 2, flank.shape[1] // 2
+        cols = [mid - j for j in range(d, 0, -1)] + [mid + j for j in range(1, d + 1)]
+        g = np.zeros(n, np.int64)
+        for c in cols:
+            g = g * 5 + flank[:, c]
+        R = n // region_size
+        t = np.zeros((R, 5 ** (2 * d), 1 + 2 * K), np.int64)
+        r = np.arange(n) // region_size
+        ok = r < R
+        np.add.at(t, (r[ok], g[ok], 0), 1)
+        np.add.at(t, (r[ok], g[ok], 1 + labels[ok]), 1)
+        for c in range(K):
+            np.add.at(t, (r[ok], g[ok], 1 + K + c), np.rint(prob[ok, c] * EV.SCALE).astype(np.int64))
+        return t
+    for k in (3, 5, 7):
+        assert np.allclose(EV._kmer_corr(table(k, n)[0], K, False), z["%s:kmer%d" % (tag, k)], rtol=0, atol=1e-7)
+    region_size = n // 10
+    score = sum(float(np.sum((1 - EV._kmer_corr_regions(table(k, region_size), K, False)) ** 2)) for k in (3, 5))
+    assert abs(score - z[tag + ":regional_score"][0]) < 1e-6 * score
+    # a region with a single observed group, or a constant column, gives NaN like Series.corr
+    t = np.zeros((2, 25, 1 + 2 * K), np.int64)
+    t[0, 3] = [5, 5, 0, 0, 0, 1, 1, 1, 1]
+    t[1, 3] = [5, 5, 0, 0, 0, 1, 1, 1, 1]
+    t[1, 4] = [7, 7, 0, 0, 0, 2, 2, 2, 2]
+    assert np.isnan(EV._kmer_corr_regions(t, K, False)).all()
