@@ -323,10 +323,50 @@ def load_pretrained(model, model_state, train_all=True, init_fc_with_pretrained=
     return model
 
 
+def validate_epoch(model, dataset, n_class=4, pred_batch_size=4096, segment_indices=None, kmer_list=(3, 5, 7), win_size_list=(100000, 500000),
+                   printer=print):
+    """The validation half of an epoch (training.py:454-520) on the device: prediction in emission order
+    (`model_predict_m`), summed cross-entropy, then the reference's Evaluator metrics before calibration (k-mer
+    correlations, regional score, regional window correlations) through mural_b200.evaluation — no pandas group-bys, no
+    per-row python.  Calibrator fitting (JAX in the reference) stays with the caller.  Returns a dict."""
+    import pandas as pd
+    from .calibration import calibrate
+    from .data import generate_site_batches
+    from .evaluation import EvalData, Evaluator
+    from .nn_utils import model_predict_m
+    if dataset.model_type != "snv":
+        raise NotImplementedError("validate_epoch: MuRaL-indel training / validation is not built (SNV only)")
+    segs = np.arange(len(dataset)) if segment_indices is None else np.asarray(segment_indices)
+    was_training = model.training
+    pred_y, total_loss = model_predict_m(model, generate_site_batches(dataset, 1 << 30, pred_batch_size, shuffle=False, segment_indices=segs),
+                                         None, dataset.genome.device, n_class)
+    rows = np.concatenate([np.arange(dataset.batch_offsets[i], dataset.batch_offsets[i + 1]) for i in segs]) if len(segs) else np.zeros(0, np.int64)
+    pos = torch.from_numpy(dataset.pos[rows]).to(pred_y.device)
+    meta = torch.from_numpy(dataset.meta[rows]).to(pred_y.device)
+    flank = dataset.genome.encode_local(pos, meta, dataset.local_radius, 1)      # data_local's us*/mid/ds* columns (prepare_local_data :400)
+    prob = calibrate(pred_y.contiguous())                                        # F.softmax(pred_y, dim=1), training.py:463
+    ev = Evaluator(EvalData(flank, meta, prob, f32=True), None, n_class, printer=printer)
+    ev.evaluate_kmer(list(kmer_list))
+    n = int(pred_y.shape[0])
+    if n >= 10:
+        ev.evaluate_regional_score(n, list(kmer_list)[:2])
+    names, start, end, strand = dataset.position_info()
+    chr_pos = pd.DataFrame({"chrom": np.asarray(names)[rows], "start": np.asarray(start)[rows], "end": np.asarray(end)[rows],
+                            "strand": np.asarray(strand)[rows]})
+    ev.evaluate_regional_corr(chr_pos, list(win_size_list))
+    printer('Validation Loss: ', total_loss / max(1, n))
+    if was_training:
+        model.train()
+    return {"valid_loss": total_loss / max(1, n), "valid_size": n, **ev.metrics}
+
+
 def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim="Adam", lr=1e-3, weight_decay=0.0, LR_gamma=0.5,
-                 min_lr=1e-6, restart_lr=1e-4, seed=0, print_every=1000, segment_indices=None):
-    """The hot loop of training.py:387-452 on site records; returns per-epoch mean losses.  Evaluation, calibrator
-    fitting and checkpoint bookkeeping stay with the caller (out of scope)."""
+                 min_lr=1e-6, restart_lr=1e-4, seed=0, print_every=1000, segment_indices=None, valid_indices=None, history=None,
+                 pred_batch_size=4096, printer=print):
+    """The hot loop of training.py:387-452 on site records; returns per-epoch mean losses.  With `valid_indices` (segment
+    indices of `dataset` held out for validation, as `random_split` does at training.py:152-168) every epoch ends with
+    `validate_epoch` and its dict is appended to `history`.  Calibrator fitting and checkpoint bookkeeping stay with the
+    caller (out of scope)."""
     from .data import generate_site_batches
     st = getattr(model, "_train_state", None) or TrainState(model, optim, lr, weight_decay, seed=seed)
     sched = StepLR(lr, (5000 * 128) // batch_size, LR_gamma, min_lr, restart_lr)
@@ -344,4 +384,9 @@ def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim=
             st.lr = sched.step()
         losses.append(float(st.loss_dev.item()) / max(1, n_sites))
         st.sync_counters()
+        if valid_indices is not None:
+            h = validate_epoch(model, dataset, model.n_class, pred_batch_size, valid_indices, printer=printer)
+            h["epoch"], h["train_loss"] = epoch, losses[-1]
+            if history is not None:
+                history.append(h)
     return losses

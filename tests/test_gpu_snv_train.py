@@ -256,3 +256,47 @@ def test_graph_step_equals_eager_step(kat, cuda_genome):
     sb2 = _batch(z, cuda_genome, 40, labels[:40])
     st.step(sb2)
     assert int(st._opt_step_dev.item()) == 6 == st.opt_step
+
+
+def test_train_epochs_with_validation_metrics(kat, cuda_genome):
+    """train_epochs with a held-out set of segments: every epoch ends with the device-side Evaluator (training.py:454-520).
+    The reported validation loss and k-mer correlations equal the oracle's on the same predictions."""
+    from oracle import evaluation_np as EN
+    from mural_b200 import PackedSiteDataset, SiteTable, generate_site_batches, model_predict_m
+    from mural_b200.training import train_epochs
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    _, genome = kat
+    names = list(genome)
+    rng = np.random.default_rng(4)
+    n = 6000
+    ch = rng.integers(0, len(names), n)
+    st = np.array([rng.integers(300, len(genome[names[c]]) - 300) for c in ch])
+    o = np.lexsort((st, ch))
+    ch, st = ch[o], st[o]
+    sd = rng.integers(0, 2, n)
+    lab = rng.choice(4, n, p=[.7, .1, .1, .1])
+    t = SiteTable(names, ch, st, st + 1, sd, lab)
+    ds = PackedSiteDataset(t, cuda_genome, 2000, cfg["local_radius"], cfg["local_order"], cfg["distal_radius"])
+    segs = np.arange(len(ds))
+    valid, train = segs[::4], np.setdiff1d(segs, segs[::4])
+    m = build_model(cfg, state, int(z["n_cat"]))
+    hist, lines = [], []
+    losses = train_epochs(m, ds, 2, 128, sampled_segments=4, lr=1e-4, segment_indices=train, valid_indices=valid, history=hist,
+                          printer=lambda *a: lines.append(a))
+    assert len(losses) == 2 and len(hist) == 2 and all(np.isfinite(losses))
+    h = hist[-1]
+    assert {"valid_loss", "kmer3", "kmer5", "kmer7", "score", "corr_list", "window100000", "window500000"} <= set(h)
+    # same model, same held-out sites through the plain prediction loop + the numpy oracle
+    pred, loss = model_predict_m(m, generate_site_batches(ds, 1 << 30, 512, segment_indices=valid), None, torch.device("cuda"), 4)
+    rows = np.concatenate([np.arange(ds.batch_offsets[i], ds.batch_offsets[i + 1]) for i in valid])
+    assert abs(loss / len(rows) - h["valid_loss"]) < 1e-6 * max(1.0, abs(h["valid_loss"])) and h["valid_size"] == len(rows)
+    prob = torch.softmax(pred, 1).cpu().numpy().astype(np.float64)
+    flank = np.empty((len(rows), 2 * cfg["local_radius"] + 1), np.int64)
+    for c in range(len(names)):
+        msk = ds.chrom[rows] == cuda_genome.chrom_index[names[c]]
+        if msk.any():
+            flank[msk] = E.kmer_windows(E.seq_to_symbols(genome[names[c]]), ds.pos[rows][msk].astype(np.int64), ds.strand[rows][msk], cfg["local_radius"], 1)
+    for k in (3, 5):
+        ref = EN.freq_kmer_comp_multi(flank, ds.label[rows].astype(np.int64), prob, k, 4)
+        assert np.allclose(h["kmer%d" % k], ref, rtol=0, atol=2e-5, equal_nan=True), (k, h["kmer%d" % k], ref)
+    assert any(isinstance(a[0], str) and a[0].startswith("Validation Loss") for a in lines)
