@@ -784,8 +784,12 @@ struct mural_snv_train {
   struct Br { float *x0, *t1, *y1, *t2, *z1, *x2, *j2, *t1b, *y1b, *t2b, *z2, *x3, *h, *gm, *gmn, *logit;
               int32_t *i1, *i2, *i3, *ig; float *mu, *is; } br[2];
   float *e0, *r1, *d1, *r2, *d2, *ll, *mu1, *is1, *mu2, *is2, *smx;
-  float* gbuf[5];
-  float *gsm[6];
+  float* gbuf[2][5];   // gradient scratch of each CNN branch
+  float* gsm[9];       // [0..2] d(logits) of the three branches; then (ga, gb) of the local chain and of each CNN branch
+  // the mid branch, the large branch and the local MLP are independent chains of small kernels between the window gather
+  // and the combine: they run on three streams (fork / join with events, also inside a captured graph)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 static int64_t off_of(const mural_snv_model* m, const std::string& n) { return m->layout[m->index.at(n)].offset; }
@@ -829,6 +833,11 @@ extern "C" int mural_snv_train_create(mural_snv_model_t* m, mural_snv_train_t** 
   CUDA_TRY(cudaMalloc((void**)&T->d_cnt, sizeof(unsigned long long) * 32));
   CUDA_TRY(cudaMalloc((void**)&T->d_step, 4));
   CUDA_TRY(cudaMemset(T->d_step, 0, 4));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&T->side[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&T->ev_join[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&T->ev_fork, cudaEventDisableTiming));
   *out = T;
   return 0;
 }
@@ -837,6 +846,11 @@ extern "C" void mural_snv_train_destroy(mural_snv_train_t* T) {
   if (!T) return;
   cudaFree(T->d_conv); cudaFree(T->d_Wt); cudaFree(T->d_Wf); cudaFree(T->d_bn); cudaFree(T->d_const);
   cudaFree(T->d_stat); cudaFree(T->d_stem); cudaFree(T->d_cnt); cudaFree(T->d_tape); cudaFree(T->d_step);
+  for (int i = 0; i < 2; ++i) {
+    if (T->side[i]) cudaStreamDestroy(T->side[i]);
+    if (T->ev_join[i]) cudaEventDestroy(T->ev_join[i]);
+  }
+  if (T->ev_fork) cudaEventDestroy(T->ev_fork);
   delete T;
 }
 
@@ -865,12 +879,10 @@ int ensure_tape(mural_snv_train* T, int64_t n) {
     Carver cv{pass ? (char*)T->d_tape : (char*)nullptr};
     T->sym = cv.take<uint8_t>(n * m->L);
     T->cat = cv.take<int32_t>(n * m->n_cat);
-    int64_t Lmax = 0;
     for (int br = 0; br < 2; ++br) {
       const BranchDev& B = m->br[br];
       auto& b = T->br[br];
       const int64_t s1 = n * B.L1 * C, s2 = n * B.L2 * C, s3 = n * B.L3 * C;
-      if (B.L1 > Lmax) Lmax = B.L1;
       b.x0 = cv.take<float>(s1); b.t1 = cv.take<float>(s1); b.y1 = cv.take<float>(s1); b.t2 = cv.take<float>(s1); b.z1 = cv.take<float>(s1);
       b.x2 = cv.take<float>(s2); b.j2 = cv.take<float>(s2); b.t1b = cv.take<float>(s2); b.y1b = cv.take<float>(s2);
       b.t2b = cv.take<float>(s2); b.z2 = cv.take<float>(s2);
@@ -883,9 +895,10 @@ int ensure_tape(mural_snv_train* T, int64_t n) {
     T->r2 = cv.take<float>(n * H2); T->d2 = cv.take<float>(n * H2); T->ll = cv.take<float>(n * NC);
     T->mu1 = cv.take<float>(H1); T->is1 = cv.take<float>(H1); T->mu2 = cv.take<float>(H2); T->is2 = cv.take<float>(H2);
     T->smx = cv.take<float>(3 * n * NC);
-    for (int i = 0; i < 5; ++i) T->gbuf[i] = cv.take<float>(n * Lmax * C);
+    for (int br = 0; br < 2; ++br)
+      for (int i = 0; i < 5; ++i) T->gbuf[br][i] = cv.take<float>(n * m->br[br].L1 * C);
     const int64_t Fmax = (H1 > K1 ? H1 : K1) > C ? (H1 > K1 ? H1 : K1) : C;
-    for (int i = 0; i < 6; ++i) T->gsm[i] = cv.take<float>(n * Fmax);
+    for (int i = 0; i < 9; ++i) T->gsm[i] = cv.take<float>(n * Fmax);
     if (!pass) {
       cudaFree(T->d_tape);
       T->d_tape = nullptr;
@@ -904,16 +917,17 @@ inline unsigned gridn(int64_t n, int b = 256) { return (unsigned)cdiv(n, b); }
 static int conv_train_fwd(mural_snv_train* T, float* P, int li, const float* x, float* y, const float* r1, const float* r2,
                           int64_t n, int L, int relu_out, cudaStream_t st) {
   const int C = T->m->cfg.channels;
+  double* stat = T->d_stat + (li / 10) * 256;  // per-branch scratch: the branches run concurrently
   const ConvDesc& d = T->h_conv[li];
   float* bn = T->d_bn + int64_t(li) * 4 * C;
   const int64_t rows = n * L;
-  CUDA_TRY(cudaMemsetAsync(T->d_stat, 0, sizeof(double) * 2 * C, st));
+  CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
   const int thr = 256, rpb = thr / C;
   int grid = (int)cdiv(rows, rpb * 8);
   if (grid > 1184) grid = 1184;
   if (grid < 1) grid = 1;
-  LAUNCH(k_stats, grid, thr, sizeof(double) * 2 * thr, st, x, rows, C, d.relu_in, T->d_stat);
-  LAUNCH(k_bn_finalize, 1, 64, 0, st, T->d_stat, double(rows), C, P, d.g, d.be, d.rm, d.rv, bn, bn + C, bn + 2 * C, bn + 3 * C);
+  LAUNCH(k_stats, grid, thr, sizeof(double) * 2 * thr, st, x, rows, C, d.relu_in, stat);
+  LAUNCH(k_bn_finalize, 1, 64, 0, st, stat, double(rows), C, P, d.g, d.be, d.rm, d.rv, bn, bn + C, bn + 2 * C, bn + 3 * C);
   ConvLayerDev cl{T->d_Wt + int64_t(li) * 7 * C * C, P + d.b, bn, bn + C, d.ks, d.relu_in};
   return conv_any(C, x, y, r1, r2, n, L, cl, relu_out, st);
 }
@@ -935,7 +949,12 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
   LAUNCH(k_sym_gather, (unsigned)n, 128, (size_t(m->L) + 15) & ~size_t(15), st, g->view, d_pos, d_meta, m->cfg.distal_radius, m->L,
          m->cfg.local_radius, m->cfg.local_order, m->n_cat, T->sym, T->cat);
   CUDA_TRY(cudaMemsetAsync(T->d_cnt, 0, sizeof(unsigned long long) * 32, st));
+  // fork: mid branch -> side[0], local MLP -> side[1]; the large branch (the longest chain) stays on the caller's stream
+  cudaStream_t const st_main = st;
+  CUDA_TRY(cudaEventRecord(T->ev_fork, st_main));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(T->side[i], T->ev_fork, 0));
   for (int br = 0; br < 2; ++br) {
+    st = br ? st_main : T->side[0];
     const BranchDev& B = m->br[br];
     auto& b = T->br[br];
     const std::string s = br ? "_2" : "";
@@ -979,6 +998,7 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
            b.logit);
   }
   // local branch (model_snv.py:452-468, 492)
+  st = T->side[1];
   LAUNCH(k_emb_fwd, gridn(n * K1), 256, 0, st, P + off_of(m, "emb_layer.weight"), T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, T->e0);
   LAUNCH(k_linear_fwd, gridn(n * H1), 256, 0, st, T->e0, P + off_of(m, "lin_layers.0.weight"), P + off_of(m, "lin_layers.0.bias"), n, K1, H1,
          1, T->r1);
@@ -990,6 +1010,12 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
          off_of(m, "bn_layers.1.running_mean"), off_of(m, "bn_layers.1.running_var"), T->mu2, T->is2, T->p_local, T->seed, T->d_step, 2u, T->d2);
   LAUNCH(k_linear_fwd, gridn(n * NC), 256, 0, st, T->d2, P + off_of(m, "local_fc.0.weight"), P + off_of(m, "local_fc.0.bias"), n, H2, NC, 0,
          T->ll);
+  // join
+  st = st_main;
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventRecord(T->ev_join[i], T->side[i]));
+    CUDA_TRY(cudaStreamWaitEvent(st, T->ev_join[i], 0));
+  }
   LAUNCH(k_combine_fwd, gridn(n, 128), 128, 0, st, T->ll, T->br[0].logit, T->br[1].logit, n, NC, T->smx, d_logp);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1002,6 +1028,7 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   const int C = T->m->cfg.channels;
   const ConvDesc& d = T->h_conv[li];
   float* bn = T->d_bn + int64_t(li) * 4 * C;
+  double* stat = T->d_stat + (li / 10) * 256;
   const int64_t rows = n * L;
   const size_t smem = sizeof(float) * (size_t(64 + d.ks - 1) * (C + 4) + size_t(64) * (C + 4)) + sizeof(int) * 64;
   int wg = (int)cdiv(rows, 64);
@@ -1019,13 +1046,13 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
 #undef WG
   ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0};
   if (int rc = conv_any(C, dy, du, nullptr, nullptr, n, L, cl, 0, st)) return rc;
-  CUDA_TRY(cudaMemsetAsync(T->d_stat, 0, sizeof(double) * 2 * C, st));
+  CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
   const int thr = 256, rpb = thr / C;
   int grid = (int)cdiv(rows, rpb * 8);
   if (grid > 1184) grid = 1184;
   if (grid < 1) grid = 1;
-  LAUNCH(k_bn_bwd_reduce, grid, thr, sizeof(double) * 2 * thr, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, T->d_stat);
-  LAUNCH(k_bn_bwd_apply, gridn(rows * C), 256, 0, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, bn, T->d_stat, double(rows), add1,
+  LAUNCH(k_bn_bwd_reduce, grid, thr, sizeof(double) * 2 * thr, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, stat);
+  LAUNCH(k_bn_bwd_apply, gridn(rows * C), 256, 0, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, bn, stat, double(rows), add1,
          add2, out, G, d.g, d.be);
   return 0;
 }
@@ -1040,10 +1067,16 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
   const float* P = d_blob;
   float* G = d_grads;
   CUDA_TRY(cudaMemsetAsync(G, 0, sizeof(float) * m->n_trainable, st));
-  float *dl = T->gsm[0], *dm = T->gsm[1], *dg = T->gsm[2], *ga = T->gsm[3], *gb = T->gsm[4];
+  float *dl = T->gsm[0], *dm = T->gsm[1], *dg = T->gsm[2];
   LAUNCH(k_combine_bwd, gridn(n, 128), 128, 0, st, d_dlogp, T->smx, n, NC, dl, dm, dg);
+  // fork as in the forward: three independent chains, each with its own scratch (gsm pairs, gbuf sets, BN-sum scratch)
+  cudaStream_t const st_main = st;
+  CUDA_TRY(cudaEventRecord(T->ev_fork, st_main));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(T->side[i], T->ev_fork, 0));
   // ---- local branch
   {
+    st = T->side[1];
+    float *ga = T->gsm[3], *gb = T->gsm[4];
     const int64_t W3 = off_of(m, "local_fc.0.weight"), W2 = off_of(m, "lin_layers.1.weight"), W1 = off_of(m, "lin_layers.0.weight");
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(H2, NC), st, dl, nullptr, T->d2, n, H2, NC, 0, G + W3, G + off_of(m, "local_fc.0.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * H2), 256, 0, st, dl, nullptr, P + W3, n, H2, NC, 0, ga);
@@ -1064,7 +1097,9 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     const std::string s = br ? "_2" : "";
     const std::string fc = br ? "distal_fc2" : "distal_fc1";
     const float* dlogit = br ? dg : dm;
-    float *G0 = T->gbuf[0], *G1 = T->gbuf[1], *G2 = T->gbuf[2], *G3 = T->gbuf[3], *D = T->gbuf[4];
+    st = br ? st_main : T->side[0];
+    float *ga = T->gsm[5 + 2 * br], *gb = T->gsm[6 + 2 * br];
+    float *G0 = T->gbuf[br][0], *G1 = T->gbuf[br][1], *G2 = T->gbuf[br][2], *G3 = T->gbuf[br][3], *D = T->gbuf[br][4];
     LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(C, NC), st, dlogit, nullptr, b.gmn, n, C, NC, 0, G + off_of(m, fc + ".2.weight"),
            G + off_of(m, fc + ".2.bias"));
     LAUNCH(k_linear_bwd_x, gridn(n * C), 256, 0, st, dlogit, nullptr, P + off_of(m, fc + ".2.weight"), n, C, NC, 0, ga);
@@ -1101,6 +1136,11 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
 #undef SB
     LAUNCH(k_stem_param_grad, 1, 256, 0, st, Gt, P, off_of(m, "conv1" + s + ".1.weight"), C, ks, stem, G, off_of(m, "conv1" + s + ".1.weight"),
            off_of(m, "conv1" + s + ".0.weight"), off_of(m, "conv1" + s + ".0.bias"));
+  }
+  st = st_main;
+  for (int i = 0; i < 2; ++i) {  // join: the caller's stream sees every gradient
+    CUDA_TRY(cudaEventRecord(T->ev_join[i], T->side[i]));
+    CUDA_TRY(cudaStreamWaitEvent(st, T->ev_join[i], 0));
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
