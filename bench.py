@@ -149,6 +149,53 @@ def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5):
                       "gradient all-reduce over NCCL when n_gpus > 1", "loss_sum_finite": bool(np.isfinite(loss))}
 
 
+# ------------------------------------------------------------------------------------------ transfer sweep leg
+def sweep_leg(genome, pos, meta, cfg0, state, n_cat, radii=(100, 200, 500, 1000, 2000, 5000), n_predict=262144, B=128, steps=20):
+    """SURVEY 8(d) config 5 (transfer sweep): one checkpoint at distal radii 100 ... 5000 (L = 201 ... 10 001; every tensor of
+    Network2 is radius-independent).  Per radius: predict sites/s on the first n_predict sites of this rank's interval (bf16
+    path, CUDA events) and fine-tuning sites/s of the fused step at batch B (all parameters trained, graph replay).  The
+    shipped Homo_sapiens/SNV/AT weights stand in for the Macaca ones (same architecture).  Rank-local, no collective."""
+    import torch
+    from mural_b200 import SiteBatch, pack_meta
+    from mural_b200.training import TrainState
+    rng = np.random.default_rng(55)
+    d_pos = torch.from_numpy(pos[:n_predict]).cuda()
+    d_meta = torch.from_numpy(meta[:n_predict]).cuda()
+    same_chrom = int(np.searchsorted(meta[:n_predict] >> 8, (meta[0] >> 8) + 1))      # keep to the first chromosome of the slice
+    d_pos, d_meta = d_pos[:same_chrom], d_meta[:same_chrom]
+    lab = rng.choice(4, size=B * (steps + 4), p=[0.952381, 0.0140095, 0.0198, 0.0138095])
+    sel = np.sort(rng.choice(same_chrom, size=len(lab), replace=False))
+    t_pos = torch.from_numpy(pos[sel]).cuda()
+    t_meta = torch.from_numpy(pack_meta(meta[sel] & 1, lab, meta[sel] >> 8)).cuda()
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for R in radii:
+        cfg = dict(cfg0, distal_radius=int(R))
+        m = build_model(cfg, state, n_cat, "bf16")
+        sb = SiteBatch(d_pos, d_meta, genome)
+        with torch.no_grad():
+            m.forward(None, sb)
+            ev0.record()
+            for _ in range(3):
+                lp = m.forward(None, sb)
+            ev1.record()
+        torch.cuda.synchronize()
+        pred = 3 * len(sb) / (ev0.elapsed_time(ev1) * 1e-3)
+        m.train()
+        ts = TrainState(m, "Adam", lr=1e-4, weight_decay=1e-5, seed=1)
+        for i in range(steps + 4):
+            if i == 4:
+                ev0.record()
+            ts.step(SiteBatch(t_pos[i * B:(i + 1) * B], t_meta[i * B:(i + 1) * B], genome))
+        ev1.record()
+        torch.cuda.synchronize()
+        out[str(R)] = {"L": 2 * int(R) + 1, "predict_sites_per_s": pred, "train_sites_per_s": B * steps / (ev0.elapsed_time(ev1) * 1e-3),
+                       "finite": bool(torch.isfinite(lp).all().item() and np.isfinite(float(ts.loss_dev.item())))}
+        del ts, m
+    return {"metric": "sites/sec per distal radius (transfer sweep, config 5)", "unit": "sites/s", "predict_sites": int(same_chrom),
+            "train_batch": B, "dtype": "bf16 predict / f32 train", "radii": out}
+
+
 # ------------------------------------------------------------------------------------------ indel leg
 def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2):
     """BASELINE configs[3] (predict half): MuRaL-indel UNet_Small with the shipped Homo_sapiens/INDEL/insertion weights
@@ -322,6 +369,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     ap.add_argument("--no-indel", action="store_true", help="skip the MuRaL-indel predict leg (BASELINE configs[3])")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the distal-radius sweep leg (SURVEY 8d config 5)")
     ap.add_argument("--no-eval", action="store_true", help="skip the validation-metrics leg (Evaluator, SURVEY 8f N3)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -458,6 +506,13 @@ def main():
         except Exception as e:
             indel = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    sweep = None
+    if rank == 0 and not a.no_sweep:
+        try:
+            sweep = sweep_leg(genome, pos, meta, cfg, state, n_cat)
+        except Exception as e:
+            sweep = {"error": "%s: %s" % (type(e).__name__, e)}
+
     evalm = None
     if rank == 0 and not a.no_eval:
         try:
@@ -477,7 +532,7 @@ def main():
                            "per-step activation workspace > L2", wall_s_timed_region=t_wall),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof, "train": train, "indel": indel, "eval_metrics": evalm}
+            "roofline": roof, "train": train, "indel": indel, "eval_metrics": evalm, "transfer_sweep": sweep}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample

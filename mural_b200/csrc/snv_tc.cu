@@ -793,6 +793,12 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     while (c2 * 2 <= chunk) c2 *= 2;
     chunk = c2;
   }
+  if (m->chunk_sites <= 0) {
+    // the per-site row buffers grow with the window (stage-1 rows L1 of both branches, 64 B each, stem out + stage-1 out +
+    // ~0.3 of that for the later stages): halve the chunk until they fit 16 GiB (524 288 sites at the shipped 1 Kb radius)
+    const double per_site = 64.0 * 2.3 * double(m->br[0].L1 + m->br[1].L1);
+    while (chunk > 4096 && double(chunk) * per_site > 16.0 * 1024 * 1024 * 1024) chunk /= 2;
+  }
   if (chunk > n) chunk = n;
   // workspace: per branch X0 (stem out), Z1, Z2 as bf16 planes, H as fp32 planes; + local logits, taps, k-mer indices.
   // On the dense path X0 / Z1 hold the stage-1 lattice and the edge pseudo-sites instead of per-site rows.

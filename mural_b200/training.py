@@ -84,6 +84,8 @@ def make_scheduler(config, train_size):
 
 
 class TrainState:
+    MAX_GRAPHS = 4   # distinct batch sizes kept as captured graphs (the full batch and the odd tail sizes that recur)
+
     def __init__(self, model, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False, use_graph=True):
         """use_graph: capture the step of the first full-size batch in CUDA graphs and replay them for every batch of that size
         (the step is ~200 small launches and launch-bound at the reference's batch of 128); other batch sizes run eagerly."""
@@ -123,8 +125,9 @@ class TrainState:
         self._lr_on_dev = float(lr)
         self._opt_step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.use_graph = bool(use_graph)
-        self._graph = None            # dict(n, genome, pos, meta, logp, dlogp, fb, opt)
+        self._graphs = {}             # batch size -> dict(n, genome, pos, meta, logp, dlogp, fb, opt); at most MAX_GRAPHS sizes
         self._graph_warm = {}         # batch size -> eager steps seen (one eager step sizes the tape before capture)
+        self._tape_n = 0              # largest batch the native workspace has been sized for
         self.n_forward = 0
         self._tracked_synced = 0
         self.grad_average = grad_average
@@ -148,9 +151,18 @@ class TrainState:
         except Exception:
             pass
 
+    def _note_batch(self, n):
+        """The native workspace (tape) is reallocated when a larger batch than any before arrives: captured graphs hold
+        pointers into the old one and are dropped."""
+        if n > self._tape_n:
+            self._tape_n = n
+            self._graphs.clear()
+            self._graph_warm.clear()
+
     # ---- pieces
     def forward(self, batch):
         n = len(batch)
+        self._note_batch(n)
         logp = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mural_snv_train_forward(self._h, batch.genome.handle, _lib.ptr(batch.pos), _lib.ptr(batch.meta), n,
@@ -228,12 +240,13 @@ class TrainState:
         n = len(batch)
         if n < 2:
             return None                                      # training.py:415: batches of one site are skipped
+        self._note_batch(n)
         if self.use_graph:
-            g = self._graph
-            if g is None and self._graph_warm.get(n, 0) >= 1:
+            g = self._graphs.get(n)
+            if g is None and self._graph_warm.get(n, 0) >= 1 and len(self._graphs) < self.MAX_GRAPHS:
                 # capture does not execute: the captured step runs at the replay below
-                g = self._graph = self._capture(batch)
-            if g is not None and g["n"] == n and g["genome"] is batch.genome and g["world"] == self._world():
+                g = self._graphs[n] = self._capture(batch)
+            if g is not None and g["genome"] is batch.genome and g["world"] == self._world():
                 g["pos"].copy_(batch.pos)
                 g["meta"].copy_(batch.meta)
                 if self._lr_on_dev != self.lr:

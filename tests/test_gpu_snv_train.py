@@ -243,7 +243,7 @@ def test_graph_step_equals_eager_step(kat, cuda_genome):
         for i in range(5):
             st.lr = 1e-4 * (0.5 ** (i // 2))
             traj.append(st.step(sb).clone())
-        assert (st._graph is not None) == use_graph
+        assert bool(st._graphs) == use_graph
         assert int(st._opt_step_dev.item()) == 5 == st.opt_step and st.n_forward == 5
         runs[key] = (traj, st.blob.clone(), float(st.loss_dev.item()))
     for a, b in zip(runs["eager"][0], runs["graph"][0]):
@@ -252,10 +252,20 @@ def test_graph_step_equals_eager_step(kat, cuda_genome):
     d = (runs["eager"][1] - runs["graph"][1]).abs().max().item()
     assert d < 5e-6 * max(1.0, runs["eager"][1].abs().max().item()), d
     assert abs(runs["eager"][2] - runs["graph"][2]) < 1e-3 * abs(runs["eager"][2])
-    # a batch of another size falls back to the eager path and keeps the counters in step
+    # a batch of another size falls back to the eager path (captured on its second appearance) and keeps the counters in step
     sb2 = _batch(z, cuda_genome, 40, labels[:40])
     st.step(sb2)
-    assert int(st._opt_step_dev.item()) == 6 == st.opt_step
+    assert int(st._opt_step_dev.item()) == 6 == st.opt_step and set(st._graphs) == {64}
+    st.step(sb2)
+    assert set(st._graphs) == {64, 40}
+    # a LARGER batch makes the library reallocate its workspace: graphs (they hold pointers into the old one) are dropped
+    n3 = 96
+    sb3 = _batch(z, cuda_genome, n3, (z["start"][:n3] % 4).astype(np.int64))
+    st.step(sb3)
+    assert not st._graphs
+    for _ in range(3):
+        out = st.step(sb)
+    assert set(st._graphs) == {64} and torch.isfinite(out).all() and int(st._opt_step_dev.item()) == 11 == st.opt_step
 
 
 def test_train_epochs_with_validation_metrics(kat, cuda_genome):
