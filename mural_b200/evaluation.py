@@ -237,7 +237,12 @@ class Evaluator:
             self.metrics['window%d' % win_size] = corr_win
         if save_valid_preds:
             import pandas as pd
-            df = pd.concat((chr_pos.reset_index(drop=True), self.data_and_prob[['mut_type'] + self.prob_names]), axis=1)
+            if self.data_and_prob is not None:
+                cols = self.data_and_prob[['mut_type'] + self.prob_names]
+            else:       # device-resident input: bring labels and probabilities back once for the file
+                cols = pd.DataFrame(self.ed.prob.cpu().numpy(), columns=self.prob_names)
+                cols.insert(0, 'mut_type', self.ed.labels_host())
+            df = pd.concat((chr_pos.reset_index(drop=True), cols), axis=1)
             df.columns = ['chrom', 'start', 'end', 'strand', 'mut_type'] + self.prob_names
             df.sort_values(['chrom', 'start'], inplace=True)
             df.to_csv(save_path + '.valid_preds.tsv.gz', sep='\t', float_format='%.4g', index=False)

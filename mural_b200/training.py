@@ -236,7 +236,8 @@ class TrainState:
     # ---- fused step
     def step(self, batch):
         """forward + CE(sum) + backward + all-reduce + clip + optimizer; returns the log-probs (loss accumulates in
-        self.loss_dev, read it with .item() once per print interval)."""
+        self.loss_dev, read it with .item() once per print interval).  On the graph path the returned tensor is the graph's
+        static output buffer: it is overwritten by the next step of the same batch size — clone it to keep it."""
         n = len(batch)
         if n < 2:
             return None                                      # training.py:415: batches of one site are skipped
