@@ -208,6 +208,25 @@ int mural_optimizer_step_dev(int32_t kind, float* d_params, const float* d_grads
                              const float* d_lr, float weight_decay, int64_t* d_step, float max_norm, float grad_scale,
                              double* d_scratch, void* stream);
 
+/* MuRaL-indel training step (UNet_Small in train() mode, model_indel.py:6-176; loop body training.py:404-452).
+ * Same protocol as the snv step: d_blob is the flat fp32 parameter buffer in the layout of mural_indel_model_tensor()
+ * (trainable tensors first, BatchNorm running statistics after them; running statistics are updated in place by forward),
+ * d_out float32 [n, n_class] = the Softplus activations UNet_Small.forward returns, the loss is CrossEntropyLoss(sum) on them
+ * (mural_ce_sum_grad), d_grads is a flat buffer of mural_indel_model_n_params() floats (same offsets; the running-statistic
+ * part stays zero) whose first n_trainable floats go to the all-reduce and mural_optimizer_step(_dev).  p_fc: Dropout of
+ * out_fc (0.1 in the reference, model_indel.py:147). */
+int mural_indel_model_config(const mural_indel_model_t* m, mural_indel_config_t* out);
+typedef struct mural_indel_train mural_indel_train_t;
+int mural_indel_train_create(mural_indel_model_t* m, mural_indel_train_t** out);
+void mural_indel_train_destroy(mural_indel_train_t* t);
+int mural_indel_train_set_dropout(mural_indel_train_t* t, float p_fc, uint64_t seed);
+int mural_indel_train_forward(mural_indel_train_t* t, const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta,
+                              int64_t n, float* d_blob, float* d_out, void* stream);
+/* same on the reference's own input tensor distal_x float32 [n, 4, 2R] */
+int mural_indel_train_forward_tensors(mural_indel_train_t* t, const float* d_distal, int64_t n, int32_t L, float* d_blob,
+                                      float* d_out, void* stream);
+int mural_indel_train_backward(mural_indel_train_t* t, float* d_blob, const float* d_dout, float* d_grads, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Calibration epilogue (run_predict.py:214-225): softmax(logp) -> FullDirichlet apply
  * (dirichletcal/calib/fulldirichlet.py:78-80, multinomial.py:60-64,235-244) -> optional Poisson

@@ -74,6 +74,13 @@ PROTOTYPES = {
     "mural_snv_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "mural_ce_sum_grad": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "mural_optimizer_step": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _i64, C.c_float, C.c_float, _vp, _vp]),
+    "mural_indel_model_config": (C.c_int, [_vp, _vp]),
+    "mural_indel_train_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mural_indel_train_destroy": (None, [_vp]),
+    "mural_indel_train_set_dropout": (C.c_int, [_vp, C.c_float, C.c_uint64]),
+    "mural_indel_train_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mural_indel_train_forward_tensors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "mural_indel_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "mural_optimizer_step_dev": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, _vp, C.c_float, C.c_float, _vp, _vp]),
     "mural_calibrate": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _vp, _vp]),
     "mural_kmer_group_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _i32, _i64, _vp, _vp]),

@@ -505,3 +505,9 @@ extern "C" int mural_indel_forward_tensors(mural_indel_model_t* m, const float* 
   cudaFree(d_sym);
   return rc;
 }
+
+extern "C" int mural_indel_model_config(const mural_indel_model_t* m, mural_indel_config_t* out) {
+  MURAL_CHECK(m && out, "NULL argument");
+  *out = m->cfg;
+  return 0;
+}

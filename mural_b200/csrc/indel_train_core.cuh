@@ -1,0 +1,262 @@
+// Training step of MuRaL-indel `UNet_Small` (MuRaL/model/model_indel.py:6-176; loop body MuRaL/training.py:404-452) as a
+// tape of generic ops: this header holds the per-work-item arithmetic of every op.
+//
+// One source, two builds: with nvcc every op is a grid-stride kernel over work items; with g++ (-DINDEL_EMU, scratch/
+// indel_train/emu.cpp) the same functors run in a serial loop on host memory — test infrastructure with which the arithmetic
+// was checked against fp64 autograd of the oracle in the GPU-less build container (scratch/indel_train/check_emu.py).
+// First version: correctness and structure (unit = conv -> train-mode BatchNorm -> activation (+ residuals), tape,
+// gradient accumulation); the kernels are plain one-item-per-thread loops, to be tiled once profiled.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define HD __host__ __device__ __forceinline__
+#ifndef INDEL_TRAIN_LAUNCH  // the library routes launches through its accounting macro (common.cuh)
+#define INDEL_TRAIN_LAUNCH(name, kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+#else
+#define HD inline
+#endif
+
+namespace indel_train {
+
+// ------------------------------------------------------------------------------------------------ execution layer
+#ifdef __CUDACC__
+template <class F>
+__global__ void __launch_bounds__(256) k_run(int64_t n, F f) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) f(i);
+}
+struct Exec {
+  cudaStream_t st = nullptr;
+  int64_t launches = 0;
+  template <class F> void run(int64_t n, const F& f) {
+    if (n <= 0) return;
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;  // grid-stride: a multiple of the SM count
+    INDEL_TRAIN_LAUNCH(F::kName, (k_run<F>), (unsigned)g, 256, st, n, f);
+    ++launches;
+  }
+  void* alloc(size_t b) { void* p = nullptr; cudaMalloc(&p, b); return p; }
+  void free_(void* p) { cudaFree(p); }
+  void zero(void* p, size_t b) { cudaMemsetAsync(p, 0, b, st); }
+};
+template <class T> HD void atomic_add(T* p, T v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(p, v);
+#else
+  *p += v;  // host instantiation of the functors is never executed in the CUDA build
+#endif
+}
+#else
+struct Exec {
+  int64_t launches = 0;
+  template <class F> void run(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); ++launches; }
+  void* alloc(size_t b) { return calloc(b ? b : 1, 1); }
+  void free_(void* p) { free(p); }
+  void zero(void* p, size_t b) { memset(p, 0, b); }
+};
+template <class T> inline void atomic_add(T* p, T v) { *p += v; }
+#endif
+
+enum Act { ACT_NONE = 0, ACT_SILU = 1, ACT_RELU = 2, ACT_SOFTPLUS = 3 };
+
+HD float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+HD float act_fwd(float z, int act) {
+  if (act == ACT_SILU) return z * sigmoidf_(z);
+  if (act == ACT_RELU) return z > 0.f ? z : 0.f;
+  if (act == ACT_SOFTPLUS) return z > 20.f ? z : log1pf(expf(z));  // nn.Softplus(beta=1, threshold=20)
+  return z;
+}
+HD float act_bwd(float z, int act) {
+  if (act == ACT_SILU) { const float s = sigmoidf_(z); return s * (1.f + z * (1.f - s)); }
+  if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == ACT_SOFTPLUS) return z > 20.f ? 1.f : sigmoidf_(z);
+  return 1.f;
+}
+HD uint32_t hash32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return uint32_t(x);
+}
+// keep-scale of element idx of a dropout layer at (seed, step): 0 or 1/(1-p)
+HD float drop_scale(float p, uint64_t seed, uint32_t step, uint64_t idx) {
+  if (p <= 0.f) return 1.f;
+  const uint32_t u = hash32(seed ^ (uint64_t(step) << 40) ^ idx);
+  return (u * (1.0f / 4294967296.0f)) < p ? 0.f : 1.f / (1.f - p);
+}
+
+// ------------------------------------------------------------------------------------------------ ops (work-item functors)
+struct ConvDims { int B, Cin, Lin, Cout, Lout, k, stride, pad, up; };  // input is read through a nearest upsample by `up`
+
+struct ConvFwd {
+  static constexpr const char* kName = "k_indel_train<ConvFwd>";  // item: output element (b, co, lo)
+  const float* x; const float* W; const float* bias; float* y; ConvDims d;
+  HD void operator()(int64_t i) const {
+    const int lo = int(i % d.Lout), co = int((i / d.Lout) % d.Cout), b = int(i / (int64_t(d.Lout) * d.Cout));
+    float acc = bias ? bias[co] : 0.f;
+    const int Lv = d.Lin * d.up;
+    for (int ci = 0; ci < d.Cin; ++ci) {
+      const float* xr = x + (int64_t(b) * d.Cin + ci) * d.Lin;
+      const float* wr = W + (int64_t(co) * d.Cin + ci) * d.k;
+      for (int t = 0; t < d.k; ++t) {
+        const int j = lo * d.stride + t - d.pad;
+        if (j >= 0 && j < Lv) acc += wr[t] * xr[j / d.up];
+      }
+    }
+    y[i] = acc;
+  }
+};
+struct ConvBwdX {
+  static constexpr const char* kName = "k_indel_train<ConvBwdX>";  // item: input element (b, ci, jin); dx += W^T dy
+  const float* dy; const float* W; float* dx; ConvDims d;
+  HD void operator()(int64_t i) const {
+    const int jin = int(i % d.Lin), ci = int((i / d.Lin) % d.Cin), b = int(i / (int64_t(d.Lin) * d.Cin));
+    float acc = 0.f;
+    for (int u = 0; u < d.up; ++u) {
+      const int j = jin * d.up + u;
+      for (int t = 0; t < d.k; ++t) {
+        const int num = j + d.pad - t;
+        if (num < 0 || num % d.stride) continue;
+        const int lo = num / d.stride;
+        if (lo >= d.Lout) continue;
+        for (int co = 0; co < d.Cout; ++co)
+          acc += W[(int64_t(co) * d.Cin + ci) * d.k + t] * dy[(int64_t(b) * d.Cout + co) * d.Lout + lo];
+      }
+    }
+    dx[i] += acc;
+  }
+};
+struct ConvBwdW {
+  static constexpr const char* kName = "k_indel_train<ConvBwdW>";  // item: (co, ci, t, b); dW += sum_lo dy * x, db += sum_lo dy
+  const float* x; const float* dy; float* dW; float* db; ConvDims d;
+  HD void operator()(int64_t i) const {
+    const int b = int(i % d.B), t = int((i / d.B) % d.k), ci = int((i / (int64_t(d.B) * d.k)) % d.Cin),
+              co = int(i / (int64_t(d.B) * d.k * d.Cin));
+    const float* dr = dy + (int64_t(b) * d.Cout + co) * d.Lout;
+    const float* xr = x + (int64_t(b) * d.Cin + ci) * d.Lin;
+    const int Lv = d.Lin * d.up;
+    float acc = 0.f, sb = 0.f;
+    for (int lo = 0; lo < d.Lout; ++lo) {
+      const int j = lo * d.stride + t - d.pad;
+      if (j >= 0 && j < Lv) acc += dr[lo] * xr[j / d.up];
+      sb += dr[lo];
+    }
+    atomic_add(dW + (int64_t(co) * d.Cin + ci) * d.k + t, acc);
+    if (db && ci == 0 && t == 0) atomic_add(db + co, sb);
+  }
+};
+struct BnStats {
+  static constexpr const char* kName = "k_indel_train<BnStats>";  // item: row (b, c); stat[c] += sum, stat[C + c] += sum of squares (double)
+  const float* x; double* stat; int C, L;
+  HD void operator()(int64_t i) const {
+    const int c = int(i % C);
+    const float* r = x + i * L;
+    double s = 0, q = 0;
+    for (int l = 0; l < L; ++l) { s += r[l]; q += double(r[l]) * r[l]; }
+    atomic_add(stat + c, s);
+    atomic_add(stat + C + c, q);
+  }
+};
+struct BnFinalize {
+  static constexpr const char* kName = "k_indel_train<BnFinalize>";  // item: channel; nn.BatchNorm1d training mode (biased var for the batch, unbiased for running_var, momentum 0.1)
+  const double* stat; double N; int C; float* rm; float* rv; float* mean; float* invstd;
+  HD void operator()(int64_t c) const {
+    const double m = stat[c] / N;
+    double var = stat[C + c] / N - m * m;
+    if (var < 0) var = 0;
+    mean[c] = float(m);
+    invstd[c] = float(1.0 / sqrt(var + 1e-5));
+    const double unb = N > 1 ? var * N / (N - 1) : var;
+    rm[c] = 0.9f * rm[c] + 0.1f * float(m);
+    rv[c] = 0.9f * rv[c] + 0.1f * float(unb);
+  }
+};
+struct UnitOut {
+  static constexpr const char* kName = "k_indel_train<UnitOut>";  // item: element; y = drop * act(bn(t)) + res1 + res2
+  const float* t; const float* mean; const float* invstd; const float* gamma; const float* beta;  // gamma == nullptr: no BN
+  const float* res1; const float* res2; float* y; int C, L, act; float p; uint64_t seed; uint32_t step;
+  HD float z_of(int64_t i) const {
+    if (!gamma) return t[i];
+    const int c = int((i / L) % C);
+    return (t[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+  }
+  HD void operator()(int64_t i) const {
+    float v = act_fwd(z_of(i), act) * drop_scale(p, seed, step, uint64_t(i));
+    if (res1) v += res1[i];
+    if (res2) v += res2[i];
+    y[i] = v;
+  }
+};
+struct UnitBwdReduce {
+  static constexpr const char* kName = "k_indel_train<UnitBwdReduce>";  // item: row (b, c); dz = dy * drop * act'(z); s1 = sum dz, s2 = sum dz * xhat; also stores dz
+  UnitOut u; const float* dy; float* dz; double* stat;
+  HD void operator()(int64_t row) const {
+    const int c = int(row % u.C);
+    double s1 = 0, s2 = 0;
+    for (int l = 0; l < u.L; ++l) {
+      const int64_t i = row * u.L + l;
+      const float g = dy[i] * drop_scale(u.p, u.seed, u.step, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
+      dz[i] = g;
+      if (u.gamma) { s1 += g; s2 += double(g) * ((u.t[i] - u.mean[c]) * u.invstd[c]); }
+    }
+    if (u.gamma) { atomic_add(stat + c, s1); atomic_add(stat + u.C + c, s2); }
+  }
+};
+struct UnitBwdApply {
+  static constexpr const char* kName = "k_indel_train<UnitBwdApply>";  // item: element; dt = gamma * invstd * (dz - s1/N - xhat * s2/N)  (in place on dz)
+  UnitOut u; float* dz; const double* stat; double N;
+  HD void operator()(int64_t i) const {
+    const int c = int((i / u.L) % u.C);
+    const float xh = (u.t[i] - u.mean[c]) * u.invstd[c];
+    dz[i] = u.gamma[c] * u.invstd[c] * (dz[i] - float(stat[c] / N) - xh * float(stat[u.C + c] / N));
+  }
+};
+struct BnParamGrad {
+  static constexpr const char* kName = "k_indel_train<BnParamGrad>";  // item: channel
+  const double* stat; int C; float* dgamma; float* dbeta;
+  HD void operator()(int64_t c) const { dgamma[c] += float(stat[C + c]); dbeta[c] += float(stat[c]); }
+};
+struct AddTo {
+  static constexpr const char* kName = "k_indel_train<AddTo>"; const float* src; float* dst; HD void operator()(int64_t i) const { dst[i] += src[i]; } };
+struct FlipCL {
+  static constexpr const char* kName = "k_indel_train<FlipCL>"; const float* x; float* y; int C, L;  // y[b, c, l] = x[b, C-1-c, L-1-l]  (torch.flip(x, [1, 2]))
+  HD void operator()(int64_t i) const {
+    const int l = int(i % L), c = int((i / L) % C); const int64_t b = i / (int64_t(L) * C);
+    y[i] = x[(b * C + (C - 1 - c)) * L + (L - 1 - l)];
+  } };
+struct AddFlipL {
+  static constexpr const char* kName = "k_indel_train<AddFlipL>"; const float* a; const float* bb; float* o; int L;  // o = a + flip(bb, [2])
+  HD void operator()(int64_t i) const { const int l = int(i % L); o[i] = a[i] + bb[i - l + (L - 1 - l)]; } };
+struct AddFlipLBwd {
+  static constexpr const char* kName = "k_indel_train<AddFlipLBwd>"; const float* d_o; float* da; float* db; int L;
+  HD void operator()(int64_t i) const { const int l = int(i % L); da[i] += d_o[i]; db[i - l + (L - 1 - l)] += d_o[i]; } };
+struct MaxL {
+  static constexpr const char* kName = "k_indel_train<MaxL>"; const float* x; float* y; int32_t* arg; int L;  // item: row (b, c)
+  HD void operator()(int64_t r) const {
+    const float* p = x + r * L; int a = 0; float m = p[0];
+    for (int l = 1; l < L; ++l) if (p[l] > m) { m = p[l]; a = l; }
+    y[r] = m; arg[r] = a;
+  } };
+struct MaxLBwd {
+  static constexpr const char* kName = "k_indel_train<MaxLBwd>"; const float* dy; const int32_t* arg; float* dx; int L;
+  HD void operator()(int64_t r) const { dx[r * L + arg[r]] += dy[r]; } };
+struct CeGrad {
+  static constexpr const char* kName = "k_indel_train<CeGrad>";  // CrossEntropyLoss(reduction='sum') on the network output (training.py:327,425); item: site
+  const float* out; const int32_t* label; int NC; float* dout; double* loss;
+  HD void operator()(int64_t i) const {
+    const float* p = out + i * NC;
+    float mx = p[0]; for (int o = 1; o < NC; ++o) mx = p[o] > mx ? p[o] : mx;
+    float s = 0.f; for (int o = 0; o < NC; ++o) s += expf(p[o] - mx);
+    const int y = label[i];
+    for (int o = 0; o < NC; ++o) dout[i * NC + o] = expf(p[o] - mx) / s - (o == y ? 1.f : 0.f);
+    atomic_add(loss, double(-(p[y] - mx - logf(s))));
+  } };
+
+}  // namespace indel_train

@@ -2,8 +2,8 @@
 
 Same constructor signature and `state_dict()` keys as the reference; the torch modules only hold parameters.
 `forward(distal_input)` accepts the reference's one-hot tensor [B,4,2R] or a `SiteBatch` (fast path: windows are
-gathered on the GPU from the packed genome).  Training of the indel model is not built yet (SURVEY §8a row M9 is
-eval-only in this round): in train() mode forward raises.
+gathered on the GPU from the packed genome).  In train() mode forward is differentiable and runs the native training tape
+(csrc/indel_train.cu through mural_b200.training.IndelTrainState).
 """
 import ctypes as C
 
@@ -95,7 +95,8 @@ class UNet_Small(nn.Module):
 
     def forward(self, distal_input, distal_radius=None):
         if self.training:
-            raise NotImplementedError("mural_b200.UNet_Small: training of the indel model is not built yet (eval forward only)")
+            from .training import unet_train_forward
+            return unet_train_forward(self, distal_input, distal_radius)
         L = _lib.lib()
         with torch.cuda.device(self._device_index()):
             if isinstance(distal_input, SiteBatch):

@@ -304,6 +304,160 @@ def network2_train_forward(model, local_input, distal_input):
     return _TrainFn.apply(st, distal_input, *st.params)
 
 
+class IndelTrainState:
+    """Training step of MuRaL-indel `UNet_Small` (training.py:404-452 with model_type 'indel') on the native
+    tape (csrc/indel_train.cu).  Same protocol as `TrainState`: the model's parameters and BatchNorm buffers become views of one
+    flat fp32 buffer, gradients land in one flat buffer (the single all-reduce of a data-parallel step), clip + optimizer are
+    the fused kernels.  The loss is CrossEntropyLoss(sum) on the Softplus outputs, as in the reference."""
+
+    def __init__(self, model, distal_radius, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False):
+        L = _lib.lib()
+        self.model = model
+        self.device = model.out_fc[2].weight.device
+        if self.device.type != "cuda":
+            raise RuntimeError("mural_b200 training runs on CUDA only")
+        if optim not in OPTIMIZERS:
+            raise ValueError("Error: unsupported optimization method %s" % optim)
+        self.kind, self.lr, self.weight_decay, self.max_norm = OPTIMIZERS[optim], float(lr), float(weight_decay), float(max_norm)
+        self.distal_radius = int(distal_radius)
+        h = model._handle(self.distal_radius)
+        self.n_blob = int(L.mural_indel_model_n_params(h))
+        self.blob = torch.empty(self.n_blob, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(self.n_blob, dtype=torch.float32, device=self.device)
+        sd = dict(model.named_parameters())
+        sd.update(dict(model.named_buffers()))
+        self.params, self.grad_views, self.n_trainable = [], [], 0
+        for i in range(L.mural_indel_model_n_tensors(h)):
+            name, off, num, buf = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int32()
+            _lib.check(L.mural_indel_model_tensor(h, i, C.byref(name), C.byref(off), C.byref(num), C.byref(buf)))
+            t = sd[name.value.decode()]
+            view = self.blob[off.value:off.value + num.value].view(t.shape)
+            view.copy_(t.detach())
+            t.data = view                                     # parameter / running statistic now lives inside the flat blob
+            if not buf.value:
+                self.params.append(t)
+                self.grad_views.append(self.grads[off.value:off.value + num.value].view(t.shape))
+                self.n_trainable = max(self.n_trainable, off.value + num.value)   # trainable tensors come first in the layout
+        self.m = torch.zeros(self.n_trainable, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros_like(self.m) if self.kind != 2 else None
+        self.vmax = torch.zeros_like(self.m) if self.kind == 1 else None
+        self.scratch = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.loss_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
+        self._lr_on_dev = float(lr)
+        self._opt_step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.opt_step = 0
+        self.n_forward = 0
+        self._tracked_synced = 0
+        self.grad_average = grad_average
+        t = C.c_void_p()
+        _lib.check(L.mural_indel_train_create(h, C.byref(t)))
+        self._h = t
+        _lib.check(L.mural_indel_train_set_dropout(self._h, float(model.out_fc[1].p), int(seed)))
+        model._train_state = self
+
+    def set_dropout(self, p_fc, seed=0):
+        _lib.check(_lib.lib().mural_indel_train_set_dropout(self._h, float(p_fc), int(seed)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().mural_indel_train_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def forward(self, batch):
+        """batch: SiteBatch (windows gathered on the device) or the reference's one-hot tensor [B, 4, 2R]."""
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            if isinstance(batch, SiteBatch):
+                n = len(batch)
+                out = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
+                _lib.check(L.mural_indel_train_forward(self._h, batch.genome.handle, _lib.ptr(batch.pos), _lib.ptr(batch.meta), n,
+                                                       _lib.ptr(self.blob), _lib.ptr(out), _lib.current_stream()))
+            else:
+                x = batch.to(self.device, torch.float32).contiguous()
+                n = x.shape[0]
+                out = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
+                _lib.check(L.mural_indel_train_forward_tensors(self._h, _lib.ptr(x), n, x.shape[2], _lib.ptr(self.blob), _lib.ptr(out),
+                                                               _lib.current_stream()))
+        self.n_forward += 1
+        self.model.mark_dirty()
+        return out
+
+    def backward(self, dout):
+        dout = dout.contiguous().to(torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_indel_train_backward(self._h, _lib.ptr(self.blob), _lib.ptr(dout), _lib.ptr(self.grads),
+                                                             _lib.current_stream()))
+        return self.grads
+
+    def step(self, batch):
+        """forward + CE(sum) + backward + all-reduce + clip + optimizer on a SiteBatch (labels in its meta)."""
+        n = len(batch)
+        if n < 2:
+            return None                                      # training.py:415
+        out = self.forward(batch)
+        dout = torch.empty_like(out)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(out), _lib.ptr(batch.meta), n, self.model.n_class, _lib.ptr(self.loss_dev),
+                                                    _lib.ptr(dout), _lib.current_stream()))
+        self.backward(dout)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(self.grads[:self.n_trainable], op=torch.distributed.ReduceOp.SUM)
+            world = torch.distributed.get_world_size()
+        self.opt_step += 1
+        if self._lr_on_dev != self.lr:
+            self._lr_dev.fill_(self.lr)
+            self._lr_on_dev = self.lr
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_optimizer_step_dev(self.kind, _lib.ptr(self.blob), _lib.ptr(self.grads), _lib.ptr(self.m),
+                                                           _lib.ptr(self.v), _lib.ptr(self.vmax), self.n_trainable, _lib.ptr(self._lr_dev),
+                                                           self.weight_decay, _lib.ptr(self._opt_step_dev), self.max_norm,
+                                                           1.0 / world if self.grad_average else 1.0, _lib.ptr(self.scratch),
+                                                           _lib.current_stream()))
+        self.model.mark_dirty()
+        return out
+
+    def sync_counters(self):
+        """num_batches_tracked follows the number of BatchNorm calls: one per training forward, two for the reverse-strand
+        stem (it is applied to the window and to its reverse complement, model_indel.py:155)."""
+        d = self.n_forward - self._tracked_synced
+        if d:
+            stem_bn = self.model.conv[1] if getattr(self.model, "use_reverse", None) else None
+            for mod in self.model.modules():
+                if isinstance(mod, torch.nn.BatchNorm1d) and mod.num_batches_tracked is not None:
+                    mod.num_batches_tracked += 2 * d if mod is stem_bn else d
+            self._tracked_synced = self.n_forward
+
+
+class _IndelTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, batch, *params):
+        ctx.state = state
+        return state.forward(batch)
+
+    @staticmethod
+    def backward(ctx, dout):
+        st = ctx.state
+        st.backward(dout)
+        return (None, None) + tuple(g.clone() for g in st.grad_views)
+
+
+def unet_train_forward(model, distal_input, distal_radius=None):
+    """UNet_Small.forward in train() mode (differentiable): the reference's loop body runs unchanged on it."""
+    if distal_radius is None:
+        if isinstance(distal_input, SiteBatch):
+            raise ValueError("distal_radius is required with a SiteBatch")
+        distal_radius = distal_input.shape[2] // 2
+    st = getattr(model, "_train_state", None)
+    if st is None or st.distal_radius != int(distal_radius):
+        st = IndelTrainState(model, distal_radius)
+    return _IndelTrainFn.apply(st, distal_input, *st.params)
+
+
 def load_pretrained(model, model_state, train_all=True, init_fc_with_pretrained=True, model_type="snv"):
     """Transfer-learning initialisation, training.py:289-320: load the pretrained state dict on the CPU copy (strict keys,
     `.layer.N` aliases included), move back, then the two switches.  As in the reference both switches only work when

@@ -1,0 +1,124 @@
+"""GPU: MuRaL-indel training step (train-mode UNet_Small forward, CE(sum) on the Softplus outputs, full backward, fused
+optimizer) vs fp64 autograd of the oracle (MuRaL/training.py:404-452, model_indel.py:6-176)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD
+from oracle import network_t as NT
+from test_gpu_indel import _model
+
+pytestmark = pytest.mark.gpu
+
+
+def _onehot(rng, B, L):
+    idx = rng.integers(0, 4, (B, L))
+    x = np.zeros((B, 4, L), np.float32)
+    for b in range(B):
+        x[b, idx[b], np.arange(L)] = 1
+    x[:, :, rng.integers(0, L, 5)] = 0.25                       # a few N columns
+    return x
+
+
+@pytest.mark.parametrize("tag,R,B", [("hs_ins", 500, 6), ("hs_del_start", 1000, 4)])
+def test_indel_train_forward_backward_vs_autograd(tag, R, B):
+    from mural_b200 import _lib
+    from mural_b200.training import IndelTrainState
+    z = np.load(os.path.join(GOLD, "indel_%s.npz" % tag))
+    m, state = _model(z)
+    down, use_rev = [int(v) for v in z["down"]], bool(z["use_reverse"])
+    NC = state["out_fc.2.weight"].shape[0]
+    rng = np.random.default_rng(3)
+    x = _onehot(rng, B, 2 * R)
+    labels = rng.integers(0, NC, B)
+    st = IndelTrainState(m, R, "Adam", lr=1e-3)
+    st.set_dropout(0.0)
+    m.train()
+    out = st.forward(torch.from_numpy(x).cuda())
+    sd = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=("running" not in k)) for k, v in state.items()
+          if "num_batches" not in k}
+    rec = NT._BNStats()
+    ref = NT.unet_small_forward(sd, x, down, use_rev, torch.float64, train=True, rec=rec)
+    assert np.abs(out.cpu().numpy() - ref.detach().numpy()).max() < 2e-4
+    loss = NT.ce_sum(ref, labels)
+    loss.backward()
+    meta = torch.from_numpy((labels << 1).astype(np.int32)).cuda()
+    dout = torch.empty_like(out)
+    _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(out), _lib.ptr(meta), B, NC, _lib.ptr(st.loss_dev), _lib.ptr(dout), _lib.current_stream()))
+    assert abs(float(st.loss_dev.item()) - float(loss.detach())) < 1e-3 * max(1.0, abs(float(loss.detach())))
+    st.backward(dout)
+    gmax = max(float(v.grad.abs().max()) for k, v in sd.items() if v.grad is not None)
+    worst = 0.0
+    for p, gv in zip(st.params, st.grad_views):
+        name = [k for k, v in m.named_parameters() if v is p][0]
+        g_ref = sd[name].grad.numpy()
+        g = gv.cpu().numpy()
+        if np.abs(g_ref).max() < 1e-9 * gmax:     # conv biases in front of a batch-statistic BatchNorm: the true gradient is exactly 0
+            assert np.abs(g).max() < 1e-4 * gmax, name
+            continue
+        err = np.abs(g - g_ref).max() / max(1e-4 * gmax, np.abs(g_ref).max())
+        worst = max(worst, err)
+        assert err < 5e-3, (name, err)
+    print(tag, "worst relative gradient error %.2e" % worst)
+    # running statistics after one training forward (the reverse-stem BatchNorm is applied twice: checked through eval below)
+    sdm = m.state_dict()
+    for bn, (mean, var_unb) in rec.stats.items():
+        if bn == "conv.1":
+            continue
+        exp_m = 0.9 * np.asarray(state[bn + ".running_mean"]) + 0.1 * mean.numpy()
+        exp_v = 0.9 * np.asarray(state[bn + ".running_var"]) + 0.1 * var_unb.numpy()
+        assert np.abs(sdm[bn + ".running_mean"].cpu().numpy() - exp_m).max() < 1e-4 * max(1, np.abs(exp_m).max()), bn
+        assert np.abs(sdm[bn + ".running_var"].cpu().numpy() - exp_v).max() < 1e-3 * max(1, np.abs(exp_v).max()), bn
+
+
+def test_indel_fused_step_and_dropin_loop(kat, cuda_genome):
+    """Sites from the packed genome: SiteBatch path == tensor path; the reference's loop body with a torch optimizer on the
+    drop-in module equals IndelTrainState.step (SGD, see test_dropin_loop_equals_fused_step)."""
+    from mural_b200 import SiteBatch, pack_meta
+    from mural_b200.training import IndelTrainState
+    z = np.load(os.path.join(GOLD, "indel_ex_indel9.npz"))
+    Rd = 500
+    n = 12
+    _, genome = kat
+    pos = torch.from_numpy(z["start"][:n].astype(np.int32)).cuda()
+    labels = (z["start"][:n] % 8).astype(np.int64)
+    meta = torch.from_numpy(pack_meta(z["strand"][:n], labels, z["chrom"][:n])).cuda()
+    sb = SiteBatch(pos, meta, cuda_genome)
+    y = torch.from_numpy(labels).cuda()
+    crit = torch.nn.CrossEntropyLoss(reduction="sum")
+    ma, _ = _model(z)
+    sta = IndelTrainState(ma, Rd, "SGD", lr=1e-4, weight_decay=1e-4)
+    sta.set_dropout(0.0)
+    ma.train()
+    a = ma.forward(sb, distal_radius=Rd)
+    b = ma.forward(cuda_genome.encode_onehot(pos, meta, Rd, "indel"))
+    assert torch.allclose(a, b, atol=1e-6)
+    ma2, _ = _model(z)
+    st2 = IndelTrainState(ma2, Rd, "SGD", lr=1e-4, weight_decay=1e-4)
+    st2.set_dropout(0.0)
+    ma2.train()
+    opt = torch.optim.SGD(ma2.parameters(), lr=1e-4, weight_decay=1e-4, momentum=0.98, nesterov=True)
+    losses = []
+    for _ in range(3):
+        preds = ma2.forward(sb, distal_radius=Rd)
+        loss = crit(preds, y)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ma2.parameters(), max_norm=10, error_if_nonfinite=False)
+        opt.step()
+        losses.append(float(loss))
+    mb, _ = _model(z)
+    stb = IndelTrainState(mb, Rd, "SGD", lr=1e-4, weight_decay=1e-4)
+    stb.set_dropout(0.0)
+    mb.train()
+    for _ in range(3):
+        stb.step(sb)
+    d = (st2.blob - stb.blob).abs().max().item()
+    assert d < 5e-6 * max(1.0, stb.blob.abs().max().item()), d
+    assert abs(float(stb.loss_dev.item()) - sum(losses)) < 1e-3 * abs(sum(losses))
+    assert np.isfinite(losses).all()
+    mb.eval()
+    with torch.no_grad():
+        assert torch.isfinite(mb.forward(sb, distal_radius=Rd)).all()
