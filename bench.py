@@ -295,6 +295,49 @@ def eval_leg(genome, pos, meta, logp, cfg, n=1_000_000, reps=5):
             "note": "includes the host sync + table copy of every launch; labels synthetic (class proportions of training.py:332)"}
 
 
+def indel_train_leg(genome, world, rank, dist, batch=32, steps=4, warmup=2):
+    """BASELINE configs[3] (training half): MuRaL-indel UNet_Small fine-tuned from the shipped Homo_sapiens/INDEL/insertion
+    weights at its own radius (L = 8000), one site every 50 bp on the '+' strand, labels iid Categorical(0.907, 0.0133 x 7),
+    fused step = train-mode forward + CE(sum) + backward + flat-gradient all-reduce (NCCL, world > 1) + clip + Adam.
+    First version of the tape (csrc/indel_train.cu): one work item per thread, no tiling yet."""
+    import torch
+    from mural_b200 import SiteBatch, model_choice, pack_meta
+    from mural_b200.training import IndelTrainState
+    z = np.load(os.path.join(ROOT, "tests", "golden", "indel_hs_ins.npz"))
+    state = {k[2:]: z[k] for k in z.files if k.startswith("w:")}
+    cfg = {"CNN_out_channels": state["uplblocks.0.0.weight"].shape[0], "CNN_kernel_size": state["uplblocks.0.0.weight"].shape[2],
+           "down_list": [int(v) for v in z["down"]], "use_reverse": bool(z["use_reverse"]), "n_class": state["out_fc.2.weight"].shape[0]}
+    m = model_choice(0, cfg, {"n_class": cfg["n_class"]}, "indel")
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
+    m.to("cuda").train()
+    Rd = int(z["distal_radius"])
+    ts = IndelTrainState(m, Rd, "Adam", lr=1e-4, weight_decay=1e-5, seed=rank)
+    n = batch * (steps + warmup)
+    rng = np.random.default_rng(777 + rank)
+    lo = 20_000 + (CHROM_LEN - 40_000) * rank // max(world, 1) // 50 * 50
+    pos = (lo + 50 * np.arange(n)) % (CHROM_LEN - 40_000) + 20_000
+    lab = rng.choice(8, size=n, p=[0.907] + [0.093 / 7] * 7)
+    d_pos = torch.from_numpy(pos.astype(np.int32)).cuda()
+    d_meta = torch.from_numpy(pack_meta(np.zeros(n, np.int64), lab, np.zeros(n, np.int64))).cuda()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(steps + warmup):
+        if i == warmup:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0.record()
+        ts.step(SiteBatch(d_pos[i * batch:(i + 1) * batch], d_meta[i * batch:(i + 1) * batch], genome))
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"metric": "sites/sec (MuRaL-indel train: fwd+bwd+clip+Adam)", "value": world * batch * steps / (ms * 1e-3), "unit": "sites/s",
+            "batch_per_gpu": batch, "ms_per_step": ms / steps, "dtype": "f32", "loss_sum_finite": bool(np.isfinite(float(ts.loss_dev.item()))),
+            "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), Adam lr 1e-4" % (Rd, 2 * Rd)}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
     """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
@@ -506,6 +549,13 @@ def main():
         except Exception as e:
             indel = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    indel_train = None
+    if not a.no_indel:
+        try:
+            indel_train = indel_train_leg(genome, world, rank, dist)
+        except Exception as e:
+            indel_train = {"error": "%s: %s" % (type(e).__name__, e)}
+
     sweep = None
     if rank == 0 and not a.no_sweep:
         try:
@@ -532,7 +582,7 @@ def main():
                            "per-step activation workspace > L2", wall_s_timed_region=t_wall),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof, "train": train, "indel": indel, "eval_metrics": evalm, "transfer_sweep": sweep}
+            "roofline": roof, "train": train, "indel": indel, "indel_train": indel_train, "eval_metrics": evalm, "transfer_sweep": sweep}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample

@@ -152,14 +152,19 @@ struct ConvBwdW {
     if (db && ci == 0 && t == 0) atomic_add(db + co, sb);
   }
 };
+constexpr int ROW_SPLIT = 64;  // work items per (b, c) row in the row reductions: item s takes positions s, s + 64, ... so that
+                               // neighbouring threads read neighbouring addresses and a batch of 8-channel rows still fills the GPU
 struct BnStats {
-  static constexpr const char* kName = "k_indel_train<BnStats>";  // item: row (b, c); stat[c] += sum, stat[C + c] += sum of squares (double)
+  static constexpr const char* kName = "k_indel_train<BnStats>";
+  // item: (row (b, c), s); stat[c] += sum, stat[C + c] += sum of squares (double)
   const float* x; double* stat; int C, L;
   HD void operator()(int64_t i) const {
-    const int c = int(i % C);
-    const float* r = x + i * L;
+    const int64_t row = i / ROW_SPLIT;
+    const int s0 = int(i % ROW_SPLIT), c = int(row % C);
+    if (s0 >= L) return;
+    const float* r = x + row * L;
     double s = 0, q = 0;
-    for (int l = 0; l < L; ++l) { s += r[l]; q += double(r[l]) * r[l]; }
+    for (int l = s0; l < L; l += ROW_SPLIT) { s += r[l]; q += double(r[l]) * r[l]; }
     atomic_add(stat + c, s);
     atomic_add(stat + C + c, q);
   }
@@ -195,12 +200,15 @@ struct UnitOut {
   }
 };
 struct UnitBwdReduce {
-  static constexpr const char* kName = "k_indel_train<UnitBwdReduce>";  // item: row (b, c); dz = dy * drop * act'(z); s1 = sum dz, s2 = sum dz * xhat; also stores dz
+  static constexpr const char* kName = "k_indel_train<UnitBwdReduce>";
+  // item: (row (b, c), s); dz = dy * drop * act'(z); s1 = sum dz, s2 = sum dz * xhat; also stores dz
   UnitOut u; const float* dy; float* dz; double* stat;
-  HD void operator()(int64_t row) const {
-    const int c = int(row % u.C);
+  HD void operator()(int64_t it) const {
+    const int64_t row = it / ROW_SPLIT;
+    const int s0 = int(it % ROW_SPLIT), c = int(row % u.C);
+    if (s0 >= u.L) return;
     double s1 = 0, s2 = 0;
-    for (int l = 0; l < u.L; ++l) {
+    for (int l = s0; l < u.L; l += ROW_SPLIT) {
       const int64_t i = row * u.L + l;
       const float g = dy[i] * drop_scale(u.p, u.seed, u.step, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
       dz[i] = g;

@@ -153,7 +153,7 @@ struct Engine {
         }
         if (u.has_bn) {
           ex.zero(dstat, sizeof(double) * 2 * tt.C);
-          ex.run(B * tt.C, BnStats{V(u.t, B), dstat, tt.C, tt.L});
+          ex.run(B * tt.C * ROW_SPLIT, BnStats{V(u.t, B), dstat, tt.C, tt.L});
           ex.run(tt.C, BnFinalize{dstat, double(B) * tt.L, tt.C, P + u.rm, P + u.rv, stats + u.stat_slot, stats + u.stat_slot + tt.C});
         }
         ex.run(B * tt.C * tt.L, unit_out(u, P, B));
@@ -183,7 +183,7 @@ struct Engine {
         if (u.res2 >= 0) ex.run(n, AddTo{G(u.out, B), G(u.res2, B)});
         const UnitOut uo = unit_out(u, P, B);
         ex.zero(dstat, sizeof(double) * 2 * tt.C);
-        ex.run(B * tt.C, UnitBwdReduce{uo, G(u.out, B), dz, dstat});
+        ex.run(B * tt.C * ROW_SPLIT, UnitBwdReduce{uo, G(u.out, B), dz, dstat});
         if (u.has_bn) {
           ex.run(tt.C, BnParamGrad{dstat, tt.C, Gp + u.gamma, Gp + u.beta});
           ex.run(n, UnitBwdApply{uo, dz, dstat, double(B) * tt.L});

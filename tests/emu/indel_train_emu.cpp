@@ -1,4 +1,7 @@
-// Host emulation build of the indel training tape (g++ -DINDEL_EMU): C entry point for scratch/indel_train/check_emu.py.
+// TEST INFRASTRUCTURE: host build (g++ -DINDEL_EMU) of the indel training tape.  The op arithmetic and the tape of
+// mural_b200/csrc/indel_train_{core,engine}.cuh are compiled as plain C++ — every "kernel" is a serial loop over its work
+// items on host memory — so that tests/test_indel_train_emu.py can check forward, loss and every gradient against fp64
+// autograd of the oracle without a GPU.  Never linked into libmural_b200.so.
 #include "../../mural_b200/csrc/indel_train_engine.cuh"
 using namespace indel_train;
 

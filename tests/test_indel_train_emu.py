@@ -1,21 +1,32 @@
-"""Container check (no GPU): the indel training tape, compiled for the host (libindel_emu.so), against fp64 autograd of the
-oracle UNet_Small in train mode — output, CE(sum) loss, every parameter gradient, running statistics."""
+"""CPU: the MuRaL-indel training tape (mural_b200/csrc/indel_train_{core,engine}.cuh) compiled for the host with g++
+(tests/emu/indel_train_emu.cpp: every kernel becomes a serial loop over its work items) against fp64 autograd of the oracle
+UNet_Small in train mode — output, CE(sum) loss, every parameter gradient, running statistics.  The same functors are what
+nvcc compiles into the CUDA kernels; tests/test_gpu_indel_train.py repeats the comparison on the device."""
 import ctypes as C
 import os
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, ROOT)
+import subprocess
+
 import numpy as np
+import pytest
 import torch
 
 from oracle import network_t as NT
 
-lib = C.CDLL(os.path.join(HERE, "libindel_emu.so"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(tag, R, B, seed=0):
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emu") / "libindel_emu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DINDEL_EMU", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "tests", "emu", "indel_train_emu.cpp")], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("tag,R,B,seed", [("hs_ins", 500, 5, 0), ("hs_del_start", 500, 4, 1), ("ex_indel9", 1000, 3, 2)])
+def test_indel_training_tape_matches_autograd(lib, tag, R, B, seed):
     z = np.load(os.path.join(ROOT, "tests", "golden", "indel_%s.npz" % tag))
     state = {k[2:]: np.asarray(z[k]) for k in z.files if k.startswith("w:") and "num_batches" not in k}
     down = [int(v) for v in z["down"]]
@@ -82,7 +93,3 @@ def run(tag, R, B, seed=0):
     assert d_out < 2e-4 and abs(loss.value - float(l_ref)) < 1e-3 * max(1, abs(float(l_ref))) and worst < 5e-3 and rs < 1e-4
 
 
-if __name__ == "__main__":
-    run("hs_ins", 500, 5)
-    run("hs_del_start", 500, 4, seed=1)
-    run("ex_indel9", 1000, 3, seed=2)
