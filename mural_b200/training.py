@@ -503,7 +503,7 @@ def validate_epoch(model, dataset, n_class=4, pred_batch_size=4096, segment_indi
     from .evaluation import EvalData, Evaluator
     from .nn_utils import model_predict_m
     if dataset.model_type != "snv":
-        raise NotImplementedError("validate_epoch: MuRaL-indel training / validation is not built (SNV only)")
+        raise NotImplementedError("validate_epoch covers MuRaL-snv; the indel Evaluator pass (k-mer lists 2/4/6 on softplus outputs) is not wired yet")
     segs = np.arange(len(dataset)) if segment_indices is None else np.asarray(segment_indices)
     was_training = model.training
     pred_y, total_loss = model_predict_m(model, generate_site_batches(dataset, 1 << 30, pred_batch_size, shuffle=False, segment_indices=segs),
