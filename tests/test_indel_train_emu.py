@@ -93,3 +93,47 @@ def test_indel_training_tape_matches_autograd(lib, tag, R, B, seed):
     assert d_out < 2e-4 and abs(loss.value - float(l_ref)) < 1e-3 * max(1, abs(float(l_ref))) and worst < 5e-3 and rs < 1e-4
 
 
+
+
+@pytest.mark.parametrize("tag", ["hs_ins", "hs_del_start"])
+def test_indel_training_tape_matches_reference_gradients(lib, tag):
+    """The same tape against the gradients of the UNMODIFIED reference UNet_Small in train mode (tests/golden/train_kat.npz,
+    float64 reference run): closes tape == reference without the oracle in between."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "train_kat.npz"))
+    w = np.load(os.path.join(ROOT, "tests", "golden", "indel_%s.npz" % tag))
+    state = {k[2:]: np.asarray(w[k]) for k in w.files if k.startswith("w:") and "num_batches" not in k}
+    down, use_rev = [int(v) for v in w["down"]], bool(w["use_reverse"])
+    x = np.ascontiguousarray(z["indel_%s:x" % tag].astype(np.float32))
+    labels = z["indel_%s:y" % tag].astype(np.int32)
+    B, _, L = x.shape
+    names = list(state)
+    offs, o = [], 0
+    for k in names:
+        offs.append(o); o += state[k].size
+    blob = np.concatenate([state[k].reshape(-1) for k in names]).astype(np.float32)
+    NC = state["out_fc.2.weight"].shape[0]
+    out = np.zeros((B, NC), np.float32)
+    grads = np.zeros_like(blob)
+    loss = C.c_double(0)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    lib.indel_train_emu_step(L // 2, state["uplblocks.0.0.weight"].shape[0], state["uplblocks.0.0.weight"].shape[2], NC,
+                             (C.c_int * 6)(*down), int(use_rev), len(names), arr, (C.c_int64 * len(names))(*offs),
+                             blob.ctypes.data_as(C.c_void_p), C.c_int64(blob.size), x.ctypes.data_as(C.c_void_p),
+                             labels.ctypes.data_as(C.c_void_p), C.c_int64(B), C.c_float(1.0), out.ctypes.data_as(C.c_void_p),
+                             grads.ctypes.data_as(C.c_void_p), C.byref(loss))
+    assert np.abs(out - z["indel_%s:out" % tag]).max() < 2e-4
+    assert abs(loss.value - float(z["indel_%s:loss" % tag])) < 1e-4 * max(1.0, abs(float(z["indel_%s:loss" % tag])))
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("indel_%s:g:" % tag))
+    checked = 0
+    for k, off in zip(names, offs):
+        key = "indel_%s:g:%s" % (tag, k)
+        if key not in z.files:
+            continue
+        g_ref = z[key].reshape(-1)
+        g = grads[off:off + g_ref.size]
+        if np.abs(g_ref).max() < 1e-9 * gmax:
+            assert np.abs(g).max() < 1e-4 * gmax, k
+            continue
+        assert np.abs(g - g_ref).max() / max(1e-4 * gmax, np.abs(g_ref).max()) < 5e-3, k
+        checked += 1
+    assert checked > 80

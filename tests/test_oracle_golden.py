@@ -130,3 +130,41 @@ def test_evaluation_oracle_matches_reference_goldens():
         for w in (100000, 500000):
             got = EN.corr_calc_sub(chrom[order], start[order], labels[order], prob[order], w, K, f32)
             assert np.allclose(got, z["%s:window%d" % (tag, w)], rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_train_mode_oracle_matches_reference_goldens():
+    """TRAIN mode (batch-statistic BatchNorm, dropout 0): output, CE(sum) loss, every parameter gradient and the updated
+    running statistics of the oracle vs the unmodified reference run in float64 (tests/golden/train_kat.npz, written by
+    oracle/make_golden_train.py).  The CUDA training paths are tested against this oracle's autograd."""
+    z = np.load(os.path.join(GOLD, "train_kat.npz"))
+    cases = [("snv_ex_ckpt6", "snv_ex_ckpt6.npz", None), ("indel_hs_ins", "indel_hs_ins.npz", True),
+             ("indel_hs_del_start", "indel_hs_del_start.npz", True)]
+    for tag, wfile, is_indel in cases:
+        w = np.load(os.path.join(GOLD, wfile))
+        state = {k[2:]: np.asarray(w[k]) for k in w.files if k.startswith("w:") and "num_batches" not in k}
+        sd = {k: torch.tensor(v.astype(np.float64), requires_grad=("running" not in k)) for k, v in state.items()}
+        x, y = z[tag + ":x"].astype(np.float64), z[tag + ":y"].astype(np.int64)
+        rec = NT._BNStats()
+        if is_indel:
+            out = NT.unet_small_forward(sd, x, [int(v) for v in w["down"]], bool(w["use_reverse"]), torch.float64, train=True, rec=rec)
+        else:
+            out = NT.network2_forward(sd, z[tag + ":cat"].astype(np.int64), x, torch.float64, train=True, rec=rec)
+        assert np.abs(out.detach().numpy() - z[tag + ":out"]).max() < 1e-9
+        loss = NT.ce_sum(out, y)
+        assert abs(float(loss.detach()) - float(z[tag + ":loss"])) < 1e-9 * max(1.0, abs(float(z[tag + ":loss"])))
+        loss.backward()
+        n_g = 0
+        for k in z.files:
+            if k.startswith(tag + ":g:"):
+                name = k[len(tag) + 3:]
+                g_ref = z[k]
+                assert np.abs(sd[name].grad.numpy() - g_ref).max() <= 1e-7 * max(1e-6, np.abs(g_ref).max()), (tag, name)
+                n_g += 1
+        assert n_g > 100
+        for bn, (mean, var_unb) in rec.stats.items():
+            if (tag + ":rm:" + bn) not in z.files:
+                continue
+            em = 0.9 * state[bn + ".running_mean"].astype(np.float64) + 0.1 * mean.numpy()
+            ev = 0.9 * state[bn + ".running_var"].astype(np.float64) + 0.1 * var_unb.numpy()
+            assert np.abs(em - z[tag + ":rm:" + bn]).max() < 1e-9 * max(1, np.abs(em).max())
+            assert np.abs(ev - z[tag + ":rv:" + bn]).max() < 1e-9 * max(1, np.abs(ev).max())
