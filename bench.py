@@ -557,7 +557,7 @@ def main():
             indel_train = {"error": "%s: %s" % (type(e).__name__, e)}
 
     sweep = None
-    if rank == 0 and not a.no_sweep:
+    if world == 1 and not a.no_sweep:   # single-GPU leg: its fine-tuning steps would otherwise enter the gradient all-reduce on one rank only
         try:
             sweep = sweep_leg(genome, pos, meta, cfg, state, n_cat)
         except Exception as e:
