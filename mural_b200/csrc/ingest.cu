@@ -7,8 +7,10 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -70,76 +72,179 @@ int for_each_line(const char* path, F&& fn) {
 
 }  // namespace
 
+namespace {
+
+// whole (inflated) file in memory; 0 ok, 1 cannot open, 2 read error
+int slurp(const char* path, std::vector<char>& data) {
+  gzFile f = gzopen(path, "rb");
+  if (!f) return 1;
+  gzbuffer(f, 1 << 20);
+  size_t used = 0;
+  data.resize(size_t(1) << 24);
+  int n;
+  while ((n = gzread(f, data.data() + used, (unsigned)std::min<size_t>(data.size() - used, size_t(1) << 30))) > 0) {
+    used += size_t(n);
+    if (data.size() - used < (size_t(1) << 22)) data.resize(data.size() * 2);
+  }
+  const bool bad = n < 0;
+  gzclose(f);
+  data.resize(used);
+  return bad ? 2 : 0;
+}
+
+struct BedPart {                     // what one thread parsed from its slice of the file
+  std::vector<std::string> names;   // first-appearance order inside the slice
+  std::map<std::string, int32_t> index;
+  std::vector<int32_t> chrom;
+  std::vector<int64_t> start, end, label;
+  std::vector<int8_t> strand;
+  int64_t lines = 0, err_line = 0;  // err_line: 1-based line inside the slice of the first malformed record
+  std::string err;
+};
+
 // BED6: chrom start end name score strand; score = label (preprocessing.py:752-754).  Same rules as
 // mural_b200.data.SiteTable.from_bed: blank lines and '#', 'track', 'browser' lines are skipped; fields split on tabs,
 // or on any whitespace when a line has fewer than three tab-separated fields; label = int(float(score)), '.'/'' -> 0.
+void parse_bed_line(const char* s, size_t len, BedPart& b) {
+  ++b.lines;
+  if (!b.err.empty()) return;
+  auto fail_line = [&](const char* what) { b.err = what; b.err_line = b.lines; };
+  size_t i = 0;
+  while (i < len && isspace((unsigned char)s[i])) ++i;
+  if (i == len) return;                                    // blank
+  if (s[0] == '#' || (len >= 5 && !memcmp(s, "track", 5)) || (len >= 7 && !memcmp(s, "browser", 7))) return;
+  const char* f[6];
+  size_t fl[6];
+  int nf = 0;
+  {
+    size_t a = 0;
+    for (size_t k = 0; k <= len && nf < 6; ++k)
+      if (k == len || s[k] == '\t') { f[nf] = s + a; fl[nf] = k - a; ++nf; a = k + 1; }
+  }
+  if (nf < 3) {                                            // whitespace-separated
+    nf = 0;
+    size_t k = 0;
+    while (k < len && nf < 6) {
+      while (k < len && isspace((unsigned char)s[k])) ++k;
+      if (k == len) break;
+      const size_t a = k;
+      while (k < len && !isspace((unsigned char)s[k])) ++k;
+      f[nf] = s + a; fl[nf] = k - a; ++nf;
+    }
+  }
+  if (nf < 3) return fail_line("fewer than 3 fields");
+  char tmp[64];
+  auto to_ll = [&](int j, long long& v) {
+    if (fl[j] == 0 || fl[j] >= sizeof tmp) return false;
+    memcpy(tmp, f[j], fl[j]); tmp[fl[j]] = 0;
+    char* endp = nullptr;
+    v = strtoll(tmp, &endp, 10);
+    return endp && *endp == 0;
+  };
+  long long st, en;
+  if (!to_ll(1, st) || !to_ll(2, en)) return fail_line("start/end are not integers");
+  long long lab = 0;
+  if (nf > 4 && !(fl[4] == 0 || (fl[4] == 1 && f[4][0] == '.'))) {
+    if (fl[4] >= sizeof tmp) return fail_line("bad score");
+    memcpy(tmp, f[4], fl[4]); tmp[fl[4]] = 0;
+    char* endp = nullptr;
+    const double d = strtod(tmp, &endp);
+    if (!endp || *endp != 0) return fail_line("bad score");
+    lab = (long long)d;                                    // int(float(score)) truncates toward zero
+  }
+  const std::string name(f[0], fl[0]);
+  auto it = b.index.find(name);
+  if (it == b.index.end()) {
+    it = b.index.emplace(name, (int32_t)b.names.size()).first;
+    b.names.push_back(name);
+  }
+  b.chrom.push_back(it->second);
+  b.start.push_back(st);
+  b.end.push_back(en);
+  b.label.push_back(lab);
+  b.strand.push_back((nf > 5 && fl[5] == 1 && f[5][0] == '+') ? 0 : 1);
+}
+
+void parse_bed_slice(const char* p, const char* e, BedPart& b) {
+  while (p < e) {
+    const char* nl = (const char*)memchr(p, '\n', size_t(e - p));
+    const char* le = nl ? nl : e;
+    size_t len = size_t(le - p);
+    if (len && p[len - 1] == '\r') --len;
+    parse_bed_line(p, len, b);
+    p = le + 1;
+  }
+}
+
+}  // namespace
+
+// The file is inflated into memory once, cut into slices at line boundaries, parsed by a pool of threads and merged in file
+// order (chromosome indices follow the order of first appearance in the FILE, as iterating a BedTool does).
 extern "C" int mural_bed_read(const char* path, mural_bed_t** out) {
   MURAL_CHECK(path && out, "NULL argument");
+  std::vector<char> data;
+  const int rc = slurp(path, data);
+  if (rc) MURAL_FAIL(rc == 1 ? std::string("cannot open ") + path : std::string("read error on ") + path);
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  size_t n_parts = std::min<size_t>(std::min<unsigned>(hw, 32u), data.size() / (size_t(4) << 20) + 1);
+  std::vector<const char*> cut(n_parts + 1);
+  const char* base = data.data();
+  const char* endp = base + data.size();
+  cut[0] = base;
+  cut[n_parts] = endp;
+  for (size_t k = 1; k < n_parts; ++k) {
+    const char* q = base + data.size() * k / n_parts;
+    if (q < cut[k - 1]) q = cut[k - 1];
+    const char* nl = q < endp ? (const char*)memchr(q, '\n', size_t(endp - q)) : nullptr;
+    cut[k] = nl ? nl + 1 : endp;
+  }
+  std::vector<BedPart> parts(n_parts);
+  {
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < n_parts; ++k) pool.emplace_back([&, k] { parse_bed_slice(cut[k], cut[k + 1], parts[k]); });
+    parse_bed_slice(cut[0], cut[1], parts[0]);
+    for (auto& t : pool) t.join();
+  }
+  int64_t line0 = 0, total = 0;
+  for (const BedPart& pt : parts) {
+    if (!pt.err.empty())
+      MURAL_FAIL("ValueError: " + std::string(path) + " line " + std::to_string(line0 + pt.err_line) + ": " + pt.err);
+    line0 += pt.lines;
+    total += (int64_t)pt.start.size();
+  }
   mural_bed* b = new mural_bed();
   std::map<std::string, int32_t> index;
-  std::string err;
-  int64_t lineno = 0;
-  const int rc = for_each_line(path, [&](const char* s, size_t len) {
-    ++lineno;
-    if (!err.empty()) return;
-    size_t i = 0;
-    while (i < len && isspace((unsigned char)s[i])) ++i;
-    if (i == len) return;                                    // blank
-    if (s[0] == '#' || (len >= 5 && !memcmp(s, "track", 5)) || (len >= 7 && !memcmp(s, "browser", 7))) return;
-    const char* f[6];
-    size_t fl[6];
-    int nf = 0;
-    {
-      size_t a = 0;
-      for (size_t k = 0; k <= len && nf < 6; ++k)
-        if (k == len || s[k] == '\t') { f[nf] = s + a; fl[nf] = k - a; ++nf; a = k + 1; }
-    }
-    if (nf < 3) {                                            // whitespace-separated
-      nf = 0;
-      size_t k = 0;
-      while (k < len && nf < 6) {
-        while (k < len && isspace((unsigned char)s[k])) ++k;
-        if (k == len) break;
-        const size_t a = k;
-        while (k < len && !isspace((unsigned char)s[k])) ++k;
-        f[nf] = s + a; fl[nf] = k - a; ++nf;
+  b->chrom.resize(total); b->start.resize(total); b->end.resize(total); b->label.resize(total); b->strand.resize(total);
+  std::vector<std::vector<int32_t>> remap(n_parts);
+  std::vector<int64_t> off(n_parts + 1, 0);
+  for (size_t k = 0; k < n_parts; ++k) {
+    for (const std::string& nm : parts[k].names) {
+      auto it = index.find(nm);
+      if (it == index.end()) {
+        it = index.emplace(nm, (int32_t)b->names.size()).first;
+        b->names.push_back(nm);
       }
+      remap[k].push_back(it->second);
     }
-    if (nf < 3) { err = "line " + std::to_string(lineno) + ": fewer than 3 fields"; return; }
-    char tmp[64];
-    auto to_ll = [&](int j, long long& v) {
-      if (fl[j] == 0 || fl[j] >= sizeof tmp) return false;
-      memcpy(tmp, f[j], fl[j]); tmp[fl[j]] = 0;
-      char* endp = nullptr;
-      v = strtoll(tmp, &endp, 10);
-      return endp && *endp == 0;
+    off[k + 1] = off[k] + (int64_t)parts[k].start.size();
+  }
+  {
+    auto copy_part = [&](size_t k) {
+      const BedPart& pt = parts[k];
+      const int64_t o = off[k], m = (int64_t)pt.start.size();
+      for (int64_t r = 0; r < m; ++r) b->chrom[o + r] = remap[k][pt.chrom[r]];
+      if (m) {
+        memcpy(b->start.data() + o, pt.start.data(), m * sizeof(int64_t));
+        memcpy(b->end.data() + o, pt.end.data(), m * sizeof(int64_t));
+        memcpy(b->label.data() + o, pt.label.data(), m * sizeof(int64_t));
+        memcpy(b->strand.data() + o, pt.strand.data(), m);
+      }
     };
-    long long st, en;
-    if (!to_ll(1, st) || !to_ll(2, en)) { err = "line " + std::to_string(lineno) + ": start/end are not integers"; return; }
-    long long lab = 0;
-    if (nf > 4 && !(fl[4] == 0 || (fl[4] == 1 && f[4][0] == '.'))) {
-      if (fl[4] >= sizeof tmp) { err = "line " + std::to_string(lineno) + ": bad score"; return; }
-      memcpy(tmp, f[4], fl[4]); tmp[fl[4]] = 0;
-      char* endp = nullptr;
-      const double d = strtod(tmp, &endp);
-      if (!endp || *endp != 0) { err = "line " + std::to_string(lineno) + ": bad score"; return; }
-      lab = (long long)d;                                    // int(float(score)) truncates toward zero
-    }
-    const std::string name(f[0], fl[0]);
-    auto it = index.find(name);
-    if (it == index.end()) {
-      it = index.emplace(name, (int32_t)b->names.size()).first;
-      b->names.push_back(name);
-    }
-    b->chrom.push_back(it->second);
-    b->start.push_back(st);
-    b->end.push_back(en);
-    b->label.push_back(lab);
-    b->strand.push_back((nf > 5 && fl[5] == 1 && f[5][0] == '+') ? 0 : 1);
-  });
-  if (rc || !err.empty()) {
-    delete b;
-    MURAL_FAIL(rc == 1 ? std::string("cannot open ") + path : (rc == 2 ? std::string("read error on ") + path : "ValueError: " + std::string(path) + " " + err));
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < n_parts; ++k) pool.emplace_back(copy_part, k);
+    copy_part(0);
+    for (auto& t : pool) t.join();
   }
   *out = b;
   return 0;
