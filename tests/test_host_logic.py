@@ -284,3 +284,32 @@ def test_evaluator_host_math_on_numpy_tables():
     t[1, 3] = [5, 5, 0, 0, 0, 1, 1, 1, 1]
     t[1, 4] = [7, 7, 0, 0, 0, 2, 2, 2, 2]
     assert np.isnan(EV._kmer_corr_regions(t, K, False)).all()
+
+
+def test_native_bed_reader_multi_slice(tmp_path):
+    """Files larger than a few MB are parsed in line-aligned slices by a thread pool: rows, chromosome numbering (order of
+    first appearance in the FILE, with chromosomes that re-appear in later slices) and the line number of a malformed
+    record must not depend on the slicing."""
+    import numpy as np
+    from mural_b200.data import SiteTable
+    rng = np.random.default_rng(12)
+    n = 600_000
+    names = np.array(["chr2L", "chrX_random_scaffold_0001", "chr10", "chrM"])
+    order = np.concatenate([np.zeros(200_000, int), np.full(150_000, 2), np.full(50_000, 0), np.full(100_000, 1), np.full(100_000, 3)])
+    start = rng.integers(0, 10**8, n)
+    strand = rng.integers(0, 2, n)
+    label = rng.integers(0, 4, n)
+    lines = ["%s\t%d\t%d\t.\t%d\t%s" % (names[c], s, s + 1, l, "+-"[d]) for c, s, l, d in zip(order, start, label, strand)]
+    path = tmp_path / "big.bed"
+    path.write_text("# header\n" + "\n".join(lines) + "\n")
+    assert path.stat().st_size > 12 << 20
+    t = SiteTable.from_bed(str(path))
+    assert t.chrom_names == ["chr2L", "chr10", "chrX_random_scaffold_0001", "chrM"]
+    remap = np.array([0, 2, 1, 3])
+    assert np.array_equal(t.chrom, remap[order]) and np.array_equal(t.start, start) and np.array_equal(t.end, start + 1)
+    assert np.array_equal(t.strand, strand) and np.array_equal(t.label, label)
+    bad = 555_555
+    lines[bad] = "chr10\tnot_a_number\t5\t.\t0\t+"
+    path.write_text("# header\n" + "\n".join(lines) + "\n")
+    with pytest.raises(ValueError, match="line %d" % (bad + 2)):
+        SiteTable.from_bed(str(path))
