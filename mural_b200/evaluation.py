@@ -42,8 +42,13 @@ class EvalData:
         """From the reference's `data_and_prob` frame: us*/mid/ds* columns, `mut_type`, `prob0..` (evaluation.py:508-511)."""
         cols = [c for c in data_and_prob.columns if c.startswith("us")]
         R = len(cols)
-        names = ["us%d" % i for i in range(R, 0, -1)] + ["mid"] + ["ds%d" % i for i in range(1, R + 1)]
-        flank = torch.from_numpy(np.ascontiguousarray(data_and_prob[names].to_numpy(dtype=np.int64))).to(device)
+        us, ds = ["us%d" % i for i in range(R, 0, -1)], ["ds%d" % i for i in range(1, R + 1)]
+        if "mid" in data_and_prob.columns:                     # snv header (get_local_header, preprocessing.py:358-375)
+            flank_np = data_and_prob[us + ["mid"] + ds].to_numpy(dtype=np.int64)
+        else:                                                  # indel header has no centre column: a dummy one keeps us_j / ds_j at mid -/+ j
+            flank_np = np.concatenate([data_and_prob[us].to_numpy(dtype=np.int64), np.zeros((len(data_and_prob), 1), np.int64),
+                                       data_and_prob[ds].to_numpy(dtype=np.int64)], 1)
+        flank = torch.from_numpy(np.ascontiguousarray(flank_np)).to(device)
         label = data_and_prob["mut_type"].to_numpy().astype(np.int64)
         prob = data_and_prob[["prob%d" % i for i in range(n_class)]].to_numpy()
         meta = torch.from_numpy(((label & 0x7f) << 1).astype(np.int32)).to(device)

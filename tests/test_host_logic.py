@@ -313,3 +313,26 @@ def test_native_bed_reader_multi_slice(tmp_path):
     path.write_text("# header\n" + "\n".join(lines) + "\n")
     with pytest.raises(ValueError, match="line %d" % (bad + 2)):
         SiteTable.from_bed(str(path))
+
+
+def test_eval_data_from_reference_frames():
+    """EvalData.from_frame on the reference's data_local headers (get_local_header, preprocessing.py:358-375): snv frames carry a
+    `mid` column, indel frames do not; either way us_j / ds_j end up j columns left / right of the centre."""
+    import numpy as np
+    import pandas as pd
+    from mural_b200.evaluation import EvalData
+    rng = np.random.default_rng(0)
+    n, R = 50, 4
+    us, ds = ["us%d" % i for i in range(R, 0, -1)], ["ds%d" % i for i in range(1, R + 1)]
+    for cols in (us + ["mid"] + ds, us + ds):
+        df = pd.DataFrame(rng.integers(0, 5, (n, len(cols))), columns=cols)
+        df["mut_type"] = rng.integers(0, 3, n)
+        for i in range(3):
+            df["prob%d" % i] = rng.random(n).astype(np.float32)
+        ed = EvalData.from_frame(df, 3, device="cpu")
+        flank = ed.flank.numpy()
+        assert flank.shape == (n, 2 * R + 1) and ed.f32 and ed.prob.dtype.is_floating_point
+        mid = R
+        for j in range(1, R + 1):
+            assert np.array_equal(flank[:, mid - j], df["us%d" % j].to_numpy()) and np.array_equal(flank[:, mid + j], df["ds%d" % j].to_numpy())
+        assert np.array_equal(ed.labels_host(), df["mut_type"].to_numpy())
