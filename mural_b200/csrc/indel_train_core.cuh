@@ -93,7 +93,8 @@ HD float drop_scale(float p, uint64_t seed, uint32_t step, uint64_t idx) {
 }
 
 // ------------------------------------------------------------------------------------------------ ops (work-item functors)
-struct ConvDims { int B, Cin, Lin, Cout, Lout, k, stride, pad, up; };  // input is read through a nearest upsample by `up`
+struct ConvDims { int B, Cin, Lin, Cout, Lout, k, stride, pad, up; };
+constexpr int CONV_W_SPLIT = 32;  // work items per (co, ci, t, b) in the weight gradient (one warp walks a row pair coalesced)  // input is read through a nearest upsample by `up`
 
 struct ConvFwd {
   static constexpr const char* kName = "k_indel_train<ConvFwd>";  // item: output element (b, co, lo)
@@ -134,16 +135,21 @@ struct ConvBwdX {
   }
 };
 struct ConvBwdW {
-  static constexpr const char* kName = "k_indel_train<ConvBwdW>";  // item: (co, ci, t, b); dW += sum_lo dy * x, db += sum_lo dy
+  static constexpr const char* kName = "k_indel_train<ConvBwdW>";
+  // item: (co, ci, t, b, s) with s the fastest index: item s takes output positions s, s + ROW_SPLIT, ... so that the threads
+  // of a warp read neighbouring positions of the same rows; dW += sum_lo dy * x, db += sum_lo dy
   const float* x; const float* dy; float* dW; float* db; ConvDims d;
   HD void operator()(int64_t i) const {
-    const int b = int(i % d.B), t = int((i / d.B) % d.k), ci = int((i / (int64_t(d.B) * d.k)) % d.Cin),
-              co = int(i / (int64_t(d.B) * d.k * d.Cin));
+    const int s0 = int(i % CONV_W_SPLIT);
+    const int64_t r = i / CONV_W_SPLIT;
+    const int b = int(r % d.B), t = int((r / d.B) % d.k), ci = int((r / (int64_t(d.B) * d.k)) % d.Cin),
+              co = int(r / (int64_t(d.B) * d.k * d.Cin));
+    if (s0 >= d.Lout) return;
     const float* dr = dy + (int64_t(b) * d.Cout + co) * d.Lout;
     const float* xr = x + (int64_t(b) * d.Cin + ci) * d.Lin;
     const int Lv = d.Lin * d.up;
     float acc = 0.f, sb = 0.f;
-    for (int lo = 0; lo < d.Lout; ++lo) {
+    for (int lo = s0; lo < d.Lout; lo += CONV_W_SPLIT) {
       const int j = lo * d.stride + t - d.pad;
       if (j >= 0 && j < Lv) acc += dr[lo] * xr[j / d.up];
       sb += dr[lo];

@@ -190,7 +190,7 @@ struct Engine {
         }
         if (u.has_conv) {
           const ConvDims d = dims(u, B);
-          ex.run(int64_t(d.Cout) * d.Cin * d.k * B, ConvBwdW{V(u.in, B), dz, Gp + u.W, u.b >= 0 ? Gp + u.b : nullptr, d});
+          ex.run(int64_t(d.Cout) * d.Cin * d.k * B * CONV_W_SPLIT, ConvBwdW{V(u.in, B), dz, Gp + u.W, u.b >= 0 ? Gp + u.b : nullptr, d});
           if (u.in != t_in) ex.run(B * d.Cin * d.Lin, ConvBwdX{dz, P + u.W, G(u.in, B), d});
         } else {
           ex.run(n, AddTo{dz, G(u.in, B)});
