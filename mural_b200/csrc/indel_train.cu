@@ -4,7 +4,7 @@
 //
 // The network is run as a tape of generic ops (indel_train_engine.cuh): unit = conv -> BatchNorm -> activation (+ residuals),
 // flips of the reverse-strand stem, max over positions.  The arithmetic of every op lives in indel_train_core.cuh and was
-// checked against fp64 autograd of the oracle through a host build of the same source (scratch/indel_train/check_emu.py).
+// checked against fp64 autograd of the oracle through a host build of the same source (tests/emu/indel_train_emu.cpp, tests/test_indel_train_emu.py).
 #include "common.cuh"
 
 #define INDEL_TRAIN_LAUNCH(name, kernel, grid, block, stream, ...) LAUNCH_N(name, kernel, grid, block, 0, stream, __VA_ARGS__)

@@ -1,9 +1,10 @@
 // Training step of MuRaL-indel `UNet_Small` (MuRaL/model/model_indel.py:6-176; loop body MuRaL/training.py:404-452) as a
 // tape of generic ops: this header holds the per-work-item arithmetic of every op.
 //
-// One source, two builds: with nvcc every op is a grid-stride kernel over work items; with g++ (-DINDEL_EMU, scratch/
-// indel_train/emu.cpp) the same functors run in a serial loop on host memory — test infrastructure with which the arithmetic
-// was checked against fp64 autograd of the oracle in the GPU-less build container (scratch/indel_train/check_emu.py).
+// One source, two builds: with nvcc every op is a grid-stride kernel over work items; with g++ (-DINDEL_EMU,
+// tests/emu/indel_train_emu.cpp) the same functors run in a serial loop on host memory — test infrastructure with which the
+// arithmetic is checked against fp64 autograd of the oracle and the reference's own gradients without a GPU
+// (tests/test_indel_train_emu.py).
 // First version: correctness and structure (unit = conv -> train-mode BatchNorm -> activation (+ residuals), tape,
 // gradient accumulation); the kernels are plain one-item-per-thread loops, to be tiled once profiled.
 #pragma once
