@@ -8,7 +8,8 @@ classes), nn_utils.py (model_choice, model_predict_m), training.py (train step),
 __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401
-from .data import PackedSiteDataset, SiteBatch, SiteTable, generate_site_batches, pack_meta, segment_order  # noqa: F401
+from .data import (PackedSiteDataset, ReferenceTupleDataset, SiteBatch, SiteTable, generate_data_batches,  # noqa: F401
+                   generate_site_batches, get_local_header, pack_meta, prepare_dataset_np, segment_order)
 from .genome import PackedGenome, read_fasta  # noqa: F401
 from .model_snv import Network2  # noqa: F401
 from .nn_utils import model_choice, model_predict_m, weights_init  # noqa: F401

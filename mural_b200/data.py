@@ -84,11 +84,29 @@ class SiteBatch:
         return int(self.pos.numel())
 
 
+def get_local_header(local_radius, local_order, model_type="snv"):
+    """Column names of the local matrix (preprocessing.py:358-380): us*/[mid]/ds* for order 1, cat1..catN above."""
+    if local_order == 1:
+        up = ["us%d" % (local_radius - i) for i in range(local_radius)]
+        down = ["ds%d" % (i + 1) for i in range(local_radius)]
+        return up + (["mid"] if model_type == "snv" else []) + down
+    n = 2 * local_radius + (1 if model_type == "snv" else 0) - (local_order - 1)
+    return ["cat%d" % (i + 1) for i in range(n)]
+
+
 class PackedSiteDataset:
     """Dataset over (segment, strand) batches like CombinedDatasetNP (preprocessing.py:850-954), holding
-    site records only.  `pos`/`meta` are in emission order; `batch_sizes` are the segment batch sizes."""
+    site records only.  `pos`/`meta` are in emission order; `batch_sizes` are the segment batch sizes.
 
-    def __init__(self, sites, genome, segment_center, local_radius, local_order, distal_radius, model_type="snv"):
+    The attributes the reference's train() / run_predict_pipline read off the dataset are all here:
+    `data_local` (frame of us*/mid/ds* + mut_type indexed by (segment, row); training.py:166, run_predict.py:150,226),
+    `cat_cols`, `cat_dims` (training.py:167,250), `cont_cols` (training.py:168), `distal_info`,
+    `get_distal_encoding_infomation()`.  They are computed lazily by the GPU encoders (bit-exact, mural_encode_local)
+    the first time they are read — the fast path (site records -> fused kernels) never needs them.
+    `reference_view()` gives a Dataset whose items are the reference's own `(y, cont_x, cat_x, distal_x)` tuples."""
+
+    def __init__(self, sites, genome, segment_center, local_radius, local_order, distal_radius, model_type="snv",
+                 cont_data=None, cont_names=None):
         self.model_type = model_type
         self.genome = genome
         self.sites = sites
@@ -102,13 +120,25 @@ class PackedSiteDataset:
         self.pos = sites.start[self.perm].astype(np.int32)
         self.strand = sites.strand[self.perm].astype(np.int8)
         self.label = sites.label[self.perm]
+        if len(self.label) and (self.label.min() < 0 or self.label.max() > 0x7f):
+            raise ValueError("BED score column (label) must be in [0, 127]; got [%d, %d]" % (self.label.min(), self.label.max()))
         self.chrom = gidx[sites.chrom[self.perm]]
         self.meta = pack_meta(self.strand, self.label, self.chrom)
         self.batch_offsets = np.r_[0, np.cumsum(self.batch_sizes)]
         self.n = len(self.batch_sizes)
         self.distal_info = True
-        self.cont_cols = []
-        self.cont_X = np.zeros((self.n, 1))
+        self.seq_cols = get_local_header(local_radius, 1, model_type)
+        self.cat_cols = get_local_header(local_radius, local_order, model_type) if local_order > 1 else self.seq_cols
+        # continuous (bigWig mean) features, FILE order in -> emission order here (preprocessing.py:429-432 concatenates
+        # get_mean_bw_for_bed's rows positionally with the emission-ordered local frame: kept as is)
+        if cont_data is not None and np.asarray(cont_data).size:
+            cont = np.asarray(cont_data, dtype=np.float64).reshape(len(self.pos), -1)
+            self.cont_cols = list(cont_names) if cont_names is not None else ["bw%d" % i for i in range(cont.shape[1])]
+            self.cont_X = cont.astype(np.float32)
+        else:
+            self.cont_cols = []
+            self.cont_X = np.zeros((self.n, 1))
+        self._local1 = self._localk = self._data_local = None
 
     def __len__(self):
         return self.n
@@ -128,6 +158,106 @@ class PackedSiteDataset:
         """get_position_info (preprocessing.py:108-121): chrom, start, end, strand in emission order."""
         names = np.array(self.sites.chrom_names, dtype=object)[self.sites.chrom[self.perm]]
         return names, self.sites.start[self.perm], self.sites.end[self.perm], np.where(self.strand == 0, "+", "-")
+
+    # ---- the reference's dataset attributes (lazy; the GPU encoders produce them bit-exactly) -------------------------
+    def _encode_local(self, order):
+        out = np.empty((len(self.pos), len(get_local_header(self.local_radius, order, self.model_type))), dtype=np.int64)
+        step = 1 << 22
+        for a in range(0, len(self.pos), step):
+            out[a:a + step] = self.genome.encode_local(self.pos[a:a + step], self.meta[a:a + step], self.local_radius, order,
+                                                       self.model_type).cpu().numpy()
+        return out
+
+    def local_codes(self, order=1):
+        """int64 [n_sites, n_cols] in emission order: order 1 = base codes (us*/mid/ds*), order k = k-mer indices (cat*)."""
+        if order == 1:
+            if self._local1 is None:
+                self._local1 = self._encode_local(1)
+                if self.model_type == "snv" and len(self._local1):
+                    # process_local_seq_snv (preprocessing.py:479-486): one oriented focal base per (segment, strand) batch
+                    mid = self._local1[:, self.local_radius]
+                    first = mid[self.batch_offsets[:-1]]
+                    if np.any(mid != np.repeat(first, self.batch_sizes)):
+                        import sys
+                        print("ERROR: The positions in input BED file have different bases (A/T and C/G mixed)! "
+                              "The ref_genome or input BED file could be wrong.", file=sys.stderr)
+                        sys.exit()
+            return self._local1
+        if order != self.local_order:
+            raise ValueError("only order 1 and local_order=%d are held" % self.local_order)
+        if self._localk is None:
+            self._localk = self._encode_local(order)
+        return self._localk
+
+    def _multi_index(self):
+        import pandas as pd
+        seg = np.repeat(np.arange(self.n), self.batch_sizes)
+        row = np.arange(len(self.pos)) - np.repeat(self.batch_offsets[:-1], self.batch_sizes)
+        return pd.MultiIndex.from_arrays([seg, row])
+
+    @property
+    def data_local(self):
+        """DataFrame `data[seq_cols + ['mut_type']]` of CombinedDatasetNP (preprocessing.py:873), MultiIndex (segment, row)."""
+        if self._data_local is None:
+            import pandas as pd
+            df = pd.DataFrame(self.local_codes(1), columns=self.seq_cols, index=self._multi_index())
+            df["mut_type"] = self.label.astype(np.float64)          # float(loc.score) (preprocessing.py:752-754)
+            self._data_local = df
+        return self._data_local
+
+    @property
+    def cat_X(self):
+        import pandas as pd
+        return pd.DataFrame(self.local_codes(self.local_order), columns=self.cat_cols, index=self._multi_index())
+
+    @property
+    def cat_dims(self):
+        """[max(col) + 1 for col in cat_cols] (preprocessing.py:889), from which train() derives emb_dims (training.py:250-255)."""
+        x = self.local_codes(self.local_order)
+        return [int(v) + 1 for v in x.max(axis=0)] if len(x) else [1] * len(self.cat_cols)
+
+    @property
+    def y(self):
+        import pandas as pd
+        return pd.Series(self.label.astype(np.float32), index=self._multi_index(), name="mut_type")
+
+    def reference_view(self):
+        """A torch Dataset with CombinedDatasetNP's item contract (preprocessing.py:934-942), for the reference's own
+        `DataLoader(ds, 1)` -> generate_data_batches -> model_predict_m / train loop."""
+        return ReferenceTupleDataset(self)
+
+
+class ReferenceTupleDataset:
+    """`ds[i]` -> `(y [m,1] float32, cont_X[i], cat_X [m,n_cat] int64, distal [m,4,W] float32)` of segment batch i, the
+    tuple CombinedDatasetNP.__getitem__ returns; windows come from the GPU encoders (mural_encode_local / _onehot)."""
+
+    def __init__(self, base):
+        self.base = base
+        for k in ("model_type", "cat_cols", "cont_cols", "seq_cols", "distal_radius", "central_radius", "distal_info", "n"):
+            setattr(self, k, getattr(base, k))
+
+    data_local = property(lambda self: self.base.data_local)
+    cat_dims = property(lambda self: self.base.cat_dims)
+    y = property(lambda self: self.base.y)
+
+    def __len__(self):
+        return self.base.n
+
+    def get_distal_encoding_infomation(self):
+        self.distal_info = True
+
+    def get_labels(self):
+        return self.base.get_labels()
+
+    def __getitem__(self, index):
+        b = self.base
+        assert index < b.n
+        a, e = b.batch_offsets[index], b.batch_offsets[index + 1]
+        cat = b.local_codes(b.local_order)[a:e]
+        oh = b.genome.encode_onehot(b.pos[a:e], b.meta[a:e], b.distal_radius, b.model_type).cpu().numpy()
+        # cont_X[index] exactly as the reference indexes it (preprocessing.py:942; Create_DatasetSegment :1205 then replaces
+        # it by zeros [m,1], so the tensor-signature forward only ever sees zeros there)
+        return b.label[a:e].astype(np.float32).reshape(-1, 1), b.cont_X[index], cat, oh
 
 
 def generate_site_batches(dataset, sampled_segments, batch_size, shuffle=False, seed=None, segment_indices=None,
@@ -156,3 +286,62 @@ def generate_site_batches(dataset, sampled_segments, batch_size, shuffle=False, 
         carry_pos, carry_meta = pos[n_full:], meta[n_full:]
         if last and len(carry_pos):
             yield SiteBatch(torch.from_numpy(carry_pos).to(dev), torch.from_numpy(carry_meta).to(dev), dataset.genome)
+
+
+def prepare_dataset_np(bed_regions, ref_genome, bw_files=(), bw_names=(), bw_radii=(), central_radius=30000, local_radius=5,
+                       local_order=1, distal_radius=50, distal_order=1, seq_only=False, without_bw_distal=False, model_type="snv"):
+    """Same signature and role as the reference's prepare_dataset_np (preprocessing.py:828-848).  `bed_regions`: a BED path
+    (plain / .gz) or a SiteTable; `ref_genome`: a FASTA path or an already packed PackedGenome.  Like the reference, bigWig
+    tracks enter as per-site window means (get_mean_bw_for_bed, :725-750) unless `seq_only`; the expanded window stays 4
+    channels (CombinedDatasetNP never adds track channels to it, :934-942)."""
+    from .genome import PackedGenome
+    if distal_order != 1:
+        raise ValueError("distal_order must be 1 (the reference's encoders only implement order 1, preprocessing.py:981)")
+    genome = ref_genome if isinstance(ref_genome, PackedGenome) else PackedGenome.from_fasta(ref_genome)
+    sites = bed_regions if isinstance(bed_regions, SiteTable) else SiteTable.from_bed(bed_regions)
+    cont = names = None
+    if len(bw_files) > 0 and not seq_only:
+        from .bigwig import mean_bw_for_sites
+        cont = mean_bw_for_sites(bw_files, bw_radii, sites, model_type)
+        names = list(bw_names)
+    return PackedSiteDataset(sites, genome, central_radius, local_radius, local_order, distal_radius, model_type, cont, names)
+
+
+def generate_data_batches(segment_loader, batch_segment, batch_size, shuffle=True, sample_workers=0):
+    """generate_data_batches (preprocessing.py:1148-1177) for the reference's tuple items: `segment_loader` iterates
+    `(y, cont_x, cat_x, distal_x)` with a leading dimension of 1 (DataLoader(dataset, 1)).  Pools `batch_segment` segments,
+    permutes inside the pool when asked, yields `(y [B,1], cont [B,1] float64 zeros, cat [B,n_cat], distal [B,4,W])`; a short
+    tail batch is prepended to the next pool and the final tail is emitted.  (Site-record datasets use
+    generate_site_batches — same order, 8 bytes per sample.)"""
+    import torch
+    carry = None
+    pool = []
+
+    def flush(last):
+        nonlocal carry, pool
+        parts = ([carry] if carry is not None else []) + pool
+        y = torch.cat([torch.as_tensor(p[0]) for p in parts])
+        cat = torch.cat([torch.as_tensor(p[1]) for p in parts])
+        dis = torch.cat([torch.as_tensor(p[2]) for p in parts])
+        if shuffle:
+            o = torch.randperm(y.shape[0])
+            y, cat, dis = y[o], cat[o], dis[o]
+        n_full = y.shape[0] // batch_size * batch_size
+        for b in range(0, n_full, batch_size):
+            yield y[b:b + batch_size], torch.zeros((batch_size, 1), dtype=torch.float64), cat[b:b + batch_size], dis[b:b + batch_size]
+        carry = (y[n_full:], cat[n_full:], dis[n_full:]) if n_full < y.shape[0] else None
+        pool = []
+        if last and carry is not None:
+            yield carry[0], torch.zeros((carry[0].shape[0], 1), dtype=torch.float64), carry[1], carry[2]
+
+    for item in segment_loader:
+        y, _, cat, dis = item
+        pool.append((torch.as_tensor(y).squeeze(0), torch.as_tensor(cat).squeeze(0), torch.as_tensor(dis).squeeze(0)))
+        if len(pool) >= batch_segment:
+            # the reference decides "last" only when the segment iterator is exhausted; peeking is not possible on a generic
+            # iterable, so a full pool is flushed as non-last and the final tail is emitted after the loop
+            yield from flush(False)
+    if pool:
+        yield from flush(True)
+    elif carry is not None:
+        yield carry[0], torch.zeros((carry[0].shape[0], 1), dtype=torch.float64), carry[1], carry[2]
