@@ -104,7 +104,11 @@ class Network2(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._dirty = True
-        return super()._apply(fn, *a, **k)
+        out = super()._apply(fn, *a, **k)
+        st = getattr(self, "_train_state", None)
+        if st is not None:
+            st.rebind()                  # the module's tensors were replaced: re-attach them to the training state's flat buffer
+        return out
 
     def _device_index(self):
         dev = self.emb_layer.weight.device

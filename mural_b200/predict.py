@@ -28,15 +28,22 @@ def shard_bounds(n, world, rank):
 
 
 def gather_rows(local, n_total, world, rank, group=None):
-    """Concatenate per-rank [n_r, k] CPU tensors on rank 0 in rank order (the only collective of predict)."""
+    """Concatenate the per-rank [n_r, k] tensors on rank 0 in rank order — the only collective of predict.  One
+    `gather` of equal-size device buffers over NCCL/NVLink (shards differ by at most one row, so each rank pads to the largest
+    shard); CPU tensors go the same way over gloo.  Returns None on the other ranks."""
     if world == 1:
         return local
     import torch.distributed as dist
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(local, parts, dst=0, group=group)
+    rows = [hi - lo for lo, hi in (shard_bounds(n_total, world, r) for r in range(world))]
+    assert local.shape[0] == rows[rank], (local.shape, rows, rank)
+    cap = max(rows)
+    buf = local.new_zeros((cap,) + tuple(local.shape[1:]))
+    buf[:rows[rank]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, parts, dst=0, group=group)
     if rank != 0:
         return None
-    out = torch.cat(parts, dim=0)
+    out = torch.cat([p[:r] for p, r in zip(parts, rows)], dim=0)
     assert out.shape[0] == n_total
     return out
 
@@ -147,10 +154,10 @@ def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator
     lo, hi = shard_bounds(n, world, rank)
     logp = predict_sites(model, ds, lo, hi)
     weights = load_calibrator_weights(calibrator_path) if calibrator_path else None
-    prob = calibrate(logp, weights, poisson_calib).cpu()
-    prob = gather_rows(prob, n, world, rank)
+    prob = gather_rows(calibrate(logp, weights, poisson_calib), n, world, rank)     # fp64 [n_r, k] on the device, NCCL gather
     if rank != 0:
         return None
+    prob = prob.cpu()
     names, start, end, strand = ds.position_info()
     if pred_file:
         write_tsv(pred_file, names, start, end, strand, ds.label, prob.numpy())   # run_predict.py:237-239

@@ -143,6 +143,12 @@ class TrainState:
     def set_dropout(self, p_emb, p_local, p_fc, seed=0):
         _lib.check(_lib.lib().mural_snv_train_set_dropout(self._h, float(p_emb), float(p_local), float(p_fc), int(seed)))
 
+    def rebind(self):
+        """Called by Network2._apply after .to() / .float() / ...: the module's tensors were replaced, so copy their
+        current values into the flat blob and point them at its views again (optimizer moments are kept).  While the model sits
+        on another device or dtype the state is detached and step() refuses to run."""
+        _rebind_views(self, self.model.native_layout())
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):
@@ -162,6 +168,7 @@ class TrainState:
     # ---- pieces
     def forward(self, batch):
         n = len(batch)
+        _check_attached(self)
         self._note_batch(n)
         logp = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -241,6 +248,7 @@ class TrainState:
         n = len(batch)
         if n < 2:
             return None                                      # training.py:415: batches of one site are skipped
+        _check_attached(self)
         self._note_batch(n)
         if self.use_graph:
             g = self._graphs.get(n)
@@ -271,6 +279,16 @@ class TrainState:
         self.apply(world)
         return logp
 
+    def sync_buffers(self):
+        """Data parallel: BatchNorm statistics are rank-local during training (DDP default); average the running
+        statistics over ranks so that the checkpoint rank 0 writes does not carry rank-0 statistics only."""
+        d = torch.distributed
+        if d.is_available() and d.is_initialized() and d.get_world_size() > 1 and self.n_blob > self.n_trainable:
+            buf = self.blob[self.n_trainable:]
+            d.all_reduce(buf, op=d.ReduceOp.SUM)
+            buf.div_(d.get_world_size())
+            self.model.mark_dirty()
+
     def sync_counters(self):
         """num_batches_tracked of every BatchNorm follows the number of training forwards (checkpoint contract)."""
         d = self.n_forward - self._tracked_synced
@@ -279,6 +297,29 @@ class TrainState:
                 if isinstance(mod, torch.nn.BatchNorm1d) and mod.num_batches_tracked is not None:
                     mod.num_batches_tracked += d
             self._tracked_synced = self.n_forward
+
+
+def _rebind_views(st, layout):
+    sd = dict(st.model.named_parameters())
+    sd.update(dict(st.model.named_buffers()))
+    ts = [sd[name] for name, _, _, _ in layout]
+    st._detached = any(t.device != st.device or t.dtype != torch.float32 for t in ts)
+    if st._detached:
+        return
+    for (name, off, num, _), t in zip(layout, ts):
+        view = st.blob[off:off + num].view(t.shape)
+        if t.data_ptr() != view.data_ptr():
+            view.copy_(t.detach())
+            t.data = view
+    if hasattr(st, "_graphs"):
+        st._graphs.clear()
+        st._graph_warm.clear()
+    st.model.mark_dirty()
+
+
+def _check_attached(st):
+    if getattr(st, "_detached", False):
+        raise RuntimeError("the model was moved off %s (or cast) after its training state was created; move it back before stepping" % st.device)
 
 
 class _TrainFn(torch.autograd.Function):
@@ -359,6 +400,17 @@ class IndelTrainState:
     def set_dropout(self, p_fc, seed=0):
         _lib.check(_lib.lib().mural_indel_train_set_dropout(self._h, float(p_fc), int(seed)))
 
+    def rebind(self):
+        """See TrainState.rebind."""
+        L = _lib.lib()
+        h = self.model._handle(self.distal_radius)
+        layout = []
+        for i in range(L.mural_indel_model_n_tensors(h)):
+            name, off, num, buf = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int32()
+            _lib.check(L.mural_indel_model_tensor(h, i, C.byref(name), C.byref(off), C.byref(num), C.byref(buf)))
+            layout.append((name.value.decode(), off.value, num.value, buf.value))
+        _rebind_views(self, layout)
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):
@@ -370,6 +422,7 @@ class IndelTrainState:
     def forward(self, batch):
         """batch: SiteBatch (windows gathered on the device) or the reference's one-hot tensor [B, 4, 2R]."""
         L = _lib.lib()
+        _check_attached(self)
         with torch.cuda.device(self.device):
             if isinstance(batch, SiteBatch):
                 n = len(batch)
@@ -528,33 +581,82 @@ def validate_epoch(model, dataset, n_class=4, pred_batch_size=4096, segment_indi
     return {"valid_loss": total_loss / max(1, n), "valid_size": n, **ev.metrics}
 
 
+def _steps_this_epoch(dataset, segs, batch_size, world, rank):
+    """Data parallel: rank r trains on segments segs[r::world]; every rank must enter the gradient all-reduce the same number
+    of times, so the number of steps is the minimum over ranks of the batches a rank will draw (full batches + a tail of at
+    least 2 sites, training.py:415)."""
+    mine = segs[rank::world]
+    n = int(sum(int(dataset.batch_sizes[i]) for i in mine))
+    steps = n // batch_size + (1 if n % batch_size >= 2 else 0)
+    if world > 1:
+        d = torch.distributed
+        t = torch.tensor([steps], dtype=torch.int64, device=dataset.genome.device if d.get_backend() == "nccl" else "cpu")
+        d.all_reduce(t, op=d.ReduceOp.MIN)
+        steps = int(t.item())
+    return mine, steps
+
+
 def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim="Adam", lr=1e-3, weight_decay=0.0, LR_gamma=0.5,
                  min_lr=1e-6, restart_lr=1e-4, seed=0, print_every=1000, segment_indices=None, valid_indices=None, history=None,
-                 pred_batch_size=4096, printer=print):
+                 pred_batch_size=4096, printer=print, lr_scheduler="StepLR", config=None):
     """The hot loop of training.py:387-452 on site records; returns per-epoch mean losses.  With `valid_indices` (segment
     indices of `dataset` held out for validation, as `random_split` does at training.py:152-168) every epoch ends with
-    `validate_epoch` and its dict is appended to `history`.  Calibrator fitting and checkpoint bookkeeping stay with the
-    caller (out of scope)."""
+    `validate_epoch` and its dict is appended to `history`.  `lr_scheduler`: 'StepLR' | 'StepLR2' | 'ROP' (training.py:364-371;
+    StepLR2 restarts every epoch at restart_lr :396-398, ROP steps on the validation loss :553-554); a reference `config` dict
+    (optim, learning_rate, weight_decay, LR_gamma, lr_scheduler, min_lr, restart_lr, batch_size) overrides the keyword
+    arguments.  With torch.distributed initialised the training segments are dealt round-robin to the ranks and every rank
+    runs the same number of steps per epoch.  Calibrator fitting and checkpoint bookkeeping stay with the caller (out of
+    scope)."""
     from .data import generate_site_batches
-    st = getattr(model, "_train_state", None) or TrainState(model, optim, lr, weight_decay, seed=seed)
-    sched = StepLR(lr, (5000 * 128) // batch_size, LR_gamma, min_lr, restart_lr)
+    if config is not None:
+        optim, lr, weight_decay = config.get("optim", optim), config.get("learning_rate", lr), config.get("weight_decay", weight_decay)
+        LR_gamma, lr_scheduler = config.get("LR_gamma", LR_gamma), config.get("lr_scheduler", lr_scheduler)
+        min_lr, restart_lr, batch_size = config.get("min_lr", min_lr), config.get("restart_lr", restart_lr), config.get("batch_size", batch_size)
+    if optim not in OPTIMIZERS:
+        raise ValueError("Error: unsupported optimization method %s" % optim)
+    if len(dataset.label) and int(dataset.label.max()) >= model.n_class:
+        raise ValueError("labels must be < n_class=%d (CrossEntropyLoss fails on out-of-range targets); max label %d" %
+                         (model.n_class, int(dataset.label.max())))
+    st = getattr(model, "_train_state", None)
+    if st is not None and (st.kind != OPTIMIZERS[optim] or st.weight_decay != float(weight_decay) or st.opt_step == 0):
+        st = None                       # a state auto-created by a train-mode forward (Adam, lr 1e-3) must not shadow the arguments
+    if st is None:
+        st = TrainState(model, optim, lr, weight_decay, seed=seed)
+    st.lr = float(lr)
+    d = torch.distributed
+    world = d.get_world_size() if d.is_available() and d.is_initialized() else 1
+    rank = d.get_rank() if world > 1 else 0
+    segs_all = np.arange(len(dataset)) if segment_indices is None else np.asarray(segment_indices)
+    segs, n_steps = _steps_this_epoch(dataset, segs_all, batch_size, world, rank)
+    train_size = int(sum(int(dataset.batch_sizes[i]) for i in segs_all))
+    sched = make_scheduler({"lr_scheduler": lr_scheduler, "learning_rate": lr, "batch_size": batch_size, "LR_gamma": LR_gamma,
+                            "min_lr": min_lr, "restart_lr": restart_lr}, max(train_size, batch_size))
+    per_batch = lr_scheduler in ("StepLR", "StepLR2")
     losses = []
     for epoch in range(epochs):
         model.train()
         st.loss_dev.zero_()
-        n_sites = 0
-        for batch in generate_site_batches(dataset, sampled_segments, batch_size, shuffle=True, seed=seed + epoch,
-                                           segment_indices=segment_indices):
+        n_sites = k = 0
+        if epoch > 0 and lr_scheduler == "StepLR2":
+            sched.lr = st.lr = restart_lr                   # training.py:396-398
+        for batch in generate_site_batches(dataset, sampled_segments, batch_size, shuffle=True, seed=seed + epoch, segment_indices=segs):
             if len(batch) < 2:
                 continue
+            if k >= n_steps:
+                break                                        # keeps the ranks' all-reduce counts equal
             st.step(batch)
+            k += 1
             n_sites += len(batch)
-            st.lr = sched.step()
+            if per_batch:
+                st.lr = sched.step()
         losses.append(float(st.loss_dev.item()) / max(1, n_sites))
         st.sync_counters()
+        st.sync_buffers()
         if valid_indices is not None:
             h = validate_epoch(model, dataset, model.n_class, pred_batch_size, valid_indices, printer=printer)
             h["epoch"], h["train_loss"] = epoch, losses[-1]
+            if lr_scheduler == "ROP":
+                st.lr = sched.step(h["valid_loss"])          # training.py:553-554
             if history is not None:
                 history.append(h)
     return losses

@@ -46,13 +46,13 @@ def _worker_predict(rank, world, port, out):
     meta = pack_meta(z["strand"], 0 * z["strand"], z["chrom"])
     sb = SiteBatch(torch.from_numpy(z["start"][lo:hi].astype(np.int32)).cuda(), torch.from_numpy(meta[lo:hi]).cuda(), pg)
     with torch.no_grad():
-        local = m.forward(None, sb).cpu()
-    full = gather_rows(local, n, world, rank)
+        local = m.forward(None, sb)
+    full = gather_rows(local, n, world, rank)                 # NCCL gather of device tensors
     if rank == 0:
         sb_all = SiteBatch(torch.from_numpy(z["start"].astype(np.int32)).cuda(), torch.from_numpy(meta).cuda(), pg)
         with torch.no_grad():
             single = m.forward(None, sb_all).cpu()
-        torch.save({"full": full, "single": single}, out)
+        torch.save({"full": full.cpu(), "single": single}, out)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -310,3 +310,51 @@ def test_train_epochs_with_validation_metrics(kat, cuda_genome):
         ref = EN.freq_kmer_comp_multi(flank, ds.label[rows].astype(np.int64), prob, k, 4)
         assert np.allclose(h["kmer%d" % k], ref, rtol=0, atol=2e-5, equal_nan=True), (k, h["kmer%d" % k], ref)
     assert any(isinstance(a[0], str) and a[0].startswith("Validation Loss") for a in lines)
+
+
+def test_training_state_survives_module_moves_and_config(kat, cuda_genome):
+    """(a) .to('cpu') / .to('cuda') (what load_pretrained does) after a TrainState exists must not detach the model's
+    tensors from the state's flat buffer; (b) train_epochs honours optim / scheduler arguments even when a train-mode forward
+    auto-created an Adam state; (c) out-of-range labels are refused."""
+    from mural_b200 import PackedSiteDataset, SiteTable
+    from mural_b200.training import OPTIMIZERS, TrainState, load_pretrained, train_epochs
+    z, cfg, state = load_snv_golden("ex_ckpt6")
+    _, genome = kat
+    m = build_model(cfg, state, int(z["n_cat"]))
+    labels = (z["start"][:64] % 4).astype(np.int64)
+    sb = _batch(z, cuda_genome, 64, labels)
+    m.train()
+    st = TrainState(m, "Adam", lr=1e-3, use_graph=False)
+    st.step(sb)
+    # (a) round trip through the CPU with a state-dict load in between
+    saved = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m.to("cpu")
+    with pytest.raises(RuntimeError):
+        st.step(sb)
+    load_pretrained(m.to("cuda"), saved)                   # cpu -> load -> cuda inside
+    w = m.local_fc[0].weight
+    assert w.data_ptr() >= st.blob.data_ptr() and w.data_ptr() < st.blob.data_ptr() + st.blob.numel() * 4
+    before = w.detach().clone()
+    st.step(sb)
+    assert not torch.equal(before, m.local_fc[0].weight.detach())          # the step updates what state_dict() reads
+    assert torch.equal(m.state_dict()["local_fc.0.weight"], st.blob[st.model.native_layout()[[n for n, *_ in st.model.native_layout()].index("local_fc.0.weight")][1]:][:w.numel()].view(w.shape))
+    # (b) optimizer / scheduler arguments win over an auto-created state
+    names = list(genome)
+    rng = np.random.default_rng(1)
+    n = 1200
+    stt = np.sort(rng.integers(300, len(genome[names[0]]) - 300, n))
+    t = SiteTable(names, np.zeros(n, int), stt, stt + 1, rng.integers(0, 2, n), rng.integers(0, 4, n))
+    ds = PackedSiteDataset(t, cuda_genome, 2000, cfg["local_radius"], cfg["local_order"], cfg["distal_radius"])
+    m2 = build_model(cfg, state, int(z["n_cat"]))
+    m2.train()
+    m2.forward(None, sb)                                                     # auto-creates an Adam state
+    assert m2._train_state.kind == OPTIMIZERS["Adam"]
+    for sched in ("StepLR2", "ROP"):
+        losses = train_epochs(m2, ds, 2, 128, optim="SGD", lr=1e-4, lr_scheduler=sched, min_lr=1e-6, restart_lr=1e-4,
+                              valid_indices=np.arange(0, len(ds), 5), printer=lambda *a: None)
+        assert m2._train_state.kind == OPTIMIZERS["SGD"] and all(np.isfinite(losses))
+    # (c) label validation
+    bad = SiteTable(names, np.zeros(4, int), stt[:4], stt[:4] + 1, np.zeros(4, int), np.array([0, 1, 2, 9]))
+    ds_bad = PackedSiteDataset(bad, cuda_genome, 2000, cfg["local_radius"], cfg["local_order"], cfg["distal_radius"])
+    with pytest.raises(ValueError):
+        train_epochs(m2, ds_bad, 1, 2)

@@ -46,3 +46,33 @@ def test_predict_sharding_gather_world2(tmp_path, n):
     idx = torch.arange(0, n, dtype=torch.float64)
     exp = torch.stack([idx, idx * 2 + 1, torch.sin(idx), idx ** 2], 1) if n else torch.empty(0, 4, dtype=torch.float64)
     assert full.shape == exp.shape and torch.equal(full, exp)
+
+
+def _worker_steps(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mural_b200.training import _steps_this_epoch
+
+    class G:
+        device = torch.device("cpu")
+
+    class DS:
+        genome = G()
+        batch_sizes = np.array([100, 3, 250, 1, 64, 64, 7])
+    mine, steps = _steps_this_epoch(DS(), np.arange(7), 64, world, rank)
+    import json
+    with open(out % rank, "w") as f:
+        json.dump([[int(v) for v in mine], int(steps)], f)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_counts_equal_world2(tmp_path):
+    """ranks that draw different numbers of batches would deadlock in the gradient all-reduce; the per-epoch step
+    count is the minimum over ranks (segments dealt round-robin)."""
+    out = str(tmp_path / "steps%d.json")
+    mp.spawn(_worker_steps, args=(2, _free_port(), out), nprocs=2, join=True)
+    import json
+    (m0, s0), (m1, s1) = json.load(open(out % 0)), json.load(open(out % 1))
+    assert m0 == [0, 2, 4, 6] and m1 == [1, 3, 5]
+    # rank 0: 421 sites -> 6 full + tail 37; rank 1: 68 sites -> 1 full + tail 4  => both run 2 steps
+    assert s0 == s1 == 2
