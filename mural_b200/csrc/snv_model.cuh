@@ -70,7 +70,6 @@ struct mural_snv_model {
   void* tc = nullptr;
   void* mlp_tc = nullptr;
   void* tail = nullptr;  // warp-level tail kernel (snv_tail.cu)
-  void* tc2 = nullptr;   // two-rows-per-lane stage kernels (snv_tc2.cu)
   // forward workspace (grown on demand)
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;

@@ -738,14 +738,12 @@ int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
     for (int stg = 0; stg < 3; ++stg) S->blob[br][stg] = S->d_w + offs[br][stg];
   m->tc = S;
   if (int rc = snv_mlp_tc_prepare(m)) return rc;
-  if (int rc = snv_tc2_prepare(m, h_blob)) return rc;
   return snv_tail_prepare(m, h_blob);
 }
 
 void snv_tc_destroy(mural_snv_model* m) {
   snv_mlp_tc_destroy(m);
   snv_tail_destroy(m);
-  snv_tc2_destroy(m);
   if (!m->tc) return;
   tc::TcState* S = (tc::TcState*)m->tc;
   cudaFree(S->d_w);
@@ -805,16 +803,8 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const bool use_dense = G != nullptr && !m->slow_stem && getenv("MURAL_NO_DENSE_STEM") == nullptr;
   const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
   const bool use_tail = m->tail != nullptr && getenv("MURAL_NO_TAIL") == nullptr;
-  // two-rows-per-lane stage kernels (snv_tc2.cu): bit-identical, measured ~15 % slower than the one-row kernels on B200
-  // (profiles/r01_stage_tc_variants.txt), so they are opt-in
-  const bool use_v2 = m->tc2 != nullptr && getenv("MURAL_TC_V2") != nullptr;
-  const int stride_rb4 = use_v2 ? snv_tc2_stride(RB4) : TILE - 2 * 4, stride_crb4 = use_v2 ? snv_tc2_stride(C_RB4) : TILE - 2 * 5;
-  // one stage launch: v2 kernels take their own weight blob; SINGLE exists only in the first generation
+  const int stride_rb4 = TILE - 2 * 4, stride_crb4 = TILE - 2 * 5;
   auto stage = [&](int mode, int fm, StageArgs sa, int br, int stg, const char* role) -> int {
-    if (use_v2) {
-      sa.wblob = snv_tc2_blob(m, br, stg);
-      return snv_tc2_launch(mode, fm, sa, st, role);
-    }
     if (mode == RB4) return fm == 2 ? launch_stage<RB4, 2>(sa, st, role) : (fm == 1 ? launch_stage<RB4, 1>(sa, st, role) : launch_stage<RB4, 0>(sa, st, role));
     return fm == 1 ? launch_stage<C_RB4, 1>(sa, st, role) : launch_stage<C_RB4, 0>(sa, st, role);
   };

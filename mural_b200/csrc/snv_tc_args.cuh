@@ -1,5 +1,4 @@
-// Arguments of the tcgen05 stage kernels (snv_tc.cu: 128-row tiles, one row per TMEM lane; snv_tc2.cu: 256-row tiles,
-// two rows per TMEM lane).
+// Arguments of the tcgen05 stage kernels (snv_tc.cu: 128-row tiles, one row per TMEM lane).
 #pragma once
 #include "snv_model.cuh"
 
@@ -46,12 +45,5 @@ struct StageArgs {
 
 
 }  // namespace tc
-
-// two-rows-per-lane stage kernels (snv_tc2.cu); launch returns -1 when unavailable
-int snv_tc2_prepare(mural_snv_model* m, const float* h_blob);
-void snv_tc2_destroy(mural_snv_model* m);
-const uint8_t* snv_tc2_blob(const mural_snv_model* m, int br, int stage);
-int snv_tc2_launch(int mode, int fm, const tc::StageArgs& a, cudaStream_t st, const char* role);
-int snv_tc2_stride(int mode);  // valid output rows per tile
 
 }  // namespace mural
