@@ -338,6 +338,111 @@ def indel_train_leg(genome, world, rank, dist, batch=32, steps=4, warmup=2):
             "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), Adam lr 1e-4" % (Rd, 2 * Rd)}
 
 
+# ------------------------------------------------------------------------------------------ sparse-site leg
+def sparse_leg(genome, chroms, model, cfg, state, mode, n=262144, steps=5, n_check=2048):
+    """Sparse-site predict (BED subsets, validation sets, every training-set predict): a seeded 1-in-100 sample of the A/T
+    sites of ALL chromosomes, in (chromosome, position) order, so the windows of neighbouring sites hardly overlap and a call
+    spans several chromosomes -> the per-site kernels (stem gather per site, RB4/C_RB4 on per-site rows), not the dense
+    lattice.  Device-timed with CUDA events, inputs resident; parity spot check of the first sites against the CPU oracle."""
+    import torch
+    from mural_b200 import SiteBatch, pack_meta
+    from oracle import encode_np as E
+    from oracle import network_t as NT
+    rng = np.random.default_rng(2718)
+    per = n // len(chroms)
+    pos_l, meta_l = [], []
+    for ci, c in enumerate(chroms):
+        span = c[: per * 220]                                   # ~ per*110 A/T sites -> keep 1 in ~100
+        idx = np.flatnonzero((span == ord("A")) | (span == ord("T")))
+        sel = np.sort(rng.choice(idx, size=per, replace=False))
+        pos_l.append(sel.astype(np.int32))
+        meta_l.append(pack_meta((span[sel] == ord("T")).astype(np.int64), np.zeros(per, np.int64), np.full(per, ci)))
+    pos, meta = np.concatenate(pos_l), np.concatenate(meta_l)
+    sb = SiteBatch(torch.from_numpy(pos).cuda(), torch.from_numpy(meta).cuda(), genome)
+    model.compute_mode = mode
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        lp = model.forward(None, sb)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(steps):
+            lp = model.forward(None, sb)
+        ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    got = lp[:n_check].cpu().numpy()
+    sym = E._ASCII2SYM[chroms[0]]
+    cat = E.kmer_windows(sym, pos[:n_check], meta[:n_check] & 1, cfg["local_radius"], cfg["local_order"])
+    oh = E.onehot_windows(sym, pos[:n_check], meta[:n_check] & 1, cfg["distal_radius"])
+    with torch.no_grad():
+        ref = NT.network2_forward(state, cat, oh, torch.float32).numpy()
+    sm = lambda x: np.exp(x - x.max(1, keepdims=True)) / np.exp(x - x.max(1, keepdims=True)).sum(1, keepdims=True)
+    return {"metric": "sites/sec (predict, sparse sites)", "value": len(pos) / (ms * 1e-3), "unit": "sites/s", "sites": int(len(pos)),
+            "ms_per_call": ms, "mode": mode, "mean_site_spacing_bp": float(np.mean(np.diff(pos_l[0]))),
+            "parity_spot_check": {"sites": n_check, "max_abs_dp": float(np.abs(sm(got) - sm(ref)).max()), "tolerance": 1e-3 if mode == "fp32" else 5e-3},
+            "config": "1-in-100 A/T sites of all %d chromosomes in one call (per-site kernels)" % len(chroms)}
+
+
+# ------------------------------------------------------------------------------------------ full pipeline leg
+def pipeline_leg(chroms, cfg, state, n_cat, world, rank, dist, mode, n_sites=4_000_000):
+    """mural_b200.predict.run_predict end to end (MuRaL/scripts/run_predict.py:34-239): FASTA + BED + checkpoint files on disk ->
+    packed genome, site order, sharded compute, calibration, ONE NCCL gather, '%.4g' TSV on rank 0.  Chromosome 1 of the
+    config-2 genome (25 Mb) and its first n_sites A/T sites; wall seconds per stage, max over ranks for the shared stages."""
+    import pickle
+    import shutil
+    import tempfile
+    import torch
+    from mural_b200.predict import run_predict
+    tmp = tempfile.mkdtemp(prefix="mural_pipe_") if rank == 0 else None
+    if world > 1:
+        box = [tmp]
+        dist.broadcast_object_list(box, src=0)
+        tmp = box[0]
+    fa, bed = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "sites.bed")
+    try:
+        if rank == 0:
+            c = chroms[0]
+            with open(fa, "wb") as f:
+                f.write(b">chr1\n")
+                rows = c[: len(c) // 100 * 100].reshape(-1, 100)
+                f.write(np.concatenate([rows, np.full((len(rows), 1), 10, np.uint8)], 1).tobytes())
+            idx = np.flatnonzero((c == ord("A")) | (c == ord("T")))[:n_sites]
+            strand = np.where(c[idx] == ord("T"), "-", "+")
+            import pandas as pd
+            pd.DataFrame({"c": "chr1", "s": idx, "e": idx + 1, "n": ".", "l": 0, "d": strand}).to_csv(bed, sep="\t", header=False, index=False)
+            m = build_model(cfg, state, n_cat, "fp32")
+            torch.save({k: v.cpu() for k, v in m.state_dict().items()}, os.path.join(tmp, "model"))
+            pickle.dump(dict(cfg, emb_dims=[(65, 2)] * n_cat, segment_center=300000), open(os.path.join(tmp, "model.config.pkl"), "wb"))
+            del m
+        if world > 1:
+            dist.barrier()
+        tm = {}
+        t0 = time.perf_counter()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):           # stdout carries the one JSON line only
+            run_predict(bed, fa, os.path.join(tmp, "model"), os.path.join(tmp, "model.config.pkl"), "", os.path.join(tmp, "pred.tsv"),
+                        compute_mode=mode, return_frame=False, timings=tm)
+        if world > 1:
+            dist.barrier()
+        total = time.perf_counter() - t0
+        size = os.path.getsize(os.path.join(tmp, "pred.tsv")) if rank == 0 else 0
+        keys = ["fasta_ingest_s", "bed_ingest_s", "site_order_s", "model_load_s", "compute_s", "calibrate_s", "gather_s"]
+        v = torch.tensor([tm.get(k, 0.0) for k in keys], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        stages = {k: round(float(x), 4) for k, x in zip(keys, v.tolist())}
+        stages["tsv_write_s"] = round(tm.get("tsv_write_s", 0.0), 4)
+        n = int(tm.get("sites", n_sites))
+        return {"metric": "sites/sec (run_predict: BED + FASTA -> calibrated TSV, wall clock)", "value": n / total, "unit": "sites/s", "sites": n,
+                "total_s": round(total, 3), "stages": stages, "tsv_bytes": int(size), "mode": mode, "n_gpus": world,
+                "config": "chr1 (25 Mb) of the config-2 genome, first %d A/T sites, segment_center 300000, one gather of fp64 [n,4]" % n}
+    finally:
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_sites_per_sec(chroms, pos, meta, cfg, state, batch=1024):
     """Oracle port of the reference CPU path: numpy window/k-mer encoders + torch CPU fp32 Network2."""
@@ -406,7 +511,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mural_b200", choices=["mural_b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MURAL_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("MURAL_BENCH_MODE", "auto"), choices=["auto", "fp32", "bf16"],
+                    help="auto = the product default (MURAL_MODE_AUTO: bf16 tensor-core path + fp32-equivalent recompute of the "
+                         "exception windows, decided on the device); bf16 / fp32 force one path")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the sparse-site predict leg (per-site kernels)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the BED+FASTA -> TSV pipeline leg (run_predict)")
     ap.add_argument("--sites-per-step", type=int, default=1048576)
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -455,17 +564,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _lib.lib()
     mode = a.mode
-    if mode == "auto":
-        mode = "probe"
     chroms = [synth_chromosome(ci) for ci in range(N_CHROM)]
     genome = PackedGenome({"chr%d" % (i + 1): c.tobytes() for i, c in enumerate(chroms)})
     S, K, W = a.sites_per_step, a.steps, a.warmup
     pos, meta = rank_sites(chroms, rank, world, S * (K + W))
-    model = build_model(cfg, state, n_cat, "fp32" if mode == "probe" else mode)
-    if mode == "probe":
-        model.refresh()
-        mode = "bf16" if L.mural_snv_tc_available(model._h) == 1 else "fp32"
-        model.compute_mode = mode
+    model = build_model(cfg, state, n_cat, mode)
+    model.refresh()
+    if mode != "fp32" and L.mural_snv_tc_available(model._h) != 1:
+        raise RuntimeError("the tcgen05 path is not available for this model shape; run with --mode fp32")
     d_pos, d_meta = torch.from_numpy(pos).cuda(), torch.from_numpy(meta).cuda()
     out = torch.empty((S, cfg["n_class"]), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -477,11 +583,15 @@ def main():
     cuts = [[0] + [int(c) + 1 for c in np.flatnonzero(np.diff(chrom_of[i * S:(i + 1) * S]))] + [S] for i in range(K + W)]
     NCb = cfg["n_class"]
 
-    def step(i):
+    auto_sites = [0]
+
+    def step(i, md=None):
         for a0, a1 in zip(cuts[i][:-1], cuts[i][1:]):
             _lib.check(L.mural_snv_forward(model._h, genome.handle, C.c_void_p(d_pos.data_ptr() + 4 * (i * S + a0)),
-                                           C.c_void_p(d_meta.data_ptr() + 4 * (i * S + a0)), a1 - a0, _lib.MODES[mode],
+                                           C.c_void_p(d_meta.data_ptr() + 4 * (i * S + a0)), a1 - a0, _lib.MODES[md or mode],
                                            C.c_void_p(out.data_ptr() + 4 * NCb * a0), C.c_void_p(stream.cuda_stream)))
+            if (md or mode) == "auto":
+                auto_sites[0] += int(L.mural_snv_last_auto_sites(model._h))
 
     def barrier():
         if world > 1:
@@ -510,6 +620,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = world * S * K / (dev_ms * 1e-3)
+    n_auto = auto_sites[0] / max(1, W + K)            # exception-window sites recomputed per step (auto mode)
+
+    # ---- the same K steps with the bf16 path alone (no exception-window recompute): reported beside the headline
+    bf16_only = None
+    if mode == "auto":
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.fill_(i & 0xff)
+            ev2[i][0].record(stream)
+            step(W + i, "bf16")
+            ev2[i][1].record(stream)
+        barrier()
+        t2 = torch.tensor([sum(s_.elapsed_time(e_) for s_, e_ in ev2)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        bf16_only = {"value": world * S * K / (float(t2.item()) * 1e-3), "unit": "sites/s", "ms_per_step": float(t2.item()) / K,
+                     "note": "MURAL_MODE_BF16 on the same steps: every site through the tcgen05 path only"}
 
     # ---- e2e: host buffers through the C-ABI host entry point
     h_pos = torch.from_numpy(pos).pin_memory(); h_meta = torch.from_numpy(meta).pin_memory()
@@ -533,6 +660,20 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * S * K / float(te.item())
+
+    sparse = None
+    if rank == 0 and not a.no_sparse:
+        try:
+            sparse = sparse_leg(genome, chroms, model, cfg, state, mode)
+        except Exception as e:
+            sparse = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    pipe = None
+    if not a.no_pipeline:
+        try:
+            pipe = pipeline_leg(chroms, cfg, state, n_cat, world, rank, dist, mode)
+        except Exception as e:
+            pipe = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- training leg (fwd + bwd + optimizer), all ranks (it contains the gradient all-reduce)
     train = None
@@ -577,12 +718,14 @@ def main():
         roof = kernel_roofline(L, step, W, K, S, mode, cfg, torch.cuda.synchronize, pos)   # rank-local: no collective here
     line = {"metric": "sites/sec (predict)", "value": value, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
+            "dtype": "f32" if mode == "fp32" else "bf16", "data": "synthetic",
             "config": dict(base_cfg, mode=mode, l2="flushed between steps (256 MiB write outside the per-step CUDA-event pairs); "
-                           "per-step activation workspace > L2", wall_s_timed_region=t_wall),
+                           "per-step activation workspace > L2", wall_s_timed_region=t_wall,
+                           exception_window_sites_per_step=n_auto if mode == "auto" else None, bf16_only=bf16_only),
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
-            "roofline": roof, "train": train, "indel": indel, "indel_train": indel_train, "eval_metrics": evalm, "transfer_sweep": sweep}
+            "roofline": roof, "sparse_predict": sparse, "pipeline": pipe, "train": train, "indel": indel, "indel_train": indel_train,
+            "eval_metrics": evalm, "transfer_sweep": sweep}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample
@@ -597,7 +740,7 @@ def main():
                 got = out[:n_s].cpu().numpy()
                 pg = np.exp(got - got.max(1, keepdims=True)); pg /= pg.sum(1, keepdims=True)
                 pr = np.exp(ref_lp - ref_lp.max(1, keepdims=True)); pr /= pr.sum(1, keepdims=True)
-                line["parity_spot_check"] = {"sites": int(n_s), "max_abs_dp": float(np.abs(pg - pr).max()), "tolerance": 5e-3 if mode == "bf16" else 1e-3,
+                line["parity_spot_check"] = {"sites": int(n_s), "max_abs_dp": float(np.abs(pg - pr).max()), "tolerance": 1e-3 if mode == "fp32" else 5e-3,
                                              "what": "GPU probabilities of the first sites of a full-size step vs the CPU oracle"}
         print(json.dumps(line))
     if world > 1:
@@ -646,7 +789,7 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
     buf = C.create_string_buffer(1 << 16)
     L.mural_profile_end(buf, len(buf))
     prof = json.loads(buf.value.decode() or "{}")
-    conv = {k: v for k, v in prof.items() if "conv" in k or "stage_tc" in k or "stage2_tc" in k}
+    conv = {k: v for k, v in prof.items() if ("stage_tc" in k if mode != "fp32" else "conv" in k)}
     if not conv:
         return None
     ms = sum(v["ms"] for v in conv.values()); n = sum(v["count"] for v in conv.values())
@@ -656,7 +799,7 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
     achieved = flops_per_launch / (ms / n * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
     executed = None
-    if pos is not None and mode == "bf16" and any("lattice" in k for k in conv):
+    if pos is not None and mode != "fp32" and any("lattice" in k for k in conv):
         ex = executed_conv_flops(pos, S, K, W, cfg["distal_radius"])
         executed = {"flops_per_launch": ex / n, "tflops": ex / (ms * 1e-3) / 1e12, "frac_of_peak": ex / (ms * 1e-3) / 1e12 / peak,
                     "share_of_algorithmic": ex / (alg * S * K),
@@ -664,7 +807,7 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
                             "site, so fewer FLOPs are executed than the per-site algorithmic count that `achieved` uses (SURVEY 8d)"}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and mode == "bf16":
+    if os.path.exists(tp) and mode != "fp32":
         tj = json.load(open(tp))      # dram__bytes_read+write of the stage kernels from the committed ncu --set full capture,
         traffic = tj["dram_bytes_per_site"] * S * K / n     # per site of a dense chunk, scaled to this run's launches
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,

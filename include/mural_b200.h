@@ -34,6 +34,8 @@ extern "C" {
 /* compute modes of the conv stack */
 #define MURAL_MODE_FP32 0 /* CUDA-core fp32 FMA; the "fp32-equivalent" mode (1e-3 gate)           */
 #define MURAL_MODE_BF16 1 /* tcgen05 implicit GEMM, bf16 operands, fp32 accumulate (5e-3 gate)   */
+#define MURAL_MODE_AUTO 2 /* product default: BF16 for every site + the fp32-equivalent path again for the sites whose
+                             expanded window holds a non-ACGT symbol or overhangs its chromosome (list built on device) */
 
 const char* mural_last_error(void);
 int mural_abi_version(void);
@@ -138,6 +140,8 @@ int mural_ce_sum(const float* d_logp, const int32_t* d_meta, int64_t n, int32_t 
                  void* stream);
 /* 1 when the tcgen05 (MURAL_MODE_BF16) path is compiled in and supports this model's shape */
 int mural_snv_tc_available(const mural_snv_model_t* m);
+/* number of sites the last MURAL_MODE_AUTO forward recomputed in the fp32-equivalent path */
+int64_t mural_snv_last_auto_sites(const mural_snv_model_t* m);
 /* sites per workspace chunk of the forward (0 = default); parity-test switch for debug taps */
 int mural_snv_set_chunk(mural_snv_model_t* m, int64_t chunk_sites);
 int mural_snv_set_debug(mural_snv_model_t* m, int32_t flags); /* bit0: keep taps, bit1: force the generic stem kernel */

@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmural_b200.so")
 
 MODEL_SNV, MODEL_INDEL = 0, 1
-MODE_FP32, MODE_BF16 = 0, 1
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "auto_bf16": 1}
+MODE_FP32, MODE_BF16, MODE_AUTO = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "auto": MODE_AUTO}
 
 
 class SnvConfig(C.Structure):
@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mural_profile_begin": (None, []),
     "mural_profile_end": (_i64, [C.c_char_p, _i64]),
     "mural_snv_tc_available": (C.c_int, [_vp]),
+    "mural_snv_last_auto_sites": (_i64, [_vp]),
     "mural_genome_create": (C.c_int, [_i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.c_int, C.POINTER(_vp)]),
     "mural_genome_destroy": (None, [_vp]),
     "mural_genome_n_chrom": (_i32, [_vp]),

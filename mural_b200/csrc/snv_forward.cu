@@ -966,6 +966,117 @@ extern "C" int mural_snv_set_chunk(mural_snv_model_t* m, int64_t chunk_sites) {
   return 0;
 }
 
+// ---- MURAL_MODE_AUTO: the bf16 tensor-core path for every site, and the fp32-equivalent path again for the sites whose
+// expanded window holds a non-ACGT symbol or overhangs its chromosome (inputs far from what the network was trained on can
+// drive activations an order of magnitude up, where bf16's relative rounding no longer stays inside the 5e-3 gate;
+// DESIGN.md 5).  The site list is built on the device; the host learns its length from a 4-byte copy that completes long
+// before the bf16 pass it is enqueued in front of, so the call stays asynchronous for the bulk of the work.
+namespace mural {
+__global__ void __launch_bounds__(256) k_exception_sites(GenomeView G, const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
+                                                         int64_t n, int R, int* __restrict__ count, int32_t* __restrict__ idx) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int chrom = meta[i] >> 8;
+  const int64_t lo = int64_t(pos[i]) - R, hi = int64_t(pos[i]) + R;  // inclusive window (preprocessing.py:524-567, snv)
+  bool exc = lo < 0 || hi >= G.chrom_len[chrom];
+  if (!exc && G.n_exc > 0) {
+    const int64_t glo = G.chrom_off[chrom] + lo, ghi = G.chrom_off[chrom] + hi;
+    int a = 0, b = G.n_exc;  // first run whose (exclusive) end lies beyond the window start
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (__ldg(G.exc_end + mid) > glo) b = mid; else a = mid + 1;
+    }
+    exc = a < G.n_exc && __ldg(G.exc_start + a) <= ghi;
+  }
+  if (exc) idx[atomicAdd(count, 1)] = int32_t(i);
+}
+__global__ void __launch_bounds__(256) k_exception_windows(const uint8_t* __restrict__ sym, int64_t n, int L, int* __restrict__ count,
+                                                           int32_t* __restrict__ idx) {
+  const int64_t site = blockIdx.x * int64_t(blockDim.x / 32) + (threadIdx.x >> 5);
+  if (site >= n) return;
+  bool exc = false;
+  for (int p = threadIdx.x & 31; p < L; p += 32) exc |= sym[site * L + p] >= 4;
+  if (__any_sync(0xffffffffu, exc) && (threadIdx.x & 31) == 0) idx[atomicAdd(count, 1)] = int32_t(site);
+}
+__global__ void __launch_bounds__(256) k_gather_sites(const int32_t* __restrict__ pos, const int32_t* __restrict__ meta,
+                                                      const int32_t* __restrict__ idx, int cnt, int32_t* __restrict__ pos2,
+                                                      int32_t* __restrict__ meta2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cnt) return;
+  pos2[j] = pos[idx[j]];
+  meta2[j] = meta[idx[j]];
+}
+__global__ void __launch_bounds__(256) k_gather_windows(const uint8_t* __restrict__ sym, const int64_t* __restrict__ cat, const int32_t* __restrict__ idx,
+                                                        int cnt, int L, int n_cat, uint8_t* __restrict__ sym2, int64_t* __restrict__ cat2) {
+  const int j = blockIdx.x;
+  if (j >= cnt) return;
+  const int64_t s = idx[j];
+  for (int p = threadIdx.x; p < L; p += blockDim.x) sym2[int64_t(j) * L + p] = sym[s * L + p];
+  for (int c = threadIdx.x; c < n_cat; c += blockDim.x) cat2[int64_t(j) * n_cat + c] = cat[s * n_cat + c];
+}
+__global__ void __launch_bounds__(256) k_scatter_rows(const float* __restrict__ src, const int32_t* __restrict__ idx, int cnt, int NC,
+                                                      float* __restrict__ dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= cnt * NC) return;
+  dst[int64_t(idx[e / NC]) * NC + e % NC] = src[e];
+}
+
+// scratch of the auto mode: [count | idx n | pos2 n | meta2 n | logp2 n*NC] (+ windows / k-mer rows on the tensor route)
+static int auto_scratch(mural_snv_model* m, int64_t bytes) {
+  if (m->auto_bytes < bytes) {
+    cudaFree(m->d_auto);
+    m->d_auto = nullptr;
+    m->auto_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_auto, bytes));
+    m->auto_bytes = bytes;
+  }
+  if (!m->h_auto) CUDA_TRY(cudaMallocHost(&m->h_auto, 64));
+  if (!m->auto_ev) CUDA_TRY(cudaEventCreateWithFlags((cudaEvent_t*)&m->auto_ev, cudaEventDisableTiming));
+  return 0;
+}
+
+int snv_forward_auto(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, const uint8_t* d_sym,
+                     const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st) {
+  if (!m->tc) return snv_forward_fp32(m, G, d_pos, d_meta, d_sym, d_cat, n, d_logp, st);  // shape without a tcgen05 path
+  MURAL_CHECK(n < (int64_t(1) << 31), "more than 2^31 sites in one call");
+  const int NC = m->cfg.n_class;
+  if (int rc = auto_scratch(m, 256 + n * (12 + 4 * NC))) return rc;
+  int* d_count = (int*)m->d_auto;
+  int32_t* idx = (int32_t*)((char*)m->d_auto + 256);
+  int32_t* pos2 = idx + n;
+  int32_t* meta2 = pos2 + n;
+  float* logp2 = (float*)(meta2 + n);
+  CUDA_TRY(cudaMemsetAsync(d_count, 0, 4, st));
+  if (G) LAUNCH(k_exception_sites, (unsigned)cdiv(n, 256), 256, 0, st, *G, d_pos, d_meta, n, m->cfg.distal_radius, d_count, idx);
+  else LAUNCH(k_exception_windows, (unsigned)cdiv(n, 8), 256, 0, st, d_sym, n, m->L, d_count, idx);
+  int* h_count = (int*)m->h_auto;
+  CUDA_TRY(cudaMemcpyAsync(h_count, d_count, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord((cudaEvent_t)m->auto_ev, st));
+  if (int rc = snv_forward_tc(m, G, d_pos, d_meta, d_sym, d_cat, n, d_logp, st)) return rc;
+  CUDA_TRY(cudaEventSynchronize((cudaEvent_t)m->auto_ev));  // completed while the bf16 pass was being enqueued
+  const int cnt = *h_count;
+  m->last_auto_sites = cnt;
+  if (cnt == 0) return 0;
+  if (G) {
+    LAUNCH(k_gather_sites, (unsigned)cdiv(cnt, 256), 256, 0, st, d_pos, d_meta, idx, cnt, pos2, meta2);
+    if (int rc = snv_forward_fp32(m, G, pos2, meta2, nullptr, nullptr, cnt, logp2, st)) return rc;
+  } else {
+    uint8_t* sym2 = nullptr;  // tensor route (parity surface): windows and k-mer rows of the flagged sites, packed
+    const int64_t sb = (int64_t(cnt) * m->L + 255) & ~int64_t(255);
+    CUDA_TRY(cudaMalloc((void**)&sym2, sb + int64_t(cnt) * m->n_cat * 8));
+    int64_t* cat2 = (int64_t*)(sym2 + sb);
+    LAUNCH(k_gather_windows, (unsigned)cnt, 128, 0, st, d_sym, d_cat, idx, cnt, m->L, m->n_cat, sym2, cat2);
+    int rc = snv_forward_fp32(m, nullptr, nullptr, nullptr, sym2, cat2, cnt, logp2, st);
+    cudaStreamSynchronize(st);
+    cudaFree(sym2);
+    if (rc) return rc;
+  }
+  LAUNCH(k_scatter_rows, (unsigned)cdiv(int64_t(cnt) * NC, 256), 256, 0, st, logp2, idx, cnt, NC, d_logp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+}  // namespace mural
+
 extern "C" int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, const int32_t* d_pos, const int32_t* d_meta,
                                  int64_t n, int32_t mode, float* d_logp, void* stream) {
   if (int rc = check_model(m)) return rc;
@@ -974,8 +1085,11 @@ extern "C" int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, 
   if (n == 0) return 0;
   if (mode == MURAL_MODE_FP32) return snv_forward_fp32(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   if (mode == MURAL_MODE_BF16) return snv_forward_tc(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
+  if (mode == MURAL_MODE_AUTO) return snv_forward_auto(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   MURAL_FAIL("unknown compute mode");
 }
+
+extern "C" int64_t mural_snv_last_auto_sites(const mural_snv_model_t* m) { return m ? m->last_auto_sites : -1; }
 
 extern "C" int mural_snv_forward_tensors(mural_snv_model_t* m, const int64_t* d_cat, const float* d_distal, int64_t n, int32_t L,
                                          int32_t mode, float* d_logp, void* stream) {
@@ -998,8 +1112,9 @@ extern "C" int mural_snv_forward_tensors(mural_snv_model_t* m, const int64_t* d_
     if (bad) rc = fail(__FILE__, __LINE__, "distal_x holds columns that are not reference one-hot vectors (bigWig channels / arbitrary floats are not supported by the table stem)");
   }
   if (rc == 0) {
-    rc = mode == MURAL_MODE_BF16 ? snv_forward_tc(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
-                                 : snv_forward_fp32(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st);
+    rc = mode == MURAL_MODE_BF16   ? snv_forward_tc(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
+         : mode == MURAL_MODE_AUTO ? snv_forward_auto(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
+                                   : snv_forward_fp32(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st);
   }
   cudaStreamSynchronize(st);
   cudaFree(d_sym);

@@ -110,6 +110,9 @@ extern "C" void mural_snv_model_destroy(mural_snv_model_t* m) {
   cudaFree(m->d_prep);
   cudaFree(m->d_ws);
   cudaFree(m->d_io);
+  cudaFree(m->d_auto);
+  if (m->h_auto) cudaFreeHost(m->h_auto);
+  if (m->auto_ev) cudaEventDestroy((cudaEvent_t)m->auto_ev);
   snv_tc_destroy(m);
   delete m;
 }

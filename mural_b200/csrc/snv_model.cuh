@@ -77,6 +77,12 @@ struct mural_snv_model {
   // persistent H2D/D2H staging of mural_snv_predict_host
   void* d_io = nullptr;
   int64_t io_bytes = 0;
+  // MURAL_MODE_AUTO scratch: device site list, pinned count, event
+  void* d_auto = nullptr;
+  int64_t auto_bytes = 0;
+  void* h_auto = nullptr;
+  void* auto_ev = nullptr;
+  int64_t last_auto_sites = 0;
   // debug taps (parity tests): host copies of intermediate activations of the last chunk
   bool debug = false;
   bool slow_stem = false;  // parity switch: force the generic per-tap stem kernel

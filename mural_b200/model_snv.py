@@ -91,7 +91,9 @@ class Network2(nn.Module):
                                    kernel_size, n_class)
         self._h = None
         self._dirty = True
-        self.compute_mode = "fp32"      # "fp32" (fp32-equivalent gate 1e-3) | "bf16" (tcgen05, gate 5e-3)
+        # "fp32" (fp32-equivalent, gate 1e-3) | "bf16" (tcgen05, gate 5e-3) | "auto" (bf16 everywhere + the fp32-equivalent
+        # path again for windows with non-ACGT symbols / chromosome overhang; the default of run_predict)
+        self.compute_mode = "fp32"
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.mark_dirty())
 
     # ------------------------------------------------------------------ native handle management

@@ -78,23 +78,6 @@ def predict_sites(model, dataset, lo, hi, batch_sites=1 << 20):
             else:
                 outs.append(model.forward(None, sb))
     logp = torch.cat(outs) if outs else torch.empty((0, model.n_class), device=dev)
-    if dataset.model_type == "snv" and getattr(model, "compute_mode", "fp32") == "auto_bf16":
-        # precision policy of compute_mode="auto": the bf16 tensor-core path everywhere, and the fp32 kernels again for the
-        # (rare) sites whose expanded window contains N / IUPAC symbols or overhangs the chromosome — inputs far from what
-        # the network was trained on can drive activations (and logits) an order of magnitude up, where bf16's relative
-        # rounding no longer stays inside the 5e-3 gate on probabilities
-        mask = dataset.genome.windows_with_exceptions(dataset.chrom[lo:hi], dataset.pos[lo:hi], dataset.distal_radius)
-        idx = np.flatnonzero(mask)
-        if len(idx):
-            model.compute_mode = "fp32"
-            try:
-                with torch.no_grad():
-                    for c in range(0, len(idx), 1 << 16):
-                        sel = idx[c:c + (1 << 16)] + lo
-                        sb = SiteBatch(torch.from_numpy(dataset.pos[sel]).to(dev), torch.from_numpy(dataset.meta[sel]).to(dev), dataset.genome)
-                        logp[torch.from_numpy(sel - lo).to(dev)] = model.forward(None, sb)
-            finally:
-                model.compute_mode = "auto_bf16"
     return logp
 
 
@@ -110,19 +93,27 @@ def format_predictions(chrom, start, end, strand, mut_type, prob):
     return df
 
 
-def write_tsv(path, chrom_names, start, end, strand, mut_type, prob, n_threads=None):
+def write_tsv(path, chrom_names, start, end, strand, mut_type, prob, n_threads=None, chrom_codes=None):
     """`pred_df.sort_values(['chrom','start']).to_csv(path, sep='\\t', float_format='%.4g', index=False)` (run_predict.py:237-239)
-    without pandas: stable sort by (chromosome name, start) here, formatting + writing in the C library (threaded)."""
+    without pandas: stable sort by (chromosome name, start) here, formatting + writing in the C library (threaded).
+    `chrom_names`: per-site names, or — with `chrom_codes` (int per site) — the list the codes index (no per-site strings)."""
     import ctypes as C
     import os
     from . import _lib
-    names = np.asarray(chrom_names, dtype=object)
-    uniq, inv = np.unique(names.astype(str), return_inverse=True)          # lexicographic, like pandas on strings
-    order = np.lexsort((np.asarray(start), inv))                            # stable: ties keep emission order
+    if chrom_codes is None:
+        uniq, inv = np.unique(np.asarray(chrom_names, dtype=object).astype(str), return_inverse=True)   # lexicographic, like pandas on strings
+    else:
+        names = np.asarray([str(c) for c in chrom_names])
+        uniq, back = np.unique(names, return_inverse=True)
+        inv = back[np.asarray(chrom_codes, dtype=np.int64)]
+    start = np.asarray(start, dtype=np.int64)
+    order = np.lexsort((start, inv))                                         # stable: ties keep emission order
     idx = np.ascontiguousarray(inv[order].astype(np.int32))
-    st = np.ascontiguousarray(np.asarray(start, dtype=np.int64)[order])
+    st = np.ascontiguousarray(start[order])
     en = np.ascontiguousarray(np.asarray(end, dtype=np.int64)[order])
-    sd = np.ascontiguousarray(np.asarray([ord(c[0]) for c in ("+", "-")], dtype=np.uint8)[(np.asarray(strand) != "+").astype(np.int64)][order])
+    strand = np.asarray(strand)
+    minus = (strand != 0) if strand.dtype.kind in "iub" else (strand != "+")
+    sd = np.ascontiguousarray(np.where(minus, np.uint8(ord("-")), np.uint8(ord("+")))[order].astype(np.uint8))
     mt = np.ascontiguousarray(np.asarray(mut_type, dtype=np.float64)[order])
     pr = np.ascontiguousarray(np.asarray(prob, dtype=np.float64)[order])
     arr = (C.c_char_p * len(uniq))(*[u.encode() for u in uniq])
@@ -131,37 +122,58 @@ def write_tsv(path, chrom_names, start, end, strand, mut_type, prob, n_threads=N
 
 
 def run_predict(test_data, ref_genome, model_path, model_config_path, calibrator_path="", pred_file=None, segment_center=None,
-                poisson_calib=False, compute_mode="auto", genome=None, model_type="snv", return_frame=True):
-    """Returns the prediction DataFrame on rank 0 (None elsewhere); writes `pred_file` when given."""
+                poisson_calib=False, compute_mode="auto", genome=None, model_type="snv", return_frame=True, timings=None):
+    """Returns the prediction DataFrame on rank 0 (None elsewhere); writes `pred_file` when given.  `timings` (a dict) receives
+    the wall seconds of every stage (device work synchronised at the stage boundaries only when it is passed)."""
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     rank = torch.distributed.get_rank() if dist_on else 0
     world = torch.distributed.get_world_size() if dist_on else 1
-    t0 = time.time()
+    t0 = t_last = time.time()
+
+    def lap(name):
+        nonlocal t_last
+        if timings is not None:
+            torch.cuda.synchronize()
+            now = time.time()
+            timings[name] = timings.get(name, 0.0) + now - t_last
+            t_last = now
     config = load_config(model_config_path)
     if not segment_center:
         segment_center = config.get("segment_center", 300000)          # run_predict.py:88-92 / commands/predict.py:84
     dev = torch.device("cuda", torch.cuda.current_device())
     if genome is None:
         genome = PackedGenome.from_fasta(ref_genome, dev)
+    lap("fasta_ingest_s")
     sites = SiteTable.from_bed(test_data)
+    lap("bed_ingest_s")
     ds = PackedSiteDataset(sites, genome, segment_center, config["local_radius"], config["local_order"], config["distal_radius"],
                            model_type=model_type)
+    lap("site_order_s")
     model = build_model_from_files(model_path, config, dev, model_type=model_type)
     if model_type == "snv":
-        model.compute_mode = "auto_bf16" if compute_mode == "auto" else compute_mode
+        model.compute_mode = compute_mode       # "auto" (MURAL_MODE_AUTO: the exception-window policy runs inside the library)
+    lap("model_load_s")
     poisson_calib = bool(poisson_calib) or model_type == "indel"          # run_predict.py:224
     n = len(ds.pos)
     lo, hi = shard_bounds(n, world, rank)
     logp = predict_sites(model, ds, lo, hi)
+    lap("compute_s")
     weights = load_calibrator_weights(calibrator_path) if calibrator_path else None
-    prob = gather_rows(calibrate(logp, weights, poisson_calib), n, world, rank)     # fp64 [n_r, k] on the device, NCCL gather
+    prob = calibrate(logp, weights, poisson_calib)                         # fp64 [n_r, k] on the device
+    lap("calibrate_s")
+    prob = gather_rows(prob, n, world, rank)                               # one NCCL gather
+    lap("gather_s")
     if rank != 0:
         return None
     prob = prob.cpu()
-    names, start, end, strand = ds.position_info()
-    if pred_file:
-        write_tsv(pred_file, names, start, end, strand, ds.label, prob.numpy())   # run_predict.py:237-239
-    df = format_predictions(names, start, end, strand, ds.label, prob.numpy()) if return_frame else None
+    if pred_file:                                                              # run_predict.py:237-239
+        write_tsv(pred_file, ds.sites.chrom_names, ds.sites.start[ds.perm], ds.sites.end[ds.perm], ds.strand, ds.label, prob.numpy(),
+                  chrom_codes=ds.sites.chrom[ds.perm])
+    lap("tsv_write_s")
+    df = format_predictions(*ds.position_info(), ds.label, prob.numpy()) if return_frame else None
+    if timings is not None:
+        timings["total_s"] = time.time() - t0
+        timings["sites"] = n
     print("predicted %d sites in %.2f s (%d rank(s))" % (n, time.time() - t0, world))
     sys.stdout.flush()
     return df

@@ -151,9 +151,9 @@ def test_indel_tsv_matches_oracle_pipeline(tmp_path, kat):
 
 
 def test_auto_mode_routes_exception_windows_to_fp32(kat, cuda_genome):
-    """compute_mode='auto': bf16 everywhere, fp32 kernels for sites whose window has N / IUPAC symbols or overhangs the
-    chromosome.  The mask equals a brute-force scan of the windows; masked rows equal the fp32 path bit for bit, the
-    others the bf16 path."""
+    """compute_mode='auto' (MURAL_MODE_AUTO, inside the library): bf16 everywhere, the fp32-equivalent path for sites whose
+    window has N / IUPAC symbols or overhangs the chromosome.  The device-built site list equals a brute-force scan of the
+    windows; masked rows equal the fp32 path bit for bit, the others the bf16 path."""
     from mural_b200 import PackedSiteDataset, SiteTable
     from mural_b200.predict import predict_sites
     from test_gpu_snv_forward import build_model
@@ -175,8 +175,21 @@ def test_auto_mode_routes_exception_windows_to_fp32(kat, cuda_genome):
     assert (mask == brute).all() and 0 < mask.sum() < n
     m = build_model(cfg, state, int(z["n_cat"]))
     out = {}
-    for mode in ("fp32", "bf16", "auto_bf16"):
+    from mural_b200 import _lib
+    for mode in ("fp32", "bf16", "auto"):
         m.compute_mode = mode
         out[mode] = predict_sites(m, ds, 0, n).cpu().numpy()
-    assert np.array_equal(out["auto_bf16"][mask], out["fp32"][mask])
-    assert np.array_equal(out["auto_bf16"][~mask], out["bf16"][~mask])
+    # MURAL_MODE_AUTO builds the same site list on the device (k_exception_sites): per chromosome call, so count the last one
+    last_chrom = ds.chrom == ds.chrom[-1]
+    assert int(_lib.lib().mural_snv_last_auto_sites(m._h)) == int(mask[last_chrom].sum())
+    assert np.array_equal(out["auto"][mask], out["fp32"][mask])
+    assert np.array_equal(out["auto"][~mask], out["bf16"][~mask])
+    # the reference's tensor signature goes the same way (windows scanned for non-ACGT columns)
+    import torch
+    sel = np.r_[np.flatnonzero(mask)[:40], np.flatnonzero(~mask)[:40]]
+    pos = torch.from_numpy(ds.pos[sel]).cuda(); meta = torch.from_numpy(ds.meta[sel]).cuda()
+    cat = cuda_genome.encode_local(pos, meta, cfg["local_radius"], cfg["local_order"])
+    oh = cuda_genome.encode_onehot(pos, meta, R)
+    with torch.no_grad():
+        t = m.forward((None, cat), oh).cpu().numpy()
+    assert np.array_equal(t, out["auto"][sel])
