@@ -150,6 +150,16 @@ int mural_snv_set_debug(mural_snv_model_t* m, int32_t flags); /* bit0: keep taps
 int mural_snv_debug_tap(mural_snv_model_t* m, const char* name, float* h_out, int64_t max_floats,
                         int64_t* n_written);
 
+/* Parity hooks for the tensor-core conv kernels of the fp32-equivalent / training paths (snv_conv_mma.cu), C = 32, ks = 3:
+ * one BatchNorm(eval affine a, b) -> Conv1d(32,32,3,padding=1) layer of Network2 (model_snv.py:794-812) on device tensors
+ * in the [n*L, 32] row layout, and its weight gradient.  impl: 0 = fp32 FMA kernel, 1 = split-bf16 MMA (two levels),
+ * 2 = split-bf16 MMA (three levels, training).  Wt is [tap][ci][co]; dW is [co][ci][tap] (+=), dbias [co] (+=). */
+int mural_conv32_layer(const float* d_in, float* d_out, const float* d_res1, const float* d_res2, int64_t n, int32_t L,
+                       const float* d_Wt, const float* d_bias, const float* d_a, const float* d_b, int32_t relu_in,
+                       int32_t relu_out, int32_t impl, void* stream);
+int mural_conv32_wgrad(const float* d_x, const float* d_dy, int64_t n, int32_t L, int32_t relu_in, const float* d_a,
+                       const float* d_b, float* d_dW, float* d_dbias, int32_t impl, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * MuRaL-indel network (UNet_Small, MuRaL/model/model_indel.py:21-176), eval forward.
  * Window of a site: [start - R + 1, start + 1 + R), length 2R (extend_interval, preprocessing.py:559-567).

@@ -35,6 +35,8 @@ PROTOTYPES = {
     "mural_profile_end": (_i64, [C.c_char_p, _i64]),
     "mural_snv_tc_available": (C.c_int, [_vp]),
     "mural_snv_last_auto_sites": (_i64, [_vp]),
+    "mural_conv32_layer": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "mural_conv32_wgrad": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mural_genome_create": (C.c_int, [_i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.c_int, C.POINTER(_vp)]),
     "mural_genome_destroy": (None, [_vp]),
     "mural_genome_n_chrom": (_i32, [_vp]),

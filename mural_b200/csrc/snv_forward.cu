@@ -729,7 +729,12 @@ int conv_any(int C, const float* in, float* out, const float* r1, const float* r
                     const ConvLayerDev& P, int relu_out, cudaStream_t st) {
   switch (C) {
     case 16: return conv_launch<16>(in, out, r1, r2, n, L, P, relu_out, st);
-    case 32: return conv_launch<32>(in, out, r1, r2, n, L, P, relu_out, st);
+    case 32: {
+      // tensor-core conv at fp32-equivalent precision (snv_conv_mma.cu); MURAL_NO_CONV_MMA=1 keeps the fp32 FMA kernel (parity switch)
+      static const bool use_mma = getenv("MURAL_NO_CONV_MMA") == nullptr;
+      if (P.ks == 3 && use_mma) return conv32_mma(in, out, r1, r2, n, L, P, relu_out, st);
+      return conv_launch<32>(in, out, r1, r2, n, L, P, relu_out, st);
+    }
     case 64: return conv_launch<64>(in, out, r1, r2, n, L, P, relu_out, st);
   }
   MURAL_FAIL("unsupported channel count");
@@ -1087,6 +1092,19 @@ extern "C" int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, 
   if (mode == MURAL_MODE_BF16) return snv_forward_tc(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   if (mode == MURAL_MODE_AUTO) return snv_forward_auto(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   MURAL_FAIL("unknown compute mode");
+}
+
+extern "C" int mural_conv32_layer(const float* d_in, float* d_out, const float* d_res1, const float* d_res2, int64_t n, int32_t L,
+                                  const float* d_Wt, const float* d_bias, const float* d_a, const float* d_b, int32_t relu_in,
+                                  int32_t relu_out, int32_t impl, void* stream) {
+  MURAL_CHECK(d_in && d_out && d_Wt && d_bias && d_a && d_b && n > 0 && L > 0, "bad argument");
+  MURAL_CHECK(impl >= 0 && impl <= 2, "impl must be 0 (fp32 FMA), 1 (two-level split MMA) or 2 (three-level split MMA)");
+  ConvLayerDev P{d_Wt, d_bias, d_a, d_b, 3, relu_in, impl == 2 ? 1 : 0};
+  int rc = impl == 0 ? conv_launch<32>(d_in, d_out, d_res1, d_res2, n, L, P, relu_out, (cudaStream_t)stream)
+                     : conv32_mma(d_in, d_out, d_res1, d_res2, n, L, P, relu_out, (cudaStream_t)stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int64_t mural_snv_last_auto_sites(const mural_snv_model_t* m) { return m ? m->last_auto_sites : -1; }

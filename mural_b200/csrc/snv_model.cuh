@@ -24,6 +24,7 @@ struct ConvLayerDev {
   const float* b;     // [C] BN shift  beta - mean*a
   int ks;
   int relu_in;  // ReLU applied to the input before the BN affine (ResBlock convs)
+  int precise = 0;  // tensor-core conv (snv_conv_mma.cu): 0 = two-level bf16 split (~1e-5 per product), 1 = three-level (fp32-level; training)
 };
 
 struct BranchDev {
@@ -147,6 +148,10 @@ int snv_head_launch(mural_snv_model* m, const float* h_mid, const float* h_large
                     float* logp, float* tg0, float* tg1, float* tl0, float* tl1, cudaStream_t st);
 int conv_any(int C, const float* in, float* out, const float* r1, const float* r2, int64_t n, int L, const ConvLayerDev& P,
              int relu_out, cudaStream_t st);
+int conv32_mma(const float* in, float* out, const float* r1, const float* r2, int64_t n, int L, const ConvLayerDev& P, int relu_out,
+               cudaStream_t st);  // snv_conv_mma.cu: C == 32, ks == 3, split-bf16 mma.sync
+int wgrad32_mma(const float* x, const float* dy, int64_t rows, int L, int relu, const float* a, const float* b, float* G, int64_t w_off,
+                int64_t b_off, cudaStream_t st);  // snv_conv_mma.cu: weight gradient of a C == 32, ks == 3 layer
 int snv_ensure_workspace(mural_snv_model* m, int64_t bytes);
 int onehot_to_symbols_checked(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, int* d_flag, cudaStream_t st);
 int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,

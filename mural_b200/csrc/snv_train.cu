@@ -8,6 +8,7 @@
 // data-parallel exchange is a single all-reduce over grads[0 : n_trainable) and the optimizer is one kernel.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snv_model.cuh"
@@ -928,7 +929,7 @@ static int conv_train_fwd(mural_snv_train* T, float* P, int li, const float* x, 
   if (grid < 1) grid = 1;
   LAUNCH(k_stats, grid, thr, sizeof(double) * 2 * thr, st, x, rows, C, d.relu_in, stat);
   LAUNCH(k_bn_finalize, 1, 64, 0, st, stat, double(rows), C, P, d.g, d.be, d.rm, d.rv, bn, bn + C, bn + 2 * C, bn + 3 * C);
-  ConvLayerDev cl{T->d_Wt + int64_t(li) * 7 * C * C, P + d.b, bn, bn + C, d.ks, d.relu_in};
+  ConvLayerDev cl{T->d_Wt + int64_t(li) * 7 * C * C, P + d.b, bn, bn + C, d.ks, d.relu_in, 1};
   return conv_any(C, x, y, r1, r2, n, L, cl, relu_out, st);
 }
 
@@ -1031,8 +1032,12 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   double* stat = T->d_stat + (li / 10) * 256;
   const int64_t rows = n * L;
   const size_t smem = sizeof(float) * (size_t(64 + d.ks - 1) * (C + 4) + size_t(64) * (C + 4)) + sizeof(int) * 64;
+  static const bool use_mma = getenv("MURAL_NO_CONV_MMA") == nullptr && getenv("MURAL_NO_WGRAD_MMA") == nullptr;
   int wg = (int)cdiv(rows, 64);
   if (wg > 296) wg = 296;
+  if (C == 32 && d.ks == 3 && use_mma) {
+    if (int rc = wgrad32_mma(x, dy, rows, L, d.relu_in, bn, bn + C, G, d.w, d.b, st)) return rc;
+  } else
 #define WG(CC)                                                                                                  \
   case CC: {                                                                                                   \
     static size_t conf = 0;                                                                                    \
@@ -1044,7 +1049,7 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   } break;
   switch (C) { WG(16) WG(32) WG(64) default: MURAL_FAIL("unsupported channel count"); }
 #undef WG
-  ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0};
+  ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0, 1};
   if (int rc = conv_any(C, dy, du, nullptr, nullptr, n, L, cl, 0, st)) return rc;
   CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
   const int thr = 256, rpb = thr / C;
@@ -1141,6 +1146,24 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
   for (int i = 0; i < 2; ++i) {  // join: the caller's stream sees every gradient
     CUDA_TRY(cudaEventRecord(T->ev_join[i], T->side[i]));
     CUDA_TRY(cudaStreamWaitEvent(st, T->ev_join[i], 0));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mural_conv32_wgrad(const float* d_x, const float* d_dy, int64_t n, int32_t L, int32_t relu_in, const float* d_a,
+                                  const float* d_b, float* d_dW, float* d_dbias, int32_t impl, void* stream) {
+  MURAL_CHECK(d_x && d_dy && d_a && d_b && d_dW && d_dbias && n > 0 && L > 0, "bad argument");
+  MURAL_CHECK(d_dbias >= d_dW, "dbias must not precede dW (both are addressed as offsets from dW)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = n * L, b_off = d_dbias - d_dW;
+  if (impl) {
+    if (int rc = wgrad32_mma(d_x, d_dy, rows, L, relu_in, d_a, d_b, d_dW, 0, b_off, st)) return rc;
+  } else {
+    const size_t smem = sizeof(float) * (size_t(64 + 3 - 1) * (32 + 4) + size_t(64) * (32 + 4)) + sizeof(int) * 64;
+    int wg = (int)cdiv(rows, 64);
+    if (wg > 296) wg = 296;
+    LAUNCH(k_wgrad<32>, wg, 256, smem, st, d_x, d_dy, rows, L, 3, relu_in, d_a, d_b, d_dW, int64_t(0), b_off);
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
