@@ -732,7 +732,10 @@ int conv_any(int C, const float* in, float* out, const float* r1, const float* r
     case 32: {
       // tensor-core conv at fp32-equivalent precision (snv_conv_mma.cu); MURAL_NO_CONV_MMA=1 keeps the fp32 FMA kernel (parity switch)
       static const bool use_mma = getenv("MURAL_NO_CONV_MMA") == nullptr;
-      if (P.ks == 3 && use_mma) return conv32_mma(in, out, r1, r2, n, L, P, relu_out, st);
+      // P.precise (training forward): the fp32 FMA kernel — a third split level costs more mma.sync issue slots than 96 FMAs
+      // (measured 174 us vs 136 us per 549k rows, scratch/mb_conv_mma.py), and forward activations at fp32 precision keep
+      // ReLU-kink flips against an fp64 reference rare
+      if (P.ks == 3 && use_mma && !P.precise) return conv32_mma(in, out, r1, r2, n, L, P, relu_out, st);
       return conv_launch<32>(in, out, r1, r2, n, L, P, relu_out, st);
     }
     case 64: return conv_launch<64>(in, out, r1, r2, n, L, P, relu_out, st);

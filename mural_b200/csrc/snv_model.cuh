@@ -24,7 +24,7 @@ struct ConvLayerDev {
   const float* b;     // [C] BN shift  beta - mean*a
   int ks;
   int relu_in;  // ReLU applied to the input before the BN affine (ResBlock convs)
-  int precise = 0;  // tensor-core conv (snv_conv_mma.cu): 0 = two-level bf16 split (~1e-5 per product), 1 = three-level (fp32-level; training)
+  int precise = 0;  // 1: fp32-level products required (training forward) -> fp32 FMA kernel; 0: two-level bf16 split MMA (~1e-5 per product)
 };
 
 struct BranchDev {

@@ -1049,7 +1049,7 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   } break;
   switch (C) { WG(16) WG(32) WG(64) default: MURAL_FAIL("unsupported channel count"); }
 #undef WG
-  ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0, 1};
+  ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0, 0};  // dgrad: two-level split MMA
   if (int rc = conv_any(C, dy, du, nullptr, nullptr, n, L, cl, 0, st)) return rc;
   CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
   const int thr = 256, rpb = thr / C;
