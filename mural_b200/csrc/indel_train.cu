@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #define INDEL_TRAIN_LAUNCH(name, kernel, grid, block, stream, ...) LAUNCH_N(name, kernel, grid, block, 0, stream, __VA_ARGS__)
+#define INDEL_TRAIN_LAUNCH_SMEM(name, kernel, grid, block, smem, stream, ...) LAUNCH_N(name, kernel, grid, block, smem, stream, __VA_ARGS__)
 #include "indel_train_engine.cuh"
 
 using namespace mural;
@@ -46,7 +47,7 @@ extern "C" int mural_indel_train_create(mural_indel_model_t* m, mural_indel_trai
 extern "C" void mural_indel_train_destroy(mural_indel_train_t* T) {
   if (!T) return;
   indel_train::Engine& E = T->E;
-  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat);
+  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.dxv); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat);
   delete T;
 }
 

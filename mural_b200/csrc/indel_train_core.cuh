@@ -30,6 +30,7 @@
 namespace indel_train {
 
 // ------------------------------------------------------------------------------------------------ execution layer
+struct ConvFwd; struct ConvBwdX; struct ConvBwdW; struct MaxL;
 #ifdef __CUDACC__
 template <class F>
 __global__ void __launch_bounds__(256) k_run(int64_t n, F f) {
@@ -48,6 +49,11 @@ struct Exec {
   void* alloc(size_t b) { void* p = nullptr; cudaMalloc(&p, b); return p; }
   void free_(void* p) { cudaFree(p); }
   void zero(void* p, size_t b) { cudaMemsetAsync(p, 0, b, st); }
+  // shared-memory-tiled fast paths (indel_train_tiled.cuh); false = not applicable, the caller runs the functor
+  bool conv_fwd(const ConvFwd& f);
+  bool conv_bwd_x(const ConvBwdX& f, float* scratch);
+  bool conv_bwd_w(const ConvBwdW& f);
+  bool max_rows(const MaxL& f, int64_t rows);
 };
 template <class T> HD void atomic_add(T* p, T v) {
 #ifdef __CUDA_ARCH__
@@ -63,6 +69,10 @@ struct Exec {
   void* alloc(size_t b) { return calloc(b ? b : 1, 1); }
   void free_(void* p) { free(p); }
   void zero(void* p, size_t b) { memset(p, 0, b); }
+  bool conv_fwd(const ConvFwd&) { return false; }
+  bool conv_bwd_x(const ConvBwdX&, float*) { return false; }
+  bool conv_bwd_w(const ConvBwdW&) { return false; }
+  bool max_rows(const MaxL&, int64_t) { return false; }
 };
 template <class T> inline void atomic_add(T* p, T v) { *p += v; }
 #endif
@@ -252,6 +262,14 @@ struct AddFlipL {
 struct AddFlipLBwd {
   static constexpr const char* kName = "k_indel_train<AddFlipLBwd>"; const float* d_o; float* da; float* db; int L;
   HD void operator()(int64_t i) const { const int l = int(i % L); da[i] += d_o[i]; db[i - l + (L - 1 - l)] += d_o[i]; } };
+struct UpReduce {
+  static constexpr const char* kName = "k_indel_train<UpReduce>";  // item: input element (b, ci, jin); dx += sum of the `up` virtual positions it was repeated to
+  const float* dxv; float* dx; int up;
+  HD void operator()(int64_t i) const {
+    float s = 0.f;
+    for (int u = 0; u < up; ++u) s += dxv[i * up + u];
+    dx[i] += s;
+  } };
 struct MaxL {
   static constexpr const char* kName = "k_indel_train<MaxL>"; const float* x; float* y; int32_t* arg; int L;  // item: row (b, c)
   HD void operator()(int64_t r) const {
@@ -275,3 +293,81 @@ struct CeGrad {
   } };
 
 }  // namespace indel_train
+
+#ifdef __CUDACC__
+#include "indel_train_tiled.cuh"
+namespace indel_train {
+#ifndef INDEL_TRAIN_LAUNCH_SMEM
+#define INDEL_TRAIN_LAUNCH_SMEM(name, kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+namespace tiled {
+inline bool tileable(const ConvDims& d) {
+  return d.stride == 1 && d.Lout >= 256 && (d.k == 1 || d.k == 5 || d.k == 7) && d.pad == (d.k - 1) / 2 && d.Lout == d.Lin * d.up;
+}
+template <int K> inline bool launch_conv(const ConvT& a, int B, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t(a.Cin) * XS + size_t(a.Cin) * K * 8);
+  if (smem > 200 * 1024) return false;
+  static size_t conf = 0;
+  if (smem > 48 * 1024 && smem > conf) {
+    if (cudaFuncSetAttribute(k_conv_tiled<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    conf = smem;
+  }
+  dim3 grid((unsigned)((a.Lout + TL - 1) / TL), (unsigned)B);
+  INDEL_TRAIN_LAUNCH_SMEM("k_indel_conv_tiled", (k_conv_tiled<K>), grid, 128, smem, st, a);
+  return true;
+}
+inline bool run_conv(const ConvT& a, int K, int B, cudaStream_t st) {
+  return K == 7 ? launch_conv<7>(a, B, st) : (K == 5 ? launch_conv<5>(a, B, st) : launch_conv<1>(a, B, st));
+}
+template <int K> inline bool launch_wgrad(WgradT a, int B, cudaStream_t st) {
+  a.RS = (TL + K - 1) | 1;
+  const size_t smem = sizeof(float) * size_t(a.Cin + a.Cout) * a.RS;
+  if (smem > 200 * 1024 || a.Cin * a.Cout > 256 * 8) return false;
+  static size_t conf = 0;
+  if (smem > 48 * 1024 && smem > conf) {
+    if (cudaFuncSetAttribute(k_wgrad_tiled<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    conf = smem;
+  }
+  int G = 296 / (B > 0 ? B : 1);
+  if (G < 1) G = 1;
+  if (G > a.n_tiles) G = a.n_tiles;
+  dim3 grid((unsigned)G, (unsigned)B);
+  INDEL_TRAIN_LAUNCH_SMEM("k_indel_wgrad_tiled", (k_wgrad_tiled<K>), grid, 256, smem, st, a);
+  return true;
+}
+}  // namespace tiled
+
+inline bool Exec::conv_fwd(const ConvFwd& f) {
+  const ConvDims& d = f.d;
+  if (!tiled::tileable(d)) return false;
+  tiled::ConvT a{f.x, f.W, f.bias, f.y, d.Cin, d.Lin, d.Cout, d.Lout, d.pad, d.up, d.Cin * d.k, d.k, 0, 0};
+  if (!tiled::run_conv(a, d.k, d.B, st)) return false;
+  ++launches;
+  return true;
+}
+inline bool Exec::conv_bwd_x(const ConvBwdX& f, float* scratch) {
+  const ConvDims& d = f.d;
+  if (!tiled::tileable(d) || (d.up > 1 && !scratch)) return false;
+  // correlation over dy with the channel axes swapped and the taps flipped; with an upsample in front the result is the
+  // gradient of the virtual upsampled input (scratch), folded back by UpReduce
+  tiled::ConvT a{f.dy, f.W, nullptr, d.up == 1 ? f.dx : scratch, d.Cout, d.Lout, d.Cin, d.Lout, d.pad, 1, d.k, d.Cin * d.k, 1, d.up == 1 ? 1 : 0};
+  if (!tiled::run_conv(a, d.k, d.B, st)) return false;
+  ++launches;
+  if (d.up > 1) run(int64_t(d.B) * d.Cin * d.Lin, UpReduce{scratch, f.dx, d.up});
+  return true;
+}
+inline bool Exec::conv_bwd_w(const ConvBwdW& f) {
+  const ConvDims& d = f.d;
+  if (!tiled::tileable(d)) return false;
+  tiled::WgradT a{f.x, f.dy, f.dW, f.db, d.Cin, d.Lin, d.Cout, d.Lout, d.pad, d.up, (d.Lout + tiled::TL - 1) / tiled::TL, 0};
+  const bool ok = d.k == 7 ? tiled::launch_wgrad<7>(a, d.B, st) : (d.k == 5 ? tiled::launch_wgrad<5>(a, d.B, st) : tiled::launch_wgrad<1>(a, d.B, st));
+  if (ok) ++launches;
+  return ok;
+}
+inline bool Exec::max_rows(const MaxL& f, int64_t rows) {
+  INDEL_TRAIN_LAUNCH_SMEM("k_indel_max_rows", tiled::k_max_rows, (unsigned)((rows + 7) / 8), 256, 0, st, f.x, f.y, f.arg, rows, f.L);
+  ++launches;
+  return true;
+}
+}  // namespace indel_train
+#endif

@@ -30,7 +30,7 @@ struct Engine {
   // buffers (device or host, see Exec)
   Exec ex;
   int64_t cap = 0;
-  float *vals = nullptr, *grads = nullptr, *dz = nullptr, *stats = nullptr;
+  float *vals = nullptr, *grads = nullptr, *dz = nullptr, *dxv = nullptr, *stats = nullptr;
   int32_t* arg = nullptr;
   double* dstat = nullptr;
   uint64_t seed = 0;
@@ -104,10 +104,11 @@ struct Engine {
 
   void ensure(int64_t B) {
     if (B <= cap) return;
-    ex.free_(vals); ex.free_(grads); ex.free_(dz); ex.free_(stats); ex.free_(arg); ex.free_(dstat);
+    ex.free_(vals); ex.free_(grads); ex.free_(dz); ex.free_(dxv); ex.free_(stats); ex.free_(arg); ex.free_(dstat);
     vals = (float*)ex.alloc(sizeof(float) * per_site * B);
     grads = (float*)ex.alloc(sizeof(float) * per_site * B);
     dz = (float*)ex.alloc(sizeof(float) * max_per_site * B);
+    dxv = (float*)ex.alloc(sizeof(float) * max_per_site * B);   // gradient of an upsampled input before it is folded back (tiled path)
     stats = (float*)ex.alloc(sizeof(float) * (n_stat + 1));
     arg = (int32_t*)ex.alloc(sizeof(int32_t) * cfg.channels * 6 * B);
     dstat = (double*)ex.alloc(sizeof(double) * 2 * 1024);
@@ -143,13 +144,15 @@ struct Engine {
         ex.run(B * t.C * t.L, AddFlipL{V(op.a, B), V(op.b, B), V(op.o, B), t.L});
       } else if (op.kind == OP_MAXL) {
         const Tensor t = tensors[op.a];
-        ex.run(B * t.C, MaxL{V(op.a, B), V(op.o, B), arg, t.L});
+        const MaxL f{V(op.a, B), V(op.o, B), arg, t.L};
+        if (!ex.max_rows(f, B * t.C)) ex.run(B * t.C, f);
       } else {
         const Unit& u = units[op.unit];
         const Tensor tt = tensors[u.t];
         if (u.has_conv) {
           const ConvDims d = dims(u, B);
-          ex.run(B * d.Cout * d.Lout, ConvFwd{V(u.in, B), P + u.W, u.b >= 0 ? P + u.b : nullptr, V(u.t, B), d});
+          const ConvFwd f{V(u.in, B), P + u.W, u.b >= 0 ? P + u.b : nullptr, V(u.t, B), d};
+          if (!ex.conv_fwd(f)) ex.run(B * d.Cout * d.Lout, f);
         }
         if (u.has_bn) {
           ex.zero(dstat, sizeof(double) * 2 * tt.C);
@@ -190,8 +193,12 @@ struct Engine {
         }
         if (u.has_conv) {
           const ConvDims d = dims(u, B);
-          ex.run(int64_t(d.Cout) * d.Cin * d.k * B * CONV_W_SPLIT, ConvBwdW{V(u.in, B), dz, Gp + u.W, u.b >= 0 ? Gp + u.b : nullptr, d});
-          if (u.in != t_in) ex.run(B * d.Cin * d.Lin, ConvBwdX{dz, P + u.W, G(u.in, B), d});
+          const ConvBwdW fw{V(u.in, B), dz, Gp + u.W, u.b >= 0 ? Gp + u.b : nullptr, d};
+          if (!ex.conv_bwd_w(fw)) ex.run(int64_t(d.Cout) * d.Cin * d.k * B * CONV_W_SPLIT, fw);
+          if (u.in != t_in) {
+            const ConvBwdX fx{dz, P + u.W, G(u.in, B), d};
+            if (!ex.conv_bwd_x(fx, dxv)) ex.run(B * d.Cin * d.Lin, fx);
+          }
         } else {
           ex.run(n, AddTo{dz, G(u.in, B)});
         }

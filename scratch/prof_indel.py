@@ -31,3 +31,27 @@ tot = sum(v["ms"] for v in prof.values()); nl = sum(v["count"] for v in prof.val
 print("%d launches, %.3f ms per 2048-site batch" % (nl, tot))
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]:
     print("   %-44s n=%4d  %8.3f ms" % (k[:44], v["count"], v["ms"]))
+
+# ---- training step (batch 32)
+from mural_b200.training import IndelTrainState
+m.train()
+ts = IndelTrainState(m, 4000, "Adam", lr=1e-4, weight_decay=1e-5, seed=0)
+B = 32
+rng = np.random.default_rng(1)
+lab = rng.choice(8, size=B * 4, p=[0.907] + [0.093 / 7] * 7)
+pos = torch.from_numpy((20000 + 50 * np.arange(B * 4)).astype(np.int32)).cuda()
+meta = torch.from_numpy(pack_meta(np.zeros(B * 4, np.int64), lab, np.zeros(B * 4, np.int64))).cuda()
+for i in range(2):
+    ts.step(SiteBatch(pos[i * B:(i + 1) * B], meta[i * B:(i + 1) * B], genome))
+torch.cuda.synchronize()
+L.mural_profile_begin()
+for i in range(2, 4):
+    ts.step(SiteBatch(pos[i * B:(i + 1) * B], meta[i * B:(i + 1) * B], genome))
+torch.cuda.synchronize()
+buf = C.create_string_buffer(1 << 16)
+L.mural_profile_end(buf, len(buf))
+prof = json.loads(buf.value.decode())
+tot = sum(v["ms"] for v in prof.values()); nl = sum(v["count"] for v in prof.values())
+print("TRAIN: %d launches / 2 steps, %.3f ms kernel time per batch-32 step" % (nl, tot / 2))
+for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]:
+    print("   %-44s n=%4d  %8.3f ms/step" % (k[:44], v["count"] // 2, v["ms"] / 2))

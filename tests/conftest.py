@@ -36,8 +36,13 @@ def load_snv_golden(tag):
     return z, cfg, state
 
 
-SNV_TAGS = ["hs_AT", "hs_CpG", "hs_nonCpG", "mm_AT", "dm_CG", "at_AT", "ex_ckpt6"]
-INDEL_TAGS = ["hs_ins", "hs_del_start", "ex_indel9"]
+# every checkpoint shipped under /root/reference/models (11 MuRaL-snv, 12 MuRaL-indel) plus the two example checkpoints
+# (oracle/make_golden.py wrote the first group of each list, oracle/make_golden_all.py the rest)
+SNV_TAGS = ["hs_AT", "hs_CpG", "hs_nonCpG", "mm_AT", "dm_CG", "at_AT", "ex_ckpt6",
+            "at_CpG", "at_nonCpG", "dm_AT", "mm_CpG", "mm_nonCpG"]
+INDEL_TAGS = ["hs_ins", "hs_del_start", "ex_indel9",
+              "hs_del_end", "at_ins", "at_del_start", "at_del_end", "dm_ins", "dm_del_start", "dm_del_end", "mm_ins", "mm_del_start",
+              "mm_del_end"]
 
 
 @pytest.fixture(scope="session")

@@ -76,7 +76,8 @@ def test_network2_oracle_matches_reference_logits(kat, tag, manifest):
         taps = {}
         lp = NT.network2_forward(state, cat, oh, torch.float32, taps=taps).numpy()
     assert np.abs(lp - z["ref_logp"]).max() < 2e-5        # fp32 CPU vs the reference module's fp32 CPU
-    assert np.abs(taps["pool1_2"].numpy()[:16] - z["tap_pool1_2"]).max() < 1e-5
+    if "tap_pool1_2" in z.files:                           # intermediate taps are stored for the first group of fixtures only
+        assert np.abs(taps["pool1_2"].numpy()[:16] - z["tap_pool1_2"]).max() < 1e-5
     # calibrator apply restatement vs the fixture computed at generation time
     prob = torch.softmax(torch.from_numpy(z["ref_logp"]), 1).numpy()
     assert np.allclose(NT.dirichlet_apply(z["cal_weights"], prob), z["cal_prob"], rtol=0, atol=1e-12)
