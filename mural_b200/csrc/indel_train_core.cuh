@@ -54,6 +54,7 @@ struct Exec {
   bool conv_bwd_x(const ConvBwdX& f, float* scratch);
   bool conv_bwd_w(const ConvBwdW& f);
   bool max_rows(const MaxL& f, int64_t rows);
+  template <class F> bool row_reduce(const F& f, int64_t rows, double* stat);   // BnStats / UnitBwdReduce: one CTA (or warp) per row
 };
 template <class T> HD void atomic_add(T* p, T v) {
 #ifdef __CUDA_ARCH__
@@ -73,6 +74,7 @@ struct Exec {
   bool conv_bwd_x(const ConvBwdX&, float*) { return false; }
   bool conv_bwd_w(const ConvBwdW&) { return false; }
   bool max_rows(const MaxL&, int64_t) { return false; }
+  template <class F> bool row_reduce(const F&, int64_t, double*) { return false; }
 };
 template <class T> inline void atomic_add(T* p, T v) { *p += v; }
 #endif
@@ -175,13 +177,16 @@ struct BnStats {
   static constexpr const char* kName = "k_indel_train<BnStats>";
   // item: (row (b, c), s); stat[c] += sum, stat[C + c] += sum of squares (double)
   const float* x; double* stat; int C, L;
+  HD int channels() const { return C; }
+  HD int length() const { return L; }
+  HD bool reduces() const { return true; }
+  HD void at(int64_t row, int l, double& s, double& q) const { const float v = x[row * L + l]; s += v; q += double(v) * v; }
   HD void operator()(int64_t i) const {
     const int64_t row = i / ROW_SPLIT;
     const int s0 = int(i % ROW_SPLIT), c = int(row % C);
     if (s0 >= L) return;
-    const float* r = x + row * L;
     double s = 0, q = 0;
-    for (int l = s0; l < L; l += ROW_SPLIT) { s += r[l]; q += double(r[l]) * r[l]; }
+    for (int l = s0; l < L; l += ROW_SPLIT) at(row, l, s, q);
     atomic_add(stat + c, s);
     atomic_add(stat + C + c, q);
   }
@@ -220,17 +225,22 @@ struct UnitBwdReduce {
   static constexpr const char* kName = "k_indel_train<UnitBwdReduce>";
   // item: (row (b, c), s); dz = dy * drop * act'(z); s1 = sum dz, s2 = sum dz * xhat; also stores dz
   UnitOut u; const float* dy; float* dz; double* stat;
+  HD int channels() const { return u.C; }
+  HD int length() const { return u.L; }
+  HD bool reduces() const { return u.gamma != nullptr; }
+  HD void at(int64_t row, int l, double& s1, double& s2) const {
+    const int c = int(row % u.C);
+    const int64_t i = row * u.L + l;
+    const float g = dy[i] * drop_scale(u.p, u.seed, u.step, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
+    dz[i] = g;
+    if (u.gamma) { s1 += g; s2 += double(g) * ((u.t[i] - u.mean[c]) * u.invstd[c]); }
+  }
   HD void operator()(int64_t it) const {
     const int64_t row = it / ROW_SPLIT;
     const int s0 = int(it % ROW_SPLIT), c = int(row % u.C);
     if (s0 >= u.L) return;
     double s1 = 0, s2 = 0;
-    for (int l = s0; l < u.L; l += ROW_SPLIT) {
-      const int64_t i = row * u.L + l;
-      const float g = dy[i] * drop_scale(u.p, u.seed, u.step, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
-      dz[i] = g;
-      if (u.gamma) { s1 += g; s2 += double(g) * ((u.t[i] - u.mean[c]) * u.invstd[c]); }
-    }
+    for (int l = s0; l < u.L; l += ROW_SPLIT) at(row, l, s1, s2);
     if (u.gamma) { atomic_add(stat + c, s1); atomic_add(stat + u.C + c, s2); }
   }
 };
@@ -316,13 +326,28 @@ template <int K> inline bool launch_conv(const ConvT& a, int B, cudaStream_t st)
   INDEL_TRAIN_LAUNCH_SMEM("k_indel_conv_tiled", (k_conv_tiled<K>), grid, 128, smem, st, a);
   return true;
 }
+template <int K> inline bool launch_conv_strided(const ConvT& a, int stride, int B, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t(a.Cin) * ((TLS - 1) * stride + K) + size_t(a.Cin) * K * 8);
+  if (smem > 200 * 1024) return false;
+  static size_t conf = 0;
+  if (smem > 48 * 1024 && smem > conf) {
+    if (cudaFuncSetAttribute(k_conv_strided<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    conf = smem;
+  }
+  dim3 grid((unsigned)((a.Lout + TLS - 1) / TLS), (unsigned)B);
+  INDEL_TRAIN_LAUNCH_SMEM("k_indel_conv_strided", (k_conv_strided<K>), grid, 128, smem, st, a, stride);
+  return true;
+}
 inline bool run_conv(const ConvT& a, int K, int B, cudaStream_t st) {
   return K == 7 ? launch_conv<7>(a, B, st) : (K == 5 ? launch_conv<5>(a, B, st) : launch_conv<1>(a, B, st));
 }
 template <int K> inline bool launch_wgrad(WgradT a, int B, cudaStream_t st) {
-  a.RS = (TL + K - 1) | 1;
-  const size_t smem = sizeof(float) * size_t(a.Cin + a.Cout) * a.RS;
-  if (smem > 200 * 1024 || a.Cin * a.Cout > 256 * 8) return false;
+  a.TLe = a.Lout < TL ? a.Lout : TL;
+  a.n_tiles = (a.Lout + a.TLe - 1) / a.TLe;
+  a.RSx = ((a.TLe - 1) * a.stride + K) | 1;
+  a.RSd = a.TLe | 1;
+  const size_t smem = sizeof(float) * (size_t(a.Cin) * a.RSx + size_t(a.Cout) * a.RSd);
+  if (smem > 200 * 1024 || (a.Cin * a.Cout > 256 * 8 && a.n_tiles > 1)) return false;   // pair batches re-stage the tile: short rows only
   static size_t conf = 0;
   if (smem > 48 * 1024 && smem > conf) {
     if (cudaFuncSetAttribute(k_wgrad_tiled<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
@@ -339,14 +364,27 @@ template <int K> inline bool launch_wgrad(WgradT a, int B, cudaStream_t st) {
 
 inline bool Exec::conv_fwd(const ConvFwd& f) {
   const ConvDims& d = f.d;
-  if (!tiled::tileable(d)) return false;
   tiled::ConvT a{f.x, f.W, f.bias, f.y, d.Cin, d.Lin, d.Cout, d.Lout, d.pad, d.up, d.Cin * d.k, d.k, 0, 0};
-  if (!tiled::run_conv(a, d.k, d.B, st)) return false;
-  ++launches;
-  return true;
+  bool ok = false;
+  if (tiled::tileable(d)) ok = tiled::run_conv(a, d.k, d.B, st);
+  else if ((d.k == 1 || d.k == 5 || d.k == 7) && d.pad == (d.k - 1) / 2)       // strided / short rows
+    ok = d.k == 7 ? tiled::launch_conv_strided<7>(a, d.stride, d.B, st)
+                  : (d.k == 5 ? tiled::launch_conv_strided<5>(a, d.stride, d.B, st) : tiled::launch_conv_strided<1>(a, d.stride, d.B, st));
+  if (ok) ++launches;
+  return ok;
 }
 inline bool Exec::conv_bwd_x(const ConvBwdX& f, float* scratch) {
   const ConvDims& d = f.d;
+  if (d.stride == 1 && d.Lout < 256 && d.Lout == d.Lin * d.up && (d.k == 1 || d.k == 5 || d.k == 7) && d.pad == (d.k - 1) / 2 &&
+      (d.up == 1 || scratch)) {   // short rows (the deep levels): the generic tile kernel on the transposed / flipped weights
+    tiled::ConvT a{f.dy, f.W, nullptr, d.up == 1 ? f.dx : scratch, d.Cout, d.Lout, d.Cin, d.Lout, d.pad, 1, d.k, d.Cin * d.k, 1, d.up == 1 ? 1 : 0};
+    const bool ok = d.k == 7 ? tiled::launch_conv_strided<7>(a, 1, d.B, st)
+                             : (d.k == 5 ? tiled::launch_conv_strided<5>(a, 1, d.B, st) : tiled::launch_conv_strided<1>(a, 1, d.B, st));
+    if (!ok) return false;
+    ++launches;
+    if (d.up > 1) run(int64_t(d.B) * d.Cin * d.Lin, UpReduce{scratch, f.dx, d.up});
+    return true;
+  }
   if (!tiled::tileable(d) || (d.up > 1 && !scratch)) return false;
   // correlation over dy with the channel axes swapped and the taps flipped; with an upsample in front the result is the
   // gradient of the virtual upsampled input (scratch), folded back by UpReduce
@@ -358,11 +396,56 @@ inline bool Exec::conv_bwd_x(const ConvBwdX& f, float* scratch) {
 }
 inline bool Exec::conv_bwd_w(const ConvBwdW& f) {
   const ConvDims& d = f.d;
-  if (!tiled::tileable(d)) return false;
-  tiled::WgradT a{f.x, f.dy, f.dW, f.db, d.Cin, d.Lin, d.Cout, d.Lout, d.pad, d.up, (d.Lout + tiled::TL - 1) / tiled::TL, 0};
+  if (!(d.k == 1 || d.k == 5 || d.k == 7) || d.pad != (d.k - 1) / 2 || d.Lout < 1) return false;   // any stride, any length
+  tiled::WgradT a{f.x, f.dy, f.dW, f.db, d.Cin, d.Lin, d.Cout, d.Lout, d.pad, d.up, d.stride, 0, 0, 0, 0};
   const bool ok = d.k == 7 ? tiled::launch_wgrad<7>(a, d.B, st) : (d.k == 5 ? tiled::launch_wgrad<5>(a, d.B, st) : tiled::launch_wgrad<1>(a, d.B, st));
   if (ok) ++launches;
   return ok;
+}
+// per-row sums of a BatchNorm pass: threads of a row walk it coalesced, the row's two sums are reduced by shuffles (+ shared
+// memory across warps) and leave as ONE pair of double atomics per row — the work-item form issues 64 pairs per row onto
+// 2*C addresses, which serialises (2.5 ms per step at batch 32)
+template <class F, int TPR>
+__global__ void __launch_bounds__(256) k_row_reduce(F f, int64_t rows, double* stat) {
+  constexpr int RPB = 256 / TPR;   // rows per block
+  __shared__ double sh[2][8];
+  const int sub = threadIdx.x / TPR, lt = threadIdx.x % TPR;
+  const int L = f.length(), C = f.channels();
+  for (int64_t row0 = int64_t(blockIdx.x) * RPB; row0 < rows; row0 += int64_t(gridDim.x) * RPB) {
+    const int64_t row = row0 + sub;
+    double s = 0, q = 0;
+    if (row < rows)
+      for (int l = lt; l < L; l += TPR) f.at(row, l, s, q);
+    if (!f.reduces()) continue;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (TPR == 32) {
+      if (lt == 0 && row < rows) { atomicAdd(stat + int(row % C), s); atomicAdd(stat + C + int(row % C), q); }
+    } else {
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+      __syncthreads();
+      if (threadIdx.x == 0 && row < rows) {
+        double ts = 0, tq = 0;
+        for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+        atomicAdd(stat + int(row % C), ts);
+        atomicAdd(stat + C + int(row % C), tq);
+      }
+    }
+  }
+}
+template <class F> inline bool Exec::row_reduce(const F& f, int64_t rows, double* stat) {
+  if (rows <= 0) return true;
+  if (f.length() > 256) {
+    const int64_t g = rows < 148 * 8 ? rows : 148 * 8;
+    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 256>), (unsigned)g, 256, 0, st, f, rows, stat);
+  } else {
+    int64_t g = (rows + 7) / 8;
+    if (g > 148 * 8) g = 148 * 8;
+    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 32>), (unsigned)g, 256, 0, st, f, rows, stat);
+  }
+  ++launches;
+  return true;
 }
 inline bool Exec::max_rows(const MaxL& f, int64_t rows) {
   INDEL_TRAIN_LAUNCH_SMEM("k_indel_max_rows", tiled::k_max_rows, (unsigned)((rows + 7) / 8), 256, 0, st, f.x, f.y, f.arg, rows, f.L);

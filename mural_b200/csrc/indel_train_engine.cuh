@@ -156,7 +156,8 @@ struct Engine {
         }
         if (u.has_bn) {
           ex.zero(dstat, sizeof(double) * 2 * tt.C);
-          ex.run(B * tt.C * ROW_SPLIT, BnStats{V(u.t, B), dstat, tt.C, tt.L});
+          const BnStats fs{V(u.t, B), dstat, tt.C, tt.L};
+          if (!ex.row_reduce(fs, B * tt.C, dstat)) ex.run(B * tt.C * ROW_SPLIT, fs);
           ex.run(tt.C, BnFinalize{dstat, double(B) * tt.L, tt.C, P + u.rm, P + u.rv, stats + u.stat_slot, stats + u.stat_slot + tt.C});
         }
         ex.run(B * tt.C * tt.L, unit_out(u, P, B));
@@ -186,7 +187,8 @@ struct Engine {
         if (u.res2 >= 0) ex.run(n, AddTo{G(u.out, B), G(u.res2, B)});
         const UnitOut uo = unit_out(u, P, B);
         ex.zero(dstat, sizeof(double) * 2 * tt.C);
-        ex.run(B * tt.C * ROW_SPLIT, UnitBwdReduce{uo, G(u.out, B), dz, dstat});
+        const UnitBwdReduce fr{uo, G(u.out, B), dz, dstat};
+        if (!ex.row_reduce(fr, B * tt.C, dstat)) ex.run(B * tt.C * ROW_SPLIT, fr);
         if (u.has_bn) {
           ex.run(tt.C, BnParamGrad{dstat, tt.C, Gp + u.gamma, Gp + u.beta});
           ex.run(n, UnitBwdApply{uo, dz, dstat, double(B) * tt.L});

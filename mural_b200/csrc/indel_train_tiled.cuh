@@ -11,7 +11,7 @@
 //     CTA = (512-position tile, sample), thread = 4 consecutive positions x 8 output channels at a time; per input channel a
 //     thread loads its 12-float window as three aligned LDS.128 and the 8 x K weights as broadcast LDS.128: 17 shared loads
 //     feed 224 FMAs at K = 7.
-//   k_wgrad_tiled<K>  dW[o][i][t] += sum_b sum_p dy[b][o][p] * xv[b][i][p + t - pad],  db[o] += sum dy
+//   k_wgrad_tiled<K>  dW[o][i][t] += sum_b sum_p dy[b][o][p] * xv[b][i][p*stride + t - pad],  db[o] += sum dy   (any stride / length)
 //     CTA = (group of 512-position tiles, sample); thread = one (o, i) pair (x a slice of the tile when there are fewer than
 //     256 pairs) holding its K accumulators in registers over all tiles of the CTA; one atomicAdd per element and CTA.
 #pragma once
@@ -91,20 +91,81 @@ __global__ void __launch_bounds__(128) k_conv_tiled(ConvT a) {
   }
 }
 
+// Strided encoder convs (stride 4 / 5 / 5 / 5 / 2; < 5 % of the FLOPs) and short rows: same tile structure, a thread takes the
+// output positions tid, tid + 128, ... of the tile and reads its taps straight from the shared tile.
+constexpr int TLS = 256;   // output positions per tile
+template <int K>
+__global__ void __launch_bounds__(128) k_conv_strided(ConvT a, int stride) {
+  extern __shared__ __align__(16) float sm[];
+  const int XR = (TLS - 1) * stride + K;
+  float* xs = sm;                              // [Cin][XR]: index q <-> virtual position p0*stride + q - pad
+  float* ws = sm + size_t(a.Cin) * XR;         // [Cin][K][8]
+  const int tid = threadIdx.x, b = blockIdx.y, p0 = blockIdx.x * TLS;
+  const int Lv = a.Lin * a.up;
+  const float* xb = a.x + int64_t(b) * a.Cin * a.Lin;
+  for (int e = tid; e < a.Cin * XR; e += 128) {
+    const int i = e / XR, q = e - i * XR;
+    const int j = p0 * stride + q - a.pad;
+    xs[e] = (j >= 0 && j < Lv) ? xb[int64_t(i) * a.Lin + (a.up == 1 ? j : j / a.up)] : 0.f;
+  }
+  for (int o0 = 0; o0 < a.Cout; o0 += 8) {
+    __syncthreads();
+    for (int e = tid; e < a.Cin * K * 8; e += 128) {
+      const int c = e & 7, t = (e >> 3) % K, i = e / (8 * K);
+      ws[e] = (o0 + c < a.Cout) ? a.W[int64_t(o0 + c) * a.so + int64_t(i) * a.si + (a.flip ? K - 1 - t : t)] : 0.f;
+    }
+    __syncthreads();
+    float acc[2][8];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[p][c] = 0.f;
+    for (int i = 0; i < a.Cin; ++i) {
+      const float* xr = xs + i * XR;
+      const float4* wr = reinterpret_cast<const float4*>(ws + i * K * 8);
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const float4 w0 = wr[2 * t], w1 = wr[2 * t + 1];
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const float xv = xr[(tid + 128 * p) * stride + t];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int o = o0 + c;
+      if (o >= a.Cout) break;
+      const float bv = a.bias ? a.bias[o] : 0.f;
+      float* yr = a.y + (int64_t(b) * a.Cout + o) * a.Lout;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int pos = p0 + tid + 128 * p;
+        if (pos < a.Lout) yr[pos] = (a.accumulate ? yr[pos] : 0.f) + acc[p][c] + bv;
+      }
+    }
+  }
+}
+
 struct WgradT {
   const float* x; const float* dy; float* dW; float* db;
-  int Cin, Lin, Cout, Lout, pad, up, n_tiles, RS;   // RS: odd row stride of the shared tiles (>= TL + K - 1)
+  int Cin, Lin, Cout, Lout, pad, up, stride, n_tiles;
+  int TLe, RSx, RSd;   // positions per tile (min(TL, Lout)); odd row strides of the shared x / dy tiles
 };
 
 template <int K>
 __global__ void __launch_bounds__(256) k_wgrad_tiled(WgradT a) {
   extern __shared__ __align__(16) float sm[];
-  float* xs = sm;                                  // [Cin][RS]: index q <-> virtual position p0 + q - pad
-  float* ds = sm + size_t(a.Cin) * a.RS;           // [Cout][RS]
+  float* xs = sm;                                  // [Cin][RSx]: index q <-> virtual position p0*stride + q - pad
+  float* ds = sm + size_t(a.Cin) * a.RSx;          // [Cout][RSd]
+  const int TLe = a.TLe, XR = (TLe - 1) * a.stride + K;
   const int tid = threadIdx.x, b = blockIdx.y;
   const int pairs = a.Cin * a.Cout;
   const int slices = pairs >= 256 ? 1 : 256 / pairs;
-  const int chunk = (TL + slices - 1) / slices;
+  const int chunk = (TLe + slices - 1) / slices;
   const int Lv = a.Lin * a.up;
   const float* xb = a.x + int64_t(b) * a.Cin * a.Lin;
   const float* db_ = a.dy + int64_t(b) * a.Cout * a.Lout;
@@ -120,48 +181,53 @@ __global__ void __launch_bounds__(256) k_wgrad_tiled(WgradT a) {
   }
   const int my_slice = slices == 1 ? 0 : tid / pairs;
   const bool active = slices == 1 || my_slice < slices;
+  // more than 256*MAXP pairs (the two deepest levels, rows of 8-16 positions): batches of pairs, each re-staging its (tiny) tiles
+  for (int pbase = 0; pbase < pairs; pbase += 256 * MAXP) {
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int p0 = tile * TL;
+    const int p0 = tile * TLe;
     __syncthreads();
-    for (int e = tid; e < a.Cin * (TL + K - 1); e += 256) {
-      const int i = e / (TL + K - 1), q = e - i * (TL + K - 1);
-      const int j = p0 + q - a.pad;
-      xs[i * a.RS + q] = (j >= 0 && j < Lv) ? xb[int64_t(i) * a.Lin + (a.up == 1 ? j : j / a.up)] : 0.f;
+    for (int e = tid; e < a.Cin * XR; e += 256) {
+      const int i = e / XR, q = e - i * XR;
+      const int j = p0 * a.stride + q - a.pad;
+      xs[i * a.RSx + q] = (j >= 0 && j < Lv) ? xb[int64_t(i) * a.Lin + (a.up == 1 ? j : j / a.up)] : 0.f;
     }
-    for (int e = tid; e < a.Cout * TL; e += 256) {
-      const int o = e / TL, q = e - o * TL;
-      ds[o * a.RS + q] = (p0 + q < a.Lout) ? db_[int64_t(o) * a.Lout + p0 + q] : 0.f;
+    for (int e = tid; e < a.Cout * TLe; e += 256) {
+      const int o = e / TLe, q = e - o * TLe;
+      ds[o * a.RSd + q] = (p0 + q < a.Lout) ? db_[int64_t(o) * a.Lout + p0 + q] : 0.f;
     }
     __syncthreads();
     if (!active) continue;
-    const int l0 = my_slice * chunk, l1 = (l0 + chunk < TL) ? l0 + chunk : TL;
+    const int l0 = my_slice * chunk, l1 = (l0 + chunk < TLe) ? l0 + chunk : TLe;
 #pragma unroll
     for (int m = 0; m < MAXP; ++m) {
-      const int pr = (slices == 1 ? tid + m * 256 : tid - my_slice * pairs);
+      const int pr = (slices == 1 ? pbase + tid + m * 256 : tid - my_slice * pairs);
       if (pr >= pairs || (slices > 1 && m > 0)) break;
       const int o = pr / a.Cin, i = pr - o * a.Cin;
-      const float* xr = xs + i * a.RS;
-      const float* dr = ds + o * a.RS;
+      const float* xr = xs + i * a.RSx;
+      const float* dr = ds + o * a.RSd;
       float sb = 0.f;
       for (int l = l0; l < l1; ++l) {
         const float d = dr[l];
         sb += d;
 #pragma unroll
-        for (int t = 0; t < K; ++t) acc[m][t] = fmaf(d, xr[l + t], acc[m][t]);
+        for (int t = 0; t < K; ++t) acc[m][t] = fmaf(d, xr[l * a.stride + t], acc[m][t]);
       }
       if (i == 0) accb[m] += sb;
     }
   }
-  if (!active) return;
+  if (active) {
 #pragma unroll
-  for (int m = 0; m < MAXP; ++m) {
-    const int pr = (slices == 1 ? tid + m * 256 : tid - my_slice * pairs);
-    if (pr >= pairs || (slices > 1 && m > 0)) break;
-    const int o = pr / a.Cin, i = pr - o * a.Cin;
+    for (int m = 0; m < MAXP; ++m) {
+      const int pr = (slices == 1 ? pbase + tid + m * 256 : tid - my_slice * pairs);
+      if (pr >= pairs || (slices > 1 && m > 0)) break;
+      const int o = pr / a.Cin, i = pr - o * a.Cin;
 #pragma unroll
-    for (int t = 0; t < K; ++t) atomicAdd(a.dW + (int64_t(o) * a.Cin + i) * K + t, acc[m][t]);
-    if (i == 0 && a.db) atomicAdd(a.db + o, accb[m]);
+      for (int t = 0; t < K; ++t) { atomicAdd(a.dW + (int64_t(o) * a.Cin + i) * K + t, acc[m][t]); acc[m][t] = 0.f; }
+      if (i == 0 && a.db) atomicAdd(a.db + o, accb[m]);
+      accb[m] = 0.f;
+    }
   }
+  }  // pair batches
 }
 
 // y[r] = max over the row, arg[r] = first index of the maximum (torch.max semantics); one warp per row
