@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MURAL_ABI_VERSION 1
+#define MURAL_ABI_VERSION 2
 
 #define MURAL_MODEL_SNV 0
 #define MURAL_MODEL_INDEL 1
@@ -109,6 +109,8 @@ typedef struct mural_snv_config {
   int32_t channels;       /* config['CNN_out_channels']                  */
   int32_t kernel_size;    /* config['CNN_kernel_size'] (conv1/2/3)       */
   int32_t n_class;        /* config['n_class']                           */
+  int32_t n_cont;         /* common_model_config['n_cont']: continuous (bigWig mean) features of the local branch
+                             (first_bn_layer + wider first Linear, model_snv.py:326-334,457-463); 0 for every shipped model */
 } mural_snv_config_t;
 
 typedef struct mural_snv_model mural_snv_model_t;
@@ -124,6 +126,11 @@ int64_t mural_snv_model_n_params(const mural_snv_model_t* m);    /* blob length 
 int64_t mural_snv_model_n_trainable(const mural_snv_model_t* m); /* leading trainable part   */
 /* Load eval-mode weights (BatchNorm running stats included in the blob); folds and uploads. */
 int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, int64_t n);
+
+/* n_cont > 0 only: the continuous features cont_x [n, n_cont] (float32, device; row i <-> site i) of the NEXT forward call
+ * (local_input[0] of Network2.forward, model_snv.py:448,457-463).  The pointer is consumed by that call.  Models with
+ * continuous features run in MURAL_MODE_FP32. */
+int mural_snv_set_cont(mural_snv_model_t* m, const float* d_cont);
 
 /* model_predict_m body (MuRaL/model/nn_utils.py:48-65) for n sites: gather + Network2.forward (eval).
  * d_logp: float32 [n, n_class] log-probabilities, exactly what Network2.forward returns. */
@@ -295,6 +302,19 @@ const char* mural_fasta_name(const mural_fasta_t* f, int32_t i);
 const char* mural_fasta_seq(const mural_fasta_t* f, int32_t i);
 int64_t mural_fasta_len(const mural_fasta_t* f, int32_t i);
 void mural_fasta_destroy(mural_fasta_t* f);
+
+/* ------------------------------------------------------------------------------------------------
+ * bigWig tracks (replaces pyBigWig in get_mean_bw_for_bed, MuRaL/data/preprocessing.py:725-750): host reader.
+ * window_means: out[i] = mean(nan_to_num(values(chrom, max(lo[i], 0), min(hi[i], chrom length)))), end exclusive; bases
+ * without data count as 0, an empty window gives NaN (np.mean of an empty array).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mural_bigwig mural_bigwig_t;
+int mural_bigwig_open(const char* path, mural_bigwig_t** out);
+int32_t mural_bigwig_n_chrom(const mural_bigwig_t* b);
+const char* mural_bigwig_chrom_name(const mural_bigwig_t* b, int32_t i);
+int64_t mural_bigwig_chrom_len(const mural_bigwig_t* b, int32_t i);
+int mural_bigwig_window_means(mural_bigwig_t* b, const char* chrom, int64_t n, const int64_t* lo, const int64_t* hi, double* out);
+void mural_bigwig_close(mural_bigwig_t* b);
 
 /* ------------------------------------------------------------------------------------------------
  * Prediction TSV (run_predict.py:228-239): pred_df.to_csv(pred_file, sep='\t', float_format='%.4g', index=False) with

@@ -16,7 +16,7 @@ MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "auto": MODE_AUTO}
 
 class SnvConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("local_radius", "local_order", "distal_radius", "hidden1", "hidden2",
-                                          "channels", "kernel_size", "n_class")]
+                                          "channels", "kernel_size", "n_class", "n_cont")]
 
 
 class IndelConfig(C.Structure):
@@ -35,6 +35,13 @@ PROTOTYPES = {
     "mural_profile_end": (_i64, [C.c_char_p, _i64]),
     "mural_snv_tc_available": (C.c_int, [_vp]),
     "mural_snv_last_auto_sites": (_i64, [_vp]),
+    "mural_snv_set_cont": (C.c_int, [_vp, _vp]),
+    "mural_bigwig_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "mural_bigwig_n_chrom": (_i32, [_vp]),
+    "mural_bigwig_chrom_name": (C.c_char_p, [_vp, _i32]),
+    "mural_bigwig_chrom_len": (_i64, [_vp, _i32]),
+    "mural_bigwig_window_means": (C.c_int, [_vp, C.c_char_p, _i64, _vp, _vp, _vp]),
+    "mural_bigwig_close": (None, [_vp]),
     "mural_conv32_layer": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "mural_conv32_wgrad": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "mural_genome_create": (C.c_int, [_i32, C.POINTER(C.c_char_p), C.POINTER(_i64), C.c_int, C.POINTER(_vp)]),

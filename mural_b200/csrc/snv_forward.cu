@@ -448,7 +448,8 @@ constexpr int MLP_THREADS = 160;
 __global__ void __launch_bounds__(MLP_THREADS) k_local_mlp(LocalDev P, const int32_t* __restrict__ cat32,
                                                            const int64_t* __restrict__ cat64, int64_t n, int n_cat,
                                                            int emb_rows, int K1, int H1, int H2, int NC,
-                                                           float* __restrict__ logits, int* __restrict__ err_flag) {
+                                                           float* __restrict__ logits, int* __restrict__ err_flag,
+                                                           const float* __restrict__ cont, int n_cont) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* xT = reinterpret_cast<float*>(smem_raw);  // [K1][TS]
   float* h1T = xT + K1 * MLP_TS;                   // [H1][TS]
@@ -458,7 +459,9 @@ __global__ void __launch_bounds__(MLP_THREADS) k_local_mlp(LocalDev P, const int
   for (int e = tid; e < MLP_TS * K1; e += MLP_THREADS) {
     const int k = e / MLP_TS, s = e - k * MLP_TS;
     float v = 0.f;
-    if (site0 + s < n) {
+    if (site0 + s < n && k >= 5 * n_cat) {
+      v = cont[(site0 + s) * n_cont + (k - 5 * n_cat)];   // continuous features follow the embeddings (model_snv.py:460); BN folded into W1
+    } else if (site0 + s < n) {
       const int64_t ci = (site0 + s) * n_cat + k / 5;
       int64_t idx = cat64 ? cat64[ci] : int64_t(cat32[ci]);
       if (idx < 0 || idx >= emb_rows) {  // nn.Embedding would raise IndexError
@@ -841,7 +844,8 @@ int snv_stem_launch_planes(mural_snv_model* m, const GenomeView* G, const int32_
 
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,
                      cudaStream_t st) {
-  const int K1 = m->k1, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2;
+  const int K1 = m->k1c, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2;   // embeddings + continuous features
+  MURAL_CHECK(m->cfg.n_cont == 0 || m->d_cont_cur != nullptr, "this model has continuous features: call mural_snv_set_cont before the forward");
   const size_t smem = sizeof(float) * MLP_TS * size_t(K1 + H1 + H2);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -849,7 +853,7 @@ int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* ca
     configured = smem;
   }
   LAUNCH(k_local_mlp, (unsigned)cdiv(ns, MLP_TS), MLP_THREADS, smem, st, m->local, cat32, cat64, ns, m->n_cat, m->emb_rows, K1, H1, H2,
-         m->cfg.n_class, logits, err_flag);
+         m->cfg.n_class, logits, err_flag, m->d_cont_cur, m->cfg.n_cont);
   return 0;
 }
 
@@ -902,6 +906,7 @@ int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_p
     if (int rc = snv_stem_launch(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                  d_sym ? d_sym + s0 * m->L : nullptr, ns, mid0, buf[0], d_cat ? nullptr : cat32, st))
       return rc;
+    m->d_cont_cur = m->d_cont ? m->d_cont + s0 * m->cfg.n_cont : nullptr;
     if (int rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, ns, llog, err_flag, st))
       return rc;
     for (int br = 1; br >= 0; --br) {  // large first (its pool-1 output sits in buf[0]), then mid
@@ -1091,10 +1096,24 @@ extern "C" int mural_snv_forward(mural_snv_model_t* m, const mural_genome_t* g, 
   MURAL_CHECK(g && (n == 0 || (d_pos && d_meta && d_logp)), "NULL argument");
   MURAL_CHECK(g->device == m->device, "genome and model live on different devices");
   if (n == 0) return 0;
+  if (m->cfg.n_cont > 0) {   // continuous-feature models: fp32-equivalent path, cont_x handed over by mural_snv_set_cont
+    MURAL_CHECK(mode == MURAL_MODE_FP32, "models with continuous features (n_cont > 0) run in MURAL_MODE_FP32");
+    MURAL_CHECK(m->d_cont != nullptr, "this model has continuous features: call mural_snv_set_cont before the forward");
+    const int rc = snv_forward_fp32(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
+    m->d_cont = m->d_cont_cur = nullptr;
+    return rc;
+  }
   if (mode == MURAL_MODE_FP32) return snv_forward_fp32(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   if (mode == MURAL_MODE_BF16) return snv_forward_tc(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   if (mode == MURAL_MODE_AUTO) return snv_forward_auto(m, &g->view, d_pos, d_meta, nullptr, nullptr, n, d_logp, (cudaStream_t)stream);
   MURAL_FAIL("unknown compute mode");
+}
+
+extern "C" int mural_snv_set_cont(mural_snv_model_t* m, const float* d_cont) {
+  MURAL_CHECK(m != nullptr, "model is NULL");
+  MURAL_CHECK(m->cfg.n_cont > 0 || d_cont == nullptr, "this model has no continuous features (n_cont == 0)");
+  m->d_cont = d_cont;
+  return 0;
 }
 
 extern "C" int mural_conv32_layer(const float* d_in, float* d_out, const float* d_res1, const float* d_res2, int64_t n, int32_t L,
@@ -1132,7 +1151,12 @@ extern "C" int mural_snv_forward_tensors(mural_snv_model_t* m, const int64_t* d_
     cudaStreamSynchronize(st);
     if (bad) rc = fail(__FILE__, __LINE__, "distal_x holds columns that are not reference one-hot vectors (bigWig channels / arbitrary floats are not supported by the table stem)");
   }
-  if (rc == 0) {
+  if (rc == 0 && m->cfg.n_cont > 0) {
+    if (mode != MURAL_MODE_FP32) rc = fail(__FILE__, __LINE__, "models with continuous features (n_cont > 0) run in MURAL_MODE_FP32");
+    else if (!m->d_cont) rc = fail(__FILE__, __LINE__, "this model has continuous features: call mural_snv_set_cont before the forward");
+    else rc = snv_forward_fp32(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st);
+    m->d_cont = m->d_cont_cur = nullptr;
+  } else if (rc == 0) {
     rc = mode == MURAL_MODE_BF16   ? snv_forward_tc(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
          : mode == MURAL_MODE_AUTO ? snv_forward_auto(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st)
                                    : snv_forward_fp32(m, nullptr, nullptr, nullptr, d_sym, d_cat, n, d_logp, st);

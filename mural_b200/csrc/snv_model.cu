@@ -52,13 +52,16 @@ extern "C" int mural_snv_model_create(const mural_snv_config_t* cfg, int device,
   m->n_cat = n_cat;
   m->emb_rows = (1 << (2 * k)) + 1;  // emb_padding_idx+1, nn_utils.py:196, model_snv.py:322
   m->k1 = 5 * n_cat;                 // embedding width is hard-coded to 5 (model_snv.py:322,325)
+  MURAL_CHECK(cfg->n_cont >= 0 && cfg->n_cont <= 64, "n_cont must be in [0,64]");
+  m->k1c = m->k1 + cfg->n_cont;
   m->L = L;
   LayoutBuilder lb;
   lb.p("emb_layer.weight", int64_t(m->emb_rows) * 5);
-  lb.p("lin_layers.0.weight", int64_t(cfg->hidden1) * m->k1);
+  lb.p("lin_layers.0.weight", int64_t(cfg->hidden1) * m->k1c);
   lb.p("lin_layers.0.bias", cfg->hidden1);
   lb.p("lin_layers.1.weight", int64_t(cfg->hidden2) * cfg->hidden1);
   lb.p("lin_layers.1.bias", cfg->hidden2);
+  if (cfg->n_cont > 0) lb.bn("first_bn_layer", cfg->n_cont);
   lb.bn("bn_layers.0", cfg->hidden1);
   lb.bn("bn_layers.1", cfg->hidden2);
   for (int br = 0; br < 2; ++br) {
@@ -197,12 +200,24 @@ extern "C" int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, i
   // the next Linear: W2' = W2*diag(a1), b2' = b2 + W2*b1.
   int64_t o_emb = F.alloc(int64_t(m->emb_rows) * 5);
   memcpy(&F.prep[o_emb], F.T("emb_layer.weight"), sizeof(float) * m->emb_rows * 5);
-  int64_t o_W1t = F.alloc(int64_t(K1) * H1), o_b1 = F.alloc(H1);
+  const int NCONT = cfg.n_cont, K1C = m->k1c;
+  int64_t o_W1t = F.alloc(int64_t(K1C) * H1), o_b1 = F.alloc(H1);
   {
-    const float* W = F.T("lin_layers.0.weight");  // [H1][K1]
-    for (int o = 0; o < H1; ++o)
-      for (int k = 0; k < K1; ++k) F.prep[o_W1t + int64_t(k) * H1 + o] = W[int64_t(o) * K1 + k];
-    memcpy(&F.prep[o_b1], F.T("lin_layers.0.bias"), sizeof(float) * H1);
+    const float* W = F.T("lin_layers.0.weight");  // [H1][K1 + n_cont]
+    const float* bi = F.T("lin_layers.0.bias");
+    // continuous features: first_bn_layer (eval affine a, b) sits in FRONT of the Linear (model_snv.py:457-463), so it folds
+    // into the extra input columns: W' = W*diag(a), bias' = bias + W*b
+    std::vector<double> a, b;
+    if (NCONT > 0) F.bn_affine("first_bn_layer", NCONT, a, b);
+    for (int o = 0; o < H1; ++o) {
+      double acc = bi[o];
+      for (int k = 0; k < K1C; ++k) {
+        double w = W[int64_t(o) * K1C + k];
+        if (k >= K1) { acc += w * b[k - K1]; w *= a[k - K1]; }
+        F.prep[o_W1t + int64_t(k) * H1 + o] = float(w);
+      }
+      F.prep[o_b1 + o] = float(acc);
+    }
   }
   int64_t o_W2t = F.alloc(int64_t(H1) * H2), o_b2 = F.alloc(H2);
   {

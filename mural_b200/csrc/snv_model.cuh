@@ -57,6 +57,9 @@ struct mural_snv_model {
   mural_snv_config_t cfg;
   int device;
   int n_cat, emb_rows, k1;  // k1 = 5*n_cat
+  int k1c = 0;              // k1 + n_cont: inputs of the first Linear (continuous features follow the embeddings, model_snv.py:460)
+  const float* d_cont = nullptr;  // cont_x of the next forward (mural_snv_set_cont); consumed by it
+  const float* d_cont_cur = nullptr;  // ... advanced to the chunk being processed
   int L;                    // 2R+1
   std::vector<mural::TensorEntry> layout;
   std::map<std::string, int> index;

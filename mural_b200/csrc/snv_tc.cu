@@ -674,7 +674,7 @@ static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = 
 // ---------------------------------------------------------------------------------------------------- host
 int snv_tc_prepare(mural_snv_model* m, const float* h_blob) {
   snv_tc_destroy(m);
-  if (m->cfg.channels != 32 || m->cfg.kernel_size != 3) return 0;  // tcgen05 path is specialised; fp32 path serves the rest
+  if (m->cfg.channels != 32 || m->cfg.kernel_size != 3 || m->cfg.n_cont > 0) return 0;  // tcgen05 path is specialised; fp32 path serves the rest
   using namespace tc;
   auto T = [&](const std::string& n) { return h_blob + m->layout[m->index.at(n)].offset; };
   std::vector<uint8_t> all;

@@ -74,11 +74,12 @@ def segment_order(chrom, start, strand, segment_center):
 
 
 class SiteBatch:
-    """A batch of site records on the device (what the fast Network2.forward consumes)."""
-    __slots__ = ("pos", "meta", "genome")
+    """A batch of site records on the device (what the fast Network2.forward consumes); `cont`: optional [n, n_cont]
+    continuous features of the sites (bigWig window means) for models with n_cont > 0."""
+    __slots__ = ("pos", "meta", "genome", "cont")
 
-    def __init__(self, pos, meta, genome):
-        self.pos, self.meta, self.genome = pos, meta, genome
+    def __init__(self, pos, meta, genome, cont=None):
+        self.pos, self.meta, self.genome, self.cont = pos, meta, genome, cont
 
     def __len__(self):
         return int(self.pos.numel())
@@ -129,10 +130,10 @@ class PackedSiteDataset:
         self.distal_info = True
         self.seq_cols = get_local_header(local_radius, 1, model_type)
         self.cat_cols = get_local_header(local_radius, local_order, model_type) if local_order > 1 else self.seq_cols
-        # continuous (bigWig mean) features, FILE order in -> emission order here (preprocessing.py:429-432 concatenates
-        # get_mean_bw_for_bed's rows positionally with the emission-ordered local frame: kept as is)
+        # continuous (bigWig window mean) features: rows arrive in FILE order (get_mean_bw_for_bed iterates the BED,
+        # preprocessing.py:725-750) and follow their site into emission order
         if cont_data is not None and np.asarray(cont_data).size:
-            cont = np.asarray(cont_data, dtype=np.float64).reshape(len(self.pos), -1)
+            cont = np.asarray(cont_data, dtype=np.float64).reshape(len(self.pos), -1)[self.perm]
             self.cont_cols = list(cont_names) if cont_names is not None else ["bw%d" % i for i in range(cont.shape[1])]
             self.cont_X = cont.astype(np.float32)
         else:
@@ -302,7 +303,7 @@ def prepare_dataset_np(bed_regions, ref_genome, bw_files=(), bw_names=(), bw_rad
     cont = names = None
     if len(bw_files) > 0 and not seq_only:
         from .bigwig import mean_bw_for_sites
-        cont = mean_bw_for_sites(bw_files, bw_radii, sites, model_type)
+        cont = mean_bw_for_sites(bw_files, bw_radii, sites)          # prepare_local_data calls get_mean_bw_for_bed with its default model_type (preprocessing.py:431)
         names = list(bw_names)
     return PackedSiteDataset(sites, genome, central_radius, local_radius, local_order, distal_radius, model_type, cont, names)
 

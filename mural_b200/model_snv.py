@@ -47,9 +47,15 @@ class Network2(nn.Module):
     def __init__(self, emb_dims, no_of_cont, lin_layer_sizes, emb_dropout, lin_layer_dropouts, in_channels, out_channels,
                  kernel_size, distal_radius, distal_order, distal_fc_dropout, n_class, emb_padding_idx=None):
         super().__init__()
-        if no_of_cont != 0 or in_channels != 4:
-            raise NotImplementedError("mural_b200.Network2: bigWig/continuous features (n_cont>0) are out of scope "
-                                      "(SURVEY.md §2 row 21); all shipped checkpoints have n_cont=0")
+        # continuous (bigWig mean) features enter the LOCAL branch (first_bn_layer + wider first Linear, model_snv.py:326-334,
+        # 457-463).  The expanded-window convs only ever see the 4 sequence channels: forward slices distal_input[:, 0:in_channels]
+        # and CombinedDatasetNP never adds track channels to it (preprocessing.py:934-942), so in_channels > 4 can only be fed by
+        # the reference's HDF5 datasets (out of scope).
+        if in_channels not in (4, 4 + no_of_cont):
+            raise ValueError("in_channels must be 4 (+ n_cont)")
+        if in_channels != 4:
+            raise NotImplementedError("mural_b200.Network2: bigWig tracks as extra channels of the expanded window (in_channels > 4) "
+                                      "exist only in the reference's HDF5 data path; pass without_bw_distal (in_channels = 4)")
         if len(lin_layer_sizes) != 2:
             raise NotImplementedError("mural_b200.Network2 expects two hidden local layers (model_choice always passes two)")
         self.n_class = n_class
@@ -88,12 +94,12 @@ class Network2(nn.Module):
         self.local_order = k
         self.local_radius = (self.no_of_cat + (k - 1) - 1) // 2
         self._cfg = _lib.SnvConfig(self.local_radius, k, distal_radius, lin_layer_sizes[0], lin_layer_sizes[1], out_channels,
-                                   kernel_size, n_class)
+                                   kernel_size, n_class, no_of_cont)
         self._h = None
         self._dirty = True
         # "fp32" (fp32-equivalent, gate 1e-3) | "bf16" (tcgen05, gate 5e-3) | "auto" (bf16 everywhere + the fp32-equivalent
         # path again for windows with non-ACGT symbols / chromosome overhang; the default of run_predict)
-        self.compute_mode = "fp32"
+        self.compute_mode = "fp32"             # models with continuous features stay in this mode
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.mark_dirty())
 
     # ------------------------------------------------------------------ native handle management
@@ -177,9 +183,16 @@ class Network2(nn.Module):
         if self._dirty:
             self.refresh()
         L = _lib.lib()
-        mode = _lib.MODES[self.compute_mode]
+        mode = _lib.MODES["fp32" if self.no_of_cont else self.compute_mode]
         dev = self._device_index()
         with torch.cuda.device(dev):
+            cont = None
+            if self.no_of_cont:                 # cont_x [n, n_cont] (model_snv.py:448): local_input[0], or SiteBatch.cont on the fast path
+                cont = distal_input.cont if isinstance(distal_input, SiteBatch) else local_input[0]
+                if cont is None or cont.shape[1] != self.no_of_cont:
+                    raise RuntimeError("cont_x with %d continuous features per site is required" % self.no_of_cont)
+                cont = cont.to(device=self.emb_layer.weight.device, dtype=torch.float32).contiguous()
+                _lib.check(L.mural_snv_set_cont(self._h, _lib.ptr(cont)))
             if isinstance(distal_input, SiteBatch):
                 n = len(distal_input)
                 out = torch.empty((n, self.n_class), dtype=torch.float32, device=distal_input.pos.device)

@@ -96,6 +96,9 @@ class TrainState:
             raise RuntimeError("mural_b200 training runs on CUDA only")
         if optim not in OPTIMIZERS:
             raise ValueError("Error: unsupported optimization method %s" % optim)         # training.py:359-361
+        if getattr(model, "no_of_cont", 0):
+            raise NotImplementedError("training with continuous features (n_cont > 0): the reference feeds them from its HDF5 "
+                                      "datasets only (out of scope, SURVEY 8f N4); prediction with such models is supported")
         self.kind, self.lr, self.weight_decay, self.max_norm = OPTIMIZERS[optim], float(lr), float(weight_decay), float(max_norm)
         layout = model.native_layout()
         self.n_blob = int(L.mural_snv_model_n_params(model._ensure_handle()))

@@ -82,13 +82,16 @@ def _branch(x, sd, sfx, pools, dtype, train, rec, taps=None):
     return F.linear(o, _t(sd, fc + ".2.weight", dtype), _t(sd, fc + ".2.bias", dtype))
 
 
-def network2_forward(sd, cat_x, distal_x, dtype=torch.float32, train=False, rec=None, taps=None):
+def network2_forward(sd, cat_x, distal_x, dtype=torch.float32, train=False, rec=None, taps=None, cont_x=None):
     """Network2.forward (model_snv.py:439-525), dropout disabled (eval, or train with p=0).
-    sd: state dict; cat_x int64 [B,n_cat]; distal_x float [B,4,L].  Returns log-probs [B,n_class]."""
+    sd: state dict; cat_x int64 [B,n_cat]; distal_x float [B,4,L]; cont_x float [B,n_cont] for models with continuous
+    features (first_bn_layer, :457-463).  Returns log-probs [B,n_class]."""
     cat_x = torch.as_tensor(cat_x).long()
     x = torch.as_tensor(distal_x).to(dtype)
     emb = _t(sd, "emb_layer.weight", dtype)
     lo = emb[cat_x].reshape(cat_x.shape[0], -1)                    # :452-454
+    if "first_bn_layer.weight" in sd and np.asarray(sd["first_bn_layer.weight"]).size > 0:     # :457-463
+        lo = torch.cat([lo, _bn(torch.as_tensor(cont_x).to(dtype), sd, "first_bn_layer", dtype, train, rec)], dim=1)
     i = 0
     while ("lin_layers.%d.weight" % i) in sd:                       # :465-468
         lo = F.relu(F.linear(lo, _t(sd, "lin_layers.%d.weight" % i, dtype), _t(sd, "lin_layers.%d.bias" % i, dtype)))

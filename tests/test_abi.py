@@ -21,7 +21,7 @@ def test_header_symbols_exported_and_bound():
         assert n in _lib.PROTOTYPES, "no ctypes prototype for %s" % n
     for n in _lib.PROTOTYPES:
         assert n in names, "%s is bound but not declared in include/mural_b200.h" % n
-    assert L.mural_abi_version() == 1
+    assert L.mural_abi_version() == 2
 
 
 def test_error_channel_without_gpu():
