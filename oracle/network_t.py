@@ -90,7 +90,8 @@ def network2_forward(sd, cat_x, distal_x, dtype=torch.float32, train=False, rec=
     x = torch.as_tensor(distal_x).to(dtype)
     emb = _t(sd, "emb_layer.weight", dtype)
     lo = emb[cat_x].reshape(cat_x.shape[0], -1)                    # :452-454
-    if "first_bn_layer.weight" in sd and np.asarray(sd["first_bn_layer.weight"]).size > 0:     # :457-463
+    fb = sd.get("first_bn_layer.weight")
+    if fb is not None and (fb.numel() if torch.is_tensor(fb) else np.asarray(fb).size) > 0:    # :457-463
         lo = torch.cat([lo, _bn(torch.as_tensor(cont_x).to(dtype), sd, "first_bn_layer", dtype, train, rec)], dim=1)
     i = 0
     while ("lin_layers.%d.weight" % i) in sd:                       # :465-468
