@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sW = smem;                              // [NL][W_LAYER], shared by all slots
   unsigned char* sSlots = sW + NL * W_LAYER;             // [NSLOT][SLOT_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlots + NSLOT * SLOT_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlots + NSLOT * SLOT_BYTES);   // [NSLOT] per-slot MMA-done barriers + 1 weight-arrival barrier
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSLOT + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = tid >> 7, lt = tid & 127;
 #ifdef MURAL_TC_TIMING
@@ -169,15 +169,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
 #endif
 
   // ---- one-time setup
-  {
-    constexpr int NV = NL * W_LAYER / 16;  // uint4 count
-    const uint4* src = reinterpret_cast<const uint4*>(a.wblob);
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-#pragma unroll
-    for (int i = 0; i < (NV + THREADS - 1) / THREADS; ++i) {
-      const int e = tid + i * THREADS;
-      if (e < NV) dst[e] = __ldg(src + e);
-    }
+  // the stage's weight blob (NL x 7 KB, contiguous, 16-byte aligned on both sides) arrives by ONE bulk async copy (TMA engine,
+  // cp.async.bulk global -> shared, completion on an mbarrier) while the threads clear the slots' halo rows
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(sSlots + NSLOT * SLOT_BYTES) + NSLOT;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(wbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t WB = NL * W_LAYER;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(wbar)), "r"(WB) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sW)),
+                 "l"(a.wblob), "r"(WB), "r"(smem_u32(wbar))
+                 : "memory");
   }
   for (int e = tid; e < NSLOT * 8; e += THREADS) {  // halo rows 0 and 129 of the 4 planes of every slot
     const int sl = e >> 3, plane = (e >> 1) & 3, row = (e & 1) ? (A_ROWS - 1) : 0;
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  mbar_wait(smem_u32(wbar), 0);  // weights have landed (written by the async proxy: directly visible to tcgen05.mma)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
   const int Lp1 = L_ + 1;
@@ -642,7 +645,7 @@ static int m_sm_count() {
 template <int MODE, int FM = 0>
 static int launch_stage(const StageArgs& a, cudaStream_t st, const char* role = "") {
   constexpr int NL = n_layers(MODE);
-  const size_t smem = size_t(NL) * W_LAYER + size_t(NSLOT) * SLOT_BYTES + NSLOT * 8 + 16;
+  const size_t smem = size_t(NL) * W_LAYER + size_t(NSLOT) * SLOT_BYTES + (NSLOT + 1) * 8 + 16;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY((cudaFuncSetAttribute(k_stage_tc<MODE, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
@@ -795,7 +798,9 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     // the per-site row buffers grow with the window (stage-1 rows L1 of both branches, 64 B each, stem out + stage-1 out +
     // ~0.3 of that for the later stages): halve the chunk until they fit 16 GiB (524 288 sites at the shipped 1 Kb radius)
     const double per_site = 64.0 * 2.3 * double(m->br[0].L1 + m->br[1].L1);
-    while (chunk > 4096 && double(chunk) * per_site > 16.0 * 1024 * 1024 * 1024) chunk /= 2;
+    static double ws_gib = -1;
+    if (ws_gib < 0) { const char* e = getenv("MURAL_TC_WS_GIB"); ws_gib = e ? atof(e) : 16.0; }
+    while (chunk > 4096 && double(chunk) * per_site > ws_gib * 1024 * 1024 * 1024) chunk /= 2;
   }
   if (chunk > n) chunk = n;
   // workspace: per branch X0 (stem out), Z1, Z2 as bf16 planes, H as fp32 planes; + local logits, taps, k-mer indices.
