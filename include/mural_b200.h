@@ -192,6 +192,12 @@ int mural_indel_forward(mural_indel_model_t* m, const mural_genome_t* g, const i
                         float* d_out, void* stream);
 /* same network on the reference's own input tensor distal_x float32 [n, 4, 2R] */
 int mural_indel_forward_tensors(mural_indel_model_t* m, const float* d_distal, int64_t n, int32_t L, float* d_out, void* stream);
+/* Kernel family of the eval forward.  mode 0 (default): one fused tensor-core kernel per U-Net level (lconv + ConvBlock
+ * [+ skip, + out_conv + position max], model_indel.py:6-19,158-173; split-bf16 products, fp32 accumulation — fp32-equivalent,
+ * gate 1e-3 of the output scale) whenever the shapes allow it (CNN_out_channels a multiple of 8, widest level <= 48 channels);
+ * mode 1: the fp32 CUDA-core kernels (one per convolution).  mural_indel_tc_available: 1 if mode 0 runs the level kernels. */
+int mural_indel_set_mode(mural_indel_model_t* m, int32_t mode);
+int mural_indel_tc_available(const mural_indel_model_t* m);
 
 /* ------------------------------------------------------------------------------------------------
  * Training step (MuRaL/training.py:404-452): train-mode forward (batch-statistic BatchNorm with running-stat

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "mural_indel_model_load": (C.c_int, [_vp, _vp, _i64]),
     "mural_indel_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "mural_indel_forward_tensors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "mural_indel_set_mode": (C.c_int, [_vp, _i32]),
+    "mural_indel_tc_available": (C.c_int, [_vp]),
     "mural_snv_train_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "mural_snv_train_destroy": (None, [_vp]),
     "mural_snv_train_set_dropout": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_uint64]),

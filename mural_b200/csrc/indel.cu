@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <string.h>
 
+#include "indel_tc.cuh"
 #include "snv_model.cuh"
 
 namespace mural {
@@ -204,6 +205,14 @@ struct mural_indel_model {
   bool loaded = false;
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
+  // tensor-core path (indel_tc.cuh): one fused kernel per U-Net level; pre-split bf16 B fragments + biases in d_tc
+  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, NC8, MT, TP, RA, n_tiles, rows_in, smem, Lin, Lout; };
+  std::vector<TcLevel> tcl;  // encoder levels 0..5, decoder steps 0..4 (levels 4..0)
+  int64_t tcWo0 = -1, tcWo1 = -1;
+  int tcKCo = 0;
+  uint32_t* d_tc = nullptr;
+  bool tc_ok = false;
+  int mode = 0;  // 0: tensor-core path when the shapes allow it, 1: fp32 CUDA-core kernels
 };
 
 extern "C" int mural_indel_model_create(const mural_indel_config_t* cfg, int device, mural_indel_model_t** out) {
@@ -273,6 +282,7 @@ extern "C" void mural_indel_model_destroy(mural_indel_model_t* m) {
   if (!m) return;
   cudaFree(m->d_prep);
   cudaFree(m->d_ws);
+  cudaFree(m->d_tc);
   delete m;
 }
 extern "C" int32_t mural_indel_model_n_tensors(const mural_indel_model_t* m) { return m ? (int32_t)m->layout.size() : 0; }
@@ -285,6 +295,141 @@ extern "C" int mural_indel_model_tensor(const mural_indel_model_t* m, int32_t i,
   if (offset) *offset = e.offset;
   if (numel) *numel = e.numel;
   if (is_buffer) *is_buffer = e.is_buffer;
+  return 0;
+}
+
+
+// ---- tensor-core path: host preparation ---------------------------------------------------------------------------------
+static inline uint32_t bf16_rn_bits(float x) {  // round to nearest even; inputs are finite
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+static inline float bf16_bits_to_float(uint32_t b) {
+  uint32_t u = b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// Folded conv weights W[t][ci][co] -> B fragments of mma.m16n8k16 over k = t*CinP + ci (zero for ci >= Cin and k >= ks*CinP):
+// [k chunk][column tile][lane] x {b0 hi, b1 hi, b0 lo, b1 lo}, a packed pair holding k (low half) and k+1.
+static int64_t make_frags(std::vector<uint32_t>& buf, const float* W, int ks, int Cin, int CinP, int Cout) {
+  const int K = ks * CinP, KC = (K + 15) / 16, NT = Cout / 8;
+  const int64_t off = (int64_t)buf.size();
+  buf.resize(off + int64_t(KC) * NT * 32 * 4, 0u);
+  auto w = [&](int k, int n) -> float {
+    if (k >= K) return 0.f;
+    const int t = k / CinP, ci = k - t * CinP;
+    return ci < Cin ? W[(int64_t(t) * Cin + ci) * Cout + n] : 0.f;
+  };
+  for (int kc = 0; kc < KC; ++kc)
+    for (int nt = 0; nt < NT; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, q = lane & 3, n = nt * 8 + g;
+        uint32_t* d = buf.data() + off + ((int64_t(kc) * NT + nt) * 32 + lane) * 4;
+        for (int h = 0; h < 2; ++h) {
+          const int k = kc * 16 + 2 * q + 8 * h;
+          const float w0 = w(k, n), w1 = w(k + 1, n);
+          const uint32_t h0 = bf16_rn_bits(w0), h1 = bf16_rn_bits(w1);
+          const uint32_t l0 = bf16_rn_bits(w0 - bf16_bits_to_float(h0)), l1 = bf16_rn_bits(w1 - bf16_bits_to_float(h1));
+          d[h] = h0 | (h1 << 16);
+          d[2 + h] = l0 | (l1 << 16);
+        }
+      }
+  return off;
+}
+
+typedef void (*LevelKernel)(const indel_tc::LevelParams);
+static LevelKernel level_kernel(int NC8, bool tail) {
+  using namespace indel_tc;
+  if (tail) return NC8 == 1 ? (LevelKernel)k_unet_level<1, 2, true> : NC8 == 2 ? (LevelKernel)k_unet_level<2, 2, true> : nullptr;
+  switch (NC8) {
+    case 1: return k_unet_level<1, 2, false>;
+    case 2: return k_unet_level<2, 2, false>;
+    case 3: return k_unet_level<3, 1, false>;
+    case 4: return k_unet_level<4, 1, false>;
+    case 5: return k_unet_level<5, 1, false>;
+    case 6: return k_unet_level<6, 1, false>;
+  }
+  return nullptr;
+}
+
+// Builds the fragment buffers and the tile geometry of the 11 level kernels; leaves tc_ok false (fp32 kernels are used) when
+// a level does not fit: channels not a multiple of 8, a level wider than 48 channels, or > 227 KB of shared memory.
+static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep) {
+  using namespace indel_tc;
+  m->tc_ok = false;
+  m->tcl.clear();
+  const int C = m->cfg.channels, ks = m->cfg.kernel_size;
+  if (C % 8 != 0 || m->ch[5] > 48) return 0;
+  std::vector<uint32_t> buf;
+  auto fbits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+  for (int step = 0; step < 11; ++step) {
+    const bool dec = step >= 6;
+    const int lvl = dec ? 4 - (step - 6) : step;
+    const int o0 = dec ? 18 + 3 * (step - 6) : 3 * step;  // lconv, conv5, conv1 of this level in m->ops
+    const mural_indel_model::Op &ol = m->ops[o0], &o5 = m->ops[o0 + 1], &o1 = m->ops[o0 + 2];
+    mural_indel_model::TcLevel T{};
+    T.NC8 = m->ch[lvl] / 8;
+    T.MT = T.NC8 <= 2 ? 2 : 1;
+    T.Cin = ol.Cin;
+    T.CinP = (ol.Cin + 7) & ~7;
+    T.stride = ol.stride;
+    T.up = ol.up;
+    T.Lin = dec ? m->len[lvl + 1] : (lvl ? m->len[lvl - 1] : m->L);
+    T.Lout = m->len[lvl];
+    if (o5.ks != 5 || o1.ks != 1 || ol.ks != ks) return 0;
+    T.Wl = make_frags(buf, prep.data() + ol.W, ks, ol.Cin, T.CinP, ol.Cout);
+    T.W5 = make_frags(buf, prep.data() + o5.W, 5, o5.Cin, o5.Cin, o5.Cout);
+    T.W1 = make_frags(buf, prep.data() + o1.W, 1, o1.Cin, o1.Cin, o1.Cout);
+    T.KCl = (ks * T.CinP + 15) / 16;
+    T.KC5 = (5 * m->ch[lvl] + 15) / 16;
+    const int Cl = m->ch[lvl];
+    T.bias = (int64_t)buf.size();
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(prep[ol.b + c]));
+    for (int c = 0; c < 2 * Cl; ++c) buf.push_back(fbits(prep[o5.b + c]));
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(prep[o1.b + c]));
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(step == 10 ? prep[m->ops[33].b + c] : 0.f));
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(step == 10 ? prep[m->ops[34].b + c] : 0.f));
+    while (buf.size() & 3) buf.push_back(0u);
+    m->tcl.push_back(T);
+  }
+  m->tcKCo = (C / 8 + 1) / 2;
+  m->tcWo0 = make_frags(buf, prep.data() + m->ops[33].W, 1, C, C, C);
+  m->tcWo1 = make_frags(buf, prep.data() + m->ops[34].W, 1, C, C, C);
+  for (int step = 0; step < 11; ++step) {
+    mural_indel_model::TcLevel& T = m->tcl[step];
+    if (!level_kernel(T.NC8, step == 10)) return 0;
+    // tile: up to RA_MAX rows of A (outputs + the +-2 halo of Conv5), shrunk until weights + tile fit the 227 KB of an SM
+    for (int ra_max = RA_MAX;; ra_max /= 2) {
+      if (ra_max < 16 * T.MT) return 0;
+      T.n_tiles = (T.Lout + (ra_max - 4) - 1) / (ra_max - 4);
+      T.TP = (T.Lout + T.n_tiles - 1) / T.n_tiles;
+      T.RA = ((T.TP + 4 + 16 * T.MT - 1) / (16 * T.MT)) * (16 * T.MT);
+      T.rows_in = (T.RA - 1) * T.stride + ks + 1;
+      LevelParams P{};
+      P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo; P.CinP = T.CinP; P.RA = T.RA; P.rows_in = T.rows_in;
+      T.smem = smem_layout(T.NC8, step == 10, P).total;
+      if (T.smem <= 227 * 1024) break;
+    }
+  }
+  for (int step = 0; step < 11; ++step) {  // levels of equal width share a kernel: opt in to the largest request
+    int need = 0;
+    for (int o = 0; o < 11; ++o)
+      if (m->tcl[o].NC8 == m->tcl[step].NC8 && (o == 10) == (step == 10)) need = std::max(need, m->tcl[o].smem);
+    static std::map<LevelKernel, int> configured;  // process-wide and monotone: several models (radii) share the kernels
+    LevelKernel k = level_kernel(m->tcl[step].NC8, step == 10);
+    if (configured[k] < need) {
+      CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+      configured[k] = need;
+    }
+  }
+  cudaFree(m->d_tc);
+  m->d_tc = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&m->d_tc, buf.size() * 4));
+  CUDA_TRY(cudaMemcpy(m->d_tc, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+  m->tc_ok = true;
   return 0;
 }
 
@@ -376,6 +521,7 @@ extern "C" int mural_indel_model_load(mural_indel_model_t* m, const float* h_blo
   m->d_prep = nullptr;
   CUDA_TRY(cudaMalloc((void**)&m->d_prep, prep.size() * sizeof(float)));
   CUDA_TRY(cudaMemcpy(m->d_prep, prep.data(), prep.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (int rc = indel_tc_prepare(m, prep)) return rc;
   m->loaded = true;
   return 0;
 }
@@ -401,8 +547,95 @@ static int run_conv(const mural_indel_model* m, int oi, const float* in, float* 
   return 0;
 }
 
+// Tensor-core forward: stem, 6 encoder levels, 5 decoder levels (the last with out_conv + position max fused), head.
+static int indel_forward_tc(mural_indel_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, const uint8_t* d_sym,
+                            int64_t n, float* d_out, cudaStream_t st) {
+  using namespace indel_tc;
+  const int C = m->cfg.channels, ks = m->cfg.kernel_size, NC = m->cfg.n_class, L = m->L;
+  // workspace per site (floats): X [L*4], encoder outputs E[0..5], two decoder buffers, position max [C]
+  int64_t dmax = 0;
+  for (int lvl = 1; lvl <= 4; ++lvl) dmax = std::max<int64_t>(dmax, int64_t(m->len[lvl]) * m->ch[lvl]);
+  int64_t per = int64_t(L) * 4 + 2 * dmax + C;
+  for (int i = 0; i < 6; ++i) per += int64_t(m->len[i]) * m->ch[i];
+  per = (per + 3) & ~int64_t(3);
+  int64_t chunk = (int64_t(2) << 30) / (per * 4);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 4096) chunk = 4096;
+  if (chunk > n) chunk = n;
+  if (m->ws_bytes < chunk * per * 4) {
+    cudaFree(m->d_ws);
+    m->d_ws = nullptr;
+    m->ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&m->d_ws, chunk * per * 4));
+    m->ws_bytes = chunk * per * 4;
+  }
+  auto al4 = [](int64_t v) { return (v + 3) & ~int64_t(3); };
+  float* w = (float*)m->d_ws;
+  float* X = w; w += al4(chunk * int64_t(L) * 4);
+  float* E[6];
+  for (int i = 0; i < 6; ++i) { E[i] = w; w += al4(chunk * int64_t(m->len[i]) * m->ch[i]); }
+  float* D[2];
+  D[0] = w; w += al4(chunk * dmax);
+  D[1] = w; w += al4(chunk * dmax);
+  float* gmax = w;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  GenomeView gv = G ? *G : GenomeView{};
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
+    const size_t ssm = sizeof(float) * ks * 64 + ((size_t(L) + 15) & ~size_t(15));
+    static size_t conf = 0;
+    if (ssm > 48 * 1024 && ssm > conf) {
+      CUDA_TRY(cudaFuncSetAttribute(k_indel_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      conf = ssm;
+    }
+    LAUNCH(k_indel_stem, (unsigned)ns, 256, ssm, st, gv, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
+           d_sym ? d_sym + s0 * L : nullptr, m->cfg.distal_radius, L, ks, m->stemT >= 0 ? m->d_prep + m->stemT : nullptr,
+           m->stemB >= 0 ? m->d_prep + m->stemB : nullptr, X);
+    LAUNCH(k_fill_f32, 64, 256, 0, st, gmax, ns * C, -INFINITY);
+    const float* x = X;
+    for (int step = 0; step < 11; ++step) {
+      const mural_indel_model::TcLevel& T = m->tcl[step];
+      const bool dec = step >= 6, tail = step == 10;
+      const int lvl = dec ? 4 - (step - 6) : step;
+      LevelParams P{};
+      P.in = x;
+      P.skip = dec ? E[lvl] : nullptr;
+      P.out = dec ? D[step & 1] : E[lvl];
+      P.gmax = gmax;
+      const uint4* tc = reinterpret_cast<const uint4*>(m->d_tc);
+      P.Wl = tc + T.Wl / 4; P.W5 = tc + T.W5 / 4; P.W1 = tc + T.W1 / 4;
+      P.Wo0 = tc + m->tcWo0 / 4; P.Wo1 = tc + m->tcWo1 / 4;
+      P.bias = reinterpret_cast<const float*>(m->d_tc) + T.bias;
+      P.Cin = T.Cin; P.CinP = T.CinP; P.ks = ks; P.stride = T.stride; P.up = T.up;
+      P.Lin = T.Lin; P.Lout = T.Lout;
+      P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo;
+      P.TP = T.TP; P.RA = T.RA; P.n_tiles = T.n_tiles; P.rows_in = T.rows_in;
+      P.n_items = ns * T.n_tiles;
+      LevelKernel k = level_kernel(T.NC8, tail);
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, T.smem);
+      if (occ < 1) occ = 1;
+      const int64_t grid = std::min<int64_t>(P.n_items, int64_t(n_sm) * occ);
+      static const char* names[11] = {"k_unet_level/enc0", "k_unet_level/enc1", "k_unet_level/enc2", "k_unet_level/enc3", "k_unet_level/enc4",
+                                      "k_unet_level/enc5", "k_unet_level/dec4", "k_unet_level/dec3", "k_unet_level/dec2", "k_unet_level/dec1",
+                                      "k_unet_level/dec0+out"};
+      LAUNCH_N(names[step], k, (unsigned)grid, THREADS, T.smem, st, P);
+      x = P.out;
+    }
+    LAUNCH(k_indel_head_tc, (unsigned)cdiv(ns * NC, 128), 128, 0, st, gmax, ns, C, m->d_prep + m->Wfc, m->d_prep + m->bfc, NC, d_out + s0 * NC);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int indel_forward(mural_indel_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, const uint8_t* d_sym,
                          int64_t n, float* d_out, cudaStream_t st) {
+  if (m->tc_ok && m->mode == 0) return indel_forward_tc(m, G, d_pos, d_meta, d_sym, n, d_out, st);
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, NC = m->cfg.n_class, L = m->L;
   // workspace per site (floats): X[L*4], per level A,E [len*ch], H [len0*2C max], decoder x / scratch
   int64_t per = int64_t(L) * 4;
@@ -511,3 +744,11 @@ extern "C" int mural_indel_model_config(const mural_indel_model_t* m, mural_inde
   *out = m->cfg;
   return 0;
 }
+
+extern "C" int mural_indel_set_mode(mural_indel_model_t* m, int32_t mode) {
+  MURAL_CHECK(m, "NULL argument");
+  MURAL_CHECK(mode == 0 || mode == 1, "ValueError: indel mode must be 0 (tensor-core level kernels when the shapes allow) or 1 (fp32 kernels)");
+  m->mode = mode;
+  return 0;
+}
+extern "C" int mural_indel_tc_available(const mural_indel_model_t* m) { return m && m->tc_ok ? 1 : 0; }

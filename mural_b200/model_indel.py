@@ -45,6 +45,9 @@ class UNet_Small(nn.Module):
         self.out_fc = nn.Sequential(nn.BatchNorm1d(ch[0]), nn.Dropout(0.1), nn.Linear(ch[0], n_class), nn.Softplus())
         self._ks, self._down, self._C = kernel_size, list(downsize), out_channels
         self._h, self._hR, self._dirty = None, None, True
+        # "auto": fused tensor-core level kernels (fp32-equivalent split-bf16 products) when the shapes allow it,
+        # "fp32": the fp32 CUDA-core kernels
+        self.compute_mode = "auto"
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.mark_dirty())
 
     def mark_dirty(self):
@@ -87,6 +90,9 @@ class UNet_Small(nn.Module):
             with torch.cuda.device(self._device_index()):
                 _lib.check(L.mural_indel_model_load(self._h, _lib.ptr(blob), blob.size))
             self._dirty = False
+        if self.compute_mode not in ("auto", "fp32"):
+            raise ValueError("compute_mode must be 'auto' or 'fp32'")
+        _lib.check(L.mural_indel_set_mode(self._h, 1 if self.compute_mode == "fp32" else 0))
         return self._h
 
     def __del__(self):

@@ -41,7 +41,50 @@ def test_indel_forward_matches_reference(kat, cuda_genome, tag, manifest):
     d = np.abs(a.cpu().numpy() - ref).max()
     print(tag, "max |out - ref| = %.2e (scale %.2f)" % (d, np.abs(ref).max()))
     assert d <= 1e-3 * max(1.0, np.abs(ref).max())            # fp32-equivalent gate
+    # the shipped shapes run the fused tensor-core level kernels by default; the fp32 CUDA-core kernels hold the same gate
+    from mural_b200 import _lib
+    assert _lib.lib().mural_indel_tc_available(m._handle(Rd)) == 1
+    m.compute_mode = "fp32"
+    with torch.no_grad():
+        c = m.forward(sb, distal_radius=Rd)
+    m.compute_mode = "auto"
+    d32 = np.abs(c.cpu().numpy() - ref).max()
+    dtc = (a - c).abs().max().item()
+    print(tag, "fp32 kernels: max |out - ref| = %.2e; tensor-core vs fp32 kernels %.2e" % (d32, dtc))
+    assert d32 <= 1e-3 * max(1.0, np.abs(ref).max()) and dtc <= 1e-3 * max(1.0, np.abs(ref).max())
     # train mode routes to the training tape (tests/test_gpu_indel_train.py pins its values): differentiable output
     m.train()
     out = m.forward(oh[:4])
     assert out.shape == (4, a.shape[1]) and out.grad_fn is not None and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("C,ks,down,R,rev", [(8, 7, [1, 4, 5, 5, 5, 2], 500, True), (8, 7, [1, 4, 5, 5, 5, 2], 1500, False),
+                                             (8, 5, [2, 2, 2, 2, 2, 2], 544, True), (8, 3, [1, 2, 3, 2, 1, 2], 1260, False),
+                                             (8, 9, [4, 1, 5, 2, 2, 1], 3000, True)])
+def test_indel_level_kernels_generic_shapes(C, ks, down, R, rev):
+    """Fused tensor-core level kernels vs the fp32 kernels and the CPU oracle on random weights: tile edges (lengths that are
+    not multiples of the tile), strides / upsampling factors other than the shipped ones, both stems."""
+    from mural_b200 import _lib, model_choice
+    from oracle import network_t as NT
+    torch.manual_seed(ks * 100 + R)
+    cfg = {"CNN_out_channels": C, "CNN_kernel_size": ks, "down_list": down, "use_reverse": rev, "n_class": 8}
+    m = model_choice(0, cfg, {"n_class": 8}, "indel")
+    for mod in m.modules():                                  # non-trivial BatchNorm statistics
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5); mod.weight.data.uniform_(0.5, 1.5); mod.bias.data.normal_(0, 0.2)
+    m.to("cuda").eval()
+    n = 5
+    idx = torch.randint(0, 4, (n, 2 * R))
+    oh = torch.nn.functional.one_hot(idx, 4).permute(0, 2, 1).float()
+    oh[0, :, 10:40] = 0.25                                   # an N run
+    with torch.no_grad():
+        a = m.forward(oh.cuda())
+        assert _lib.lib().mural_indel_tc_available(m._handle(R)) == 1
+        m.compute_mode = "fp32"
+        b = m.forward(oh.cuda())
+        sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        ref = NT.unet_small_forward(sd, oh.numpy(), down, rev, torch.float64).numpy()
+    scale = max(1.0, np.abs(ref).max())
+    da, db = np.abs(a.cpu().numpy() - ref).max(), np.abs(b.cpu().numpy() - ref).max()
+    print("C=%d ks=%d down=%s R=%d: tensor-core %.2e, fp32 kernels %.2e (scale %.2f)" % (C, ks, down, R, da, db, scale))
+    assert da <= 1e-3 * scale and db <= 1e-3 * scale
