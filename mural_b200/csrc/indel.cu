@@ -206,7 +206,7 @@ struct mural_indel_model {
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
   // tensor-core path (indel_tc.cuh): one fused kernel per U-Net level; pre-split bf16 B fragments + biases in d_tc
-  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, NC8, MT, TP, RA, n_tiles, rows_in, smem, Lin, Lout; };
+  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, NC8, MT, NW, SG, TP, RA, RS, n_tiles, rows_in, smem, Lin, Lout; };
   std::vector<TcLevel> tcl;  // encoder levels 0..5, decoder steps 0..4 (levels 4..0)
   int64_t tcWo0 = -1, tcWo1 = -1;
   int tcKCo = 0;
@@ -341,16 +341,26 @@ static int64_t make_frags(std::vector<uint32_t>& buf, const float* W, int ks, in
 }
 
 typedef void (*LevelKernel)(const indel_tc::LevelParams);
-static LevelKernel level_kernel(int NC8, bool tail) {
+// Row tiles per warp by level width: narrow levels are long, wide levels hold many column tiles per row tile in registers.
+static int level_mt(int NC8) { return NC8 <= 2 ? 2 : 1; }
+// resident CTAs per SM allowed by the register file (ptxas -v of the instantiations below)
+static int level_reg_ctas(int NC8, int NW) { return NW == 16 ? 1 : NC8 == 1 ? 4 : NC8 <= 4 ? 2 + (NC8 >= 3) : 2; }
+static LevelKernel level_kernel(int NC8, int NW, bool tail) {
   using namespace indel_tc;
-  if (tail) return NC8 == 1 ? (LevelKernel)k_unet_level<1, 2, true> : NC8 == 2 ? (LevelKernel)k_unet_level<2, 2, true> : nullptr;
-  switch (NC8) {
-    case 1: return k_unet_level<1, 2, false>;
-    case 2: return k_unet_level<2, 2, false>;
-    case 3: return k_unet_level<3, 1, false>;
-    case 4: return k_unet_level<4, 1, false>;
-    case 5: return k_unet_level<5, 1, false>;
-    case 6: return k_unet_level<6, 1, false>;
+  if (tail) return NW != 8 ? nullptr : NC8 == 1 ? (LevelKernel)k_unet_level<1, 2, 8, true> : NC8 == 2 ? (LevelKernel)k_unet_level<2, 2, 8, true> : nullptr;
+  if (NW == 8) switch (NC8) {
+    case 1: return k_unet_level<1, 2, 8, false>;
+    case 2: return k_unet_level<2, 2, 8, false>;
+    case 3: return k_unet_level<3, 1, 8, false>;
+    case 4: return k_unet_level<4, 1, 8, false>;
+    case 5: return k_unet_level<5, 1, 8, false>;
+    case 6: return k_unet_level<6, 1, 8, false>;
+  }
+  if (NW == 16) switch (NC8) {  // wide levels: the weights leave room for one CTA per SM, so that CTA brings 16 warps
+    case 3: return k_unet_level<3, 1, 16, false>;
+    case 4: return k_unet_level<4, 1, 16, false>;
+    case 5: return k_unet_level<5, 1, 16, false>;
+    case 6: return k_unet_level<6, 1, 16, false>;
   }
   return nullptr;
 }
@@ -372,7 +382,8 @@ static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep
     const mural_indel_model::Op &ol = m->ops[o0], &o5 = m->ops[o0 + 1], &o1 = m->ops[o0 + 2];
     mural_indel_model::TcLevel T{};
     T.NC8 = m->ch[lvl] / 8;
-    T.MT = T.NC8 <= 2 ? 2 : 1;
+    T.MT = level_mt(T.NC8);
+    T.NW = 8;
     T.Cin = ol.Cin;
     T.CinP = (ol.Cin + 7) & ~7;
     T.stride = ol.stride;
@@ -400,26 +411,52 @@ static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep
   m->tcWo1 = make_frags(buf, prep.data() + m->ops[34].W, 1, C, C, C);
   for (int step = 0; step < 11; ++step) {
     mural_indel_model::TcLevel& T = m->tcl[step];
-    if (!level_kernel(T.NC8, step == 10)) return 0;
-    // tile: up to RA_MAX rows of A (outputs + the +-2 halo of Conv5), shrunk until weights + tile fit the 227 KB of an SM
-    for (int ra_max = RA_MAX;; ra_max /= 2) {
-      if (ra_max < 16 * T.MT) return 0;
+    if (!level_kernel(T.NC8, 8, step == 10)) return 0;
+    // tile: up to RA_MAX rows of A (outputs + the +-2 halo of Conv5); levels shorter than a tile may put SG sites into one
+    // work item so that every warp of the CTA has a row tile.  Candidates must fit the 227 KB of an SM.
+    auto shape = [&](int ra_max, int sg) {
       T.n_tiles = (T.Lout + (ra_max - 4) - 1) / (ra_max - 4);
       T.TP = (T.Lout + T.n_tiles - 1) / T.n_tiles;
       T.RA = ((T.TP + 4 + 16 * T.MT - 1) / (16 * T.MT)) * (16 * T.MT);
       T.rows_in = (T.RA - 1) * T.stride + ks + 1;
+      T.RS = (T.rows_in + T.stride - 1) / T.stride;
+      T.SG = T.n_tiles == 1 ? sg : 1;
       LevelParams P{};
-      P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo; P.CinP = T.CinP; P.RA = T.RA; P.rows_in = T.rows_in;
+      P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo; P.CinP = T.CinP; P.RA = T.RA; P.rows_in = T.rows_in; P.RS = T.RS;
+      P.stride = T.stride; P.SG = T.SG;
       T.smem = smem_layout(T.NC8, step == 10, P).total;
-      if (T.smem <= 227 * 1024) break;
+    };
+    // score = useful rows per tile x share of warps that get a row tile x an occupancy factor (few resident warps cannot hide
+    // the phase barriers and the global-load latency; measured on the shipped shapes: 8 warps ~0.55, 16 ~0.8 of the 24+ rate)
+    double best = -1.0;
+    int best_ra = 0, best_sg = 0, best_nw = 0;
+    for (int nw : {8, 16}) {
+      if (!level_kernel(T.NC8, nw, step == 10)) continue;
+      T.NW = nw;
+      for (int ra_max = RA_MAX; ra_max >= 16 * T.MT; ra_max /= 2)
+        for (int sg = 1; sg <= 16; sg *= 2) {
+          shape(ra_max, sg);
+          if (T.SG != sg) break;  // several tiles per site: no site groups
+          if (T.smem > 227 * 1024) break;
+          const int tiles = T.SG * (T.RA / 16), per_round = T.NW * T.MT;
+          const double util = double(tiles) / double(((tiles + per_round - 1) / per_round) * per_round);
+          const double useful = double(T.Lout) / double(T.n_tiles * T.RA);
+          const int ctas = std::min((227 * 1024) / T.smem, level_reg_ctas(T.NC8, nw));
+          const double occ = sqrt(std::min(1.0, double(ctas * nw) / 24.0));
+          const double score = useful * util * occ;
+          if (score > best + 1e-9) { best = score; best_ra = ra_max; best_sg = sg; best_nw = nw; }
+        }
     }
+    if (best < 0) return 0;
+    T.NW = best_nw;
+    shape(best_ra, best_sg);
   }
   for (int step = 0; step < 11; ++step) {  // levels of equal width share a kernel: opt in to the largest request
     int need = 0;
     for (int o = 0; o < 11; ++o)
-      if (m->tcl[o].NC8 == m->tcl[step].NC8 && (o == 10) == (step == 10)) need = std::max(need, m->tcl[o].smem);
+      if (m->tcl[o].NC8 == m->tcl[step].NC8 && m->tcl[o].NW == m->tcl[step].NW && (o == 10) == (step == 10)) need = std::max(need, m->tcl[o].smem);
     static std::map<LevelKernel, int> configured;  // process-wide and monotone: several models (radii) share the kernels
-    LevelKernel k = level_kernel(m->tcl[step].NC8, step == 10);
+    LevelKernel k = level_kernel(m->tcl[step].NC8, m->tcl[step].NW, step == 10);
     if (configured[k] < need) {
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
       configured[k] = need;
@@ -614,9 +651,13 @@ static int indel_forward_tc(mural_indel_model* m, const GenomeView* G, const int
       P.Cin = T.Cin; P.CinP = T.CinP; P.ks = ks; P.stride = T.stride; P.up = T.up;
       P.Lin = T.Lin; P.Lout = T.Lout;
       P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo;
-      P.TP = T.TP; P.RA = T.RA; P.n_tiles = T.n_tiles; P.rows_in = T.rows_in;
-      P.n_items = ns * T.n_tiles;
-      LevelKernel k = level_kernel(T.NC8, tail);
+      P.TP = T.TP; P.RA = T.RA; P.n_tiles = T.n_tiles; P.rows_in = T.rows_in; P.RS = T.RS; P.SG = T.SG;
+      P.magic_stride = T.stride > 1 ? uint32_t(((1ull << 32) + T.stride - 1) / T.stride) : 0u;
+      P.magic_up = T.up > 1 ? uint32_t(((1ull << 32) + T.up - 1) / T.up) : 0u;
+      P.n_sites = ns;
+      P.n_items = cdiv(ns, T.SG) * T.n_tiles;
+      LevelKernel k = level_kernel(T.NC8, T.NW, tail);
+      const int THREADS = T.NW * 32;
       int occ = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, T.smem);
       if (occ < 1) occ = 1;

@@ -27,8 +27,12 @@
 namespace mural {
 namespace indel_tc {
 
-constexpr int NW = 8;           // warps per CTA
-constexpr int THREADS = NW * 32;
+#ifndef MURAL_INDEL_MINB1
+#define MURAL_INDEL_MINB1 4
+#endif
+#ifndef MURAL_INDEL_MINB2
+#define MURAL_INDEL_MINB2 2
+#endif
 constexpr int RA_MAX = 256;     // A rows (lconv outputs incl. the +-2 halo of Conv5) per tile
 
 // pitch (elements) of a channels-last shared-memory row of c elements (c % 8 == 0) such that pitch/8 is odd:
@@ -47,11 +51,15 @@ struct LevelParams {
   const uint4* Wo1;
   const float* bias;  // bl[C] | b5[2C] | b1[C] | bo0[C] | bo1[C]
   int Cin, CinP, ks, stride, up;
+  uint32_t magic_stride, magic_up;  // ceil(2^32 / d): x / d == __umulhi(x, magic) for 0 <= x < 2^20, d <= 16 (d == 1 handled apart)
   int Lin, Lout;
   int KCl, KC5, KCo;
   int TP, RA, n_tiles;
-  int rows_in;        // staged input rows per tile: (RA-1)*stride + ks + 1
-  int64_t n_items;    // n_sites * n_tiles
+  int SG;             // sites per work item (> 1 only when n_tiles == 1: short levels share a CTA so that every warp has a tile)
+  int rows_in;        // staged input rows per tile and site: (RA-1)*stride + ks + 1
+  int RS;             // rows per stride phase of the staged input: ceil(rows_in / stride)
+  int64_t n_sites;
+  int64_t n_items;    // ceil(n_sites / SG) * n_tiles
 };
 
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -60,14 +68,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// three products of the two-level split, small terms first
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint4& b) {
-  mma_bf16(d, al, b.x, b.y);
-  mma_bf16(d, ah, b.z, b.w);
-  mma_bf16(d, ah, b.x, b.y);
-}
-__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t a) {  // a: shared-space byte address
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -77,36 +78,51 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
   __nv_bfloat162 l = __floats2bfloat162_rn(x - hx, y - hy);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }  // as indel.cu apply_act
+__device__ __forceinline__ float silu(float x) {  // x * rcp(1 + 2^(-x log2 e)): two MUFU ops, ~3 ulp (x -> -inf: x * 0)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
+__device__ __forceinline__ int div_magic(int x, int d, uint32_t magic) { return d == 1 ? x : int(__umulhi(uint32_t(x), magic)); }
+
+// The three products of the two-level split for MT row tiles x one column tile, small terms first, issued term-major across
+// the row tiles so that an MMA does not wait on the one just before it.  (Separate accumulators for the cross terms were
+// measured: +80 registers, occupancy 40 -> 12 warps per SM, 35 % slower.)
+template <int MT>
+__device__ __forceinline__ void mma3(float (&d)[MT][4], const uint32_t (&ah)[MT][4], const uint32_t (&al)[MT][4], const uint4& b) {
+#ifdef MURAL_INDEL_MMA_CHAIN
+#pragma unroll
+  for (int i = 0; i < MT; ++i) { mma_bf16(d[i], al[i], b.x, b.y); mma_bf16(d[i], ah[i], b.z, b.w); mma_bf16(d[i], ah[i], b.x, b.y); }
+#else
+#pragma unroll
+  for (int i = 0; i < MT; ++i) mma_bf16(d[i], al[i], b.x, b.y);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) mma_bf16(d[i], ah[i], b.z, b.w);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) mma_bf16(d[i], ah[i], b.x, b.y);
+#endif
+}
 
 // accumulator fragments of column tiles (2j, 2j+1) -> split A fragment of k chunk j after f(acc + bias)
 template <int ACT>  // 0 none, 1 SiLU, 2 ReLU
-__device__ __forceinline__ void chain_frag(const float (&c0)[4], const float* c1, const float* bias0, const float* bias1, int q,
-                                           uint32_t (&ah)[4], uint32_t (&al)[4]) {
+__device__ __forceinline__ void chain_frag(const float* c0, const float* c1, const float* bias0, const float* bias1, int q, uint32_t (&ah)[4],
+                                           uint32_t (&al)[4]) {
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = c0[e] + bias0[2 * q + (e & 1)];
-  if (c1) {
+  for (int e = 0; e < 4; ++e) v[e] = c0[e] + (bias0 ? bias0[2 * q + (e & 1)] : 0.f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[4 + e] = c1[e] + bias1[2 * q + (e & 1)];
-  } else {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[4 + e] = 0.f;
-  }
+  for (int e = 0; e < 4; ++e) v[4 + e] = c1 ? c1[e] + (bias1 ? bias1[2 * q + (e & 1)] : 0.f) : 0.f;
   if (ACT == 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = silu(v[e]);
   } else if (ACT == 2) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-  }
-  if (!c1) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[4 + e] = 0.f;
   }
   split2(v[0], v[1], ah[0], al[0]);  // row g,   k 2q..2q+1
   split2(v[2], v[3], ah[1], al[1]);  // row g+8
@@ -116,8 +132,8 @@ __device__ __forceinline__ void chain_frag(const float (&c0)[4], const float* c1
 
 // shared-memory carve-up, identical on host and device
 struct Smem {
-  int oWl, oW5, oW1, oWo0, oWo1, oBias, oXhi, oXlo, oAf, oAhi, oAlo, total;
-  int PinP, PA, PC;
+  int oWl, oW5, oW1, oWo0, oWo1, oBias, oOff, oXhi, oXlo, oAf, oAhi, oAlo, total;
+  int PinP, PA, PC, xs, as;  // xs / as: elements per site of the X / A operand arrays
 };
 __host__ __device__ inline Smem smem_layout(int NC8, bool tail, const LevelParams& P) {
   Smem s;
@@ -129,22 +145,25 @@ __host__ __device__ inline Smem smem_layout(int NC8, bool tail, const LevelParam
   s.oWo0 = o; o += tail ? P.KCo * NC8 * 512 : 0;
   s.oWo1 = o; o += tail ? P.KCo * NC8 * 512 : 0;
   s.oBias = o; o += 6 * C * 4;
+  s.oOff = o; o += (P.KCl + P.KC5) * 2 * 4;  // element offset of (k chunk, k half) inside the X / A operand: no div / mod in the k loops
   s.PinP = pitch8(P.CinP);
   s.PA = pitch8(C);
   s.PC = pitch8(C);
+  s.xs = P.RS * P.stride * s.PinP;  // stride phases of RS rows each
+  s.as = (P.RA + 8) * s.PC;
   o = (o + 15) & ~15;
-  s.oXhi = o; o += ((P.rows_in * s.PinP * 2 + 15) & ~15);
-  s.oXlo = o; o += ((P.rows_in * s.PinP * 2 + 15) & ~15);
-  s.oAf = o; o += P.RA * s.PA * 4;
-  s.oAhi = o; o += (P.RA + 8) * s.PC * 2;
-  s.oAlo = o; o += (P.RA + 8) * s.PC * 2;
+  s.oXhi = o; o += P.SG * s.xs * 2;
+  s.oXlo = o; o += P.SG * s.xs * 2;
+  s.oAf = o; o += P.SG * P.RA * s.PA * 4;
+  s.oAhi = o; o += P.SG * s.as * 2;
+  s.oAlo = o; o += P.SG * s.as * 2;
   s.total = o;
   return s;
 }
 
-template <int NC8, int MT, bool TAIL>
-__global__ void __launch_bounds__(THREADS) k_unet_level(const LevelParams P) {
-  constexpr int C = 8 * NC8, NH8 = 2 * NC8;
+template <int NC8, int MT, int NW, bool TAIL>
+__global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 == 2 ? MURAL_INDEL_MINB2 : 1) k_unet_level(const LevelParams P) {
+  constexpr int C = 8 * NC8, NH8 = 2 * NC8, THREADS = NW * 32;
   extern __shared__ __align__(16) unsigned char smraw[];
   const Smem S = smem_layout(NC8, TAIL, P);
   const uint4* sWl = reinterpret_cast<const uint4*>(smraw + S.oWl);
@@ -162,6 +181,7 @@ __global__ void __launch_bounds__(THREADS) k_unet_level(const LevelParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lkh = lane >> 4;  // ldmatrix: row of this lane's address, k half
   const int PinP = S.PinP, PA = S.PA, PC = S.PC;
+  const int mt_site = P.RA >> 4;  // row tiles per site
 
   // ---- once per CTA: weights (pre-split B fragments, straight copy), biases, zero tail rows of the A operand
   {
@@ -173,208 +193,232 @@ __global__ void __launch_bounds__(THREADS) k_unet_level(const LevelParams P) {
     for (int e = tid; e < no; e += THREADS) { d[(S.oWo0 >> 4) + e] = __ldg(P.Wo0 + e); d[(S.oWo1 >> 4) + e] = __ldg(P.Wo1 + e); }
     float* db = reinterpret_cast<float*>(smraw + S.oBias);
     for (int e = tid; e < 6 * C; e += THREADS) db[e] = (e < (TAIL ? 6 : 4) * C) ? __ldg(P.bias + e) : 0.f;
-    for (int e = tid; e < 8 * PC; e += THREADS) { Ahi[P.RA * PC + e] = __float2bfloat16(0.f); Alo[P.RA * PC + e] = __float2bfloat16(0.f); }
+    for (int sg = 0; sg < P.SG; ++sg)
+      for (int e = tid; e < 8 * PC; e += THREADS) {
+        Ahi[sg * S.as + P.RA * PC + e] = __float2bfloat16(0.f);
+        Alo[sg * S.as + P.RA * PC + e] = __float2bfloat16(0.f);
+      }
+    int* doff = reinterpret_cast<int*>(smraw + S.oOff);
+    for (int e = tid; e < 2 * (P.KCl + P.KC5); e += THREADS) {
+      const bool l = e < 2 * P.KCl;
+      const int k = (l ? e : e - 2 * P.KCl) * 8, cw = l ? P.CinP : C;
+      const int t = k / cw, c = k - t * cw;
+      const int td = l ? t / P.stride : 0;
+      doff[e] = l ? ((t - td * P.stride) * P.RS + td) * PinP + c : t * PC + c;
+    }
   }
+  const int* offL = reinterpret_cast<const int*>(smraw + S.oOff);
+  const int* off5 = offL + 2 * P.KCl;
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(smraw);
   const int half = P.ks >> 1;
   const int Lv = P.Lin * P.up;
   const int cg_in = P.CinP >> 2;  // 4-channel groups per staged row
+  const int n_stage = P.RS * P.stride * cg_in;  // every slot of the stride-phase layout (a bijection of j < RS*stride)
+  const int st_dj = THREADS / cg_in, st_dc = THREADS - st_dj * cg_in;  // (row, group) advance of one staging step
 
-  for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-    const int64_t site = item / P.n_tiles;
-    const int tile = int(item - site * P.n_tiles);
+  int64_t grp = blockIdx.x / P.n_tiles;
+  int tile = blockIdx.x - int(grp) * P.n_tiles;
+  const int d_grp = gridDim.x / P.n_tiles, d_tile = gridDim.x - d_grp * P.n_tiles;
+  for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x, grp += d_grp, tile += d_tile) {
+    if (tile >= P.n_tiles) { tile -= P.n_tiles; ++grp; }
+    const int64_t site0 = grp * P.SG;
     const int p0 = tile * P.TP;
     __syncthreads();  // previous item's readers of X / A are done (first pass: orders the weight staging)
-    // ---- stage the input rows of this tile: virtual (upsampled) positions v0 .. v0 + rows_in - 1, split to bf16 hi / lo
+    // ---- stage the input rows of this tile: virtual (upsampled) positions v0 + j, split to bf16 hi / lo.  Row j is stored at
+    //      slot (j % stride) * RS + j / stride: the rows that consecutive outputs read for one tap are consecutive 16-byte-pitch
+    //      slots (conflict-free ldmatrix for any stride).
     {
       const int v0 = (p0 - 2) * P.stride - half;
-      const float* ins = P.in + site * int64_t(P.Lin) * P.Cin;
-      for (int e = tid; e < P.rows_in * cg_in; e += THREADS) {
-        const int j = e / cg_in, c4 = (e - j * cg_in) * 4;
-        const int v = v0 + j;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v >= 0 && v < Lv && c4 < P.Cin) x = __ldg(reinterpret_cast<const float4*>(ins + int64_t(P.up == 1 ? v : v / P.up) * P.Cin + c4));
-        uint2 h, l;
-        split2(x.x, x.y, h.x, l.x);
-        split2(x.z, x.w, h.y, l.y);
-        *reinterpret_cast<uint2*>(Xhi + j * PinP + c4) = h;
-        *reinterpret_cast<uint2*>(Xlo + j * PinP + c4) = l;
+      for (int sg = 0; sg < P.SG; ++sg) {
+        const int64_t site = site0 + sg;
+        const bool site_ok = site < P.n_sites;
+        const float* ins = P.in + site * int64_t(P.Lin) * P.Cin;
+        __nv_bfloat16 *xh = Xhi + sg * S.xs, *xl = Xlo + sg * S.xs;
+        int j = tid / cg_in, cgi = tid - j * cg_in;
+        for (int e = tid; e < n_stage; e += THREADS) {
+          const int v = v0 + j, c4 = cgi * 4;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (site_ok && v >= 0 && v < Lv && c4 < P.Cin)
+            x = __ldg(reinterpret_cast<const float4*>(ins + int64_t(div_magic(v, P.up, P.magic_up)) * P.Cin + c4));
+          const int jd = div_magic(j, P.stride, P.magic_stride);
+          const int slot = (j - jd * P.stride) * P.RS + jd;
+          uint2 h, l;
+          split2(x.x, x.y, h.x, l.x);
+          split2(x.z, x.w, h.y, l.y);
+          *reinterpret_cast<uint2*>(xh + slot * PinP + c4) = h;
+          *reinterpret_cast<uint2*>(xl + slot * PinP + c4) = l;
+          j += st_dj; cgi += st_dc;
+          if (cgi >= cg_in) { cgi -= cg_in; ++j; }
+        }
       }
     }
     __syncthreads();
-    // ---- phase 1: A = lconv(X) for rows [p0-2, p0-2+RA)
-    for (int mt0 = warp * MT; mt0 * 16 < P.RA; mt0 += NW * MT) {
-      float acc[MT][NC8][4];
+    // ---- phase 1: A = lconv(X) for rows [p0-2, p0-2+RA) of every site of the item
+    for (int mt0 = warp * MT; mt0 < P.SG * mt_site; mt0 += NW * MT) {
+      const int sg = P.SG == 1 ? 0 : mt0 / mt_site, ml = mt0 - sg * mt_site;
+      const uint32_t xh = sm_base + S.oXhi + 2 * (sg * S.xs + (ml * 16 + lrow) * PinP), xl = xh + (S.oXlo - S.oXhi);
+      float accm[NC8][MT][4];
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+      for (int n = 0; n < NC8; ++n)
 #pragma unroll
-        for (int n = 0; n < NC8; ++n)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[i][n][e] = 0.f;
-      int t = 0, c = 8 * lkh;  // (tap, channel) of k = kc*16 + 8*lkh
-      while (c >= P.CinP) { c -= P.CinP; ++t; }
+          for (int e = 0; e < 4; ++e) accm[n][i][e] = 0.f;
       for (int kc = 0; kc < P.KCl; ++kc) {
         uint32_t ah[MT][4], al[MT][4];
+        const int base = 2 * offL[2 * kc + lkh];  // (tap, channel) of k = kc*16 + 8*lkh as a byte offset
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          const int off = (((mt0 + i) * 16 + lrow) * P.stride + t) * PinP + c;
-          ldsm4(ah[i], Xhi + off);
-          ldsm4(al[i], Xlo + off);
+          ldsm4(ah[i], xh + base + i * 32 * PinP);
+          ldsm4(al[i], xl + base + i * 32 * PinP);
         }
 #pragma unroll
         for (int n = 0; n < NC8; ++n) {
           const uint4 b = sWl[(kc * NC8 + n) * 32 + lane];
-#pragma unroll
-          for (int i = 0; i < MT; ++i) mma3(acc[i][n], ah[i], al[i], b);
+          mma3<MT>(accm[n], ah, al, b);
         }
-        c += 16;
-        while (c >= P.CinP) { c -= P.CinP; ++t; }
       }
+      float* af = Af + sg * P.RA * PA;
+      __nv_bfloat16 *ahs = Ahi + sg * S.as, *als = Alo + sg * S.as;
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-          const int r = (mt0 + i) * 16 + g + 8 * hrow;
+          const int r = (ml + i) * 16 + g + 8 * hrow;
           const int pos = p0 - 2 + r;
           const bool valid = pos >= 0 && pos < P.Lout;  // Conv5 pads A with zeros outside the sequence
 #pragma unroll
           for (int n = 0; n < NC8; ++n) {
             const int col = n * 8 + 2 * q;
-            const float v0 = valid ? acc[i][n][2 * hrow] + bl[col] : 0.f;
-            const float v1 = valid ? acc[i][n][2 * hrow + 1] + bl[col + 1] : 0.f;
-            *reinterpret_cast<float2*>(Af + r * PA + col) = make_float2(v0, v1);
+            const float v0 = valid ? accm[n][i][2 * hrow] + bl[col] : 0.f;
+            const float v1 = valid ? accm[n][i][2 * hrow + 1] + bl[col + 1] : 0.f;
+            *reinterpret_cast<float2*>(af + r * PA + col) = make_float2(v0, v1);
             uint32_t h, l;
             split2(v0, v1, h, l);
-            *reinterpret_cast<uint32_t*>(Ahi + r * PC + col) = h;
-            *reinterpret_cast<uint32_t*>(Alo + r * PC + col) = l;
+            *reinterpret_cast<uint32_t*>(ahs + r * PC + col) = h;
+            *reinterpret_cast<uint32_t*>(als + r * PC + col) = l;
           }
         }
     }
     __syncthreads();
     // ---- phase 2: Conv5 -> SiLU -> Conv1x1 -> + A (+ skip) [-> out_conv -> max]
-    float tmax[NC8][2];
-    if (TAIL) {
+    for (int mt0 = warp * MT; mt0 < P.SG * mt_site; mt0 += NW * MT) {
+      const int sg = P.SG == 1 ? 0 : mt0 / mt_site, ml = mt0 - sg * mt_site;
+      if (ml * 16 >= P.TP) continue;
+      const int64_t site = site0 + sg;
+      const bool site_ok = site < P.n_sites;
+      const uint32_t ahs = sm_base + S.oAhi + 2 * (sg * S.as + (ml * 16 + lrow) * PC), als = ahs + (S.oAlo - S.oAhi);
+      const float* af = Af + sg * P.RA * PA;
+      const float* skipp = P.skip ? P.skip + site * int64_t(P.Lout) * C : nullptr;
+      float* outp = TAIL ? nullptr : P.out + site * int64_t(P.Lout) * C;
+      float acc5[NH8][MT][4];
 #pragma unroll
-      for (int n = 0; n < NC8; ++n) tmax[n][0] = tmax[n][1] = -INFINITY;
-    }
-    for (int mt0 = warp * MT; mt0 * 16 < P.TP; mt0 += NW * MT) {
-      float acc5[MT][NH8][4];
+      for (int n = 0; n < NH8; ++n)
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int n = 0; n < NH8; ++n)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc5[i][n][e] = 0.f;
-      int t = 0, c = 8 * lkh;
-      while (c >= C) { c -= C; ++t; }
+          for (int e = 0; e < 4; ++e) acc5[n][i][e] = 0.f;
       for (int kc = 0; kc < P.KC5; ++kc) {
         uint32_t ah[MT][4], al[MT][4];
+        const int base = 2 * off5[2 * kc + lkh];
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          const int off = ((mt0 + i) * 16 + lrow + t) * PC + c;
-          ldsm4(ah[i], Ahi + off);
-          ldsm4(al[i], Alo + off);
+          ldsm4(ah[i], ahs + base + i * 32 * PC);
+          ldsm4(al[i], als + base + i * 32 * PC);
         }
 #pragma unroll
         for (int n = 0; n < NH8; ++n) {
           const uint4 b = sW5[(kc * NH8 + n) * 32 + lane];
-#pragma unroll
-          for (int i = 0; i < MT; ++i) mma3(acc5[i][n], ah[i], al[i], b);
+          mma3<MT>(acc5[n], ah, al, b);
         }
-        c += 16;
-        while (c >= C) { c -= C; ++t; }
       }
-      float acc1[MT][NC8][4];
+      float acc1[NC8][MT][4];
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+      for (int n = 0; n < NC8; ++n)
 #pragma unroll
-        for (int n = 0; n < NC8; ++n)
+        for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc1[i][n][e] = 0.f;
+          for (int e = 0; e < 4; ++e) acc1[n][i][e] = 0.f;
 #pragma unroll
       for (int j = 0; j < NC8; ++j) {  // k chunk j of Conv1x1 = hidden channels 16j .. 16j+15 = column tiles 2j, 2j+1 of Conv5
         uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) chain_frag<1>(acc5[i][2 * j], acc5[i][2 * j + 1], b5 + 16 * j, b5 + 16 * j + 8, q, ah[i], al[i]);
+        for (int i = 0; i < MT; ++i) chain_frag<1>(acc5[2 * j][i], acc5[2 * j + 1][i], b5 + 16 * j, b5 + 16 * j + 8, q, ah[i], al[i]);
 #pragma unroll
         for (int n = 0; n < NC8; ++n) {
           const uint4 b = sW1[(j * NC8 + n) * 32 + lane];
-#pragma unroll
-          for (int i = 0; i < MT; ++i) mma3(acc1[i][n], ah[i], al[i], b);
+          mma3<MT>(acc1[n], ah, al, b);
         }
       }
       // epilogue: + bias + A (residual of the ConvBlock) + encoder skip
+      bool valid[MT][2];
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        bool valid[2];
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-          const int m = (mt0 + i) * 16 + g + 8 * hrow;
+          const int m = (ml + i) * 16 + g + 8 * hrow;
           const int pos = p0 + m;
-          valid[hrow] = m < P.TP && pos < P.Lout;
-          const int64_t o = (site * P.Lout + pos) * int64_t(C);
+          valid[i][hrow] = site_ok && m < P.TP && pos < P.Lout;
+          const int o = pos * C;
 #pragma unroll
           for (int n = 0; n < NC8; ++n) {
             const int col = n * 8 + 2 * q;
-            float2 v = make_float2(acc1[i][n][2 * hrow] + b1[col], acc1[i][n][2 * hrow + 1] + b1[col + 1]);
+            float2 v = make_float2(acc1[n][i][2 * hrow] + b1[col], acc1[n][i][2 * hrow + 1] + b1[col + 1]);
             if (m + 2 < P.RA) {
-              const float2 a = *reinterpret_cast<const float2*>(Af + (m + 2) * PA + col);
+              const float2 a = *reinterpret_cast<const float2*>(af + (m + 2) * PA + col);
               v.x += a.x; v.y += a.y;
             }
-            if (valid[hrow]) {
-              if (P.skip) { const float2 s = __ldg(reinterpret_cast<const float2*>(P.skip + o + col)); v.x += s.x; v.y += s.y; }
-              if (!TAIL) *reinterpret_cast<float2*>(P.out + o + col) = v;
+            if (valid[i][hrow]) {
+              if (P.skip) { const float2 sk = __ldg(reinterpret_cast<const float2*>(skipp + o + col)); v.x += sk.x; v.y += sk.y; }
+              if (!TAIL) *reinterpret_cast<float2*>(outp + o + col) = v;
             }
-            acc1[i][n][2 * hrow] = v.x;
-            acc1[i][n][2 * hrow + 1] = v.y;
+            acc1[n][i][2 * hrow] = v.x;
+            acc1[n][i][2 * hrow + 1] = v.y;
           }
         }
-        if (TAIL) {  // out_conv.0 (+BN, ReLU) and out_conv.3 chained in registers; running max of the pre-Softplus value
-          float zero4[4] = {0.f, 0.f, 0.f, 0.f};
-          float a0[NC8][4], a1[NC8][4];
+      if (TAIL) {  // out_conv.0 (+BN, ReLU) and out_conv.3 chained in registers; max of the pre-Softplus value over the positions
+        float a0[NC8][MT][4], a1[NC8][MT][4];
 #pragma unroll
-          for (int n = 0; n < NC8; ++n)
+        for (int n = 0; n < NC8; ++n)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a0[n][e] = a1[n][e] = 0.f;
+          for (int i = 0; i < MT; ++i)
 #pragma unroll
-          for (int j = 0; j < (NC8 + 1) / 2; ++j) {
-            uint32_t ah[4], al[4];
-            chain_frag<0>(acc1[i][2 * j], (2 * j + 1 < NC8) ? acc1[i][(2 * j + 1 < NC8) ? 2 * j + 1 : 0] : nullptr, zero4, zero4, 0, ah, al);
+            for (int e = 0; e < 4; ++e) a0[n][i][e] = a1[n][i][e] = 0.f;
 #pragma unroll
-            for (int n = 0; n < NC8; ++n) {
-              const uint4 b = sWo0[(j * NC8 + n) * 32 + lane];
-              mma3(a0[n], ah, al, b);
-            }
-          }
+        for (int j = 0; j < (NC8 + 1) / 2; ++j) {
+          uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-          for (int j = 0; j < (NC8 + 1) / 2; ++j) {
-            uint32_t ah[4], al[4];
-            chain_frag<2>(a0[2 * j], (2 * j + 1 < NC8) ? a0[(2 * j + 1 < NC8) ? 2 * j + 1 : 0] : nullptr, bo0 + 16 * j, bo0 + 16 * j + 8, q, ah, al);
+          for (int i = 0; i < MT; ++i)
+            chain_frag<0>(acc1[2 * j][i], (2 * j + 1 < NC8) ? acc1[(2 * j + 1 < NC8) ? 2 * j + 1 : 0][i] : nullptr, nullptr, nullptr, q, ah[i], al[i]);
 #pragma unroll
-            for (int n = 0; n < NC8; ++n) {
-              const uint4 b = sWo1[(j * NC8 + n) * 32 + lane];
-              mma3(a1[n], ah, al, b);
-            }
-          }
-#pragma unroll
-          for (int n = 0; n < NC8; ++n) {
-            const int col = n * 8 + 2 * q;
-            if (valid[0]) { tmax[n][0] = fmaxf(tmax[n][0], a1[n][0] + bo1[col]); tmax[n][1] = fmaxf(tmax[n][1], a1[n][1] + bo1[col + 1]); }
-            if (valid[1]) { tmax[n][0] = fmaxf(tmax[n][0], a1[n][2] + bo1[col]); tmax[n][1] = fmaxf(tmax[n][1], a1[n][3] + bo1[col + 1]); }
-          }
+          for (int n = 0; n < NC8; ++n) mma3<MT>(a0[n], ah, al, sWo0[(j * NC8 + n) * 32 + lane]);
         }
+#pragma unroll
+        for (int j = 0; j < (NC8 + 1) / 2; ++j) {
+          uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            chain_frag<2>(a0[2 * j][i], (2 * j + 1 < NC8) ? a0[(2 * j + 1 < NC8) ? 2 * j + 1 : 0][i] : nullptr, bo0 + 16 * j, bo0 + 16 * j + 8, q, ah[i], al[i]);
+#pragma unroll
+          for (int n = 0; n < NC8; ++n) mma3<MT>(a1[n], ah, al, sWo1[(j * NC8 + n) * 32 + lane]);
+        }
+#pragma unroll
+        for (int n = 0; n < NC8; ++n)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+              if (valid[i][0]) v = fmaxf(v, a1[n][i][e]);
+              if (valid[i][1]) v = fmaxf(v, a1[n][i][2 + e]);
+            }
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            const int col = n * 8 + 2 * q + e;
+            if (g == 0 && v > -INFINITY) atomic_max_float(P.gmax + site * C + col, v + bo1[col]);
+          }
       }
-    }
-    if (TAIL) {
-#pragma unroll
-      for (int n = 0; n < NC8; ++n)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float v = tmax[n][e];
-          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
-          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
-          v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-          if (g == 0 && v > -INFINITY) atomic_max_float(P.gmax + site * C + n * 8 + 2 * q + e, v);
-        }
     }
   }
 }

@@ -3,6 +3,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import bench
+import mural_b200._lib as _L0
+if os.environ.get("MURAL_LIB"): _L0.LIB_PATH = os.environ["MURAL_LIB"]
 from mural_b200 import PackedGenome, SiteBatch, _lib, model_choice, pack_meta
 L = _lib.lib()
 chroms = [bench.synth_chromosome(0)]
