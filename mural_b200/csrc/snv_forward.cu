@@ -876,7 +876,7 @@ int snv_ensure_workspace(mural_snv_model* m, int64_t bytes) {
 }
 
 int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
-                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st) {
+                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st, bool aux_ws) {
   const int C = m->cfg.channels, NC = m->cfg.n_class;
   const BranchDev &Bm = m->br[0], &Bl = m->br[1];
   const int64_t Lmax = Bl.L1 > Bm.L1 ? Bl.L1 : Bm.L1;
@@ -885,8 +885,21 @@ int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_p
   const int64_t per_site = 4 * Lmax * C + int64_t(Bm.L1) * C + int64_t(Bm.L3 + Bl.L3) * C + 3 * NC + 2 * C + m->n_cat;
   int64_t chunk = m->chunk_sites > 0 ? m->chunk_sites : 2048;
   if (chunk > n) chunk = n;
-  if (int rc = snv_ensure_workspace(m, chunk * per_site * 4 + 256)) return rc;
-  float* w = (float*)m->d_ws;
+  float* w;
+  if (aux_ws) {
+    const int64_t bytes = chunk * per_site * 4 + 256;
+    if (m->ws2_bytes < bytes) {
+      cudaFree(m->d_ws2);
+      m->d_ws2 = nullptr;
+      m->ws2_bytes = 0;
+      CUDA_TRY(cudaMalloc(&m->d_ws2, bytes));
+      m->ws2_bytes = bytes;
+    }
+    w = (float*)m->d_ws2;
+  } else {
+    if (int rc = snv_ensure_workspace(m, chunk * per_site * 4 + 256)) return rc;
+    w = (float*)m->d_ws;
+  }
   float* buf[4];
   for (int i = 0; i < 4; ++i) { buf[i] = w; w += chunk * Lmax * C; }
   float* mid0 = w; w += chunk * int64_t(Bm.L1) * C;
@@ -1045,6 +1058,8 @@ static int auto_scratch(mural_snv_model* m, int64_t bytes) {
   }
   if (!m->h_auto) CUDA_TRY(cudaMallocHost(&m->h_auto, 64));
   if (!m->auto_ev) CUDA_TRY(cudaEventCreateWithFlags((cudaEvent_t*)&m->auto_ev, cudaEventDisableTiming));
+  if (!m->aux_ev) CUDA_TRY(cudaEventCreateWithFlags((cudaEvent_t*)&m->aux_ev, cudaEventDisableTiming));
+  if (!m->aux_stream) CUDA_TRY(cudaStreamCreateWithFlags((cudaStream_t*)&m->aux_stream, cudaStreamNonBlocking));
   return 0;
 }
 
@@ -1071,8 +1086,15 @@ int snv_forward_auto(mural_snv_model* m, const GenomeView* G, const int32_t* d_p
   m->last_auto_sites = cnt;
   if (cnt == 0) return 0;
   if (G) {
-    LAUNCH(k_gather_sites, (unsigned)cdiv(cnt, 256), 256, 0, st, d_pos, d_meta, idx, cnt, pos2, meta2);
-    if (int rc = snv_forward_fp32(m, G, pos2, meta2, nullptr, nullptr, cnt, logp2, st)) return rc;
+    // The recompute is a few thousand sites in ~50 small kernels: on the caller's stream it would run after the bf16 pass and
+    // cost its full latency-bound time (0.9 ms per 2^20-site call).  The site list is final (the host has just read its
+    // length), so it goes to a side stream with its own workspace and fills idle SM resources while the bf16 pass, whose
+    // enqueue has only just finished, executes; the caller's stream joins before the scatter.
+    cudaStream_t ax = (cudaStream_t)m->aux_stream;
+    LAUNCH(k_gather_sites, (unsigned)cdiv(cnt, 256), 256, 0, ax, d_pos, d_meta, idx, cnt, pos2, meta2);
+    if (int rc = snv_forward_fp32(m, G, pos2, meta2, nullptr, nullptr, cnt, logp2, ax, true)) return rc;
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)m->aux_ev, ax));
+    CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)m->aux_ev, 0));
   } else {
     uint8_t* sym2 = nullptr;  // tensor route (parity surface): windows and k-mer rows of the flagged sites, packed
     const int64_t sb = (int64_t(cnt) * m->L + 255) & ~int64_t(255);

@@ -1,7 +1,9 @@
 // Local branch of Network2 on the tensor cores (MURAL_MODE_BF16): embedding gather + Linear(K1,H1)·ReLU·BN +
 // Linear(H1,H2)·ReLU·BN + Linear(H2,n_class)   (MuRaL/model/model_snv.py:452-468, 492; eval BN folded forward).
 //
-// One CTA = 128 sites = the 128 rows of every MMA (thread = site = TMEM lane); the three GEMMs are chained on chip:
+// One CTA = 128 sites = the 128 rows of every MMA; two warpgroups share a tile (thread = site = TMEM lane, the warpgroups
+// take alternate 8/16-column groups of the gather and of the accumulator read-back, which are the latency-bound parts of the
+// per-tile chain); the three GEMMs are chained on chip:
 //   A operand (activations, K-major SWIZZLE_NONE planes [k/8][128 rows][8] in shared memory)  x  B operand (weights
 //   [k/8][N][8], resident in shared memory for the whole kernel)  ->  fp32 accumulator in TMEM  ->  tcgen05.ld, ReLU,
 //   -> next layer's A operand.
@@ -20,8 +22,9 @@ namespace mural {
 namespace mlptc {
 
 constexpr int TILE = 128;
+constexpr int THREADS = 256;      // two warpgroups per tile
 constexpr int PLANE = TILE * 16;  // bytes of one 8-column plane of an A operand
-constexpr int NPF = 24;           // k-mer indices per site the register prefetch can hold
+constexpr int NPF = 12;           // k-mer indices per thread the register prefetch can hold (n_cat <= 2 * NPF)
 
 struct Dims {
   int n_cat, K1, H1, H2, NC, emb_rows;
@@ -77,7 +80,7 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t* __restrict__ wblob, const float* __restrict__ emb,
+__global__ void __launch_bounds__(THREADS, 1) k_local_mlp_tc(Dims d, const uint8_t* __restrict__ wblob, const float* __restrict__ emb,
                                                           const int32_t* __restrict__ cat32, const int64_t* __restrict__ cat64,
                                                           int64_t n, float* __restrict__ logits, int* __restrict__ err_flag) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -88,9 +91,10 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (TILE - 1), wg = tid >> 7;   // site of the tile / warpgroup
   const int LO = (d.maxKp / 8) * PLANE;              // byte offset of the lo planes
-  for (int e = tid; e < d.w_bytes / 16; e += TILE) reinterpret_cast<uint4*>(sW)[e] = __ldg(reinterpret_cast<const uint4*>(wblob) + e);
-  for (int e = tid; e < d.emb_rows * 5; e += TILE) sEmb[e] = __ldg(emb + e);
+  for (int e = tid; e < d.w_bytes / 16; e += THREADS) reinterpret_cast<uint4*>(sW)[e] = __ldg(reinterpret_cast<const uint4*>(wblob) + e);
+  for (int e = tid; e < d.emb_rows * 5; e += THREADS) sEmb[e] = __ldg(emb + e);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;  // a warp reaches the TMEM lanes of its quarter of the warpgroup
   const uint32_t D1 = tmem, D2 = tmem + 256, D3 = tmem + 384;  // P1 <= 256, P2 <= 128 columns (checked on the host)
   const uint32_t barA = smem_u32(&bar);
   const uint32_t aBase = smem_u32(sA), wBase = smem_u32(sW);
@@ -135,22 +139,30 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
   };
   // ReLU(D[:, 0..P)) -> next A operand (hi/lo planes), column `one_col` forced to 1.0 (bias column of the next layer)
   auto relu_to_A = [&](uint32_t dcol, int P, int one_col) {
-    for (int c = 0; c < P / 16; ++c) {
-      uint32_t v[16];
-      TMEM_LD16(v, dcol + lane_off + 16 * c);
+    // 16-column groups alternate between the warpgroups; two loads in flight per wait
+    for (int c0 = wg; c0 < P / 16; c0 += 4) {
+      uint32_t v[2][16];
+      const bool two = c0 + 2 < P / 16;
+      TMEM_LD16(v[0], dcol + lane_off + 16 * c0);
+      if (two) TMEM_LD16(v[1], dcol + lane_off + 16 * (c0 + 2));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float x0 = fmaxf(__uint_as_float(v[2 * i]), 0.f), x1 = fmaxf(__uint_as_float(v[2 * i + 1]), 0.f);
-        if (16 * c + 2 * i == one_col) x0 = 1.f;
-        if (16 * c + 2 * i + 1 == one_col) x1 = 1.f;
-        split2(x0, x1, hi[i], lo[i]);
-      }
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const int c = c0 + 2 * u;
+        uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        *reinterpret_cast<uint4*>(sA + (2 * c + h) * PLANE + tid * 16) = make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-        *reinterpret_cast<uint4*>(sA + LO + (2 * c + h) * PLANE + tid * 16) = make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+        for (int i = 0; i < 8; ++i) {
+          float x0 = fmaxf(__uint_as_float(v[u][2 * i]), 0.f), x1 = fmaxf(__uint_as_float(v[u][2 * i + 1]), 0.f);
+          if (16 * c + 2 * i == one_col) x0 = 1.f;
+          if (16 * c + 2 * i + 1 == one_col) x1 = 1.f;
+          split2(x0, x1, hi[i], lo[i]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<uint4*>(sA + (2 * c + h) * PLANE + row * 16) = make_uint4(hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+          *reinterpret_cast<uint4*>(sA + LO + (2 * c + h) * PLANE + row * 16) = make_uint4(lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+        }
       }
     }
   };
@@ -159,8 +171,8 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
   int pf[NPF];  // prefetched int32 k-mer indices of the next tile (n_cat <= NPF, checked on the host)
 #pragma unroll
   for (int i = 0; i < NPF; ++i) {
-    const int64_t gi = int64_t(blockIdx.x) * TILE * d.n_cat + tid + i * TILE;
-    pf[i] = (cat32 && tid + i * TILE < TILE * d.n_cat && gi < n * d.n_cat) ? __ldg(cat32 + gi) : 0;
+    const int64_t gi = int64_t(blockIdx.x) * TILE * d.n_cat + tid + i * THREADS;
+    pf[i] = (cat32 && tid + i * THREADS < TILE * d.n_cat && gi < n * d.n_cat) ? __ldg(cat32 + gi) : 0;
   }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t site0 = tile * TILE;
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
     if (cat32) {
 #pragma unroll
       for (int i = 0; i < NPF; ++i) {
-        const int e = tid + i * TILE;
+        const int e = tid + i * THREADS;
         if (e < TILE * d.n_cat) {
           int idx = pf[i];
           if (idx < 0 || idx >= d.emb_rows) {  // nn.Embedding would raise IndexError
@@ -182,11 +194,11 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
       const int64_t next0 = (tile + gridDim.x) * TILE * d.n_cat;
 #pragma unroll
       for (int i = 0; i < NPF; ++i) {
-        const int64_t gi = next0 + tid + i * TILE;
-        pf[i] = (tid + i * TILE < TILE * d.n_cat && gi < n * d.n_cat) ? __ldg(cat32 + gi) : 0;
+        const int64_t gi = next0 + tid + i * THREADS;
+        pf[i] = (tid + i * THREADS < TILE * d.n_cat && gi < n * d.n_cat) ? __ldg(cat32 + gi) : 0;
       }
     } else {
-      for (int e = tid; e < TILE * d.n_cat; e += TILE) {
+      for (int e = tid; e < TILE * d.n_cat; e += THREADS) {
         const int64_t gi = site0 * d.n_cat + e;
         int64_t idx = 0;
         if (gi < n * d.n_cat) {
@@ -203,8 +215,8 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
     // ---- embedding gather -> A1: thread = site; column k = 5*j + e is component e of the embedding of k-mer j,
     // column K1 = 1.0 (bias), one 16-byte store per 8-column plane
     {
-      const int32_t* myCat = sCat + tid * d.n_cat;
-      for (int pl = 0; pl < d.K1p / 8; ++pl) {
+      const int32_t* myCat = sCat + row * d.n_cat;
+      for (int pl = wg; pl < d.K1p / 8; pl += 2) {  // 8-column planes alternate between the warpgroups
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -223,8 +235,8 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
           }
           split2(x[0], x[1], hi[i], lo[i]);
         }
-        *reinterpret_cast<uint4*>(sA + pl * PLANE + tid * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sA + LO + pl * PLANE + tid * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(sA + pl * PLANE + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + LO + pl * PLANE + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
     gemm(D1, d.K1p, d.P1, 0);
@@ -232,14 +244,14 @@ __global__ void __launch_bounds__(TILE, 1) k_local_mlp_tc(Dims d, const uint8_t*
     gemm(D2, d.P1, d.P2, 1);
     relu_to_A(D2, d.P2, d.H2);
     gemm(D3, d.P2, 16, 2);
-    {
+    if (wg == 0) {
       uint32_t v[16];
       TMEM_LD16(v, D3 + lane_off);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (site0 + tid < n) {
+      if (site0 + row < n) {
 #pragma unroll
         for (int o = 0; o < 16; ++o)
-          if (o < d.NC) logits[(site0 + tid) * d.NC + o] = __uint_as_float(v[o]);
+          if (o < d.NC) logits[(site0 + row) * d.NC + o] = __uint_as_float(v[o]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,7 +286,7 @@ int snv_mlp_tc_prepare(mural_snv_model* m) {
   d.K1p = ru16(d.K1 + 1); d.P1 = ru16(d.H1 + 1); d.P2 = ru16(d.H2 + 1);
   d.maxKp = d.K1p > d.P1 ? d.K1p : d.P1;
   if (d.P2 > d.maxKp) d.maxKp = d.P2;
-  if (d.P1 > 256 || d.P2 > 128 || d.NC > 16 || d.n_cat > NPF) return 0;  // TMEM column plan / one N=16 head MMA
+  if (d.P1 > 256 || d.P2 > 128 || d.NC > 16 || d.n_cat > 2 * NPF) return 0;  // TMEM column plan / one N=16 head MMA
   const int Kp[3] = {d.K1p, d.P1, d.P2}, Np[3] = {d.P1, d.P2, 16};
   int off = 0;
   for (int l = 0; l < 3; ++l)
@@ -332,7 +344,7 @@ int snv_local_launch_tc(mural_snv_model* m, const int32_t* cat32, const int64_t*
   }
   const int64_t tiles = cdiv(ns, TILE);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  LAUNCH(k_local_mlp_tc, grid, TILE, smem, st, S->d, S->d_w, m->local.emb, cat32, cat64, ns, logits, err_flag);
+  LAUNCH(k_local_mlp_tc, grid, THREADS, smem, st, S->d, S->d_w, m->local.emb, cat32, cat64, ns, logits, err_flag);
   return 0;
 }
 

@@ -116,6 +116,9 @@ extern "C" void mural_snv_model_destroy(mural_snv_model_t* m) {
   cudaFree(m->d_auto);
   if (m->h_auto) cudaFreeHost(m->h_auto);
   if (m->auto_ev) cudaEventDestroy((cudaEvent_t)m->auto_ev);
+  if (m->aux_ev) cudaEventDestroy((cudaEvent_t)m->aux_ev);
+  if (m->aux_stream) cudaStreamDestroy((cudaStream_t)m->aux_stream);
+  cudaFree(m->d_ws2);
   snv_tc_destroy(m);
   delete m;
 }

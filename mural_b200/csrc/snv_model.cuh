@@ -87,6 +87,11 @@ struct mural_snv_model {
   void* h_auto = nullptr;
   void* auto_ev = nullptr;
   int64_t last_auto_sites = 0;
+  // ... its fp32-equivalent recompute runs on a side stream, concurrently with the bf16 pass, in its own workspace
+  void* aux_stream = nullptr;
+  void* aux_ev = nullptr;
+  void* d_ws2 = nullptr;
+  int64_t ws2_bytes = 0;
   // debug taps (parity tests): host copies of intermediate activations of the last chunk
   bool debug = false;
   bool slow_stem = false;  // parity switch: force the generic per-tap stem kernel
@@ -157,6 +162,7 @@ int wgrad32_mma(const float* x, const float* dy, int64_t rows, int L, int relu, 
                 int64_t b_off, cudaStream_t st);  // snv_conv_mma.cu: weight gradient of a C == 32, ks == 3 layer
 int snv_ensure_workspace(mural_snv_model* m, int64_t bytes);
 int onehot_to_symbols_checked(const float* d_onehot, int64_t n, int32_t W, uint8_t* d_sym, int* d_flag, cudaStream_t st);
+// aux_ws: use the side workspace (d_ws2) so that the call may run concurrently with a forward that owns d_ws
 int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta,
-                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st);
+                     const uint8_t* d_sym, const int64_t* d_cat, int64_t n, float* d_logp, cudaStream_t st, bool aux_ws = false);
 }
