@@ -97,8 +97,101 @@ def build_model(cfg, state, n_cat, mode):
     return m
 
 
+
+# ------------------------------------------------------------------------------------------ per-leg roofline / CPU baselines
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def leg_roofline(flops_per_site, sites_per_s, n_gpus, what):
+    """Whole-leg tensor roofline: algorithmic FLOPs per site x sites/s per GPU over the measured sustained bf16
+    peak.  The legs below are timed as whole steps (no per-kernel split), so this is the step's fraction, not a kernel's."""
+    peaks, src = _peaks()
+    peak = peaks["bf16_tflops_sustained"]
+    ach = flops_per_site * sites_per_s / max(n_gpus, 1) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "flops_per_site": flops_per_site, "what": what, "peak_source": src + " (bf16 sustained)"}
+
+
+def snv_train_flops(L=2001):
+    """fwd + dgrad + wgrad ~= 3 x stage-S + 2 x stage-G wgrad: 19.2 M + 3.4 M FLOP/site at L = 2001."""
+    L1 = (L - 1) // 15 + 1; L2 = (L1 - 1) // 7 + 1; L3 = (L2 - 1) // 3 + 1
+    large = 24576 * L1 + 30720 * L2 + 6144 * L3
+    return 3 * (2402304 + large + 43112) + 2 * (768 * L + 768 * 201)
+
+
+def unet_flops(C, ks, down, L, use_reverse=True):
+    """Dense conv FLOPs (multiply-add = 2) of UNet_Small.forward per site (model_indel.py:151-176): 113 379 328 for the shipped
+    human configuration (C=8, k=7, strides 1,4,5,5,5,2, L=8000)."""
+    ch = [C * (i + 1) for i in range(6)]
+    ln, x = [], L
+    for s in down:
+        x = (x - 1) // s + 1
+        ln.append(x)
+    f = 0
+    for i in range(6):
+        cin = ch[i - 1] if i else 4
+        f += 2 * ln[i] * (ks * cin * ch[i] + 5 * ch[i] * 2 * ch[i] + 2 * ch[i] * ch[i])
+    for i in range(5):
+        c = ch[4 - i]
+        f += 2 * ln[4 - i] * (ks * ch[5 - i] * c + 5 * c * 2 * c + 2 * c * c)
+    f += 2 * ln[0] * 2 * C * C
+    if use_reverse:                                          # strand-symmetric stem: the 4 -> 4 conv applied twice (:154-155)
+        f += 2 * 2 * L * ks * 4 * 4
+    return f
+
+
+def cpu_unet(state, cfg, Rd, genome_sym, pos, train=False, labels=None, budget_s=12.0, batch=8):
+    """Oracle port of the reference CPU path for MuRaL-indel (numpy one-hot windows + torch CPU fp32 UNet_Small; with train=True
+    one forward + CE(sum) + backward per batch, autograd of the oracle) on as many `batch`-site batches as fit `budget_s`."""
+    import torch
+    from oracle import encode_np as E
+    from oracle import network_t as NT
+    torch.set_num_threads(os.cpu_count())
+    sd = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=(train and "running" not in k and "num_batches" not in k))
+          for k, v in state.items()}
+    done, outs, t0 = 0, [], time.perf_counter()
+    while done + batch <= len(pos) and (done == 0 or time.perf_counter() - t0 < budget_s):
+        p = pos[done:done + batch]
+        oh = E.onehot_windows(genome_sym, p, np.zeros(len(p), np.int64), Rd, "indel")
+        if train:
+            out = NT.unet_small_forward(sd, oh, cfg["down_list"], cfg["use_reverse"], torch.float32, train=True)
+            NT.ce_sum(out, labels[done:done + batch]).backward()
+        else:
+            with torch.no_grad():
+                outs.append(NT.unet_small_forward(sd, oh, cfg["down_list"], cfg["use_reverse"], torch.float32).numpy())
+        done += batch
+    dt = time.perf_counter() - t0
+    return done / dt, dt, done, (np.concatenate(outs) if outs else None)
+
+
+def cpu_snv_train(chroms, pos, meta_lab, cfg, state, batch=128, budget_s=12.0):
+    """Oracle port of the reference CPU training step for MuRaL-snv: numpy encoders + train-mode Network2 (batch-statistic
+    BatchNorm, dropout off) + CE(sum) + backward (torch autograd on CPU, fp32); optimizer step not included."""
+    import torch
+    from oracle import encode_np as E
+    from oracle import network_t as NT
+    torch.set_num_threads(os.cpu_count())
+    sd = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=("running" not in k and "num_batches" not in k))
+          for k, v in state.items()}
+    sym = E._ASCII2SYM[chroms[0]]
+    done, t0 = 0, time.perf_counter()
+    while done + batch <= len(pos) and (done == 0 or time.perf_counter() - t0 < budget_s):
+        p, mt = pos[done:done + batch], meta_lab[done:done + batch]
+        cat = E.kmer_windows(sym, p, mt & 1, cfg["local_radius"], cfg["local_order"])
+        oh = E.onehot_windows(sym, p, mt & 1, cfg["distal_radius"])
+        out = NT.network2_forward(sd, cat, oh, torch.float32, train=True)
+        NT.ce_sum(out, (mt >> 1) & 0x7f).backward()
+        done += batch
+    dt = time.perf_counter() - t0
+    return done / dt, dt, done
+
+
 # ------------------------------------------------------------------------------------------ train leg
-def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5):
+def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5, chroms=None, cpu_legs=False):
     """BASELINE configs[2] on the same genome: MuRaL-snv training from scratch (local 10 bp 3-mers, expanded 1 Kb,
     Adam lr 1e-3), fused step = forward + CE(sum) + backward + flat-gradient all-reduce (NCCL, world > 1) + global-norm
     clip + Adam, one batch per GPU per step.  Sites: a seeded random subset of this rank's A/T sites (sorted), labels
@@ -143,10 +236,24 @@ def train_leg(genome, pos, meta, world, rank, dist, steps=30, warmup=5):
         ms = float(t.item())
         out["batch_%d" % B] = {"sites_per_s": world * B * (k_tot - w) / (ms * 1e-3), "ms_per_step": ms / (k_tot - w), "steps": k_tot - w}
     loss = float(ts.loss_dev.item())
-    return {"metric": "sites/sec (train: fwd+bwd+clip+Adam, fused step)", "value": out["batch_128"]["sites_per_s"], "unit": "sites/s",
-            "batch_per_gpu": 128, "large_batch": out["batch_4096"], "small_batch": out["batch_128"], "dtype": "f32",
-            "config": "MuRaL-snv from scratch, local 10bp 3-mers + expanded 1Kb, Adam lr 1e-3, batch per GPU as stated; "
-                      "gradient all-reduce over NCCL when n_gpus > 1", "loss_sum_finite": bool(np.isfinite(loss))}
+    res = {"metric": "sites/sec (train: fwd+bwd+clip+Adam, fused step)", "value": out["batch_128"]["sites_per_s"], "unit": "sites/s",
+           "batch_per_gpu": 128, "large_batch": out["batch_4096"], "small_batch": out["batch_128"], "dtype": "f32",
+           "config": "MuRaL-snv from scratch, local 10bp 3-mers + expanded 1Kb, Adam lr 1e-3, batch per GPU as stated; "
+                     "gradient all-reduce over NCCL when n_gpus > 1", "loss_sum_finite": bool(np.isfinite(loss))}
+    fl = snv_train_flops(2001)
+    res["roofline"] = leg_roofline(fl, out["batch_4096"]["sites_per_s"], world, "whole training step at batch 4096 per GPU (fp32-equivalent "
+                                   "arithmetic: fp32 FMA forward, split-bf16 mma.sync dgrad / wgrad)")
+    res["roofline"]["batch_128"] = leg_roofline(fl, out["batch_128"]["sites_per_s"], world, "batch 128 per GPU")["frac"]
+    if rank == 0 and cpu_legs:
+        sd0 = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        on0 = np.flatnonzero((meta >> 8) == 0)                  # the CPU sample stays on the first chromosome
+        sel = np.sort(rng.choice(on0, size=min(1024, len(on0)), replace=False))
+        lab = rng.choice(4, size=len(sel), p=[0.952381, 0.0140095, 0.0198, 0.0138095])
+        v, dt, done = cpu_snv_train(chroms, pos[sel], pack_meta(meta[sel] & 1, lab, meta[sel] >> 8), cfg, sd0)
+        res["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d sites in batches of 128: numpy encoders + train-mode Network2 forward + CE(sum) + backward "
+                                         "(torch CPU fp32 autograd of the oracle, no optimizer step), %.1f s" % (done, dt)}
+    return res
 
 
 # ------------------------------------------------------------------------------------------ transfer sweep leg
@@ -197,10 +304,10 @@ def sweep_leg(genome, pos, meta, cfg0, state, n_cat, radii=(100, 200, 500, 1000,
 
 
 # ------------------------------------------------------------------------------------------ indel leg
-def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2):
+def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2, chroms=None, cpu_legs=False):
     """BASELINE configs[3] (predict half): MuRaL-indel UNet_Small with the shipped Homo_sapiens/INDEL/insertion weights
     (tests/golden/indel_hs_ins.npz), one site every 50 bp on the '+' strand of this rank's interval, expanded radius as
-    in the checkpoint's config.  fp32 kernels (the indel network has no tcgen05 path yet)."""
+    in the checkpoint's config.  Default kernels: the fused tensor-core level kernels (csrc/indel_tc.cuh)."""
     import torch
     from mural_b200 import SiteBatch, model_choice, pack_meta
     z = np.load(os.path.join(ROOT, "tests", "golden", "indel_hs_ins.npz"))
@@ -231,9 +338,37 @@ def indel_leg(genome, world, rank, dist, batch=2048, steps=5, warmup=2):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"metric": "sites/sec (MuRaL-indel predict)", "value": world * batch * steps / (ms * 1e-3), "unit": "sites/s", "batch_per_gpu": batch,
-            "ms_per_step": ms / steps, "dtype": "f32", "finite": bool(torch.isfinite(out).all().item()),
-            "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), sites every 50 bp" % (Rd, 2 * Rd)}
+    from mural_b200 import _lib
+    tc = _lib.lib().mural_indel_tc_available(m._handle(Rd)) == 1
+    sps = world * batch * steps / (ms * 1e-3)
+    res = {"metric": "sites/sec (MuRaL-indel predict)", "value": sps, "unit": "sites/s", "batch_per_gpu": batch,
+           "ms_per_step": ms / steps, "dtype": "bf16 x2 split (fp32-equivalent), fp32 accumulate" if tc else "f32",
+           "kernels": "fused tensor-core level kernels (k_unet_level, mma.sync)" if tc else "fp32 CUDA-core kernels",
+           "finite": bool(torch.isfinite(out).all().item()),
+           "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), sites every 50 bp" % (Rd, 2 * Rd)}
+    fl = unet_flops(cfg["CNN_out_channels"], cfg["CNN_kernel_size"], cfg["down_list"], 2 * Rd, cfg["use_reverse"])
+    res["roofline"] = leg_roofline(fl, sps, world, "whole predict step (stem + 11 level kernels + head); every product is evaluated as three "
+                                   "bf16 MMAs (hi*hi + hi*lo + lo*hi), so the executed tensor work is 3x the algorithmic count used here")
+    m.compute_mode = "fp32"                                  # the CUDA-core kernels on the same sites, for the record
+    with torch.no_grad():
+        m.forward(SiteBatch(d_pos[:batch], d_meta[:batch], genome), distal_radius=Rd)
+        torch.cuda.synchronize(); ev0.record()
+        o32 = m.forward(SiteBatch(d_pos[:batch], d_meta[:batch], genome), distal_radius=Rd)
+        ev1.record(); torch.cuda.synchronize()
+    res["fp32_kernels_sites_per_s"] = batch / (ev0.elapsed_time(ev1) * 1e-3)
+    m.compute_mode = "auto"
+    if rank == 0 and cpu_legs:
+        from oracle import encode_np as E
+        v, dt, done, ref = cpu_unet(state, cfg, Rd, E._ASCII2SYM[chroms[0]], pos[:64].astype(np.int64))
+        with torch.no_grad():
+            got = m.forward(SiteBatch(d_pos[:done], d_meta[:done], genome), distal_radius=Rd).cpu().numpy()
+        res["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "first %d sites in batches of 8: numpy one-hot windows + torch CPU fp32 UNet_Small (oracle), %.1f s" % (done, dt)}
+        scale = float(max(1.0, np.abs(ref).max()))
+        res["parity_spot_check"] = {"sites": int(done), "max_abs_diff": float(np.abs(got - ref).max()), "scale": scale,
+                                    "tolerance": 1e-3 * scale, "what": "GPU outputs vs the CPU oracle on the same sites (fp32-equivalent gate)"}
+        assert res["parity_spot_check"]["max_abs_diff"] <= res["parity_spot_check"]["tolerance"], res["parity_spot_check"]
+    return res
 
 
 def eval_leg(genome, pos, meta, logp, cfg, n=1_000_000, reps=5):
@@ -295,11 +430,11 @@ def eval_leg(genome, pos, meta, logp, cfg, n=1_000_000, reps=5):
             "note": "includes the host sync + table copy of every launch; labels synthetic (class proportions of training.py:332)"}
 
 
-def indel_train_leg(genome, world, rank, dist, batch=32, steps=4, warmup=2):
+def indel_train_leg(genome, world, rank, dist, batch=32, steps=20, warmup=3, chroms=None, cpu_legs=False):
     """BASELINE configs[3] (training half): MuRaL-indel UNet_Small fine-tuned from the shipped Homo_sapiens/INDEL/insertion
     weights at its own radius (L = 8000), one site every 50 bp on the '+' strand, labels iid Categorical(0.907, 0.0133 x 7),
     fused step = train-mode forward + CE(sum) + backward + flat-gradient all-reduce (NCCL, world > 1) + clip + Adam.
-    First version of the tape (csrc/indel_train.cu): one work item per thread, no tiling yet."""
+    Tape of shared-memory-tiled fp32 kernels (csrc/indel_train.cu, indel_train_tiled.cuh)."""
     import torch
     from mural_b200 import SiteBatch, model_choice, pack_meta
     from mural_b200.training import IndelTrainState
@@ -333,9 +468,87 @@ def indel_train_leg(genome, world, rank, dist, batch=32, steps=4, warmup=2):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"metric": "sites/sec (MuRaL-indel train: fwd+bwd+clip+Adam)", "value": world * batch * steps / (ms * 1e-3), "unit": "sites/s",
-            "batch_per_gpu": batch, "ms_per_step": ms / steps, "dtype": "f32", "loss_sum_finite": bool(np.isfinite(float(ts.loss_dev.item()))),
-            "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), Adam lr 1e-4" % (Rd, 2 * Rd)}
+    sps = world * batch * steps / (ms * 1e-3)
+    res = {"metric": "sites/sec (MuRaL-indel train: fwd+bwd+clip+Adam)", "value": sps, "unit": "sites/s",
+           "batch_per_gpu": batch, "ms_per_step": ms / steps, "dtype": "f32", "loss_sum_finite": bool(np.isfinite(float(ts.loss_dev.item()))),
+           "config": "UNet_Small, Homo_sapiens/INDEL/insertion weights, expanded radius %d (L=%d), Adam lr 1e-4" % (Rd, 2 * Rd)}
+    fl = 3 * unet_flops(cfg["CNN_out_channels"], cfg["CNN_kernel_size"], cfg["down_list"], 2 * Rd, cfg["use_reverse"])
+    res["roofline"] = leg_roofline(fl, sps, world, "whole training step at batch %d per GPU (fwd + dgrad + wgrad ~= 3 x forward FLOPs; fp32 CUDA-core "
+                                   "tiled kernels)" % batch)
+    if rank == 0 and cpu_legs:
+        from oracle import encode_np as E
+        v, dt, done, _ = cpu_unet(state, cfg, Rd, E._ASCII2SYM[chroms[0]], pos[:64].astype(np.int64), train=True, labels=lab[:64], batch=8)
+        res["cpu_baseline"] = {"value": v, "unit": "sites/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d sites in batches of 8: numpy one-hot windows + train-mode UNet_Small forward + CE(sum) + backward "
+                                         "(torch CPU fp32 autograd of the oracle, no optimizer step), %.1f s" % (done, dt)}
+    return res
+
+
+
+# ------------------------------------------------------------------------------------------ context: torch eager on this GPU
+def torch_eager_leg(genome, pos, meta, cfg, state, n_cat):
+    """Opt-in context numbers (BASELINE.md par. 4, item 5): the reference networks' arithmetic as plain PyTorch library calls on
+    the SAME GPU (cuDNN / cuBLAS, eager, TF32 allowed as the reference's GPU environment would run it) — the oracle's
+    torch-functional restatement fed with device tensors; inputs are the reference's own tensors (one-hot [B,4,L] + int64 k-mer
+    indices), produced here by the device encoders and NOT timed.  Stated beside the product numbers, never as a target."""
+    import torch
+    from mural_b200 import model_choice, pack_meta, weights_init
+    from oracle import network_t as NT
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    res = {"note": "torch %s eager, TF32 allowed, inputs pre-encoded on the device (not timed)" % torch.__version__}
+    dev = torch.device("cuda")
+    sd = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in state.items()}
+
+    def timeit(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    for B in (128, 4096):
+        d_pos = torch.from_numpy(pos[:B]).cuda(); d_meta = torch.from_numpy(meta[:B]).cuda()
+        cat = genome.encode_local(d_pos, d_meta, cfg["local_radius"], cfg["local_order"])
+        oh = genome.encode_onehot(d_pos, d_meta, cfg["distal_radius"])
+        with torch.no_grad():
+            t = timeit(lambda: NT.network2_forward(sd, cat, oh, torch.float32), 5)
+        res["snv_predict_batch_%d" % B] = {"sites_per_s": B / t, "ms": t * 1e3}
+        sdt = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        lab = torch.randint(0, 4, (B,), device=dev)
+
+        def train_step():
+            for v in sdt.values():
+                if v.requires_grad:
+                    v.grad = None
+            NT.ce_sum(NT.network2_forward(sdt, cat, oh, torch.float32, train=True), lab).backward()
+        t = timeit(train_step, 5)
+        res["snv_train_fwd_bwd_batch_%d" % B] = {"sites_per_s": B / t, "ms": t * 1e3}
+    z = np.load(os.path.join(ROOT, "tests", "golden", "indel_hs_ins.npz"))
+    ist = {k[2:]: torch.as_tensor(np.asarray(z[k])).to(dev) for k in z.files if k.startswith("w:")}
+    down, rev, Rd = [int(v) for v in z["down"]], bool(z["use_reverse"]), int(z["distal_radius"])
+    for B, tr in ((256, False), (32, True)):
+        p = torch.from_numpy((20000 + 50 * np.arange(B)).astype(np.int32)).cuda()
+        mt = torch.from_numpy(pack_meta(np.zeros(B, np.int64), np.zeros(B, np.int64), np.zeros(B, np.int64))).cuda()
+        oh = genome.encode_onehot(p, mt, Rd, "indel")
+        if not tr:
+            with torch.no_grad():
+                t = timeit(lambda: NT.unet_small_forward(ist, oh, down, rev, torch.float32), 3)
+            res["indel_predict_batch_%d" % B] = {"sites_per_s": B / t, "ms": t * 1e3}
+        else:
+            sdt = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in ist.items()}
+            lab = torch.randint(0, 8, (B,), device=dev)
+
+            def istep():
+                for v in sdt.values():
+                    if v.requires_grad:
+                        v.grad = None
+                NT.ce_sum(NT.unet_small_forward(sdt, oh, down, rev, torch.float32, train=True), lab).backward()
+            t = timeit(istep, 3)
+            res["indel_train_fwd_bwd_batch_%d" % B] = {"sites_per_s": B / t, "ms": t * 1e3}
+    return res
 
 
 # ------------------------------------------------------------------------------------------ sparse-site leg
@@ -522,6 +735,8 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     ap.add_argument("--no-indel", action="store_true", help="skip the MuRaL-indel predict leg (BASELINE configs[3])")
     ap.add_argument("--no-sweep", action="store_true", help="skip the distal-radius sweep leg (SURVEY 8d config 5)")
+    ap.add_argument("--torch-eager", action="store_true", help="opt-in context leg: the oracle's torch-functional networks as eager "
+                    "PyTorch (cuDNN/cuBLAS, TF32) on this GPU, for predict and fwd+bwd (BASELINE.md par. 4 item 5)")
     ap.add_argument("--no-eval", action="store_true", help="skip the validation-metrics leg (Evaluator, SURVEY 8f N3)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -675,25 +890,26 @@ def main():
         except Exception as e:
             pipe = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    cpu_legs = world == 1 and not a.no_cpu_baseline   # CPU-port baselines of the secondary legs: rank 0 at N = 1 only
     # ---- training leg (fwd + bwd + optimizer), all ranks (it contains the gradient all-reduce)
     train = None
     if not a.no_train:
         try:
-            train = train_leg(genome, pos, meta, world, rank, dist)
+            train = train_leg(genome, pos, meta, world, rank, dist, chroms=chroms, cpu_legs=cpu_legs)
         except Exception as e:  # the predict line must survive a failure here
             train = {"error": "%s: %s" % (type(e).__name__, e)}
 
     indel = None
     if not a.no_indel:
         try:
-            indel = indel_leg(genome, world, rank, dist)
+            indel = indel_leg(genome, world, rank, dist, chroms=chroms, cpu_legs=cpu_legs)
         except Exception as e:
             indel = {"error": "%s: %s" % (type(e).__name__, e)}
 
     indel_train = None
     if not a.no_indel:
         try:
-            indel_train = indel_train_leg(genome, world, rank, dist)
+            indel_train = indel_train_leg(genome, world, rank, dist, chroms=chroms, cpu_legs=cpu_legs)
         except Exception as e:
             indel_train = {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -703,6 +919,13 @@ def main():
             sweep = sweep_leg(genome, pos, meta, cfg, state, n_cat)
         except Exception as e:
             sweep = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    eager = None
+    if rank == 0 and world == 1 and a.torch_eager:
+        try:
+            eager = torch_eager_leg(genome, pos, meta, cfg, state, n_cat)
+        except Exception as e:
+            eager = {"error": "%s: %s" % (type(e).__name__, e)}
 
     evalm = None
     if rank == 0 and not a.no_eval:
@@ -725,7 +948,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": 8 * S, "d2h_bytes_per_step": 4 * cfg["n_class"] * S},
             "roofline": roof, "sparse_predict": sparse, "pipeline": pipe, "train": train, "indel": indel, "indel_train": indel_train,
-            "eval_metrics": evalm, "transfer_sweep": sweep}
+            "eval_metrics": evalm, "transfer_sweep": sweep, "torch_eager_same_gpu": eager}
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             n_s = a.cpu_sample
