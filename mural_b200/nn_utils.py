@@ -76,7 +76,10 @@ def model_predict_m(model, dataloader, criterion, device, n_class, distal=True, 
         for item in dataloader:
             batch_count += 1
             if isinstance(item, SiteBatch):
-                preds = model.forward(None, item)
+                if model_type == "indel":                            # UNet_Small.forward(distal_x) (nn_utils.py:59-61)
+                    preds = model.forward(item, distal_radius=getattr(dataloader, "distal_radius", None) or getattr(model, "_hR", None))
+                else:
+                    preds = model.forward(None, item)
                 with torch.cuda.device(preds.device):
                     _lib.check(L.mural_ce_sum(_lib.ptr(preds), _lib.ptr(item.meta), len(item), n_class, _lib.ptr(loss_dev),
                                               _lib.current_stream()))

@@ -477,6 +477,15 @@ class IndelTrainState:
         self.model.mark_dirty()
         return out
 
+    def sync_buffers(self):
+        """Data parallel: average the rank-local BatchNorm running statistics over ranks (see TrainState.sync_buffers)."""
+        d = torch.distributed
+        if d.is_available() and d.is_initialized() and d.get_world_size() > 1 and self.n_blob > self.n_trainable:
+            buf = self.blob[self.n_trainable:]
+            d.all_reduce(buf, op=d.ReduceOp.SUM)
+            buf.div_(d.get_world_size())
+            self.model.mark_dirty()
+
     def sync_counters(self):
         """num_batches_tracked follows the number of BatchNorm calls: one per training forward, two for the reverse-strand
         stem (it is applied to the window and to its reverse complement, model_indel.py:155)."""
@@ -558,16 +567,25 @@ def validate_epoch(model, dataset, n_class=4, pred_batch_size=4096, segment_indi
     from .data import generate_site_batches
     from .evaluation import EvalData, Evaluator
     from .nn_utils import model_predict_m
-    if dataset.model_type != "snv":
-        raise NotImplementedError("validate_epoch covers MuRaL-snv; the indel Evaluator pass (k-mer lists 2/4/6 on softplus outputs) is not wired yet")
+    indel = dataset.model_type == "indel"
+    if indel and tuple(kmer_list) == (3, 5, 7):
+        kmer_list = (2, 4, 6)                                 # training.py:495: even k for indel (data_local has no centre column)
     segs = np.arange(len(dataset)) if segment_indices is None else np.asarray(segment_indices)
     was_training = model.training
-    pred_y, total_loss = model_predict_m(model, generate_site_batches(dataset, 1 << 30, pred_batch_size, shuffle=False, segment_indices=segs),
-                                         None, dataset.genome.device, n_class)
+
+    class _Batches:                                          # carries the window radius UNet_Small.forward needs with site records
+        distal_radius = dataset.distal_radius
+
+        def __iter__(self):
+            return iter(generate_site_batches(dataset, 1 << 30, pred_batch_size, shuffle=False, segment_indices=segs))
+    pred_y, total_loss = model_predict_m(model, _Batches(), None, dataset.genome.device, n_class, model_type=dataset.model_type)
     rows = np.concatenate([np.arange(dataset.batch_offsets[i], dataset.batch_offsets[i + 1]) for i in segs]) if len(segs) else np.zeros(0, np.int64)
     pos = torch.from_numpy(dataset.pos[rows]).to(pred_y.device)
     meta = torch.from_numpy(dataset.meta[rows]).to(pred_y.device)
-    flank = dataset.genome.encode_local(pos, meta, dataset.local_radius, 1)      # data_local's us*/mid/ds* columns (prepare_local_data :400)
+    flank = dataset.genome.encode_local(pos, meta, dataset.local_radius, 1, dataset.model_type)   # data_local's us*/[mid]/ds* columns (prepare_local_data :400)
+    if indel:                                                # EvalData's layout has a centre column; indel frames have none (evaluation.py)
+        r = dataset.local_radius
+        flank = torch.cat([flank[:, :r], torch.zeros_like(flank[:, :1]), flank[:, r:]], dim=1)
     prob = calibrate(pred_y.contiguous())                                        # F.softmax(pred_y, dim=1), training.py:463
     ev = Evaluator(EvalData(flank, meta, prob, f32=True), None, n_class, printer=printer)
     ev.evaluate_kmer(list(kmer_list))
@@ -624,7 +642,8 @@ def train_epochs(model, dataset, epochs, batch_size, sampled_segments=10, optim=
     if st is not None and (st.kind != OPTIMIZERS[optim] or st.weight_decay != float(weight_decay) or st.opt_step == 0):
         st = None                       # a state auto-created by a train-mode forward (Adam, lr 1e-3) must not shadow the arguments
     if st is None:
-        st = TrainState(model, optim, lr, weight_decay, seed=seed)
+        st = (IndelTrainState(model, dataset.distal_radius, optim, lr, weight_decay, seed=seed) if dataset.model_type == "indel"
+              else TrainState(model, optim, lr, weight_decay, seed=seed))
     st.lr = float(lr)
     d = torch.distributed
     world = d.get_world_size() if d.is_available() and d.is_initialized() else 1

@@ -108,7 +108,7 @@ def test_indel_fused_step_and_dropin_loop(kat, cuda_genome):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(ma2.parameters(), max_norm=10, error_if_nonfinite=False)
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     mb, _ = _model(z)
     stb = IndelTrainState(mb, Rd, "SGD", lr=1e-4, weight_decay=1e-4)
     stb.set_dropout(0.0)
@@ -122,3 +122,52 @@ def test_indel_fused_step_and_dropin_loop(kat, cuda_genome):
     mb.eval()
     with torch.no_grad():
         assert torch.isfinite(mb.forward(sb, distal_radius=Rd)).all()
+
+
+def test_indel_train_epochs_with_validation_metrics(kat, cuda_genome):
+    """train_epochs on a MuRaL-indel dataset: the native training tape per batch, then per epoch the validation half of
+    training.py:454-520 with model_type 'indel' — prediction through UNet_Small, CE(sum) on the Softplus outputs, Evaluator with
+    kmer_list [2, 4, 6].  Loss and k-mer correlations equal the numpy oracle's on the same predictions."""
+    from oracle import encode_np as E
+    from oracle import evaluation_np as EN
+    from mural_b200 import PackedSiteDataset, SiteBatch, SiteTable
+    from mural_b200.training import train_epochs
+    z = np.load(os.path.join(GOLD, "indel_hs_ins.npz"))
+    m, state = _model(z)
+    _, genome = kat
+    names = list(genome)
+    rng = np.random.default_rng(11)
+    n, R, r_loc = 900, 500, 5
+    ch = rng.integers(0, len(names), n)
+    st = np.array([rng.integers(R + 10, len(genome[names[c]]) - R - 10) for c in ch])
+    o = np.lexsort((st, ch))
+    ch, st = ch[o], st[o]
+    sd = rng.integers(0, 2, n)
+    lab = rng.choice(8, n, p=[.65] + [.05] * 7)
+    ds = PackedSiteDataset(SiteTable(names, ch, st, st + 1, sd, lab), cuda_genome, 2000, r_loc, 1, R, "indel")
+    segs = np.arange(len(ds))
+    valid, train = segs[::3], np.setdiff1d(segs, segs[::3])
+    hist, lines = [], []
+    losses = train_epochs(m, ds, 2, 32, sampled_segments=4, lr=1e-5, segment_indices=train, valid_indices=valid, history=hist,
+                          printer=lambda *a: lines.append(a))
+    assert len(losses) == 2 and len(hist) == 2 and all(np.isfinite(losses))
+    h = hist[-1]
+    assert {"valid_loss", "kmer2", "kmer4", "kmer6", "score"} <= set(h), sorted(h)
+    rows = np.concatenate([np.arange(ds.batch_offsets[i], ds.batch_offsets[i + 1]) for i in valid])
+    assert h["valid_size"] == len(rows)
+    m.eval()
+    with torch.no_grad():
+        pred = m.forward(SiteBatch(torch.from_numpy(ds.pos[rows]).cuda(), torch.from_numpy(ds.meta[rows]).cuda(), cuda_genome), distal_radius=R)
+    labels = ds.label[rows].astype(np.int64)
+    loss = float(torch.nn.functional.cross_entropy(pred.double(), torch.from_numpy(labels).cuda(), reduction="sum").item())
+    assert abs(loss / len(rows) - h["valid_loss"]) < 1e-5 * max(1.0, abs(h["valid_loss"]))
+    prob = torch.softmax(pred, 1).cpu().numpy().astype(np.float64)
+    flank = np.empty((len(rows), 2 * r_loc), np.int64)
+    for c in range(len(names)):
+        msk = ds.chrom[rows] == cuda_genome.chrom_index[names[c]]
+        if msk.any():
+            flank[msk] = E.kmer_windows(E.seq_to_symbols(genome[names[c]]), ds.pos[rows][msk].astype(np.int64), ds.strand[rows][msk], r_loc, 1, "indel")
+    flank = np.concatenate([flank[:, :r_loc], np.zeros((len(rows), 1), np.int64), flank[:, r_loc:]], 1)   # dummy centre column
+    for k in (2, 4):
+        ref = EN.freq_kmer_comp_multi(flank, labels, prob, k, 8)
+        assert np.allclose(h["kmer%d" % k], ref, rtol=0, atol=2e-5, equal_nan=True), (k, h["kmer%d" % k], ref)
