@@ -206,7 +206,7 @@ struct mural_indel_model {
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
   // tensor-core path (indel_tc.cuh): one fused kernel per U-Net level; pre-split bf16 B fragments + biases in d_tc
-  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, NC8, MT, NW, SG, TP, RA, RS, n_tiles, rows_in, smem, Lin, Lout; };
+  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, F, HA, dmin, ND, NC8, MT, NW, SG, TP, RA, RS, n_tiles, rows_in, smem, Lin, Lout; };
   std::vector<TcLevel> tcl;  // encoder levels 0..5, decoder steps 0..4 (levels 4..0)
   int64_t tcWo0 = -1, tcWo1 = -1;
   int tcKCo = 0;
@@ -341,22 +341,28 @@ static int64_t make_frags(std::vector<uint32_t>& buf, const float* W, int ks, in
 }
 
 typedef void (*LevelKernel)(const indel_tc::LevelParams);
-// Row tiles per warp by level width: narrow levels are long, wide levels hold many column tiles per row tile in registers.
-static int level_mt(int NC8) { return NC8 <= 2 ? 2 : 1; }
-// resident CTAs per SM allowed by the register file (ptxas -v of the instantiations below)
-static int level_reg_ctas(int NC8, int NW) { return NW == 16 ? 1 : NC8 == 1 ? 4 : NC8 <= 4 ? 2 + (NC8 >= 3) : 2; }
-static LevelKernel level_kernel(int NC8, int NW, bool tail) {
+// Kernel instantiations: (column tiles NC8 = C/8, row tiles per warp MT, warps per CTA NW).  Narrow levels are long: two row
+// tiles per warp reuse each weight fragment twice; wide levels hold many column tiles per row tile in registers (MT = 1), and
+// when their weights leave room for one CTA per SM only, that CTA brings 16 warps.
+static LevelKernel level_kernel(int NC8, int MT, int NW, bool tail) {
   using namespace indel_tc;
-  if (tail) return NW != 8 ? nullptr : NC8 == 1 ? (LevelKernel)k_unet_level<1, 2, 8, true> : NC8 == 2 ? (LevelKernel)k_unet_level<2, 2, 8, true> : nullptr;
+  if (tail) {
+    if (NW != 8) return nullptr;
+    if (NC8 == 1) return MT == 2 ? (LevelKernel)k_unet_level<1, 2, 8, true> : MT == 1 ? (LevelKernel)k_unet_level<1, 1, 8, true> : nullptr;
+    if (NC8 == 2) return MT == 2 ? (LevelKernel)k_unet_level<2, 2, 8, true> : MT == 1 ? (LevelKernel)k_unet_level<2, 1, 8, true> : nullptr;
+    return nullptr;
+  }
+  if (MT == 2 && NW == 8) return NC8 == 1 ? (LevelKernel)k_unet_level<1, 2, 8, false> : NC8 == 2 ? (LevelKernel)k_unet_level<2, 2, 8, false> : nullptr;
+  if (MT != 1) return nullptr;
   if (NW == 8) switch (NC8) {
-    case 1: return k_unet_level<1, 2, 8, false>;
-    case 2: return k_unet_level<2, 2, 8, false>;
+    case 1: return k_unet_level<1, 1, 8, false>;
+    case 2: return k_unet_level<2, 1, 8, false>;
     case 3: return k_unet_level<3, 1, 8, false>;
     case 4: return k_unet_level<4, 1, 8, false>;
     case 5: return k_unet_level<5, 1, 8, false>;
     case 6: return k_unet_level<6, 1, 8, false>;
   }
-  if (NW == 16) switch (NC8) {  // wide levels: the weights leave room for one CTA per SM, so that CTA brings 16 warps
+  if (NW == 16) switch (NC8) {
     case 3: return k_unet_level<3, 1, 16, false>;
     case 4: return k_unet_level<4, 1, 16, false>;
     case 5: return k_unet_level<5, 1, 16, false>;
@@ -364,6 +370,8 @@ static LevelKernel level_kernel(int NC8, int NW, bool tail) {
   }
   return nullptr;
 }
+// resident CTAs per SM allowed by the register file (ptxas -v of the instantiations above)
+static int level_reg_ctas(int NC8, int NW) { return NW == 16 ? 1 : NC8 == 1 ? 4 : NC8 <= 4 ? 2 + (NC8 >= 3) : 2; }
 
 // Builds the fragment buffers and the tile geometry of the 11 level kernels; leaves tc_ok false (fp32 kernels are used) when
 // a level does not fit: channels not a multiple of 8, a level wider than 48 channels, or > 227 KB of shared memory.
@@ -373,90 +381,119 @@ static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep
   m->tcl.clear();
   const int C = m->cfg.channels, ks = m->cfg.kernel_size;
   if (C % 8 != 0 || m->ch[5] > 48) return 0;
+  m->tcKCo = (C / 8 + 1) / 2;
   std::vector<uint32_t> buf;
   auto fbits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+  auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
   for (int step = 0; step < 11; ++step) {
-    const bool dec = step >= 6;
+    const bool dec = step >= 6, tail = step == 10;
     const int lvl = dec ? 4 - (step - 6) : step;
     const int o0 = dec ? 18 + 3 * (step - 6) : 3 * step;  // lconv, conv5, conv1 of this level in m->ops
     const mural_indel_model::Op &ol = m->ops[o0], &o5 = m->ops[o0 + 1], &o1 = m->ops[o0 + 2];
+    if (o5.ks != 5 || o1.ks != 1 || ol.ks != ks) return 0;
     mural_indel_model::TcLevel T{};
     T.NC8 = m->ch[lvl] / 8;
-    T.MT = level_mt(T.NC8);
-    T.NW = 8;
     T.Cin = ol.Cin;
     T.CinP = (ol.Cin + 7) & ~7;
     T.stride = ol.stride;
-    T.up = ol.up;
     T.Lin = dec ? m->len[lvl + 1] : (lvl ? m->len[lvl - 1] : m->L);
     T.Lout = m->len[lvl];
-    if (o5.ks != 5 || o1.ks != 1 || ol.ks != ks) return 0;
-    T.Wl = make_frags(buf, prep.data() + ol.W, ks, ol.Cin, T.CinP, ol.Cout);
+    T.KC5 = (5 * m->ch[lvl] + 15) / 16;
+    // lconv weights as written (unfolded) and, for a decoder level, with the nearest upsampling folded in: output position
+    // F*m + ph, tap t reads low-resolution row m + floor((ph + t - half) / F); per phase ph the taps with the same row offset d
+    // are summed (fp64) into Wf[ph][d - dmin] (ND = dmax - dmin + 1 taps instead of ks).
+    const int64_t Wl_plain = make_frags(buf, prep.data() + ol.W, ks, ol.Cin, T.CinP, ol.Cout);
+    int64_t Wl_fold = -1;
+    int fF = 1, f_dmin = 0, fND = ks;
+    if (ol.up > 1 && ol.stride == 1) {
+      fF = ol.up;
+      const int half = ks / 2;
+      f_dmin = fdiv(-half, fF);
+      fND = fdiv(fF - 1 + ks - 1 - half, fF) - f_dmin + 1;
+      std::vector<float> Wf(size_t(fND) * ol.Cin * ol.Cout);
+      for (int ph = 0; ph < fF; ++ph) {
+        std::vector<double> acc(Wf.size(), 0.0);
+        for (int t = 0; t < ks; ++t) {
+          const int d = fdiv(ph + t - half, fF) - f_dmin;
+          for (int e = 0; e < ol.Cin * ol.Cout; ++e) acc[size_t(d) * ol.Cin * ol.Cout + e] += double(prep[ol.W + size_t(t) * ol.Cin * ol.Cout + e]);
+        }
+        for (size_t e = 0; e < Wf.size(); ++e) Wf[e] = float(acc[e]);
+        const int64_t off = make_frags(buf, Wf.data(), fND, ol.Cin, T.CinP, ol.Cout);
+        if (ph == 0) Wl_fold = off;
+      }
+    }
     T.W5 = make_frags(buf, prep.data() + o5.W, 5, o5.Cin, o5.Cin, o5.Cout);
     T.W1 = make_frags(buf, prep.data() + o1.W, 1, o1.Cin, o1.Cin, o1.Cout);
-    T.KCl = (ks * T.CinP + 15) / 16;
-    T.KC5 = (5 * m->ch[lvl] + 15) / 16;
     const int Cl = m->ch[lvl];
     T.bias = (int64_t)buf.size();
     for (int c = 0; c < Cl; ++c) buf.push_back(fbits(prep[ol.b + c]));
     for (int c = 0; c < 2 * Cl; ++c) buf.push_back(fbits(prep[o5.b + c]));
     for (int c = 0; c < Cl; ++c) buf.push_back(fbits(prep[o1.b + c]));
-    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(step == 10 ? prep[m->ops[33].b + c] : 0.f));
-    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(step == 10 ? prep[m->ops[34].b + c] : 0.f));
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(tail ? prep[m->ops[33].b + c] : 0.f));
+    for (int c = 0; c < Cl; ++c) buf.push_back(fbits(tail ? prep[m->ops[34].b + c] : 0.f));
     while (buf.size() & 3) buf.push_back(0u);
-    m->tcl.push_back(T);
-  }
-  m->tcKCo = (C / 8 + 1) / 2;
-  m->tcWo0 = make_frags(buf, prep.data() + m->ops[33].W, 1, C, C, C);
-  m->tcWo1 = make_frags(buf, prep.data() + m->ops[34].W, 1, C, C, C);
-  for (int step = 0; step < 11; ++step) {
-    mural_indel_model::TcLevel& T = m->tcl[step];
-    if (!level_kernel(T.NC8, 8, step == 10)) return 0;
-    // tile: up to RA_MAX rows of A (outputs + the +-2 halo of Conv5); levels shorter than a tile may put SG sites into one
-    // work item so that every warp of the CTA has a row tile.  Candidates must fit the 227 KB of an SM.
-    auto shape = [&](int ra_max, int sg) {
-      T.n_tiles = (T.Lout + (ra_max - 4) - 1) / (ra_max - 4);
-      T.TP = (T.Lout + T.n_tiles - 1) / T.n_tiles;
-      T.RA = ((T.TP + 4 + 16 * T.MT - 1) / (16 * T.MT)) * (16 * T.MT);
-      T.rows_in = (T.RA - 1) * T.stride + ks + 1;
+
+    // ---- shape of the level kernel: (folded?, MT, NW, tile rows, site group), all candidates that fit the 227 KB of an SM;
+    // cost = tensor work per site / (share of warps that get a row tile x occupancy factor).  Few resident warps cannot hide
+    // the phase barriers and the global-load latency (measured on the shipped shapes: 8 warps ~0.55, 16 ~0.8 of the 24+ rate).
+    auto shape = [&](bool fold, int MT, int NW, int ra_max, int sg) {
+      T.MT = MT; T.NW = NW;
+      T.F = fold ? fF : 1; T.HA = fold ? fF : 2; T.dmin = fold ? f_dmin : 0; T.ND = fold ? fND : ks;
+      T.up = fold ? 1 : ol.up;                                // folded: the kernel stages low-resolution rows
+      T.Wl = fold ? Wl_fold : Wl_plain;
+      T.KCl = (T.ND * T.CinP + 15) / 16;
+      const int unit = 16 * MT * T.F;                         // a row tile holds one phase: RA is a multiple of F row-tile groups
+      const int cap = ((ra_max + unit - 1) / unit) * unit;
+      const int usable = ((cap - T.HA - 2) / T.F) * T.F;      // outputs per tile (a multiple of F: tiles start on a phase-0 position);
+                                                              // the rest is the halo of Conv5 (+ alignment when folded)
+      if (usable < T.F) return false;
+      T.n_tiles = (T.Lout + usable - 1) / usable;
+      T.TP = (((T.Lout + T.n_tiles - 1) / T.n_tiles + T.F - 1) / T.F) * T.F;
+      T.RA = ((T.TP + T.HA + 2 + unit - 1) / unit) * unit;
+      T.rows_in = T.F > 1 ? T.RA / T.F + T.ND : (T.RA - 1) * T.stride + ks + 1;
       T.RS = (T.rows_in + T.stride - 1) / T.stride;
       T.SG = T.n_tiles == 1 ? sg : 1;
       LevelParams P{};
       P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo; P.CinP = T.CinP; P.RA = T.RA; P.rows_in = T.rows_in; P.RS = T.RS;
-      P.stride = T.stride; P.SG = T.SG;
-      T.smem = smem_layout(T.NC8, step == 10, P).total;
+      P.stride = T.stride; P.SG = T.SG; P.F = T.F; P.HA = T.HA;
+      T.smem = smem_layout(T.NC8, tail, P).total;
+      return T.SG == sg && T.smem <= 227 * 1024;
     };
-    // score = useful rows per tile x share of warps that get a row tile x an occupancy factor (few resident warps cannot hide
-    // the phase barriers and the global-load latency; measured on the shipped shapes: 8 warps ~0.55, 16 ~0.8 of the 24+ rate)
     double best = -1.0;
-    int best_ra = 0, best_sg = 0, best_nw = 0;
-    for (int nw : {8, 16}) {
-      if (!level_kernel(T.NC8, nw, step == 10)) continue;
-      T.NW = nw;
-      for (int ra_max = RA_MAX; ra_max >= 16 * T.MT; ra_max /= 2)
-        for (int sg = 1; sg <= 16; sg *= 2) {
-          shape(ra_max, sg);
-          if (T.SG != sg) break;  // several tiles per site: no site groups
-          if (T.smem > 227 * 1024) break;
-          const int tiles = T.SG * (T.RA / 16), per_round = T.NW * T.MT;
-          const double util = double(tiles) / double(((tiles + per_round - 1) / per_round) * per_round);
-          const double useful = double(T.Lout) / double(T.n_tiles * T.RA);
-          const int ctas = std::min((227 * 1024) / T.smem, level_reg_ctas(T.NC8, nw));
-          const double occ = sqrt(std::min(1.0, double(ctas * nw) / 24.0));
-          const double score = useful * util * occ;
-          if (score > best + 1e-9) { best = score; best_ra = ra_max; best_sg = sg; best_nw = nw; }
+    int bF = 0, bMT = 0, bNW = 0, bRA = 0, bSG = 0;
+    for (int fold = 0; fold <= (Wl_fold >= 0 ? 1 : 0); ++fold)
+      for (int MT : {2, 1})
+        for (int NW : {8, 16}) {
+          if (!level_kernel(T.NC8, MT, NW, tail)) continue;
+          for (int ra_max = RA_MAX; ra_max >= 16; ra_max /= 2)
+            for (int sg = 1; sg <= 16; sg *= 2) {
+              if (!shape(fold != 0, MT, NW, ra_max, sg)) break;
+              const int tiles = T.SG * (T.RA / 16), per_round = NW * MT;
+              const double util = double(tiles) / double(((tiles + per_round - 1) / per_round) * per_round);
+              const int ctas = std::min((227 * 1024) / T.smem, level_reg_ctas(T.NC8, NW));
+              const double occ = sqrt(std::min(1.0, double(ctas * NW) / 24.0));
+              const double work = double(T.n_tiles) * T.RA * (double(T.KCl) * T.NC8 + 2.0 * T.KC5 * T.NC8 + double(T.NC8) * T.NC8);
+              const double score = util * occ / work;
+              if (score > best * (1.0 + 1e-9)) { best = score; bF = fold; bMT = MT; bNW = NW; bRA = ra_max; bSG = sg; }
+            }
         }
-    }
     if (best < 0) return 0;
-    T.NW = best_nw;
-    shape(best_ra, best_sg);
+    shape(bF != 0, bMT, bNW, bRA, bSG);
+    if (getenv("MURAL_INDEL_DEBUG"))
+      fprintf(stderr, "indel level %2d: NC8=%d fold=%d(F=%d ND=%d) MT=%d NW=%d Lout=%d n_tiles=%d TP=%d RA=%d SG=%d KCl=%d smem=%d\n", step, T.NC8,
+              bF, T.F, T.ND, T.MT, T.NW, T.Lout, T.n_tiles, T.TP, T.RA, T.SG, T.KCl, T.smem);
+    m->tcl.push_back(T);
   }
-  for (int step = 0; step < 11; ++step) {  // levels of equal width share a kernel: opt in to the largest request
+  m->tcWo0 = make_frags(buf, prep.data() + m->ops[33].W, 1, C, C, C);
+  m->tcWo1 = make_frags(buf, prep.data() + m->ops[34].W, 1, C, C, C);
+  for (int step = 0; step < 11; ++step) {  // levels of equal shape share a kernel: opt in to the largest request
+    const mural_indel_model::TcLevel& T = m->tcl[step];
     int need = 0;
     for (int o = 0; o < 11; ++o)
-      if (m->tcl[o].NC8 == m->tcl[step].NC8 && m->tcl[o].NW == m->tcl[step].NW && (o == 10) == (step == 10)) need = std::max(need, m->tcl[o].smem);
+      if (level_kernel(m->tcl[o].NC8, m->tcl[o].MT, m->tcl[o].NW, o == 10) == level_kernel(T.NC8, T.MT, T.NW, step == 10))
+        need = std::max(need, m->tcl[o].smem);
     static std::map<LevelKernel, int> configured;  // process-wide and monotone: several models (radii) share the kernels
-    LevelKernel k = level_kernel(m->tcl[step].NC8, m->tcl[step].NW, step == 10);
+    LevelKernel k = level_kernel(T.NC8, T.MT, T.NW, step == 10);
     if (configured[k] < need) {
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
       configured[k] = need;
@@ -630,6 +667,8 @@ static int indel_forward_tc(mural_indel_model* m, const GenomeView* G, const int
       CUDA_TRY(cudaFuncSetAttribute(k_indel_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
       conf = ssm;
     }
+    // (building the network input inside the first level kernel while staging was measured: +0.5 ms on that kernel for the
+    // 0.2 ms of this one — a per-tile symbol fetch and two extra barriers in a latency-bound loop.  Kept separate.)
     LAUNCH(k_indel_stem, (unsigned)ns, 256, ssm, st, gv, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
            d_sym ? d_sym + s0 * L : nullptr, m->cfg.distal_radius, L, ks, m->stemT >= 0 ? m->d_prep + m->stemT : nullptr,
            m->stemB >= 0 ? m->d_prep + m->stemB : nullptr, X);
@@ -652,11 +691,12 @@ static int indel_forward_tc(mural_indel_model* m, const GenomeView* G, const int
       P.Lin = T.Lin; P.Lout = T.Lout;
       P.KCl = T.KCl; P.KC5 = T.KC5; P.KCo = m->tcKCo;
       P.TP = T.TP; P.RA = T.RA; P.n_tiles = T.n_tiles; P.rows_in = T.rows_in; P.RS = T.RS; P.SG = T.SG;
+      P.F = T.F; P.HA = T.HA; P.dmin = T.dmin;
       P.magic_stride = T.stride > 1 ? uint32_t(((1ull << 32) + T.stride - 1) / T.stride) : 0u;
       P.magic_up = T.up > 1 ? uint32_t(((1ull << 32) + T.up - 1) / T.up) : 0u;
       P.n_sites = ns;
       P.n_items = cdiv(ns, T.SG) * T.n_tiles;
-      LevelKernel k = level_kernel(T.NC8, T.NW, tail);
+      LevelKernel k = level_kernel(T.NC8, T.MT, T.NW, tail);
       const int THREADS = T.NW * 32;
       int occ = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, T.smem);

@@ -44,7 +44,7 @@ struct LevelParams {
   const float* skip;  // [site][Lout][C] encoder output added at the end (decoder) or NULL
   float* out;         // [site][Lout][C] (not TAIL)
   float* gmax;        // [site][C] running max of the pre-Softplus out_conv output (TAIL), pre-filled with -inf
-  const uint4* Wl;    // B fragments [KCl][NC8][32 lanes] {b0 hi, b1 hi, b0 lo, b1 lo}
+  const uint4* Wl;    // B fragments [F phases][KCl][NC8][32 lanes] {b0 hi, b1 hi, b0 lo, b1 lo}
   const uint4* W5;    // [KC5][2*NC8][32]
   const uint4* W1;    // [NC8][NC8][32]
   const uint4* Wo0;   // [KCo][NC8][32] (TAIL)
@@ -55,6 +55,8 @@ struct LevelParams {
   int Lin, Lout;
   int KCl, KC5, KCo;
   int TP, RA, n_tiles;
+  int F, HA, dmin;    // decoder levels fold the nearest upsampling by F into the weights (see phase 1): F phases of RA/F rows; HA = rows
+                      // of A in front of the tile's first output (2 = the Conv5 halo, or F when folded); dmin = first low-res tap offset
   int SG;             // sites per work item (> 1 only when n_tiles == 1: short levels share a CTA so that every warp has a tile)
   int rows_in;        // staged input rows per tile and site: (RA-1)*stride + ks + 1
   int RS;             // rows per stride phase of the staged input: ceil(rows_in / stride)
@@ -139,7 +141,7 @@ __host__ __device__ inline Smem smem_layout(int NC8, bool tail, const LevelParam
   Smem s;
   const int C = 8 * NC8;
   int o = 0;
-  s.oWl = o; o += P.KCl * NC8 * 512;
+  s.oWl = o; o += P.F * P.KCl * NC8 * 512;
   s.oW5 = o; o += P.KC5 * 2 * NC8 * 512;
   s.oW1 = o; o += NC8 * NC8 * 512;
   s.oWo0 = o; o += tail ? P.KCo * NC8 * 512 : 0;
@@ -150,7 +152,7 @@ __host__ __device__ inline Smem smem_layout(int NC8, bool tail, const LevelParam
   s.PA = pitch8(C);
   s.PC = pitch8(C);
   s.xs = P.RS * P.stride * s.PinP;  // stride phases of RS rows each
-  s.as = (P.RA + 8) * s.PC;
+  s.as = (P.RA + 8 + P.HA) * s.PC;  // + zero rows behind the tile: k overrun of the last taps
   o = (o + 15) & ~15;
   s.oXhi = o; o += P.SG * s.xs * 2;
   s.oXlo = o; o += P.SG * s.xs * 2;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
   // ---- once per CTA: weights (pre-split B fragments, straight copy), biases, zero tail rows of the A operand
   {
     uint4* d = reinterpret_cast<uint4*>(smraw);
-    const int nl = P.KCl * NC8 * 32, n5 = P.KC5 * NH8 * 32, n1 = NC8 * NC8 * 32, no = TAIL ? P.KCo * NC8 * 32 : 0;
+    const int nl = P.F * P.KCl * NC8 * 32, n5 = P.KC5 * NH8 * 32, n1 = NC8 * NC8 * 32, no = TAIL ? P.KCo * NC8 * 32 : 0;
     for (int e = tid; e < nl; e += THREADS) d[(S.oWl >> 4) + e] = __ldg(P.Wl + e);
     for (int e = tid; e < n5; e += THREADS) d[(S.oW5 >> 4) + e] = __ldg(P.W5 + e);
     for (int e = tid; e < n1; e += THREADS) d[(S.oW1 >> 4) + e] = __ldg(P.W1 + e);
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
     float* db = reinterpret_cast<float*>(smraw + S.oBias);
     for (int e = tid; e < 6 * C; e += THREADS) db[e] = (e < (TAIL ? 6 : 4) * C) ? __ldg(P.bias + e) : 0.f;
     for (int sg = 0; sg < P.SG; ++sg)
-      for (int e = tid; e < 8 * PC; e += THREADS) {
+      for (int e = tid; e < (8 + P.HA) * PC; e += THREADS) {
         Ahi[sg * S.as + P.RA * PC + e] = __float2bfloat16(0.f);
         Alo[sg * S.as + P.RA * PC + e] = __float2bfloat16(0.f);
       }
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
     //      slot (j % stride) * RS + j / stride: the rows that consecutive outputs read for one tap are consecutive 16-byte-pitch
     //      slots (conflict-free ldmatrix for any stride).
     {
-      const int v0 = (p0 - 2) * P.stride - half;
+      const int v0 = P.F > 1 ? p0 / P.F - 1 + P.dmin : (p0 - P.HA) * P.stride - half;   // folded levels stage low-resolution rows
       for (int sg = 0; sg < P.SG; ++sg) {
         const int64_t site = site0 + sg;
         const bool site_ok = site < P.n_sites;
@@ -253,10 +255,18 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
       }
     }
     __syncthreads();
-    // ---- phase 1: A = lconv(X) for rows [p0-2, p0-2+RA) of every site of the item
+    // ---- phase 1: A = lconv(X) for rows [p0-HA, p0-HA+RA) of every site of the item.
+    //      Decoder levels (nn.Upsample(scale_factor=F) in front of the conv, model_indel.py:90-117): output position F*m + ph reads
+    //      the low-resolution rows m + floor((ph + t - half) / F), t = 0..ks-1 — at most ceil((ks-1)/F)+1 distinct rows — so the
+    //      taps that hit the same row are summed on the host into one weight per (phase ph, row offset): K shrinks from ks*Cin to
+    //      ND*Cin (112 -> 48 at the top level) and nothing is replicated in shared memory.  Rows of one phase form the row tiles
+    //      (tile index = ph * RP/16 + ...); the zero padding of the upsampled signal coincides with that of the low-res rows.
+    const int mt_phase = mt_site / P.F;  // row tiles per phase
     for (int mt0 = warp * MT; mt0 < P.SG * mt_site; mt0 += NW * MT) {
       const int sg = P.SG == 1 ? 0 : mt0 / mt_site, ml = mt0 - sg * mt_site;
-      const uint32_t xh = sm_base + S.oXhi + 2 * (sg * S.xs + (ml * 16 + lrow) * PinP), xl = xh + (S.oXlo - S.oXhi);
+      const int ph = P.F == 1 ? 0 : ml / mt_phase, mi0 = (ml - ph * mt_phase) * 16;
+      const uint32_t xh = sm_base + S.oXhi + 2 * (sg * S.xs + (mi0 + lrow) * PinP), xl = xh + (S.oXlo - S.oXhi);
+      const uint4* wl = sWl + ph * P.KCl * NC8 * 32;
       float accm[NC8][MT][4];
 #pragma unroll
       for (int n = 0; n < NC8; ++n)
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
         }
 #pragma unroll
         for (int n = 0; n < NC8; ++n) {
-          const uint4 b = sWl[(kc * NC8 + n) * 32 + lane];
+          const uint4 b = wl[(kc * NC8 + n) * 32 + lane];
           mma3<MT>(accm[n], ah, al, b);
         }
       }
@@ -284,8 +294,8 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
       for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-          const int r = (ml + i) * 16 + g + 8 * hrow;
-          const int pos = p0 - 2 + r;
+          const int r = (mi0 + i * 16 + g + 8 * hrow) * P.F + ph;
+          const int pos = p0 - P.HA + r;
           const bool valid = pos >= 0 && pos < P.Lout;  // Conv5 pads A with zeros outside the sequence
 #pragma unroll
           for (int n = 0; n < NC8; ++n) {
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
       if (ml * 16 >= P.TP) continue;
       const int64_t site = site0 + sg;
       const bool site_ok = site < P.n_sites;
-      const uint32_t ahs = sm_base + S.oAhi + 2 * (sg * S.as + (ml * 16 + lrow) * PC), als = ahs + (S.oAlo - S.oAhi);
+      const uint32_t ahs = sm_base + S.oAhi + 2 * (sg * S.as + (ml * 16 + lrow + P.HA - 2) * PC), als = ahs + (S.oAlo - S.oAhi);
       const float* af = Af + sg * P.RA * PA;
       const float* skipp = P.skip ? P.skip + site * int64_t(P.Lout) * C : nullptr;
       float* outp = TAIL ? nullptr : P.out + site * int64_t(P.Lout) * C;
@@ -364,8 +374,8 @@ __global__ void __launch_bounds__(NW * 32, NC8 == 1 ? MURAL_INDEL_MINB1 : NC8 ==
           for (int n = 0; n < NC8; ++n) {
             const int col = n * 8 + 2 * q;
             float2 v = make_float2(acc1[n][i][2 * hrow] + b1[col], acc1[n][i][2 * hrow + 1] + b1[col + 1]);
-            if (m + 2 < P.RA) {
-              const float2 a = *reinterpret_cast<const float2*>(af + (m + 2) * PA + col);
+            if (m + P.HA < P.RA) {
+              const float2 a = *reinterpret_cast<const float2*>(af + (m + P.HA) * PA + col);
               v.x += a.x; v.y += a.y;
             }
             if (valid[i][hrow]) {
