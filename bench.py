@@ -1029,7 +1029,9 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
                     "note": "dense-site reuse: stage 1 is evaluated once per genomic position and strand (lattice) plus 19 edge rows per "
                             "site, so fewer FLOPs are executed than the per-site algorithmic count that `achieved` uses (SURVEY 8d)"}
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")          # ncu capture of the current round's stage kernels ...
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")      # ... else the round-1 capture
     if os.path.exists(tp) and mode != "fp32":
         tj = json.load(open(tp))      # dram__bytes_read+write of the stage kernels from the committed ncu --set full capture,
         traffic = tj["dram_bytes_per_site"] * S * K / n     # per site of a dense chunk, scaled to this run's launches

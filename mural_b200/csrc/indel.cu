@@ -722,9 +722,11 @@ static int indel_forward(mural_indel_model* m, const GenomeView* G, const int32_
   int64_t per = int64_t(L) * 4;
   for (int i = 0; i < 6; ++i) per += 2 * int64_t(m->len[i]) * m->ch[i];
   per += int64_t(m->len[0]) * 2 * C;          // H (largest at level 0: len0 * 2C; every level has len*2ch <= that? checked below)
-  per += 2 * int64_t(m->len[0]) * C;          // decoder ping-pong at the widest level
-  int64_t hmax = 0;
+  int64_t hmax = 0, dmax = 0;                 // widest hidden tensor; widest decoder output (level 0 only when every stride is > 1:
+                                              // a down_list entry of 1 keeps the length while the channels grow — found by memcheck)
   for (int i = 0; i < 6; ++i) hmax = std::max<int64_t>(hmax, int64_t(m->len[i]) * 2 * m->ch[i]);
+  for (int i = 0; i < 5; ++i) dmax = std::max<int64_t>(dmax, int64_t(m->len[i]) * m->ch[i]);
+  per += 2 * dmax;                            // decoder ping-pong
   per += hmax;
   int64_t chunk = (int64_t(768) << 20) / (per * 4);
   if (chunk < 1) chunk = 1;
@@ -742,7 +744,7 @@ static int indel_forward(mural_indel_model* m, const GenomeView* G, const int32_
   float *A[6], *E[6];
   for (int i = 0; i < 6; ++i) { A[i] = w; w += chunk * int64_t(m->len[i]) * m->ch[i]; E[i] = w; w += chunk * int64_t(m->len[i]) * m->ch[i]; }
   float* H = w; w += chunk * (int64_t(m->len[0]) * 2 * C + hmax);
-  float* D0 = w; w += chunk * int64_t(m->len[0]) * C;
+  float* D0 = w; w += chunk * dmax;
   float* D1 = w;
   GenomeView gv = G ? *G : GenomeView{};
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
