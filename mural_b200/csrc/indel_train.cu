@@ -47,7 +47,13 @@ extern "C" int mural_indel_train_create(mural_indel_model_t* m, mural_indel_trai
 extern "C" void mural_indel_train_destroy(mural_indel_train_t* T) {
   if (!T) return;
   indel_train::Engine& E = T->E;
-  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.dxv); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat);
+  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.dz_b); cudaFree(E.dxv); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat);
+  if (E.ex.side_st) {
+    cudaStreamDestroy(E.ex.side_st);
+    cudaEventDestroy(E.ex.ev_dz);
+    cudaEventDestroy(E.ex.ev_w[0]);
+    cudaEventDestroy(E.ex.ev_w[1]);
+  }
   delete T;
 }
 
@@ -76,7 +82,7 @@ extern "C" int mural_indel_train_forward(mural_indel_train_t* T, const mural_gen
   MURAL_CHECK(n >= 2, "BatchNorm in training mode needs more than one site per batch");  // training.py:415 skips them
   indel_train::Engine& E = T->E;
   E.ensure(n);
-  MURAL_CHECK(E.vals && E.grads && E.dz, "cudaMalloc of the training workspace failed");
+  MURAL_CHECK(E.vals && E.grads && E.dz && E.dz_b, "cudaMalloc of the training workspace failed");
   // one-hot windows of the batch, [n, 4, 2R] (seq_ohe_encoder, preprocessing.py:756-816), straight into the input tensor
   if (int rc = mural_encode_onehot(g, d_pos, d_meta, n, E.cfg.radius, MURAL_MODEL_INDEL, E.V(E.t_in, n), stream)) return rc;
   return train_forward(T, n, d_blob, d_out, (cudaStream_t)stream);
@@ -89,7 +95,7 @@ extern "C" int mural_indel_train_forward_tensors(mural_indel_train_t* T, const f
   indel_train::Engine& E = T->E;
   MURAL_CHECK(L == 2 * E.cfg.radius, "distal_x length does not match the model's distal_radius");
   E.ensure(n);
-  MURAL_CHECK(E.vals && E.grads && E.dz, "cudaMalloc of the training workspace failed");
+  MURAL_CHECK(E.vals && E.grads && E.dz && E.dz_b, "cudaMalloc of the training workspace failed");
   CUDA_TRY(cudaMemcpyAsync(E.V(E.t_in, n), d_distal, sizeof(float) * n * 4 * L, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return train_forward(T, n, d_blob, d_out, (cudaStream_t)stream);
 }

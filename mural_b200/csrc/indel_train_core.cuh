@@ -39,6 +39,24 @@ __global__ void __launch_bounds__(256) k_run(int64_t n, F f) {
 struct Exec {
   cudaStream_t st = nullptr;
   int64_t launches = 0;
+  // Weight gradients leave the backward chain: nothing downstream reads them before the optimizer, so they run on a side stream
+  // while the main stream goes on with the input gradient (at the reference's batch of 32 no kernel of the chain fills the GPU).
+  // dz (the gradient in front of a unit's conv) alternates between two buffers; slot `par` may be overwritten again only after
+  // the weight-gradient kernel that read it has finished (wait_w).
+  cudaStream_t main_st = nullptr, side_st = nullptr;
+  cudaEvent_t ev_dz = nullptr, ev_w[2] = {nullptr, nullptr};
+  bool w_pending[2] = {false, false};
+  void side_init() {
+    if (!side_st) {
+      cudaStreamCreateWithFlags(&side_st, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_dz, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_w[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_w[1], cudaEventDisableTiming);
+    }
+  }
+  void wait_w(int par) { if (w_pending[par]) { cudaStreamWaitEvent(st, ev_w[par], 0); w_pending[par] = false; } }
+  void begin_w() { side_init(); main_st = st; cudaEventRecord(ev_dz, st); cudaStreamWaitEvent(side_st, ev_dz, 0); st = side_st; }
+  void end_w(int par) { cudaEventRecord(ev_w[par], side_st); w_pending[par] = true; st = main_st; }
   template <class F> void run(int64_t n, const F& f) {
     if (n <= 0) return;
     int64_t g = (n + 255) / 256;
@@ -66,6 +84,9 @@ template <class T> HD void atomic_add(T* p, T v) {
 #else
 struct Exec {
   int64_t launches = 0;
+  void wait_w(int) {}
+  void begin_w() {}
+  void end_w(int) {}
   template <class F> void run(int64_t n, const F& f) { for (int64_t i = 0; i < n; ++i) f(i); ++launches; }
   void* alloc(size_t b) { return calloc(b ? b : 1, 1); }
   void free_(void* p) { free(p); }

@@ -30,7 +30,7 @@ struct Engine {
   // buffers (device or host, see Exec)
   Exec ex;
   int64_t cap = 0;
-  float *vals = nullptr, *grads = nullptr, *dz = nullptr, *dxv = nullptr, *stats = nullptr;
+  float *vals = nullptr, *grads = nullptr, *dz = nullptr, *dz_b = nullptr, *dxv = nullptr, *stats = nullptr;
   int32_t* arg = nullptr;
   double* dstat = nullptr;
   uint64_t seed = 0;
@@ -104,10 +104,11 @@ struct Engine {
 
   void ensure(int64_t B) {
     if (B <= cap) return;
-    ex.free_(vals); ex.free_(grads); ex.free_(dz); ex.free_(dxv); ex.free_(stats); ex.free_(arg); ex.free_(dstat);
+    ex.free_(vals); ex.free_(grads); ex.free_(dz); ex.free_(dz_b); ex.free_(dxv); ex.free_(stats); ex.free_(arg); ex.free_(dstat);
     vals = (float*)ex.alloc(sizeof(float) * per_site * B);
     grads = (float*)ex.alloc(sizeof(float) * per_site * B);
     dz = (float*)ex.alloc(sizeof(float) * max_per_site * B);
+    dz_b = (float*)ex.alloc(sizeof(float) * max_per_site * B);  // second slot: see Exec::wait_w
     dxv = (float*)ex.alloc(sizeof(float) * max_per_site * B);   // gradient of an upsampled input before it is folded back (tiled path)
     stats = (float*)ex.alloc(sizeof(float) * (n_stat + 1));
     arg = (int32_t*)ex.alloc(sizeof(int32_t) * cfg.channels * 6 * B);
@@ -170,6 +171,8 @@ struct Engine {
   void backward(float* P, float* Gp, int64_t B, const float* d_out) {
     ex.zero(grads, sizeof(float) * per_site * B);
     ex.run(B * cfg.n_class, AddTo{d_out, G(t_out, B)});
+    float* const dz_slot[2] = {this->dz, dz_b};
+    int par = 0;
     for (int oi = int(ops.size()) - 1; oi >= 0; --oi) {
       const Op& op = ops[oi];
       if (op.kind == OP_FLIP_CL) continue;  // input of the network: no gradient needed
@@ -183,6 +186,9 @@ struct Engine {
         const Unit& u = units[op.unit];
         const Tensor tt = tensors[u.t];
         const int64_t n = B * tt.C * tt.L;
+        par ^= 1;
+        float* const dz = dz_slot[par];
+        ex.wait_w(par);                      // the weight-gradient kernel that read this slot two units ago
         if (u.res1 >= 0) ex.run(n, AddTo{G(u.out, B), G(u.res1, B)});
         if (u.res2 >= 0) ex.run(n, AddTo{G(u.out, B), G(u.res2, B)});
         const UnitOut uo = unit_out(u, P, B);
@@ -196,7 +202,9 @@ struct Engine {
         if (u.has_conv) {
           const ConvDims d = dims(u, B);
           const ConvBwdW fw{V(u.in, B), dz, Gp + u.W, u.b >= 0 ? Gp + u.b : nullptr, d};
+          ex.begin_w();                      // side stream (CUDA build): parameter gradients are read by the optimizer only
           if (!ex.conv_bwd_w(fw)) ex.run(int64_t(d.Cout) * d.Cin * d.k * B * CONV_W_SPLIT, fw);
+          ex.end_w(par);
           if (u.in != t_in) {
             const ConvBwdX fx{dz, P + u.W, G(u.in, B), d};
             if (!ex.conv_bwd_x(fx, dxv)) ex.run(B * d.Cin * d.Lin, fx);
@@ -206,6 +214,8 @@ struct Engine {
         }
       }
     }
+    ex.wait_w(0);                            // the caller's stream continues (all-reduce, optimizer) after every weight gradient
+    ex.wait_w(1);
   }
 };
 
