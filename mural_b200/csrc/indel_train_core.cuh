@@ -335,6 +335,14 @@ namespace tiled {
 inline bool tileable(const ConvDims& d) {
   return d.stride == 1 && d.Lout >= 256 && (d.k == 1 || d.k == 5 || d.k == 7) && d.pad == (d.k - 1) / 2 && d.Lout == d.Lin * d.up;
 }
+// At the reference's batch of 32 a (tile, sample) grid of the deeper levels is a few dozen CTAs that each walk all output-channel
+// chunks in turn: split the chunks over grid.z until the grid has ~4 CTAs per SM (the input tile is re-staged per z slice).
+inline int z_split(int base_ctas, int Cout) {
+  const int chunks = (Cout + 7) / 8;
+  int z = (4 * 148 + base_ctas - 1) / (base_ctas > 0 ? base_ctas : 1);
+  if (z > chunks) z = chunks;
+  return z < 1 ? 1 : z;
+}
 template <int K> inline bool launch_conv(const ConvT& a, int B, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t(a.Cin) * XS + size_t(a.Cin) * K * 8);
   if (smem > 200 * 1024) return false;
@@ -343,7 +351,7 @@ template <int K> inline bool launch_conv(const ConvT& a, int B, cudaStream_t st)
     if (cudaFuncSetAttribute(k_conv_tiled<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     conf = smem;
   }
-  dim3 grid((unsigned)((a.Lout + TL - 1) / TL), (unsigned)B);
+  dim3 grid((unsigned)((a.Lout + TL - 1) / TL), (unsigned)B, (unsigned)z_split(int((a.Lout + TL - 1) / TL) * B, a.Cout));
   INDEL_TRAIN_LAUNCH_SMEM("k_indel_conv_tiled", (k_conv_tiled<K>), grid, 128, smem, st, a);
   return true;
 }
@@ -355,7 +363,7 @@ template <int K> inline bool launch_conv_strided(const ConvT& a, int stride, int
     if (cudaFuncSetAttribute(k_conv_strided<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     conf = smem;
   }
-  dim3 grid((unsigned)((a.Lout + TLS - 1) / TLS), (unsigned)B);
+  dim3 grid((unsigned)((a.Lout + TLS - 1) / TLS), (unsigned)B, (unsigned)z_split(int((a.Lout + TLS - 1) / TLS) * B, a.Cout));
   INDEL_TRAIN_LAUNCH_SMEM("k_indel_conv_strided", (k_conv_strided<K>), grid, 128, smem, st, a, stride);
   return true;
 }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) k_conv_tiled(ConvT a) {
     const int j = p0 + q - XO;
     xs[e] = (j >= 0 && j < Lv) ? xb[int64_t(i) * a.Lin + (a.up == 1 ? j : j / a.up)] : 0.f;
   }
-  for (int o0 = 0; o0 < a.Cout; o0 += 8) {
+  for (int o0 = blockIdx.z * 8; o0 < a.Cout; o0 += 8 * gridDim.z) {   // output-channel chunks may be split over grid.z (small grids)
     __syncthreads();                       // xs ready (first pass) / previous chunk's weight reads done
     for (int e = tid; e < a.Cin * K * 8; e += 128) {
       const int c = e & 7, t = (e >> 3) % K, i = e / (8 * K);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) k_conv_strided(ConvT a, int stride) {
     const int j = p0 * stride + q - a.pad;
     xs[e] = (j >= 0 && j < Lv) ? xb[int64_t(i) * a.Lin + (a.up == 1 ? j : j / a.up)] : 0.f;
   }
-  for (int o0 = 0; o0 < a.Cout; o0 += 8) {
+  for (int o0 = blockIdx.z * 8; o0 < a.Cout; o0 += 8 * gridDim.z) {   // output-channel chunks may be split over grid.z (small grids)
     __syncthreads();
     for (int e = tid; e < a.Cin * K * 8; e += 128) {
       const int c = e & 7, t = (e >> 3) % K, i = e / (8 * K);
