@@ -88,3 +88,38 @@ def test_indel_level_kernels_generic_shapes(C, ks, down, R, rev):
     da, db = np.abs(a.cpu().numpy() - ref).max(), np.abs(b.cpu().numpy() - ref).max()
     print("C=%d ks=%d down=%s R=%d: tensor-core %.2e, fp32 kernels %.2e (scale %.2f)" % (C, ks, down, R, da, db, scale))
     assert da <= 1e-3 * scale and db <= 1e-3 * scale
+
+
+def test_indel_level_kernels_batch_edges(kat, cuda_genome):
+    """Tensor-core level kernels on awkward batch sizes: 1-3 sites, a count that is not a multiple of any site group, more sites
+    than one workspace chunk (4096) — equal to the fp32 kernels within the gate, identical from run to run (the position max is
+    a float atomic max: order-independent), and rows do not depend on what else is in the batch."""
+    from mural_b200 import SiteBatch, pack_meta
+    z = np.load(os.path.join(GOLD, "indel_at_ins.npz"))          # R = 2000: a 4100-site batch stays small
+    m, _ = _model(z)
+    Rd = int(z["distal_radius"])
+    _, genome = kat
+    names = list(genome)
+    rng = np.random.default_rng(5)
+    n = 4100
+    ch = rng.integers(0, len(names), n)
+    st = np.array([rng.integers(0, len(genome[names[c]])) for c in ch])      # windows may overhang the chromosome ends (N imputation)
+    sd = rng.integers(0, 2, n)
+    pos = torch.from_numpy(st.astype(np.int32)).cuda()
+    meta = torch.from_numpy(pack_meta(sd, 0 * sd, ch)).cuda()
+    with torch.no_grad():
+        full = m.forward(SiteBatch(pos, meta, cuda_genome), distal_radius=Rd)
+        again = m.forward(SiteBatch(pos, meta, cuda_genome), distal_radius=Rd)
+        assert torch.equal(full, again)
+        for k in (1, 2, 3, 37):
+            part = m.forward(SiteBatch(pos[:k], meta[:k], cuda_genome), distal_radius=Rd)
+            assert torch.equal(part, full[:k]), k
+        tail = m.forward(SiteBatch(pos[4090:], meta[4090:], cuda_genome), distal_radius=Rd)
+        assert torch.equal(tail, full[4090:])
+        m.compute_mode = "fp32"
+        ref = m.forward(SiteBatch(pos[:512], meta[:512], cuda_genome), distal_radius=Rd)
+        ref_tail = m.forward(SiteBatch(pos[4000:], meta[4000:], cuda_genome), distal_radius=Rd)
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((full[:512] - ref).abs().max()) <= 1e-3 * scale
+    assert float((full[4000:] - ref_tail).abs().max()) <= 1e-3 * scale
+    assert bool(torch.isfinite(full).all())
