@@ -791,6 +791,11 @@ struct mural_snv_train {
   // and the combine: they run on three streams (fork / join with events, also inside a captured graph)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  // weight gradients leave the backward chains (nothing reads them before the optimizer): one more stream per conv branch;
+  // ev_w[br] = completion of the branch's latest weight-gradient kernel, awaited before a buffer it reads is overwritten
+  cudaStream_t wside[2] = {nullptr, nullptr};
+  cudaEvent_t ev_wfork[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr};
+  bool w_pending[2] = {false, false};
 };
 
 static int64_t off_of(const mural_snv_model* m, const std::string& n) { return m->layout[m->index.at(n)].offset; }
@@ -837,6 +842,9 @@ extern "C" int mural_snv_train_create(mural_snv_model_t* m, mural_snv_train_t** 
   for (int i = 0; i < 2; ++i) {
     CUDA_TRY(cudaStreamCreateWithFlags(&T->side[i], cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&T->ev_join[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&T->wside[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&T->ev_wfork[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&T->ev_w[i], cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventCreateWithFlags(&T->ev_fork, cudaEventDisableTiming));
   *out = T;
@@ -850,6 +858,9 @@ extern "C" void mural_snv_train_destroy(mural_snv_train_t* T) {
   for (int i = 0; i < 2; ++i) {
     if (T->side[i]) cudaStreamDestroy(T->side[i]);
     if (T->ev_join[i]) cudaEventDestroy(T->ev_join[i]);
+    if (T->wside[i]) cudaStreamDestroy(T->wside[i]);
+    if (T->ev_wfork[i]) cudaEventDestroy(T->ev_wfork[i]);
+    if (T->ev_w[i]) cudaEventDestroy(T->ev_w[i]);
   }
   if (T->ev_fork) cudaEventDestroy(T->ev_fork);
   delete T;
@@ -1036,6 +1047,14 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   static const bool use_mma = getenv("MURAL_NO_CONV_MMA") == nullptr && getenv("MURAL_NO_WGRAD_MMA") == nullptr;
   int wg = (int)cdiv(rows, 64);
   if (wg > 296) wg = 296;
+  // the weight gradient reads x and dy only and feeds nothing downstream: fork it onto the branch's weight-gradient stream
+  // (captured as a parallel graph branch); the chain joins it before a buffer it reads can be overwritten (wait_wgrad)
+  const int wbr = li / 10;
+  cudaStream_t st_chain = st;
+  const bool prev_pending = T->w_pending[wbr];
+  CUDA_TRY(cudaEventRecord(T->ev_wfork[wbr], st_chain));
+  CUDA_TRY(cudaStreamWaitEvent(T->wside[wbr], T->ev_wfork[wbr], 0));
+  st = T->wside[wbr];
   if (C == 32 && d.ks == 3 && use_mma) {
     if (int rc = wgrad32_mma(x, dy, rows, L, d.relu_in, bn, bn + C, G, d.w, d.b, st)) return rc;
   } else
@@ -1050,6 +1069,7 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   } break;
   switch (C) { WG(16) WG(32) WG(64) default: MURAL_FAIL("unsupported channel count"); }
 #undef WG
+  st = st_chain;
   ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0, 0};  // dgrad: two-level split MMA
   if (int rc = conv_any(C, dy, du, nullptr, nullptr, n, L, cl, 0, st)) return rc;
   CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
@@ -1058,8 +1078,20 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   if (grid > 1184) grid = 1184;
   if (grid < 1) grid = 1;
   LAUNCH(k_bn_bwd_reduce, grid, thr, sizeof(double) * 2 * thr, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, stat);
+  // `out` may be the dy the PREVIOUS layer's weight gradient is still reading (the gradient buffers rotate): join that one first
+  if (prev_pending) CUDA_TRY(cudaStreamWaitEvent(st, T->ev_w[wbr], 0));
   LAUNCH(k_bn_bwd_apply, gridn(rows * C), 256, 0, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, bn, stat, double(rows), add1,
          add2, out, G, d.g, d.be);
+  CUDA_TRY(cudaEventRecord(T->ev_w[wbr], T->wside[wbr]));   // after the wait above: ev_w now stands for THIS layer's weight gradient
+  T->w_pending[wbr] = true;
+  return 0;
+}
+// the chain is about to overwrite a buffer the branch's latest weight gradient may still read (pool backward, stem, end of chain)
+static int wait_wgrad(mural_snv_train* T, int br, cudaStream_t st) {
+  if (T->w_pending[br]) {
+    CUDA_TRY(cudaStreamWaitEvent(st, T->ev_w[br], 0));
+    T->w_pending[br] = false;
+  }
   return 0;
 }
 
@@ -1068,6 +1100,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
   MURAL_CHECK(T->n > 0, "backward without a preceding forward");
   mural_snv_model* m = T->m;
   cudaStream_t st = (cudaStream_t)stream;
+  T->w_pending[0] = T->w_pending[1] = false;
   const int64_t n = T->n;
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, NC = m->cfg.n_class, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2, K1 = m->k1;
   const float* P = d_blob;
@@ -1114,6 +1147,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     LAUNCH(k_gmax_bwd, gridn(n * B.L3 * C), 256, 0, st, gb, b.ig, b.h, G0, n, B.L3, C);  // G0 = d(conv3 out)
     const int base = br * 10;
     if (int rc = conv_train_bwd(T, P, G, base + 9, b.x3, G0, D, nullptr, nullptr, G1, n, B.L3, st)) return rc;   // G1 = d x3
+    if (int rc = wait_wgrad(T, br, st)) return rc;
     LAUNCH(k_pool_bwd, gridn(n * B.L2 * C), 256, 0, st, G1, b.i3, G0, n, B.L2, B.L3, C, B.pool[2][1], B.pool[2][2]);  // G0 = d z2
     // stage 2: z2 = y1b + C8(t2b) + j2 ; t2b = C7(y1b) ; y1b = j2 + C6(t1b) ; t1b = C5(j2) ; j2 = C4(x2)
     if (int rc = conv_train_bwd(T, P, G, base + 8, b.t2b, G0, D, nullptr, nullptr, G1, n, B.L2, st)) return rc;  // G1 = d t2b
@@ -1121,6 +1155,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     if (int rc = conv_train_bwd(T, P, G, base + 6, b.t1b, G2, D, nullptr, nullptr, G1, n, B.L2, st)) return rc;  // G1 = d t1b
     if (int rc = conv_train_bwd(T, P, G, base + 5, b.j2, G1, D, G0, G2, G3, n, B.L2, st)) return rc;             // G3 = d j2
     if (int rc = conv_train_bwd(T, P, G, base + 4, b.x2, G3, D, nullptr, nullptr, G1, n, B.L2, st)) return rc;   // G1 = d x2
+    if (int rc = wait_wgrad(T, br, st)) return rc;
     LAUNCH(k_pool_bwd, gridn(n * B.L1 * C), 256, 0, st, G1, b.i2, G0, n, B.L1, B.L2, C, B.pool[1][1], B.pool[1][2]);  // G0 = d z1
     // stage 1: z1 = y1 + C3(t2) + x0 ; t2 = C2(y1) ; y1 = x0 + C1(t1) ; t1 = C0(x0)
     if (int rc = conv_train_bwd(T, P, G, base + 3, b.t2, G0, D, nullptr, nullptr, G1, n, B.L1, st)) return rc;   // G1 = d t2
@@ -1128,6 +1163,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     if (int rc = conv_train_bwd(T, P, G, base + 1, b.t1, G2, D, nullptr, nullptr, G1, n, B.L1, st)) return rc;   // G1 = d t1
     if (int rc = conv_train_bwd(T, P, G, base + 0, b.x0, G1, D, G0, G2, G3, n, B.L1, st)) return rc;             // G3 = d x0
     // stem
+    if (int rc = wait_wgrad(T, br, st)) return rc;   // joins the branch's weight-gradient stream into the chain (and so into ev_join)
     float* stem = T->d_stem + br * (16 + 2 * int64_t(ks) * 16 * C);
     float* Gt = stem + 16 + int64_t(ks) * 16 * C;
     CUDA_TRY(cudaMemsetAsync(Gt, 0, sizeof(float) * ks * 16 * C, st));
