@@ -951,7 +951,7 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
   mural_snv_model* m = T->m;
   cudaStream_t st = (cudaStream_t)stream;
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, NC = m->cfg.n_class, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2, K1 = m->k1;
-  MURAL_CHECK(m->cfg.n_cont == 0, "training with continuous features (n_cont > 0) is not built: the reference feeds them from its HDF5 datasets only (out of scope)");
+  MURAL_CHECK(m->cfg.n_cont == 0, "training with continuous features (n_cont > 0) is not built in this library (prediction with them is: mural_snv_set_cont)");
   MURAL_CHECK(ks * C * C <= 48 * 256, "unsupported conv shape for training (CNN_kernel_size * C^2 must be <= 12288)");
   if (int rc = ensure_tape(T, n)) return rc;
   T->n = n;

@@ -97,8 +97,8 @@ class TrainState:
         if optim not in OPTIMIZERS:
             raise ValueError("Error: unsupported optimization method %s" % optim)         # training.py:359-361
         if getattr(model, "no_of_cont", 0):
-            raise NotImplementedError("training with continuous features (n_cont > 0): the reference feeds them from its HDF5 "
-                                      "datasets only (out of scope, SURVEY 8f N4); prediction with such models is supported")
+            raise NotImplementedError("training with continuous features (n_cont > 0, --without_bw_distal) is not built in "
+                                      "mural_b200; prediction with such models is (SURVEY 8f N4)")
         self.kind, self.lr, self.weight_decay, self.max_norm = OPTIMIZERS[optim], float(lr), float(weight_decay), float(max_norm)
         layout = model.native_layout()
         self.n_blob = int(L.mural_snv_model_n_params(model._ensure_handle()))
