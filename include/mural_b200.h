@@ -128,8 +128,9 @@ int64_t mural_snv_model_n_trainable(const mural_snv_model_t* m); /* leading trai
 int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, int64_t n);
 
 /* n_cont > 0 only: the continuous features cont_x [n, n_cont] (float32, device; row i <-> site i) of the NEXT forward call
- * (local_input[0] of Network2.forward, model_snv.py:448,457-463).  The pointer is consumed by that call.  Models with
- * continuous features run in MURAL_MODE_FP32. */
+ * (local_input[0] of Network2.forward, model_snv.py:448,457-463).  The pointer is consumed by that call — mural_snv_forward* or
+ * mural_snv_train_forward (which keeps reading it until the matching mural_snv_train_backward has run: first_bn_layer's
+ * gradients).  Models with continuous features run in MURAL_MODE_FP32. */
 int mural_snv_set_cont(mural_snv_model_t* m, const float* d_cont);
 
 /* model_predict_m body (MuRaL/model/nn_utils.py:48-65) for n sites: gather + Network2.forward (eval).

@@ -163,7 +163,10 @@ __device__ __forceinline__ void win_max_any(int w, const float (&v)[DT_RUN + DT_
 // (3 table rows summed per position, same order as the per-site stem), the window maxima are computed with static
 // indexing per width, and every store is one packed bf16 pair.
 template <int C>
-__global__ void __launch_bounds__(256, 2) k_dense_tables(GenomeView G, const ChunkInfo* __restrict__ info, DenseBranch b0, DenseBranch b1,
+#ifndef MURAL_DT_MINB
+#define MURAL_DT_MINB 2
+#endif
+__global__ void __launch_bounds__(256, MURAL_DT_MINB) k_dense_tables(GenomeView G, const ChunkInfo* __restrict__ info, DenseBranch b0, DenseBranch b1,
                                                       int cap, __nv_bfloat16* __restrict__ tables) {
   static_assert(C == 32, "channel-pair mapping assumes 16 lanes x 2 channels");
   if (!info->dense) return;

@@ -50,7 +50,10 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // Lane (j = lane / 4, i = lane % 4) of a two-site tile owns pooled row j of both sites, 32-bit word i of each plane.
-__global__ void __launch_bounds__(WARPS * 32, 3) k_tail(Branch b0, Branch b1, const float* __restrict__ local_logits, int64_t n, int NC,
+#ifndef MURAL_TAIL_MINB
+#define MURAL_TAIL_MINB 3
+#endif
+__global__ void __launch_bounds__(WARPS * 32, MURAL_TAIL_MINB) k_tail(Branch b0, Branch b1, const float* __restrict__ local_logits, int64_t n, int NC,
                                                      float* __restrict__ logp, float* __restrict__ tg0, float* __restrict__ tg1,
                                                      float* __restrict__ tl0, float* __restrict__ tl1) {
   __shared__ float s_lg[WARPS][2][BATCH][16];

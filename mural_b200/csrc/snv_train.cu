@@ -385,9 +385,11 @@ __global__ void k_linear_bwd_x(const float* __restrict__ dy, const float* __rest
   dx[e] = acc;
 }
 // BatchNorm1d over the batch of an [n][F] tensor + dropout; one block per feature
+// ldy: row stride of y (0 = F): the continuous features are normalised straight into the tail columns of the first Linear's input
 __global__ void k_bn1d_fwd(const float* __restrict__ x, int64_t n, int F, float* __restrict__ P, int64_t g, int64_t be, int64_t rm,
                            int64_t rv, float* __restrict__ mu, float* __restrict__ invstd, float p_drop, uint64_t seed,
-                           const uint32_t* __restrict__ step_p, uint32_t layer, float* __restrict__ y) {
+                           const uint32_t* __restrict__ step_p, uint32_t layer, float* __restrict__ y, int ldy = 0) {
+  if (ldy == 0) ldy = F;
   __shared__ double sh[2][256];
   const uint32_t step = __ldg(step_p);
   const int f = blockIdx.x;
@@ -418,21 +420,22 @@ __global__ void k_bn1d_fwd(const float* __restrict__ x, int64_t n, int F, float*
   const float ga = P[g + f], bb = P[be + f];
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const float v = (x[i * F + f] - float(mean)) * is * ga + bb;
-    y[i * F + f] = v * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
+    y[i * ldy + f] = v * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
   }
 }
 // backward of dropout(BN1d(x)): dx, dgamma, dbeta
 __global__ void k_bn1d_bwd(const float* __restrict__ dy, const float* __restrict__ x, int64_t n, int F, const float* __restrict__ P,
                            int64_t g, const float* __restrict__ mu, const float* __restrict__ invstd, float p_drop, uint64_t seed,
                            const uint32_t* __restrict__ step_p, uint32_t layer, float* __restrict__ dx, float* __restrict__ G, int64_t g_off,
-                           int64_t be_off) {
+                           int64_t be_off, int lddy = 0) {   // lddy: row stride of dy (0 = F); dx == NULL: parameter gradients only
   __shared__ double sh[2][256];
+  if (lddy == 0) lddy = F;
   const uint32_t step = __ldg(step_p);
   const int f = blockIdx.x;
   const float m = mu[f], is = invstd[f], ga = P[g + f];
   double s = 0, q = 0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = dy[i * F + f] * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
+    const float d = dy[i * lddy + f] * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
     s += d;
     q += double(d) * ((x[i * F + f] - m) * is);
   }
@@ -448,31 +451,33 @@ __global__ void k_bn1d_bwd(const float* __restrict__ dy, const float* __restrict
     G[be_off + f] += float(sh[0][0]);
     G[g_off + f] += float(sh[1][0]);
   }
+  if (!dx) return;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = dy[i * F + f] * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
+    const float d = dy[i * lddy + f] * drop_scale(p_drop, seed, step, layer, uint64_t(i) * F + f);
     const float xh = (x[i * F + f] - m) * is;
     dx[i * F + f] = ga * is * (d - s1 - xh * s2);
   }
 }
+// ld: row stride of y / dy (K1 + n_cont: the normalised continuous features follow the embeddings, model_snv.py:457-463)
 __global__ void k_emb_fwd(const float* __restrict__ E, const int32_t* __restrict__ cat, int64_t n, int n_cat, float p_drop,
-                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ y) {
+                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ y, int ld) {
   const uint32_t step = __ldg(step_p);
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int K1 = n_cat * 5;
   if (e >= n * K1) return;
   const int k = int(e % K1);
   const int64_t i = e / K1;
-  y[e] = E[cat[i * n_cat + k / 5] * 5 + k % 5] * drop_scale(p_drop, seed, step, 100, uint64_t(e));
+  y[i * ld + k] = E[cat[i * n_cat + k / 5] * 5 + k % 5] * drop_scale(p_drop, seed, step, 100, uint64_t(e));
 }
 __global__ void k_emb_bwd(const float* __restrict__ dy, const int32_t* __restrict__ cat, int64_t n, int n_cat, float p_drop,
-                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ gE) {
+                          uint64_t seed, const uint32_t* __restrict__ step_p, float* __restrict__ gE, int ld) {
   const uint32_t step = __ldg(step_p);
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   const int K1 = n_cat * 5;
   if (e >= n * K1) return;
   const int k = int(e % K1);
   const int64_t i = e / K1;
-  atomicAdd(gE + cat[i * n_cat + k / 5] * 5 + k % 5, dy[e] * drop_scale(p_drop, seed, step, 100, uint64_t(e)));
+  atomicAdd(gE + cat[i * n_cat + k / 5] * 5 + k % 5, dy[i * ld + k] * drop_scale(p_drop, seed, step, 100, uint64_t(e)));
 }
 // dropout applied in place on an [n][F] tensor (distal_fc: BatchNorm -> Dropout -> Linear; BN handled by k_bn1d_fwd)
 
@@ -784,7 +789,8 @@ struct mural_snv_train {
   int32_t* cat = nullptr;
   struct Br { float *x0, *t1, *y1, *t2, *z1, *x2, *j2, *t1b, *y1b, *t2b, *z2, *x3, *h, *gm, *gmn, *logit;
               int32_t *i1, *i2, *i3, *ig; float *mu, *is; } br[2];
-  float *e0, *r1, *d1, *r2, *d2, *ll, *mu1, *is1, *mu2, *is2, *smx;
+  float *e0, *r1, *d1, *r2, *d2, *ll, *mu1, *is1, *mu2, *is2, *smx, *mu0, *is0;
+  const float* cont = nullptr;   // cont_x of the last forward (kept for the backward of first_bn_layer)
   float* gbuf[2][5];   // gradient scratch of each CNN branch
   float* gsm[9];       // [0..2] d(logits) of the three branches; then (ga, gb) of the local chain and of each CNN branch
   // the mid branch, the large branch and the local MLP are independent chains of small kernels between the window gather
@@ -903,13 +909,15 @@ int ensure_tape(mural_snv_train* T, int64_t n) {
       b.i1 = cv.take<int32_t>(s1); b.i2 = cv.take<int32_t>(s2); b.i3 = cv.take<int32_t>(s3); b.ig = cv.take<int32_t>(n * C);
       b.mu = cv.take<float>(C); b.is = cv.take<float>(C);
     }
-    T->e0 = cv.take<float>(n * K1); T->r1 = cv.take<float>(n * H1); T->d1 = cv.take<float>(n * H1);
+    const int K1c = m->k1c > 0 ? m->k1c : K1;
+    T->e0 = cv.take<float>(n * K1c); T->r1 = cv.take<float>(n * H1); T->d1 = cv.take<float>(n * H1);
+    T->mu0 = cv.take<float>(K1c - K1 + 1); T->is0 = cv.take<float>(K1c - K1 + 1);
     T->r2 = cv.take<float>(n * H2); T->d2 = cv.take<float>(n * H2); T->ll = cv.take<float>(n * NC);
     T->mu1 = cv.take<float>(H1); T->is1 = cv.take<float>(H1); T->mu2 = cv.take<float>(H2); T->is2 = cv.take<float>(H2);
     T->smx = cv.take<float>(3 * n * NC);
     for (int br = 0; br < 2; ++br)
       for (int i = 0; i < 5; ++i) T->gbuf[br][i] = cv.take<float>(n * m->br[br].L1 * C);
-    const int64_t Fmax = (H1 > K1 ? H1 : K1) > C ? (H1 > K1 ? H1 : K1) : C;
+    const int64_t Fmax = (H1 > K1c ? H1 : K1c) > C ? (H1 > K1c ? H1 : K1c) : C;
     for (int i = 0; i < 9; ++i) T->gsm[i] = cv.take<float>(n * Fmax);
     if (!pass) {
       cudaFree(T->d_tape);
@@ -951,7 +959,8 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
   mural_snv_model* m = T->m;
   cudaStream_t st = (cudaStream_t)stream;
   const int C = m->cfg.channels, ks = m->cfg.kernel_size, NC = m->cfg.n_class, H1 = m->cfg.hidden1, H2 = m->cfg.hidden2, K1 = m->k1;
-  MURAL_CHECK(m->cfg.n_cont == 0, "training with continuous features (n_cont > 0) is not built in this library (prediction with them is: mural_snv_set_cont)");
+  const int NCT = m->cfg.n_cont, K1c = K1 + NCT;
+  MURAL_CHECK(NCT == 0 || m->d_cont != nullptr, "this model has continuous features: call mural_snv_set_cont before the training forward");
   MURAL_CHECK(ks * C * C <= 48 * 256, "unsupported conv shape for training (CNN_kernel_size * C^2 must be <= 12288)");
   if (int rc = ensure_tape(T, n)) return rc;
   T->n = n;
@@ -1012,8 +1021,14 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
   }
   // local branch (model_snv.py:452-468, 492)
   st = T->side[1];
-  LAUNCH(k_emb_fwd, gridn(n * K1), 256, 0, st, P + off_of(m, "emb_layer.weight"), T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, T->e0);
-  LAUNCH(k_linear_fwd, gridn(n * H1), 256, 0, st, T->e0, P + off_of(m, "lin_layers.0.weight"), P + off_of(m, "lin_layers.0.bias"), n, K1, H1,
+  LAUNCH(k_emb_fwd, gridn(n * K1), 256, 0, st, P + off_of(m, "emb_layer.weight"), T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, T->e0, K1c);
+  T->cont = m->d_cont;
+  m->d_cont = m->d_cont_cur = nullptr;   // consumed, as in the eval forward
+  if (NCT > 0)   // first_bn_layer(cont_data), batch statistics, no dropout, concatenated behind the embeddings (model_snv.py:457-463)
+    LAUNCH(k_bn1d_fwd, NCT, 256, 0, st, T->cont, n, NCT, P, off_of(m, "first_bn_layer.weight"), off_of(m, "first_bn_layer.bias"),
+           off_of(m, "first_bn_layer.running_mean"), off_of(m, "first_bn_layer.running_var"), T->mu0, T->is0, 0.f, T->seed, T->d_step, 0u,
+           T->e0 + K1, K1c);
+  LAUNCH(k_linear_fwd, gridn(n * H1), 256, 0, st, T->e0, P + off_of(m, "lin_layers.0.weight"), P + off_of(m, "lin_layers.0.bias"), n, K1c, H1,
          1, T->r1);
   LAUNCH(k_bn1d_fwd, H1, 256, 0, st, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), off_of(m, "bn_layers.0.bias"),
          off_of(m, "bn_layers.0.running_mean"), off_of(m, "bn_layers.0.running_var"), T->mu1, T->is1, T->p_local, T->seed, T->d_step, 1u, T->d1);
@@ -1125,9 +1140,13 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     LAUNCH(k_linear_bwd_x, gridn(n * H1), 256, 0, st, gb, T->r2, P + W2, n, H1, H2, 1, ga);
     LAUNCH(k_bn1d_bwd, H1, 256, 0, st, ga, T->r1, n, H1, P, off_of(m, "bn_layers.0.weight"), T->mu1, T->is1, T->p_local, T->seed, T->d_step, 1u, gb,
            G, off_of(m, "bn_layers.0.weight"), off_of(m, "bn_layers.0.bias"));
-    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(K1, H1), st, gb, T->r1, T->e0, n, K1, H1, 1, G + W1, G + off_of(m, "lin_layers.0.bias"));
-    LAUNCH(k_linear_bwd_x, gridn(n * K1), 256, 0, st, gb, T->r1, P + W1, n, K1, H1, 1, ga);
-    LAUNCH(k_emb_bwd, gridn(n * K1), 256, 0, st, ga, T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, G + off_of(m, "emb_layer.weight"));
+    const int NCT = m->cfg.n_cont, K1c = K1 + NCT;
+    LAUNCH(k_linear_bwd_w, lbw_grid(n), 256, lbw_smem(K1c, H1), st, gb, T->r1, T->e0, n, K1c, H1, 1, G + W1, G + off_of(m, "lin_layers.0.bias"));
+    LAUNCH(k_linear_bwd_x, gridn(n * K1c), 256, 0, st, gb, T->r1, P + W1, n, K1c, H1, 1, ga);
+    LAUNCH(k_emb_bwd, gridn(n * K1), 256, 0, st, ga, T->cat, n, m->n_cat, T->p_emb, T->seed, T->d_step, G + off_of(m, "emb_layer.weight"), K1c);
+    if (NCT > 0)   // first_bn_layer: parameter gradients only (cont_x is an input)
+      LAUNCH(k_bn1d_bwd, NCT, 256, 0, st, ga + K1, T->cont, n, NCT, P, off_of(m, "first_bn_layer.weight"), T->mu0, T->is0, 0.f, T->seed, T->d_step,
+             0u, (float*)nullptr, G, off_of(m, "first_bn_layer.weight"), off_of(m, "first_bn_layer.bias"), K1c);
   }
   // ---- CNN branches
   for (int br = 0; br < 2; ++br) {

@@ -96,9 +96,7 @@ class TrainState:
             raise RuntimeError("mural_b200 training runs on CUDA only")
         if optim not in OPTIMIZERS:
             raise ValueError("Error: unsupported optimization method %s" % optim)         # training.py:359-361
-        if getattr(model, "no_of_cont", 0):
-            raise NotImplementedError("training with continuous features (n_cont > 0, --without_bw_distal) is not built in "
-                                      "mural_b200; prediction with such models is (SURVEY 8f N4)")
+        self.n_cont = int(getattr(model, "no_of_cont", 0) or 0)   # bigWig window means behind the embeddings (model_snv.py:457-463)
         self.kind, self.lr, self.weight_decay, self.max_norm = OPTIMIZERS[optim], float(lr), float(weight_decay), float(max_norm)
         layout = model.native_layout()
         self.n_blob = int(L.mural_snv_model_n_params(model._ensure_handle()))
@@ -169,12 +167,25 @@ class TrainState:
             self._graph_warm.clear()
 
     # ---- pieces
+    def _cont_of(self, batch):
+        """cont_x [n, n_cont] of a batch as a contiguous fp32 device tensor (None for models without continuous features)."""
+        if not self.n_cont:
+            return None
+        cont = getattr(batch, "cont", None)
+        if cont is None or cont.shape[0] != len(batch) or cont.shape[1] != self.n_cont:
+            raise RuntimeError("cont_x with %d continuous features per site is required (SiteBatch.cont)" % self.n_cont)
+        return cont.to(device=self.device, dtype=torch.float32).contiguous()
+
     def forward(self, batch):
         n = len(batch)
         _check_attached(self)
         self._note_batch(n)
         logp = torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)
+        cont = self._cont_of(batch)
+        self._cont_keep = cont                               # read again by the backward of first_bn_layer
         with torch.cuda.device(self.device):
+            if cont is not None:
+                _lib.check(_lib.lib().mural_snv_set_cont(self.model._ensure_handle(), _lib.ptr(cont)))
             _lib.check(_lib.lib().mural_snv_train_forward(self._h, batch.genome.handle, _lib.ptr(batch.pos), _lib.ptr(batch.meta), n,
                                                           _lib.ptr(self.blob), _lib.ptr(logp), _lib.current_stream()))
         self.n_forward += 1
@@ -211,9 +222,11 @@ class TrainState:
                                                            self.weight_decay, _lib.ptr(self._opt_step_dev), self.max_norm, scale,
                                                            _lib.ptr(self.scratch), _lib.current_stream()))
 
-    def _launch_forward_backward(self, genome, pos, meta, n, logp, dlogp):
+    def _launch_forward_backward(self, genome, pos, meta, n, logp, dlogp, cont=None):
         L = _lib.lib()
         with torch.cuda.device(self.device):
+            if cont is not None:
+                _lib.check(L.mural_snv_set_cont(self.model._ensure_handle(), _lib.ptr(cont)))
             _lib.check(L.mural_snv_train_forward(self._h, genome.handle, _lib.ptr(pos), _lib.ptr(meta), n, _lib.ptr(self.blob),
                                                  _lib.ptr(logp), _lib.current_stream()))
             _lib.check(L.mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(meta), n, self.model.n_class, _lib.ptr(self.loss_dev), _lib.ptr(dlogp),
@@ -234,11 +247,13 @@ class TrainState:
              "logp": torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device),
              "world": self._world()}
         g["dlogp"] = torch.empty_like(g["logp"])
+        c0 = self._cont_of(batch)
+        g["cont"] = c0.clone() if c0 is not None else None   # static buffer of the graph, refilled per step
         torch.cuda.synchronize(self.device)
         g["fb"], g["opt"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         # thread-local capture mode: CUDA calls of other threads (NCCL watchdog, clock sampler) must not invalidate the capture
         with torch.cuda.graph(g["fb"], capture_error_mode="thread_local"):
-            self._launch_forward_backward(g["genome"], g["pos"], g["meta"], n, g["logp"], g["dlogp"])
+            self._launch_forward_backward(g["genome"], g["pos"], g["meta"], n, g["logp"], g["dlogp"], g["cont"])
         with torch.cuda.graph(g["opt"], capture_error_mode="thread_local"):
             self._launch_optimizer(g["world"])
         return g
@@ -261,6 +276,8 @@ class TrainState:
             if g is not None and g["genome"] is batch.genome and g["world"] == self._world():
                 g["pos"].copy_(batch.pos)
                 g["meta"].copy_(batch.meta)
+                if g["cont"] is not None:
+                    g["cont"].copy_(self._cont_of(batch))
                 if self._lr_on_dev != self.lr:
                     self._lr_dev.fill_(self.lr)
                     self._lr_on_dev = self.lr

@@ -52,6 +52,45 @@ def test_network2_with_continuous_features(kat, cuda_genome):
     assert np.abs(d - a).max() > 1e-3
     with pytest.raises(RuntimeError):
         m.forward(None, SiteBatch(pos, meta, cuda_genome))                     # cont_x missing
+    # ---- train mode: first_bn_layer on batch statistics, the wider first Linear, gradients vs fp64 autograd of the oracle.
+    # (The reference's numpy batch pipeline hands cont_x = zeros to its training loop, Create_DatasetSegment, preprocessing.py:1209;
+    # the training kernels take the real features through SiteBatch.cont.)
+    from mural_b200 import _lib
     from mural_b200.training import TrainState
-    with pytest.raises(NotImplementedError):
-        TrainState(m)
+    from oracle import encode_np as E
+    from oracle import network_t as NT
+    n = 40
+    labels = (z["start"][:n] % 4).astype(np.int64)
+    st = TrainState(m, "Adam", lr=1e-3)
+    st.set_dropout(0, 0, 0)
+    m.train()
+    sb = SiteBatch(pos[:n], torch.from_numpy(pack_meta(z["strand"][:n], labels, z["chrom"][:n])).cuda(), cuda_genome, cont=cont[:n])
+    logp = st.forward(sb)
+    _, genome = kat
+    names = list(genome)
+    cat_o = np.empty((n, n_cat), np.int64)
+    oh_o = np.empty((n, 4, 2 * cfg["distal_radius"] + 1), np.float32)
+    for ci in range(len(names)):
+        msk = z["chrom"][:n] == ci
+        if msk.any():
+            sym = E.seq_to_symbols(genome[names[ci]])
+            cat_o[msk] = E.kmer_windows(sym, z["start"][:n][msk], z["strand"][:n][msk], cfg["local_radius"], cfg["local_order"])
+            oh_o[msk] = E.onehot_windows(sym, z["start"][:n][msk], z["strand"][:n][msk], cfg["distal_radius"])
+    sd64 = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=("running" not in k)) for k, v in state.items()
+            if "num_batches" not in k}
+    refo = NT.network2_forward(sd64, cat_o, oh_o, torch.float64, train=True, cont_x=z["cont"][:n].astype(np.float64))
+    assert np.abs(logp.cpu().numpy() - refo.detach().numpy()).max() < 2e-4
+    NT.ce_sum(refo, labels).backward()
+    dlogp = torch.empty_like(logp)
+    _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(sb.meta), n, 4, _lib.ptr(st.loss_dev), _lib.ptr(dlogp), _lib.current_stream()))
+    g = st.backward(dlogp).cpu().numpy()
+    for name, off, num, is_buf in m.native_layout():
+        if is_buf or not (name.startswith("first_bn_layer") or name.startswith("lin_layers.0") or name.startswith("emb_layer")):
+            continue
+        ref_g = sd64[name].grad.numpy().reshape(-1)
+        err = np.abs(g[off:off + num] - ref_g).max() / max(1e-6, np.abs(ref_g).max())
+        assert err < 5e-3, (name, err)
+    # two fused steps (graph capture on the second) run and keep the loss finite
+    for _ in range(3):
+        st.step(sb)
+    assert np.isfinite(float(st.loss_dev.item()))
