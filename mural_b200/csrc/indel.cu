@@ -206,7 +206,7 @@ struct mural_indel_model {
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
   // tensor-core path (indel_tc.cuh): one fused kernel per U-Net level; pre-split bf16 B fragments + biases in d_tc
-  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, F, HA, dmin, ND, NC8, MT, NW, SG, TP, RA, RS, n_tiles, rows_in, smem, Lin, Lout; };
+  struct TcLevel { int64_t Wl, W5, W1, bias; int KCl, KC5, Cin, CinP, stride, up, F, HA, dmin, ND, NC8, MT, NW, SG, TP, RA, RS, n_tiles, rows_in, smem, Lin, Lout, occ; };
   std::vector<TcLevel> tcl;  // encoder levels 0..5, decoder steps 0..4 (levels 4..0)
   int64_t tcWo0 = -1, tcWo1 = -1;
   int tcKCo = 0;
@@ -487,7 +487,7 @@ static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep
   m->tcWo0 = make_frags(buf, prep.data() + m->ops[33].W, 1, C, C, C);
   m->tcWo1 = make_frags(buf, prep.data() + m->ops[34].W, 1, C, C, C);
   for (int step = 0; step < 11; ++step) {  // levels of equal shape share a kernel: opt in to the largest request
-    const mural_indel_model::TcLevel& T = m->tcl[step];
+    const mural_indel_model::TcLevel T = m->tcl[step];
     int need = 0;
     for (int o = 0; o < 11; ++o)
       if (level_kernel(m->tcl[o].NC8, m->tcl[o].MT, m->tcl[o].NW, o == 10) == level_kernel(T.NC8, T.MT, T.NW, step == 10))
@@ -498,6 +498,9 @@ static int indel_tc_prepare(mural_indel_model* m, const std::vector<float>& prep
       CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
       configured[k] = need;
     }
+    int occ = 1;   // resident CTAs per SM of this level's launch: the persistent grid is n_sm * occ
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, T.NW * 32, T.smem));
+    m->tcl[step].occ = occ < 1 ? 1 : occ;
   }
   cudaFree(m->d_tc);
   m->d_tc = nullptr;
@@ -698,10 +701,7 @@ static int indel_forward_tc(mural_indel_model* m, const GenomeView* G, const int
       P.n_items = cdiv(ns, T.SG) * T.n_tiles;
       LevelKernel k = level_kernel(T.NC8, T.MT, T.NW, tail);
       const int THREADS = T.NW * 32;
-      int occ = 1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, T.smem);
-      if (occ < 1) occ = 1;
-      const int64_t grid = std::min<int64_t>(P.n_items, int64_t(n_sm) * occ);
+      const int64_t grid = std::min<int64_t>(P.n_items, int64_t(n_sm) * T.occ);
       static const char* names[11] = {"k_unet_level/enc0", "k_unet_level/enc1", "k_unet_level/enc2", "k_unet_level/enc3", "k_unet_level/enc4",
                                       "k_unet_level/enc5", "k_unet_level/dec4", "k_unet_level/dec3", "k_unet_level/dec2", "k_unet_level/dec1",
                                       "k_unet_level/dec0+out"};

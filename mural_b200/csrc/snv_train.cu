@@ -54,24 +54,39 @@ __global__ void k_prep_conv(const float* __restrict__ P, const ConvDesc* __restr
 }
 
 // ---------------------------------------------------------------------------------------------- per-channel stats
-// sums of act(x) and act(x)^2 over all rows (train-mode BatchNorm1d over (B, L)); double accumulation
+// sums of act(x) and act(x)^2 over all rows (train-mode BatchNorm1d over (B, L)); double accumulation.
+// A thread owns 4 channels (one 16-byte load per row) and walks rows two at a time: at batch 4096 the pass is HBM-bound and the
+// scalar one-load-in-flight form reached 25 % of the bandwidth (8 KB in flight per SM against the ~28 KB Little's law asks for).
 __global__ void k_stats(const float* __restrict__ x, int64_t rows, int C, int relu, double* __restrict__ out) {
-  extern __shared__ double sh[];  // [2][blockDim]
-  const int c = threadIdx.x % C, lane_r = threadIdx.x / C, rpb = blockDim.x / C;
-  double s = 0, q = 0;
-  for (int64_t r = int64_t(blockIdx.x) * rpb + lane_r; r < rows; r += int64_t(gridDim.x) * rpb) {
-    float v = x[r * C + c];
-    if (relu) v = fmaxf(v, 0.f);
-    s += v;
-    q += double(v) * v;
+  extern __shared__ double sh[];  // [2][4 * blockDim]
+  const int C4 = C >> 2, c4 = threadIdx.x % C4, lane_r = threadIdx.x / C4, rpb = blockDim.x / C4;
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const int64_t stride = int64_t(gridDim.x) * rpb;
+  auto acc = [&](float4 v) {
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    s[0] += v.x; q[0] += double(v.x) * v.x;
+    s[1] += v.y; q[1] += double(v.y) * v.y;
+    s[2] += v.z; q[2] += double(v.z) * v.z;
+    s[3] += v.w; q[3] += double(v.w) * v.w;
+  };
+  int64_t r = int64_t(blockIdx.x) * rpb + lane_r;
+  if (lane_r < rpb) {
+    for (; r + stride < rows; r += 2 * stride) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + r * C) + c4);
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + (r + stride) * C) + c4);
+      acc(v0);
+      acc(v1);
+    }
+    if (r < rows) acc(__ldg(reinterpret_cast<const float4*>(x + r * C) + c4));
   }
-  sh[threadIdx.x] = s;
-  sh[blockDim.x + threadIdx.x] = q;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sh[threadIdx.x * 4 + k] = s[k]; sh[4 * blockDim.x + threadIdx.x * 4 + k] = q[k]; }
   __syncthreads();
-  if (threadIdx.x < C) {
-    for (int k = 1; k < rpb; ++k) { s += sh[k * C + threadIdx.x]; q += sh[blockDim.x + k * C + threadIdx.x]; }
-    atomicAdd(out + c, s);
-    atomicAdd(out + C + c, q);
+  if (threadIdx.x < C) {   // channel c = 4 * c4' + k lives at slot (lane_r * C4 + c4') * 4 + k = lane_r * C + c
+    double ts = 0, tq = 0;
+    for (int k = 0; k < rpb; ++k) { ts += sh[k * C + threadIdx.x]; tq += sh[4 * blockDim.x + k * C + threadIdx.x]; }
+    atomicAdd(out + threadIdx.x, ts);
+    atomicAdd(out + C + threadIdx.x, tq);
   }
 }
 
@@ -96,51 +111,72 @@ __global__ void k_bn_finalize(const double* __restrict__ st, double N, int C, fl
 }
 
 // ---------------------------------------------------------------------------------------------- conv backward
-// s1 = sum du, s2 = sum du * zhat with zhat = (act(x) - mu) * invstd
+// s1 = sum du, s2 = sum du * zhat with zhat = (act(x) - mu) * invstd   (4 channels per thread, two rows in flight: see k_stats)
 __global__ void k_bn_bwd_reduce(const float* __restrict__ du, const float* __restrict__ x, int64_t rows, int C, int relu,
                                 const float* __restrict__ mu, const float* __restrict__ invstd, double* __restrict__ out) {
   extern __shared__ double sh[];
-  const int c = threadIdx.x % C, lane_r = threadIdx.x / C, rpb = blockDim.x / C;
-  const float m = mu[c], is = invstd[c];
-  double s = 0, q = 0;
-  for (int64_t r = int64_t(blockIdx.x) * rpb + lane_r; r < rows; r += int64_t(gridDim.x) * rpb) {
-    float v = x[r * C + c];
-    if (relu) v = fmaxf(v, 0.f);
-    const float d = du[r * C + c];
-    s += d;
-    q += double(d) * ((v - m) * is);
+  const int C4 = C >> 2, c4 = threadIdx.x % C4, lane_r = threadIdx.x / C4, rpb = blockDim.x / C4;
+  const float4 m = *reinterpret_cast<const float4*>(mu + 4 * c4), is = *reinterpret_cast<const float4*>(invstd + 4 * c4);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const int64_t stride = int64_t(gridDim.x) * rpb;
+  auto acc = [&](float4 v, const float4 d) {
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    s[0] += d.x; q[0] += double(d.x) * ((v.x - m.x) * is.x);
+    s[1] += d.y; q[1] += double(d.y) * ((v.y - m.y) * is.y);
+    s[2] += d.z; q[2] += double(d.z) * ((v.z - m.z) * is.z);
+    s[3] += d.w; q[3] += double(d.w) * ((v.w - m.w) * is.w);
+  };
+  int64_t r = int64_t(blockIdx.x) * rpb + lane_r;
+  if (lane_r < rpb) {
+    for (; r + stride < rows; r += 2 * stride) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + r * C) + c4), d0 = __ldg(reinterpret_cast<const float4*>(du + r * C) + c4);
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + (r + stride) * C) + c4);
+      const float4 d1 = __ldg(reinterpret_cast<const float4*>(du + (r + stride) * C) + c4);
+      acc(v0, d0);
+      acc(v1, d1);
+    }
+    if (r < rows) acc(__ldg(reinterpret_cast<const float4*>(x + r * C) + c4), __ldg(reinterpret_cast<const float4*>(du + r * C) + c4));
   }
-  sh[threadIdx.x] = s;
-  sh[blockDim.x + threadIdx.x] = q;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sh[threadIdx.x * 4 + k] = s[k]; sh[4 * blockDim.x + threadIdx.x * 4 + k] = q[k]; }
   __syncthreads();
   if (threadIdx.x < C) {
-    for (int k = 1; k < rpb; ++k) { s += sh[k * C + threadIdx.x]; q += sh[blockDim.x + k * C + threadIdx.x]; }
-    atomicAdd(out + c, s);
-    atomicAdd(out + C + c, q);
+    double ts = 0, tq = 0;
+    for (int k = 0; k < rpb; ++k) { ts += sh[k * C + threadIdx.x]; tq += sh[4 * blockDim.x + k * C + threadIdx.x]; }
+    atomicAdd(out + threadIdx.x, ts);
+    atomicAdd(out + C + threadIdx.x, tq);
   }
 }
 
-// dx = relu'(x) * a * (du - s1/N - zhat*s2/N); out = dx (+ add1) (+ add2); block 0 also emits dgamma, dbeta
+// dx = relu'(x) * a * (du - s1/N - zhat*s2/N); out = dx (+ add1) (+ add2); block 0 also emits dgamma, dbeta.  One thread = 4 channels
+// of a row (16-byte loads / stores).
 __global__ void k_bn_bwd_apply(const float* __restrict__ du, const float* __restrict__ x, int64_t rows, int C, int relu,
                                const float* __restrict__ mu, const float* __restrict__ invstd, const float* __restrict__ a,
                                const double* __restrict__ st, double N, const float* __restrict__ add1,
                                const float* __restrict__ add2, float* __restrict__ out, float* __restrict__ G, int64_t g_off,
                                int64_t be_off) {
-  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t e4 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x < C) {
     atomicAdd(G + be_off + threadIdx.x, float(st[threadIdx.x]));
     atomicAdd(G + g_off + threadIdx.x, float(st[C + threadIdx.x]));
   }
-  if (e >= rows * C) return;
-  const int c = int(e % C);
-  const float xv = x[e];
-  const float z = relu ? fmaxf(xv, 0.f) : xv;
-  const float zh = (z - mu[c]) * invstd[c];
-  float dz = a[c] * (du[e] - float(st[c] / N) - zh * float(st[C + c] / N));
-  if (relu && xv <= 0.f) dz = 0.f;
-  if (add1) dz += add1[e];
-  if (add2) dz += add2[e];
-  out[e] = dz;
+  const int C4 = C >> 2;
+  if (e4 >= rows * C4) return;
+  const int c = int(e4 % C4) * 4;
+  const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e4), d = __ldg(reinterpret_cast<const float4*>(du) + e4);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {d.x, d.y, d.z, d.w};
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float z = relu ? fmaxf(xs[k], 0.f) : xs[k];
+    const float zh = (z - mu[c + k]) * invstd[c + k];
+    float dz = a[c + k] * (ds[k] - float(st[c + k] / N) - zh * float(st[C + c + k] / N));
+    if (relu && xs[k] <= 0.f) dz = 0.f;
+    o[k] = dz;
+  }
+  if (add1) { const float4 t = __ldg(reinterpret_cast<const float4*>(add1) + e4); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+  if (add2) { const float4 t = __ldg(reinterpret_cast<const float4*>(add2) + e4); o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w; }
+  reinterpret_cast<float4*>(out)[e4] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // dW[co][ci][t] += sum_r dy[r][co] * u[r+t-pad][ci] (u = a*act(x)+b inside the site, 0 outside), dbias[co] += sum_r dy
@@ -942,11 +978,11 @@ static int conv_train_fwd(mural_snv_train* T, float* P, int li, const float* x, 
   float* bn = T->d_bn + int64_t(li) * 4 * C;
   const int64_t rows = n * L;
   CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
-  const int thr = 256, rpb = thr / C;
-  int grid = (int)cdiv(rows, rpb * 8);
+  const int thr = 256, rpb = thr / (C / 4);   // a thread owns 4 channels of a row
+  int grid = (int)cdiv(rows, rpb * 4);
   if (grid > 1184) grid = 1184;
   if (grid < 1) grid = 1;
-  LAUNCH(k_stats, grid, thr, sizeof(double) * 2 * thr, st, x, rows, C, d.relu_in, stat);
+  LAUNCH(k_stats, grid, thr, sizeof(double) * 8 * thr, st, x, rows, C, d.relu_in, stat);
   LAUNCH(k_bn_finalize, 1, 64, 0, st, stat, double(rows), C, P, d.g, d.be, d.rm, d.rv, bn, bn + C, bn + 2 * C, bn + 3 * C);
   ConvLayerDev cl{T->d_Wt + int64_t(li) * 7 * C * C, P + d.b, bn, bn + C, d.ks, d.relu_in, 1};
   return conv_any(C, x, y, r1, r2, n, L, cl, relu_out, st);
@@ -1088,14 +1124,14 @@ static int conv_train_bwd(mural_snv_train* T, const float* P, float* G, int li, 
   ConvLayerDev cl{T->d_Wf + int64_t(li) * 7 * C * C, T->d_const + C, T->d_const, T->d_const + C, d.ks, 0, 0};  // dgrad: two-level split MMA
   if (int rc = conv_any(C, dy, du, nullptr, nullptr, n, L, cl, 0, st)) return rc;
   CUDA_TRY(cudaMemsetAsync(stat, 0, sizeof(double) * 2 * C, st));
-  const int thr = 256, rpb = thr / C;
-  int grid = (int)cdiv(rows, rpb * 8);
+  const int thr = 256, rpb = thr / (C / 4);
+  int grid = (int)cdiv(rows, rpb * 4);
   if (grid > 1184) grid = 1184;
   if (grid < 1) grid = 1;
-  LAUNCH(k_bn_bwd_reduce, grid, thr, sizeof(double) * 2 * thr, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, stat);
+  LAUNCH(k_bn_bwd_reduce, grid, thr, sizeof(double) * 8 * thr, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, stat);
   // `out` may be the dy the PREVIOUS layer's weight gradient is still reading (the gradient buffers rotate): join that one first
   if (prev_pending) CUDA_TRY(cudaStreamWaitEvent(st, T->ev_w[wbr], 0));
-  LAUNCH(k_bn_bwd_apply, gridn(rows * C), 256, 0, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, bn, stat, double(rows), add1,
+  LAUNCH(k_bn_bwd_apply, gridn(rows * (C / 4)), 256, 0, st, du, x, rows, C, d.relu_in, bn + 2 * C, bn + 3 * C, bn, stat, double(rows), add1,
          add2, out, G, d.g, d.be);
   CUDA_TRY(cudaEventRecord(T->ev_w[wbr], T->wside[wbr]));   // after the wait above: ev_w now stands for THIS layer's weight gradient
   T->w_pending[wbr] = true;
