@@ -666,14 +666,26 @@ __global__ void __launch_bounds__(128) k_stem_train(const uint8_t* __restrict__ 
     hi = hi > L0 ? L0 : hi;
     float mx = -FLT_MAX;
     int am = lo;
-    for (int p = lo; p < hi; ++p) {
-      float v = sB[c];
-      for (int t = 0; t < ks; ++t) {
-        const int q = p + t - half;
-        const int s = (q >= 0 && q < L0) ? sym[q] : SYM_PAD;
-        v += sT[(t * 16 + s) * C + c];
+    if (ks == 3) {   // shipped kernel size: the three symbols of a position slide along the bin (one symbol load per position)
+      const float* t0 = sT + c;
+      const float b = sB[c];
+      int s0 = lo >= 1 ? sym[lo - 1] : SYM_PAD, s1 = sym[lo];
+      for (int p = lo; p < hi; ++p) {
+        const int s2 = p + 1 < L0 ? sym[p + 1] : SYM_PAD;
+        const float v = ((b + t0[s0 * C]) + t0[(16 + s1) * C]) + t0[(32 + s2) * C];   // same summation order as the generic loop
+        if (v > mx) { mx = v; am = p; }
+        s0 = s1; s1 = s2;
       }
-      if (v > mx) { mx = v; am = p; }
+    } else {
+      for (int p = lo; p < hi; ++p) {
+        float v = sB[c];
+        for (int t = 0; t < ks; ++t) {
+          const int q = p + t - half;
+          const int s = (q >= 0 && q < L0) ? sym[q] : SYM_PAD;
+          v += sT[(t * 16 + s) * C + c];
+        }
+        if (v > mx) { mx = v; am = p; }
+      }
     }
     out[(site * L1) * int64_t(C) + e] = mx;
     idx[(site * L1) * int64_t(C) + e] = am;
@@ -1226,7 +1238,7 @@ extern "C" int mural_snv_train_backward(mural_snv_train_t* T, const float* d_blo
     const size_t smem = sizeof(float) * (size_t(ks) * 16 * C + C);
 #define SB(CC)                                                                                                       \
   case CC:                                                                                                          \
-    LAUNCH(k_stem_bwd<CC>, 296, 256, smem, st, G3, b.i1, T->sym, n, m->L, ks, B.L0, off0, B.L1, Gt,                  \
+    LAUNCH(k_stem_bwd<CC>, 148 * 8, 256, smem, st, G3, b.i1, T->sym, n, m->L, ks, B.L0, off0, B.L1, Gt,                  \
            G + off_of(m, "conv1" + s + ".1.bias"));                                                                 \
     break;
     switch (C) { SB(16) SB(32) SB(64) default: MURAL_FAIL("unsupported channel count"); }
