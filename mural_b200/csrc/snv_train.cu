@@ -659,7 +659,10 @@ __global__ void __launch_bounds__(128) k_stem_train(const uint8_t* __restrict__ 
   for (int i = threadIdx.x; i < L0; i += blockDim.x) sym[i] = sym_g[site * L + off0 + i];
   __syncthreads();
   const int half = ks / 2;
-  for (int e = threadIdx.x; e < L1 * C; e += blockDim.x) {
+  // grid.y slices of the site's bins: at small batches one CTA per site leaves SMs idle and its serial walk over all bins is on
+  // the critical path of the step
+  const int jb = (L1 + gridDim.y - 1) / gridDim.y, j0 = blockIdx.y * jb, j1 = (j0 + jb < L1) ? j0 + jb : L1;
+  for (int e = j0 * C + threadIdx.x; e < j1 * C; e += blockDim.x) {
     const int j = e / C, c = e - j * C;
     int lo = j * ps - pp, hi = lo + pk;
     lo = lo < 0 ? 0 : lo;
@@ -1035,6 +1038,10 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
            off_of(m, "conv1" + s + ".0.running_mean"), off_of(m, "conv1" + s + ".0.running_var"), off_of(m, "conv1" + s + ".1.weight"), C,
            ks, stem, stem + 16);
     const size_t smem = sizeof(float) * (size_t(ks) * 16 * C + C) + ((size_t(B.L0) + 15) & ~size_t(15));
+    unsigned stem_parts = (unsigned)((8 * 148 + n - 1) / n);   // ~8 CTAs of 128 threads per SM in all
+    if (stem_parts > 8) stem_parts = 8;
+    if (stem_parts > (unsigned)B.L1) stem_parts = (unsigned)B.L1;
+    if (stem_parts < 1) stem_parts = 1;
 #define STEMT(CC)                                                                                                         \
   case CC: {                                                                                                             \
     static size_t conf = 0;                                                                                              \
@@ -1042,7 +1049,7 @@ extern "C" int mural_snv_train_forward(mural_snv_train_t* T, const mural_genome_
       CUDA_TRY(cudaFuncSetAttribute(k_stem_train<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
       conf = smem;                                                                                                       \
     }                                                                                                                    \
-    LAUNCH(k_stem_train<CC>, (unsigned)n, 128, smem, st, T->sym, m->L, ks, stem + 16, P + off_of(m, "conv1" + s + ".1.bias"), B.L0, \
+    LAUNCH(k_stem_train<CC>, dim3((unsigned)n, stem_parts), 128, smem, st, T->sym, m->L, ks, stem + 16, P + off_of(m, "conv1" + s + ".1.bias"), B.L0, \
            off0, B.L1, B.pool[0][0], B.pool[0][1], B.pool[0][2], b.x0, b.i1);                                            \
   } break;
     switch (C) { STEMT(16) STEMT(32) STEMT(64) default: MURAL_FAIL("unsupported channel count"); }
