@@ -434,27 +434,34 @@ inline bool Exec::conv_bwd_w(const ConvBwdW& f) {
 // per-row sums of a BatchNorm pass: threads of a row walk it coalesced, the row's two sums are reduced by shuffles (+ shared
 // memory across warps) and leave as ONE pair of double atomics per row — the work-item form issues 64 pairs per row onto
 // 2*C addresses, which serialises (2.5 ms per step at batch 32)
+// segs > 1 (long rows, few of them — the top levels at batch 32 are 256-512 rows of 8000): a row is cut into `segs` pieces that
+// go to different CTAs, each leaving its own pair of atomics.
 template <class F, int TPR>
-__global__ void __launch_bounds__(256) k_row_reduce(F f, int64_t rows, double* stat) {
+__global__ void __launch_bounds__(256) k_row_reduce(F f, int64_t rows_in, double* stat, int segs) {
   constexpr int RPB = 256 / TPR;   // rows per block
   __shared__ double sh[2][8];
   const int sub = threadIdx.x / TPR, lt = threadIdx.x % TPR;
   const int L = f.length(), C = f.channels();
+  const int Ls = (L + segs - 1) / segs;
+  const int64_t rows = rows_in * segs;   // virtual rows = (row, segment)
   for (int64_t row0 = int64_t(blockIdx.x) * RPB; row0 < rows; row0 += int64_t(gridDim.x) * RPB) {
-    const int64_t row = row0 + sub;
+    const int64_t vrow = row0 + sub;
+    const int64_t row = vrow / segs;
+    const int seg = int(vrow - row * segs);
+    const int l_end = (seg + 1) * Ls < L ? (seg + 1) * Ls : L;
     double s = 0, q = 0;
-    if (row < rows)
-      for (int l = lt; l < L; l += TPR) f.at(row, l, s, q);
+    if (vrow < rows)
+      for (int l = seg * Ls + lt; l < l_end; l += TPR) f.at(row, l, s, q);
     if (!f.reduces()) continue;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
     if (TPR == 32) {
-      if (lt == 0 && row < rows) { atomicAdd(stat + int(row % C), s); atomicAdd(stat + C + int(row % C), q); }
+      if (lt == 0 && vrow < rows) { atomicAdd(stat + int(row % C), s); atomicAdd(stat + C + int(row % C), q); }
     } else {
       __syncthreads();
       if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
       __syncthreads();
-      if (threadIdx.x == 0 && row < rows) {
+      if (threadIdx.x == 0 && vrow < rows) {
         double ts = 0, tq = 0;
         for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
         atomicAdd(stat + int(row % C), ts);
@@ -466,12 +473,16 @@ __global__ void __launch_bounds__(256) k_row_reduce(F f, int64_t rows, double* s
 template <class F> inline bool Exec::row_reduce(const F& f, int64_t rows, double* stat) {
   if (rows <= 0) return true;
   if (f.length() > 256) {
-    const int64_t g = rows < 148 * 8 ? rows : 148 * 8;
-    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 256>), (unsigned)g, 256, 0, st, f, rows, stat);
+    int segs = int((148 * 8) / rows);                          // aim at ~8 CTAs per SM
+    const int max_segs = f.length() / 512 > 0 ? f.length() / 512 : 1;   // at least 512 positions (2 per thread) per piece
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    const int64_t g = rows * segs < 148 * 8 ? rows * segs : 148 * 8;
+    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 256>), (unsigned)g, 256, 0, st, f, rows, stat, segs);
   } else {
     int64_t g = (rows + 7) / 8;
     if (g > 148 * 8) g = 148 * 8;
-    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 32>), (unsigned)g, 256, 0, st, f, rows, stat);
+    INDEL_TRAIN_LAUNCH_SMEM(F::kName, (k_row_reduce<F, 32>), (unsigned)g, 256, 0, st, f, rows, stat, 1);
   }
   ++launches;
   return true;

@@ -87,7 +87,7 @@ def test_train_forward_backward_vs_autograd(kat, cuda_genome, tag):
     dlogp = torch.empty_like(logp)
     _lib.check(_lib.lib().mural_ce_sum_grad(_lib.ptr(logp), _lib.ptr(sb.meta), n, 4, _lib.ptr(st.loss_dev), _lib.ptr(dlogp),
                                             _lib.current_stream()))
-    assert abs(float(st.loss_dev.item()) - float(loss)) < 1e-3 * max(1.0, abs(float(loss)))
+    assert abs(float(st.loss_dev.item()) - float(loss.detach())) < 1e-3 * max(1.0, abs(float(loss.detach())))
     g = st.backward(dlogp).cpu().numpy()
     worst, rel = _check_grads(m.native_layout(), g, sd64, tag)
     print(tag, "worst relative gradient error %.2e (tensors without a ReLU-kink event), whole-gradient relative L2 %.2e" % (worst, rel))
