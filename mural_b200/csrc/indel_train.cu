@@ -47,7 +47,7 @@ extern "C" int mural_indel_train_create(mural_indel_model_t* m, mural_indel_trai
 extern "C" void mural_indel_train_destroy(mural_indel_train_t* T) {
   if (!T) return;
   indel_train::Engine& E = T->E;
-  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.dz_b); cudaFree(E.dxv); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat);
+  cudaFree(E.vals); cudaFree(E.grads); cudaFree(E.dz); cudaFree(E.dz_b); cudaFree(E.dxv); cudaFree(E.stats); cudaFree(E.arg); cudaFree(E.dstat); cudaFree(E.step_mem);
   if (E.ex.side_st) {
     cudaStreamDestroy(E.ex.side_st);
     cudaEventDestroy(E.ex.ev_dz);

@@ -127,6 +127,11 @@ HD float drop_scale(float p, uint64_t seed, uint32_t step, uint64_t idx) {
 }
 
 // ------------------------------------------------------------------------------------------------ ops (work-item functors)
+struct BumpStep {   // one work item: advances the dropout stream position at the start of a training forward
+  static constexpr const char* kName = "k_indel_train<BumpStep>";
+  uint32_t* p;
+  HD void operator()(int64_t) const { *p += 1u; }
+};
 struct ConvDims { int B, Cin, Lin, Cout, Lout, k, stride, pad, up; };
 constexpr int CONV_W_SPLIT = 32;  // work items per (co, ci, t, b) in the weight gradient (one warp walks a row pair coalesced)  // input is read through a nearest upsample by `up`
 
@@ -229,14 +234,15 @@ struct BnFinalize {
 struct UnitOut {
   static constexpr const char* kName = "k_indel_train<UnitOut>";  // item: element; y = drop * act(bn(t)) + res1 + res2
   const float* t; const float* mean; const float* invstd; const float* gamma; const float* beta;  // gamma == nullptr: no BN
-  const float* res1; const float* res2; float* y; int C, L, act; float p; uint64_t seed; uint32_t step;
+  const float* res1; const float* res2; float* y; int C, L, act; float p; uint64_t seed;
+  const uint32_t* step_p;   // dropout stream position, read from memory so that a captured step graph advances it (BumpStep)
   HD float z_of(int64_t i) const {
     if (!gamma) return t[i];
     const int c = int((i / L) % C);
     return (t[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
   }
   HD void operator()(int64_t i) const {
-    float v = act_fwd(z_of(i), act) * drop_scale(p, seed, step, uint64_t(i));
+    float v = act_fwd(z_of(i), act) * drop_scale(p, seed, *step_p, uint64_t(i));
     if (res1) v += res1[i];
     if (res2) v += res2[i];
     y[i] = v;
@@ -252,7 +258,7 @@ struct UnitBwdReduce {
   HD void at(int64_t row, int l, double& s1, double& s2) const {
     const int c = int(row % u.C);
     const int64_t i = row * u.L + l;
-    const float g = dy[i] * drop_scale(u.p, u.seed, u.step, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
+    const float g = dy[i] * drop_scale(u.p, u.seed, *u.step_p, uint64_t(i)) * act_bwd(u.z_of(i), u.act);
     dz[i] = g;
     if (u.gamma) { s1 += g; s2 += double(g) * ((u.t[i] - u.mean[c]) * u.invstd[c]); }
   }

@@ -34,7 +34,7 @@ struct Engine {
   int32_t* arg = nullptr;
   double* dstat = nullptr;
   uint64_t seed = 0;
-  uint32_t step = 0;
+  uint32_t* step_mem = nullptr;   // dropout stream position (device memory in the CUDA build), bumped by every forward
 
   int tensor(int C, int L) { tensors.push_back({C, L, per_site}); per_site += int64_t(C) * L;
     if (int64_t(C) * L > max_per_site) max_per_site = int64_t(C) * L; return int(tensors.size()) - 1; }
@@ -113,6 +113,7 @@ struct Engine {
     stats = (float*)ex.alloc(sizeof(float) * (n_stat + 1));
     arg = (int32_t*)ex.alloc(sizeof(int32_t) * cfg.channels * 6 * B);
     dstat = (double*)ex.alloc(sizeof(double) * 2 * 1024);
+    if (!step_mem) { step_mem = (uint32_t*)ex.alloc(sizeof(uint32_t)); ex.zero(step_mem, sizeof(uint32_t)); }
     cap = B;
   }
   float* V(int t, int64_t B) { return vals + tensors[t].off * B; }
@@ -124,7 +125,7 @@ struct Engine {
     o.t = V(u.t, B); o.mean = stats + u.stat_slot; o.invstd = stats + u.stat_slot + to.C;
     o.gamma = u.has_bn ? P + u.gamma : nullptr; o.beta = u.has_bn ? P + u.beta : nullptr;
     o.res1 = u.res1 >= 0 ? V(u.res1, B) : nullptr; o.res2 = u.res2 >= 0 ? V(u.res2, B) : nullptr;
-    o.y = V(u.out, B); o.C = to.C; o.L = to.L; o.act = u.act; o.p = u.p_drop; o.seed = seed ^ (uint64_t(u.out) << 48); o.step = step;
+    o.y = V(u.out, B); o.C = to.C; o.L = to.L; o.act = u.act; o.p = u.p_drop; o.seed = seed ^ (uint64_t(u.out) << 48); o.step_p = step_mem;
     return o;
   }
   ConvDims dims(const Unit& u, int64_t B) {
@@ -135,7 +136,7 @@ struct Engine {
   // x: [B, 4, L] one-hot windows already in vals of t_in (caller copies / gathers them there); P: parameter blob (running
   // statistics are updated in place); out: [B, n_class]
   void forward(float* P, int64_t B) {
-    ++step;
+    ex.run(1, BumpStep{step_mem});
     for (const Op& op : ops) {
       if (op.kind == OP_FLIP_CL) {
         const Tensor t = tensors[op.a];

@@ -371,8 +371,16 @@ class IndelTrainState:
     flat fp32 buffer, gradients land in one flat buffer (the single all-reduce of a data-parallel step), clip + optimizer are
     the fused kernels.  The loss is CrossEntropyLoss(sum) on the Softplus outputs, as in the reference."""
 
-    def __init__(self, model, distal_radius, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False):
+    MAX_GRAPHS = 4
+
+    def __init__(self, model, distal_radius, optim="Adam", lr=1e-3, weight_decay=0.0, max_norm=10.0, seed=0, grad_average=False,
+                 use_graph=True):
+        """use_graph: capture the step of a batch size in CUDA graphs (forward + CE + backward | clip + optimizer, the data-parallel
+        all-reduce eagerly between them) after one eager step of that size and replay them; the dropout stream position, the
+        learning rate and the optimizer step are read from device memory, so replays stay in step with the eager form."""
         L = _lib.lib()
+        self.use_graph = bool(use_graph)
+        self._graphs, self._graph_warm = {}, {}
         self.model = model
         self.device = model.out_fc[2].weight.device
         if self.device.type != "cuda":
@@ -466,11 +474,64 @@ class IndelTrainState:
                                                              _lib.current_stream()))
         return self.grads
 
+    def _launch_optimizer(self, world):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mural_optimizer_step_dev(self.kind, _lib.ptr(self.blob), _lib.ptr(self.grads), _lib.ptr(self.m),
+                                                           _lib.ptr(self.v), _lib.ptr(self.vmax), self.n_trainable, _lib.ptr(self._lr_dev),
+                                                           self.weight_decay, _lib.ptr(self._opt_step_dev), self.max_norm,
+                                                           1.0 / world if self.grad_average else 1.0, _lib.ptr(self.scratch),
+                                                           _lib.current_stream()))
+
+    def _world(self):
+        d = torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+    def _capture(self, batch):
+        n = len(batch)
+        L = _lib.lib()
+        g = {"genome": batch.genome, "pos": batch.pos.clone(), "meta": batch.meta.clone(), "world": self._world(),
+             "out": torch.empty((n, self.model.n_class), dtype=torch.float32, device=self.device)}
+        g["dout"] = torch.empty_like(g["out"])
+        torch.cuda.synchronize(self.device)
+        g["fb"], g["opt"] = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g["fb"], capture_error_mode="thread_local"):
+            with torch.cuda.device(self.device):
+                _lib.check(L.mural_indel_train_forward(self._h, g["genome"].handle, _lib.ptr(g["pos"]), _lib.ptr(g["meta"]), n,
+                                                       _lib.ptr(self.blob), _lib.ptr(g["out"]), _lib.current_stream()))
+                _lib.check(L.mural_ce_sum_grad(_lib.ptr(g["out"]), _lib.ptr(g["meta"]), n, self.model.n_class, _lib.ptr(self.loss_dev),
+                                               _lib.ptr(g["dout"]), _lib.current_stream()))
+                _lib.check(L.mural_indel_train_backward(self._h, _lib.ptr(self.blob), _lib.ptr(g["dout"]), _lib.ptr(self.grads),
+                                                        _lib.current_stream()))
+        with torch.cuda.graph(g["opt"], capture_error_mode="thread_local"):
+            self._launch_optimizer(g["world"])
+        return g
+
     def step(self, batch):
-        """forward + CE(sum) + backward + all-reduce + clip + optimizer on a SiteBatch (labels in its meta)."""
+        """forward + CE(sum) + backward + all-reduce + clip + optimizer on a SiteBatch (labels in its meta).  On the graph path the
+        returned tensor is the graph's static output buffer (overwritten by the next step of the same batch size)."""
         n = len(batch)
         if n < 2:
             return None                                      # training.py:415
+        if self.use_graph and isinstance(batch, SiteBatch):
+            _check_attached(self)
+            g = self._graphs.get(n)
+            if g is None and self._graph_warm.get(n, 0) >= 1 and len(self._graphs) < self.MAX_GRAPHS:
+                g = self._graphs[n] = self._capture(batch)
+            if g is not None and g["genome"] is batch.genome and g["world"] == self._world():
+                g["pos"].copy_(batch.pos)
+                g["meta"].copy_(batch.meta)
+                if self._lr_on_dev != self.lr:
+                    self._lr_dev.fill_(self.lr)
+                    self._lr_on_dev = self.lr
+                g["fb"].replay()
+                self.n_forward += 1
+                if g["world"] > 1:
+                    torch.distributed.all_reduce(self.grads[:self.n_trainable], op=torch.distributed.ReduceOp.SUM)
+                g["opt"].replay()
+                self.opt_step += 1
+                self.model.mark_dirty()
+                return g["out"]
+            self._graph_warm[n] = self._graph_warm.get(n, 0) + 1
         out = self.forward(batch)
         dout = torch.empty_like(out)
         with torch.cuda.device(self.device):

@@ -171,3 +171,35 @@ def test_indel_train_epochs_with_validation_metrics(kat, cuda_genome):
     for k in (2, 4):
         ref = EN.freq_kmer_comp_multi(flank, labels, prob, k, 8)
         assert np.allclose(h["kmer%d" % k], ref, rtol=0, atol=2e-5, equal_nan=True), (k, h["kmer%d" % k], ref)
+
+
+def test_indel_graph_step_equals_eager_step(kat, cuda_genome):
+    """IndelTrainState.step replayed from CUDA graphs (forward + CE + backward | clip + optimizer, weight gradients on their side
+    stream inside the capture) == the eager step, with the out_fc dropout ON (its stream position lives in device memory and is
+    advanced inside the graph) and a learning-rate change between steps."""
+    from mural_b200 import SiteBatch, pack_meta
+    from mural_b200.training import IndelTrainState
+    z = np.load(os.path.join(GOLD, "indel_ex_indel9.npz"))
+    Rd, n = 500, 16
+    pos = torch.from_numpy(z["start"][:2 * n].astype(np.int32)).cuda()
+    labels = (z["start"][:2 * n] % 8).astype(np.int64)
+    meta = torch.from_numpy(pack_meta(z["strand"][:2 * n], labels, z["chrom"][:2 * n])).cuda()
+    batches = [SiteBatch(pos[:n], meta[:n], cuda_genome), SiteBatch(pos[n:], meta[n:], cuda_genome)]
+    blobs, losses, used = [], [], []
+    for use_graph in (False, False, True):
+        m, _ = _model(z)
+        st = IndelTrainState(m, Rd, "Adam", lr=1e-4, weight_decay=1e-5, seed=7, use_graph=use_graph)
+        st.set_dropout(0.1, seed=7)
+        m.train()
+        for i in range(6):
+            if i == 3:
+                st.lr = 5e-5
+            st.step(batches[i % 2])
+        blobs.append(st.blob.clone()); losses.append(float(st.loss_dev.item())); used.append(len(st._graphs))
+    assert used == [0, 0, 1]
+    scale = max(1.0, blobs[0].abs().max().item())
+    d_ee = (blobs[0] - blobs[1]).abs().max().item()          # two eager runs: the float atomics of the weight gradients reorder
+    d_ge = (blobs[0] - blobs[2]).abs().max().item()
+    print("eager vs eager %.2e, graph vs eager %.2e (scale %.2f); losses %r" % (d_ee, d_ge, scale, losses))
+    assert d_ge <= max(10 * d_ee, 2e-5 * scale), (d_ee, d_ge)
+    assert abs(losses[0] - losses[2]) <= 1e-4 * abs(losses[0])
