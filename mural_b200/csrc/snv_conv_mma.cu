@@ -49,8 +49,11 @@ __device__ __forceinline__ void split3(float x, float y, uint32_t& hi, uint32_t&
 // NS = 3: x = hi + mid + lo, the six products down to 2^-24 (fp32-level): the training forward / dgrad, whose BatchNorm
 // backward and bias gradients are sums with heavy cancellation (a conv bias in front of a train-mode BatchNorm has a
 // mathematically vanishing gradient), where 16 mantissa bits show up as 1e-2 relative errors.
+#ifndef MURAL_CMMA_MINB
+#define MURAL_CMMA_MINB 4
+#endif
 template <int NS>
-__global__ void __launch_bounds__(128, NS == 2 ? 4 : 3) k_conv_mma(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ res1,
+__global__ void __launch_bounds__(128, NS == 2 ? MURAL_CMMA_MINB : 3) k_conv_mma(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ res1,
                                                                   const float* __restrict__ res2, int64_t rows, int L, ConvLayerDev P, int relu_out) {
   __shared__ __align__(16) float us[(TILE + 2) * US];
   __shared__ uint32_t wp[NS][K2 * WS];  // [hi|(mid)|lo][k-pair][co]
@@ -171,7 +174,7 @@ int conv32_mma(const float* in, float* out, const float* r1, const float* r2, in
                cudaStream_t st) {
   const int64_t rows = n * L;
   const int64_t tiles = cdiv(rows, cmma::TILE);
-  const int64_t cap = int64_t(m_sm_count()) * 4;
+  const int64_t cap = int64_t(m_sm_count()) * (P.precise ? 3 : MURAL_CMMA_MINB);
   if (P.precise) LAUNCH_N("k_conv_mma<3>", cmma::k_conv_mma<3>, (unsigned)(tiles < cap ? tiles : cap), 128, 0, st, in, out, r1, r2, rows, L, P, relu_out);
   else LAUNCH_N("k_conv_mma<2>", cmma::k_conv_mma<2>, (unsigned)(tiles < cap ? tiles : cap), 128, 0, st, in, out, r1, r2, rows, L, P, relu_out);
   return 0;
