@@ -30,8 +30,18 @@ tests/test_gpu_snv_tc.py::test_bf16_forward_matches_reference[hs_AT]
 tests/test_gpu_predict_pipeline.py::test_auto_mode_routes_exception_windows_to_fp32
 tests/test_gpu_indel_train.py::test_indel_fused_step_and_dropin_loop
 tests/test_gpu_snv_train.py::test_graph_step_equals_eager_step'
+# c: kernels changed after set b — upsample-folded U-Net level kernels and batch edges, vectorised BatchNorm passes / stems /
+# weight-gradient side streams of the MuRaL-snv training step, continuous features in train mode, segmented row reductions,
+# grid.z-split convs and the graph-replayed step of MuRaL-indel training
+SEL_c='tests/test_gpu_indel.py::test_indel_forward_matches_reference[at_ins]
+tests/test_gpu_indel.py::test_indel_level_kernels_batch_edges
+tests/test_gpu_snv_train.py::test_train_forward_backward_vs_autograd[ex_ckpt6]
+tests/test_gpu_snv_train.py::test_graph_step_equals_eager_step
+tests/test_gpu_snv_cont.py
+tests/test_gpu_indel_train.py::test_indel_train_forward_backward_vs_autograd[hs_ins-500-6]
+tests/test_gpu_indel_train.py::test_indel_graph_step_equals_eager_step'
 SET=${SET:-a}
-if [ "$SET" = b ]; then SEL=$SEL_b; else SEL=$SEL_a; fi
+if [ "$SET" = b ]; then SEL=$SEL_b; elif [ "$SET" = c ]; then SEL=$SEL_c; else SEL=$SEL_a; fi
 for tool in $TOOLS; do
   i=0
   for t in $SEL; do
