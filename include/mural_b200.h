@@ -331,6 +331,8 @@ void mural_bigwig_close(mural_bigwig_t* b);
 int mural_write_tsv(const char* path, int64_t n, int32_t n_class, const char* const* chrom_names, const int32_t* chrom_idx,
                     const int64_t* start, const int64_t* end, const char* strand, const double* mut_type, const double* prob,
                     int32_t n_threads);
+/* the writer's "%.4g" formatter on one value (parity hook: tests compare it with printf); out32: >= 32 bytes, NUL-terminated */
+int mural_format_g4(double v, char* out32);
 
 #ifdef __cplusplus
 }

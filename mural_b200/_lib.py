@@ -111,6 +111,7 @@ PROTOTYPES = {
     "mural_fasta_len": (_i64, [_vp, _i32]),
     "mural_fasta_destroy": (None, [_vp]),
     "mural_write_tsv": (C.c_int, [C.c_char_p, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "mural_format_g4": (C.c_int, [C.c_double, C.c_char_p]),
 }
 
 _lib = None

@@ -336,3 +336,29 @@ def test_eval_data_from_reference_frames():
         for j in range(1, R + 1):
             assert np.array_equal(flank[:, mid - j], df["us%d" % j].to_numpy()) and np.array_equal(flank[:, mid + j], df["ds%d" % j].to_numpy())
         assert np.array_equal(ed.labels_host(), df["mut_type"].to_numpy())
+
+
+def test_tsv_float_formatter_equals_printf():
+    """The TSV writer's own "%.4g" (one multiplication by a power of ten, printf only next to rounding ties) must be byte-identical
+    to printf — which is what pandas' float_format applies per value (run_predict.py:236) — on probabilities of every magnitude,
+    exact short decimals, rounding boundaries, negative values, zeros and non-finite values."""
+    import ctypes as C
+    from mural_b200 import _lib
+    L = _lib.lib()
+    buf = C.create_string_buffer(64)
+
+    def f(v):
+        L.mural_format_g4(float(v), buf)
+        return buf.value.decode()
+    special = [0.0, -0.0, 1.0, 2.0, 3.0, 0.5, 0.25, 0.1, 0.12345, 0.123449999, 0.99995, 0.99994999, 9999.5, 9999.4999, 99995.0, 1e-4,
+               9.9995e-5, 1e-5, 1.2345e-5, 123456789.0, 1e19, 1e-19, 1e-20, 5e-324, 1e300, float("inf"), -float("inf"), -1.5e-7, 0.00012345,
+               1234.5, 1234.4999999999, 0.1 + 0.2, 1 / 3, 2 / 3, 0.952381, 1e4, 9999.0, 1000.0, 0.001, 12.5, 100.0]
+    for v in special:
+        assert f(v) == "%.4g" % v, (v, f(v), "%.4g" % v)
+    assert f(float("nan")).lstrip("-") == "nan"
+    rng = np.random.default_rng(0)
+    for xs in (rng.random(20000), rng.random(20000) * 1e-4, rng.random(20000) * 1e-8,
+               10 ** rng.uniform(-22, 22, 40000) * rng.choice([-1, 1], 40000),
+               np.arange(10000, 100000, 37)[:, None] * 10.0 ** np.array([-9, -8, -5, -4, -1, 0])[None, :]):
+        for v in np.asarray(xs).ravel():
+            assert f(v) == "%.4g" % v, (repr(float(v)), f(v), "%.4g" % v)
