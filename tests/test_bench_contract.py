@@ -20,3 +20,13 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["sites_per_step_per_gpu"] == 1024 and "workload" in d["config"]
+
+
+def test_roofline_flop_counts_match_the_survey():
+    """The algorithmic FLOP counts the secondary bench legs report against are SURVEY 8d's: 113 379 328 conv FLOP per site for the
+    shipped human MuRaL-indel configuration, 3 x stage-S + 2 x stage-G wgrad = 22.6 M per site for a MuRaL-snv training step."""
+    import bench
+    assert bench.unet_flops(8, 7, [1, 4, 5, 5, 5, 2], 8000, True) == 113379328
+    assert bench.unet_flops(8, 7, [1, 4, 5, 5, 5, 2], 8000, False) == 113379328 - 2 * 2 * 8000 * 7 * 4 * 4
+    assert bench.snv_train_flops(2001) == 3 * 6396008 + 2 * (768 * 2001 + 768 * 201)
+    assert abs(bench.snv_train_flops(2001) - 22.6e6) < 0.1e6
