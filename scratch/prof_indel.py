@@ -16,7 +16,7 @@ cfg = {"CNN_out_channels": state["uplblocks.0.0.weight"].shape[0], "CNN_kernel_s
 m = model_choice(0, cfg, {"n_class": cfg["n_class"]}, "indel")
 m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
 m.to("cuda").eval()
-n = 2048
+n = int(os.environ.get("NSITES", "2048"))
 pos = torch.from_numpy((20000 + 50 * np.arange(n)).astype(np.int32)).cuda()
 meta = torch.from_numpy(pack_meta(np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64))).cuda()
 sb = SiteBatch(pos, meta, genome)
@@ -30,7 +30,7 @@ buf = C.create_string_buffer(1 << 16)
 L.mural_profile_end(buf, len(buf))
 prof = json.loads(buf.value.decode())
 tot = sum(v["ms"] for v in prof.values()); nl = sum(v["count"] for v in prof.values())
-print("%d launches, %.3f ms per 2048-site batch" % (nl, tot))
+print("%d launches, %.3f ms per %d-site batch -> %.0f sites/s" % (nl, tot, n, n / tot * 1e3))
 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]:
     print("   %-44s n=%4d  %8.3f ms" % (k[:44], v["count"], v["ms"]))
 
