@@ -395,7 +395,8 @@ bool snv_lattice_supported(const mural_snv_model* m) {
 // (int*, 1 = the dense path produced the stem output) so that the per-site kernel can skip itself.
 int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
-                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice, const ChunkInfo** d_info) {
+                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice, const ChunkInfo** d_info,
+                          const SideStream* side) {
   const int C = m->cfg.channels;
   MURAL_CHECK(C == 32, "dense stem is built for C == 32");
   const int cap = int(snv_dense_cap(chunk));
@@ -430,10 +431,18 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
   if (lattice) {
     LatIn li[2];
     for (int br = 0; br < 2; ++br) li[br] = LatIn{reinterpret_cast<uint4*>(lattice[br].lat_in), lattice[br].lat_ra, m->br[br].pool[0][1]};
-    LAUNCH(k_lattice_in<32>, 148 * 4, 256, 0, st, info, li[0], li[1], cap, tables);
+    cudaStream_t sl = st;
+    if (side) {
+      sl = side->s;
+      CUDA_TRY(cudaEventRecord(side->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(sl, side->fork, 0));
+    }
+    LAUNCH(k_lattice_in<32>, 148 * 4, 256, 0, sl, info, li[0], li[1], cap, tables);
+    if (side) CUDA_TRY(cudaEventRecord(side->join, sl));
   }
   MURAL_CHECK(ns * int64_t(m->br[1].L1 > LAT_EL ? m->br[1].L1 : LAT_EL) * 4 < (int64_t(1) << 31), "chunk too large for the stem gather's 32-bit indices");
   LAUNCH(k_stem_gather<32>, 148 * 8, 256, 0, st, *G, info, d_pos, d_meta, ns, m->cfg.distal_radius, gb[0], gb[1], cap, tables);
+  if (lattice && side) CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
   *d_flag = &info->dense;
   if (d_info) *d_info = info;
   CUDA_TRY(cudaGetLastError());

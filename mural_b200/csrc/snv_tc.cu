@@ -623,9 +623,15 @@ __global__ void __launch_bounds__(256) k_head_tc(HeadTc b0, HeadTc b1, const flo
     }
 }
 
+constexpr int N_SIDE = 3, N_SIDE_EV = 16;
 struct TcState {
   uint8_t* d_w = nullptr;         // all stage blobs back to back
   const uint8_t* blob[2][3] = {};  // [branch][stage]
+  // side streams of the dense path (snv_forward_tc): the passes that are not stage kernels are latency-bound and run beside each
+  // other: [0] lattice transpose / lattice pools, [1] local branch + tail, [2] second edge pool
+  cudaStream_t side[N_SIDE] = {};
+  cudaEvent_t ev[N_SIDE_EV] = {};
+  int ev_next = 0;
 };
 
 static inline int64_t rows_of(int64_t ns, int L) { return ns * (L + 1) + 1; }
@@ -750,6 +756,10 @@ void snv_tc_destroy(mural_snv_model* m) {
   if (!m->tc) return;
   tc::TcState* S = (tc::TcState*)m->tc;
   cudaFree(S->d_w);
+  for (cudaStream_t q : S->side)
+    if (q) cudaStreamDestroy(q);
+  for (cudaEvent_t e : S->ev)
+    if (e) cudaEventDestroy(e);
   delete S;
   m->tc = nullptr;
 }
@@ -809,11 +819,33 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   const bool use_mlp_tc = getenv("MURAL_NO_MLP_TC") == nullptr;
   const bool use_tail = m->tail != nullptr && getenv("MURAL_NO_TAIL") == nullptr;
   const int stride_rb4 = TILE - 2 * 4, stride_crb4 = TILE - 2 * 5;
-  auto stage = [&](int mode, int fm, StageArgs sa, int br, int stg, const char* role) -> int {
+  auto stage = [&](int mode, int fm, const StageArgs& sa, const char* role) -> int {
     if (mode == RB4) return fm == 2 ? launch_stage<RB4, 2>(sa, st, role) : (fm == 1 ? launch_stage<RB4, 1>(sa, st, role) : launch_stage<RB4, 0>(sa, st, role));
     return fm == 1 ? launch_stage<C_RB4, 1>(sa, st, role) : launch_stage<C_RB4, 0>(sa, st, role);
   };
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
+  // Dense path: the stage kernels stay in order on the caller's stream (each fills the GPU); the latency-bound passes around them
+  // go to side streams so that they overlap each other: the local branch beside the stem tables, the lattice transpose beside
+  // the special-row gather, the four pool passes of a chunk beside each other, the tail of chunk c beside the stem of chunk c+1.
+  static int env_side = -1;
+  if (env_side < 0) { const char* e = getenv("MURAL_TC_SIDE_STREAMS"); env_side = e ? atoi(e) : 1; }
+  // (the per-kernel profile of bench.py times every kernel alone: one stream there)
+  const bool multi = use_lat && use_tail && env_side != 0 && !g_prof;
+  static int pool_grid = -1;
+  if (pool_grid < 0) { const char* e = getenv("MURAL_POOL_GRID"); pool_grid = e ? atoi(e) : 6; }
+  if (multi && !S->side[0]) {
+    for (int i = 0; i < N_SIDE; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&S->side[i], cudaStreamNonBlocking));
+    for (int i = 0; i < N_SIDE_EV; ++i) CUDA_TRY(cudaEventCreateWithFlags(&S->ev[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s_lat = multi ? S->side[0] : st, s_loc = multi ? S->side[1] : st, s_ep = multi ? S->side[2] : st;
+  // `to` continues after everything queued on `from` so far (a wait captures the record that precedes it, so the ring is safe)
+  auto dep = [&](cudaStream_t from, cudaStream_t to) -> int {
+    if (from == to) return 0;
+    cudaEvent_t e = S->ev[S->ev_next++ % N_SIDE_EV];
+    CUDA_TRY(cudaEventRecord(e, from));
+    CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+  };
   int64_t floats = 0;
   int64_t ra[2][4], lat_ra[2] = {0, 0}, edge_ra[2] = {0, 0}, epool_ra[2] = {0, 0};
   int nlo[2] = {0, 0}, nhi[2] = {0, 0};
@@ -873,50 +905,85 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   CUDA_TRY(cudaMemsetAsync(err_flag, 0, 4, st));
   if (use_dense) CUDA_TRY(cudaMemsetAsync(dense_scratch, 0, 256, st));  // ChunkInfo + k_chunk_span scratch words
 
+  if (int rc = dep(st, s_loc)) return rc;  // the local / tail stream starts behind the caller's queue and the memsets above
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const int64_t ns = (n - s0 < chunk) ? (n - s0) : chunk;
     if (s0 % super == 0) {  // (chunk divides 2^20 or n <= 2^20, so chunks never straddle a super-chunk)
+      // s_loc runs in order behind the tails that read the previous super-chunk's logits, and beside the stem of this chunk
       const int64_t nsup = (n - s0 < super) ? (n - s0) : super;
       if (!d_cat)
-        if (int rc = snv_local_idx_launch(m, G, d_pos + s0, d_meta + s0, nsup, cat32, st)) return rc;
-      int rc = use_mlp_tc ? snv_local_launch_tc(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st) : -1;
-      if (rc < 0) rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, st);
+        if (int rc = snv_local_idx_launch(m, G, d_pos + s0, d_meta + s0, nsup, cat32, s_loc)) return rc;
+      int rc = use_mlp_tc ? snv_local_launch_tc(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, s_loc) : -1;
+      if (rc < 0) rc = snv_local_launch(m, d_cat ? nullptr : cat32, d_cat ? d_cat + s0 * m->n_cat : nullptr, nsup, llog, err_flag, s_loc);
       if (rc) return rc;
     }
     const float* llog_c = llog + (s0 % super) * NC;
     const int* dense_flag = nullptr;
     const ChunkInfo* info = nullptr;
-    if (use_dense)
+    if (use_dense) {
+      SideStream sd{s_lat, nullptr, nullptr};
+      if (multi) { sd.fork = S->ev[S->ev_next++ % N_SIDE_EV]; sd.join = S->ev[S->ev_next++ % N_SIDE_EV]; }
       if (int rc = snv_dense_stem_launch(m, G, d_pos + s0, d_meta + s0, ns, chunk, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                         dense_scratch, &dense_flag, st, use_lat ? lb : nullptr, &info))
+                                         dense_scratch, &dense_flag, st, use_lat ? lb : nullptr, &info, multi ? &sd : nullptr))
         return rc;
+    }
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
                                         nullptr, st, /*out_bf16=*/true, dense_flag))
       return rc;
-    for (int br = 1; br >= 0; --br) {
+    // per-site arguments of stage 1 (two ResBlocks + outer skip at length L1) and stage 2 (pool2 fused in the loader + conv2 + two
+    // ResBlocks + skip at length L2); on a dense chunk the per-site kernels exit on the device and the lattice / edge roles run
+    StageArgs a1[2], a2[2];
+    for (int br = 0; br < 2; ++br) {
       const BranchDev& B = m->br[br];
-      const char* sfx = br ? "_2" : "";
-      if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], true, ra[br][0], ns, B.L1, st)) return rc;
       StageArgs a{};
       a.lat_branch = -1;
-      // stage 1: two ResBlocks + outer skip at length L1 (per-site rows; skipped on the device when the chunk is dense)
       a.in = reinterpret_cast<const uint4*>(bufs[br][0]); a.out = bufs[br][1]; a.wblob = S->blob[br][0];
       a.in_rows_alloc = ra[br][0]; a.out_rows_alloc = ra[br][1];
       a.rows = rows_of(ns, B.L1); a.L = B.L1; a.Lin = B.L1; a.pk = 0; a.ps = 1; a.pp = 0;
       a.n_tiles = (int)cdiv(a.rows, stride_rb4);
       if (use_lat) { a.info = info; a.want = 0; }
-      if (int rc = stage(RB4, 0, a, br, 0, use_lat ? "/site" : "")) return rc;
-      if (use_lat) {
+      a1[br] = a;
+      a.in = reinterpret_cast<const uint4*>(bufs[br][1]); a.out = bufs[br][2]; a.wblob = S->blob[br][1];
+      a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
+      a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
+      a.n_tiles = (int)cdiv(a.rows, stride_crb4);
+      a2[br] = a;
+    }
+    // stage 3 (pool3 + conv3 + ReLU at length L3) as a stage kernel, for shapes the warp-level tail kernel does not take
+    auto stage3 = [&](int br) -> int {
+      if (use_tail) return 0;
+      const BranchDev& B = m->br[br];
+      StageArgs a = a2[br];
+      a.info = nullptr;
+      a.in = reinterpret_cast<const uint4*>(bufs[br][2]); a.out = bufs[br][3]; a.wblob = S->blob[br][2];
+      a.in_rows_alloc = ra[br][2]; a.out_rows_alloc = ra[br][3];
+      a.rows = rows_of(ns, B.L3); a.L = B.L3; a.Lin = B.L2; a.pk = B.pool[2][0]; a.ps = B.pool[2][1]; a.pp = B.pool[2][2];
+      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 1);
+      return launch_stage<SINGLE>(a, st);
+    };
+    if (use_lat) {
+      StageArgs l2[2];
+      EdgePool ep[2];
+      for (int br = 1; br >= 0; --br) {
+        const BranchDev& B = m->br[br];
+        if (int rc = stage(RB4, 0, a1[br], "/site")) return rc;
         // stage 1 on the lattice (geometry read from info on the device; grid sized for the largest lattice) ...
-        StageArgs l = a;
+        StageArgs l = a1[br];
         l.want = 1; l.lat_branch = br;
         l.in = reinterpret_cast<const uint4*>(lb[br].lat_in); l.out = lb[br].lat_out;
         l.in_rows_alloc = l.out_rows_alloc = lb[br].lat_ra;
         l.n_tiles = (int)cdiv(lb[br].lat_ra, stride_rb4);
-        if (int rc = stage(RB4, 1, l, br, 0, "/lattice")) return rc;
-        // ... and on the per-site edge pseudo-sites
-        StageArgs e = a;
+        if (int rc = stage(RB4, 1, l, "/lattice")) return rc;
+        // ... whose pool-2 maxima overwrite the (now dead) lattice input
+        if (int rc = dep(st, s_lat)) return rc;
+        LAUNCH(k_lattice_pool, 148 * pool_grid, 256, 0, s_lat, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
+               reinterpret_cast<uint4*>(lb[br].lat_in), lb[br].lat_ra);
+      }
+      for (int br = 1; br >= 0; --br) {
+        const BranchDev& B = m->br[br];
+        // stage 1 on the per-site edge pseudo-sites
+        StageArgs e = a1[br];
         e.want = 1;
         e.in = nullptr; e.out = lb[br].edge_out;
         e.in_rows_alloc = e.out_rows_alloc = lb[br].edge_ra;
@@ -929,20 +996,9 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         e.pos = d_pos + s0; e.meta = d_meta + s0;
         e.ps1 = B.pool[0][1]; e.pp1 = B.pool[0][2]; e.pk1 = B.pool[0][0];
         e.off0 = br ? 0 : m->L / 2 - 100; e.R = m->cfg.distal_radius; e.br = br;
-        if (int rc = stage(RB4, 2, e, br, 0, "/edge")) return rc;
-      }
-      if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
-      // stage 2: pool2 (fused in the loader) + conv2 + two ResBlocks + skip at length L2
-      a.in = reinterpret_cast<const uint4*>(bufs[br][1]); a.out = bufs[br][2]; a.wblob = S->blob[br][1];
-      a.in_rows_alloc = ra[br][1]; a.out_rows_alloc = ra[br][2];
-      a.rows = rows_of(ns, B.L2); a.L = B.L2; a.Lin = B.L1; a.pk = B.pool[1][0]; a.ps = B.pool[1][1]; a.pp = B.pool[1][2];
-      a.n_tiles = (int)cdiv(a.rows, stride_crb4);
-      if (int rc = stage(C_RB4, 0, a, br, 1, use_lat ? "/site" : "")) return rc;
-      if (use_lat) {
-        // pooled lattice rows overwrite the (now dead) lattice input
-        LAUNCH(k_lattice_pool, 148 * 4, 256, 0, st, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
-               reinterpret_cast<uint4*>(lb[br].lat_in), lb[br].lat_ra);
-        StageArgs l = a;
+        if (int rc = stage(RB4, 2, e, "/edge")) return rc;
+        // pool-2 maxima of the bins that touch edge rows (the first branch's pass runs beside the second branch's edge kernel tail)
+        StageArgs l = a2[br];
         l.want = 1;
         l.lat = reinterpret_cast<const uint4*>(lb[br].lat_out); l.lat_ra = lb[br].lat_ra;
         l.lat2 = reinterpret_cast<const uint4*>(lb[br].lat_in);
@@ -951,24 +1007,38 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         l.ps1 = B.pool[0][1]; l.pp1 = B.pool[0][2]; l.pk1 = B.pool[0][0];
         l.off0 = br ? 0 : m->L / 2 - 100; l.R = m->cfg.distal_radius; l.br = br;
         l.epool = reinterpret_cast<const uint4*>(epool[br]); l.epool_ra = epool_ra[br]; l.nlo = nlo[br]; l.nhi = nhi[br];
-        EdgePool ep{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
-                    br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
-        LAUNCH(k_edge_pool, 148 * 4, 256, 0, st, info, ep);
-        if (int rc = stage(C_RB4, 1, l, br, 1, "/lattice")) return rc;
+        l2[br] = l;
+        ep[br] = EdgePool{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
+                          br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
+        cudaStream_t se = br ? s_ep : st;
+        if (int rc = dep(st, se)) return rc;
+        LAUNCH(k_edge_pool, 148 * pool_grid, 256, 0, se, info, ep[br]);
       }
-      if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
-      if (use_tail) continue;  // stage 3 and the heads run in the warp-level tail kernel below
-      // stage 3: pool3 + conv3 + ReLU at length L3
-      a.info = nullptr;
-      a.in = reinterpret_cast<const uint4*>(bufs[br][2]); a.out = bufs[br][3]; a.wblob = S->blob[br][2];
-      a.in_rows_alloc = ra[br][2]; a.out_rows_alloc = ra[br][3];
-      a.rows = rows_of(ns, B.L3); a.L = B.L3; a.Lin = B.L2; a.pk = B.pool[2][0]; a.ps = B.pool[2][1]; a.pp = B.pool[2][2];
-      a.n_tiles = (int)cdiv(a.rows, TILE - 2 * 1);
-      if (int rc = launch_stage<SINGLE>(a, st)) return rc;
+      if (int rc = dep(s_lat, st)) return rc;
+      if (int rc = dep(s_ep, st)) return rc;
+      if (s0 > 0)
+        if (int rc = dep(s_loc, st)) return rc;  // the previous chunk's tail still reads the stage-2 rows
+      for (int br = 1; br >= 0; --br) {
+        if (int rc = stage(C_RB4, 0, a2[br], "/site")) return rc;
+        if (int rc = stage(C_RB4, 1, l2[br], "/lattice")) return rc;
+        if (int rc = stage3(br)) return rc;
+      }
+    } else {
+      for (int br = 1; br >= 0; --br) {
+        const BranchDev& B = m->br[br];
+        const char* sfx = br ? "_2" : "";
+        if (int rc = save_tap_planes(m, (std::string("pool1") + sfx).c_str(), bufs[br][0], true, ra[br][0], ns, B.L1, st)) return rc;
+        if (int rc = stage(RB4, 0, a1[br], "")) return rc;
+        if (int rc = save_tap_planes(m, (std::string("rb1") + sfx).c_str(), bufs[br][1], true, ra[br][1], ns, B.L1, st)) return rc;
+        if (int rc = stage(C_RB4, 0, a2[br], "")) return rc;
+        if (int rc = save_tap_planes(m, (std::string("rb2") + sfx).c_str(), bufs[br][2], true, ra[br][2], ns, B.L2, st)) return rc;
+        if (int rc = stage3(br)) return rc;
+      }
     }
+    if (int rc = dep(st, s_loc)) return rc;  // tail (and heads) behind the local branch, beside the next chunk's stem
     if (use_tail) {
       if (int rc = snv_tail_launch(m, bufs[0][2], ra[0][2], bufs[1][2], ra[1][2], llog_c, ns, d_logp + s0 * NC, m->debug ? tg0 : nullptr,
-                                   m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr, st))
+                                   m->debug ? tg1 : nullptr, m->debug ? tl0 : nullptr, m->debug ? tl1 : nullptr, s_loc))
         return rc;
     } else {
       HeadTc hb[2] = {{bufs[0][3], ra[0][3], m->br[0].Wfc, m->br[0].bfc, m->br[0].L3},
@@ -991,6 +1061,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
       if (int rc = flat("logit_local", llog_c, ns * NC)) return rc;
     }
   }
+  if (int rc = dep(s_loc, st)) return rc;
   CUDA_TRY(cudaGetLastError());
   if (d_cat) {
     int flag = 0;
