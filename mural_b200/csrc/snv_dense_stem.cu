@@ -16,7 +16,7 @@
 // Stage-1 lattice (same idea one level up).  An interior pooled bin j of a site is W_pk[g0 + j*ps] with g0 fixed by the
 // site, so the first ResBlock pair (4 convs at stride-ps1 spacing) of every row whose receptive field stays clear of the
 // window ends is a function of the genomic position alone: Y1[g] = RB(W[g-4ps], ..., W[g+4ps]).  We evaluate it ONCE
-// per genomic position and strand on 2*ps1 phase-major pseudo-sites (k_lattice_in feeds the ordinary stage kernel),
+// per genomic position and strand on 2*ps1 phase-major pseudo-sites (the stage kernel's lattice loader reads the full-bin table rows in place),
 // and per site only the LAT_EO rows at each window end, as one 18-row edge pseudo-site whose rows 1..16 are table rows
 // read in place by the stage kernel and whose rows 0 and 17 are written by k_stem_gather in edge mode.
 // The stage-2 loader (snv_tc.cu) max-pools across lattice rows and edge rows.  Every row goes through the same
@@ -227,38 +227,6 @@ __global__ void __launch_bounds__(256, MURAL_DT_MINB) k_dense_tables(GenomeView 
   }
 }
 
-// full-bin sliding maxima -> phase-major lattice rows (bf16 planes): pseudo-site u = strand*ps + phase, step mm
-// ('-' strand steps run against the genome so that the oriented conv taps line up with the '+' ones)
-struct LatIn {
-  uint4* out;
-  int64_t ra;
-  int ps;
-};
-template <int C>
-__global__ void __launch_bounds__(256) k_lattice_in(const ChunkInfo* __restrict__ info, LatIn l0, LatIn l1, int cap,
-                                                    const __nv_bfloat16* __restrict__ tables) {
-  if (!info->dense) return;
-  constexpr int PL = C / 8;
-#pragma unroll 1
-  for (int br = 0; br < 2; ++br) {
-    const LatIn& B = br ? l1 : l0;
-    const int M = info->M[br];
-    const int64_t total = int64_t(2) * B.ps * M * PL;
-    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
-      const int q = int(e % PL);
-      const int64_t um = e / PL;
-      const int mm = int(um % M), u = int(um / M);
-      const int strand = u >= B.ps, phase = u - strand * B.ps;
-      const int m = strand ? M - 1 - mm : mm;
-      const int x = m * B.ps + phase;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (x < info->n_pos && info->has[strand])
-        v = *reinterpret_cast<const uint4*>(tables + ((size_t(strand * 2 + br) * 3) * size_t(cap) + size_t(x)) * C + 8 * q);
-      B.out[int64_t(q) * B.ra + 1 + int64_t(u) * (M + 1) + mm] = v;
-    }
-  }
-}
-
 struct GatherBranch {
   void* out;           // bf16 planes [C/8][rows_alloc][8]
   int64_t rows_alloc;
@@ -395,8 +363,7 @@ bool snv_lattice_supported(const mural_snv_model* m) {
 // (int*, 1 = the dense path produced the stem output) so that the per-site kernel can skip itself.
 int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
-                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice, const ChunkInfo** d_info,
-                          const SideStream* side) {
+                          const int** d_flag, cudaStream_t st, const LatticeBufs* lattice, const ChunkInfo** d_info) {
   const int C = m->cfg.channels;
   MURAL_CHECK(C == 32, "dense stem is built for C == 32");
   const int cap = int(snv_dense_cap(chunk));
@@ -428,21 +395,8 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
     conf = true;
   }
   LAUNCH(k_dense_tables<32>, (unsigned)cdiv(cap, DT_POS), 256, smem, st, *G, info, db[0], db[1], cap, tables);
-  if (lattice) {
-    LatIn li[2];
-    for (int br = 0; br < 2; ++br) li[br] = LatIn{reinterpret_cast<uint4*>(lattice[br].lat_in), lattice[br].lat_ra, m->br[br].pool[0][1]};
-    cudaStream_t sl = st;
-    if (side) {
-      sl = side->s;
-      CUDA_TRY(cudaEventRecord(side->fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(sl, side->fork, 0));
-    }
-    LAUNCH(k_lattice_in<32>, 148 * 4, 256, 0, sl, info, li[0], li[1], cap, tables);
-    if (side) CUDA_TRY(cudaEventRecord(side->join, sl));
-  }
   MURAL_CHECK(ns * int64_t(m->br[1].L1 > LAT_EL ? m->br[1].L1 : LAT_EL) * 4 < (int64_t(1) << 31), "chunk too large for the stem gather's 32-bit indices");
   LAUNCH(k_stem_gather<32>, 148 * 8, 256, 0, st, *G, info, d_pos, d_meta, ns, m->cfg.distal_radius, gb[0], gb[1], cap, tables);
-  if (lattice && side) CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
   *d_flag = &info->dense;
   if (d_info) *d_info = info;
   CUDA_TRY(cudaGetLastError());

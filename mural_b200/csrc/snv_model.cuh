@@ -137,9 +137,6 @@ struct ChunkInfo {
 constexpr int LAT_EO = 5;   // stage-1 output rows per window end that depend on the site (4 convs + the clipped first/last bin)
 constexpr int LAT_EI = 9;   // stage-1 input rows per window end those outputs read
 constexpr int LAT_EL = 2 * LAT_EI;  // length of a site's edge pseudo-site: [rows 0..8 | rows L1-9..L1-1]
-struct SideStream {         // a second stream + two events: k_lattice_in runs beside k_stem_gather (both only read the tables)
-  cudaStream_t s; cudaEvent_t fork, join;
-};
 struct LatticeBufs {        // per branch; all bf16 planes [4][ra][8]
   void* lat_in; void* lat_out; int64_t lat_ra;
   void* edge_in; void* edge_out; int64_t edge_ra;
@@ -150,7 +147,7 @@ size_t snv_dense_bytes(const mural_snv_model* m, int64_t chunk);
 int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t ns,
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
                           const int** d_flag, cudaStream_t st, const LatticeBufs* lattice = nullptr,
-                          const ChunkInfo** d_info = nullptr, const SideStream* side = nullptr);
+                          const ChunkInfo** d_info = nullptr);
 int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                          int32_t* cat32, cudaStream_t st);
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,

@@ -284,6 +284,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_stage_tc(StageArgs a) {
           for (int q = 0; q < 4; ++q) x[q] = __ldg(row + q);
         }
       }
+    } else if (MODE == RB4 && LAT) {
+      // stage-1 lattice: pseudo-site u = strand*ps1 + phase walks the full-bin table of its strand in steps of ps1 ('-' strand
+      // against the genome, so that the oriented conv taps line up with the '+' ones); rows are read in place from the stem tables
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = make_uint4(0, 0, 0, 0);
+      if (live) {
+        const int strand = site >= a.ps1, phase = site - strand * a.ps1;
+        const int xx = (strand ? L_ - 1 - p : p) * a.ps1 + phase;
+        if (xx < a.info->n_pos && a.info->has[strand]) {
+          const uint4* row = a.tab[strand] + int64_t(xx) * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = __ldg(row + q);
+        }
+      }
     } else if (MODE == RB4) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) x[q] = live ? __ldg(a.in + q * a.in_rows_alloc + r) : make_uint4(0, 0, 0, 0);
@@ -628,7 +642,7 @@ struct TcState {
   uint8_t* d_w = nullptr;         // all stage blobs back to back
   const uint8_t* blob[2][3] = {};  // [branch][stage]
   // side streams of the dense path (snv_forward_tc): the passes that are not stage kernels are latency-bound and run beside each
-  // other: [0] lattice transpose / lattice pools, [1] local branch + tail, [2] second edge pool
+  // other: [0] lattice pools, [1] local branch + tail, [2] second edge pool
   cudaStream_t side[N_SIDE] = {};
   cudaEvent_t ev[N_SIDE_EV] = {};
   int ev_next = 0;
@@ -825,8 +839,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
   };
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
   // Dense path: the stage kernels stay in order on the caller's stream (each fills the GPU); the latency-bound passes around them
-  // go to side streams so that they overlap each other: the local branch beside the stem tables, the lattice transpose beside
-  // the special-row gather, the four pool passes of a chunk beside each other, the tail of chunk c beside the stem of chunk c+1.
+  // go to side streams so that they overlap each other: the local branch beside the stem tables, the four pool passes of a chunk beside each other, the tail of chunk c beside the stem of chunk c+1.
   static int env_side = -1;
   if (env_side < 0) { const char* e = getenv("MURAL_TC_SIDE_STREAMS"); env_side = e ? atoi(e) : 1; }
   // (the per-kernel profile of bench.py times every kernel alone: one stream there)
@@ -920,13 +933,10 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     const float* llog_c = llog + (s0 % super) * NC;
     const int* dense_flag = nullptr;
     const ChunkInfo* info = nullptr;
-    if (use_dense) {
-      SideStream sd{s_lat, nullptr, nullptr};
-      if (multi) { sd.fork = S->ev[S->ev_next++ % N_SIDE_EV]; sd.join = S->ev[S->ev_next++ % N_SIDE_EV]; }
+    if (use_dense)
       if (int rc = snv_dense_stem_launch(m, G, d_pos + s0, d_meta + s0, ns, chunk, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
-                                         dense_scratch, &dense_flag, st, use_lat ? lb : nullptr, &info, multi ? &sd : nullptr))
+                                         dense_scratch, &dense_flag, st, use_lat ? lb : nullptr, &info))
         return rc;
-    }
     if (int rc = snv_stem_launch_planes(m, G, d_pos ? d_pos + s0 : nullptr, d_meta ? d_meta + s0 : nullptr,
                                         d_sym ? d_sym + s0 * m->L : nullptr, ns, bufs[0][0], ra[0][0], bufs[1][0], ra[1][0],
                                         nullptr, st, /*out_bf16=*/true, dense_flag))
@@ -965,17 +975,20 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     if (use_lat) {
       StageArgs l2[2];
       EdgePool ep[2];
+      const uint4* tab0 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dense_scratch) + 256);
       for (int br = 1; br >= 0; --br) {
         const BranchDev& B = m->br[br];
         if (int rc = stage(RB4, 0, a1[br], "/site")) return rc;
         // stage 1 on the lattice (geometry read from info on the device; grid sized for the largest lattice) ...
         StageArgs l = a1[br];
         l.want = 1; l.lat_branch = br;
-        l.in = reinterpret_cast<const uint4*>(lb[br].lat_in); l.out = lb[br].lat_out;
+        l.in = nullptr; l.out = lb[br].lat_out;   // input rows: the full-bin stem tables, read in place by the loader
         l.in_rows_alloc = l.out_rows_alloc = lb[br].lat_ra;
         l.n_tiles = (int)cdiv(lb[br].lat_ra, stride_rb4);
+        for (int sd = 0; sd < 2; ++sd) l.tab[sd] = tab0 + int64_t((sd * 2 + br) * 3) * snv_dense_cap(chunk) * 4;
+        l.ps1 = B.pool[0][1];
         if (int rc = stage(RB4, 1, l, "/lattice")) return rc;
-        // ... whose pool-2 maxima overwrite the (now dead) lattice input
+        // ... whose pool-2 maxima go to the lattice-shaped part of the stem buffer
         if (int rc = dep(st, s_lat)) return rc;
         LAUNCH(k_lattice_pool, 148 * pool_grid, 256, 0, s_lat, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
                reinterpret_cast<uint4*>(lb[br].lat_in), lb[br].lat_ra);
@@ -989,7 +1002,6 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         e.in_rows_alloc = e.out_rows_alloc = lb[br].edge_ra;
         e.rows = rows_of(ns, LAT_EL); e.L = e.Lin = LAT_EL;
         e.n_tiles = (int)cdiv(e.rows, stride_rb4);
-        const uint4* tab0 = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(dense_scratch) + 256);
         for (int sd = 0; sd < 2; ++sd) e.tab[sd] = tab0 + int64_t((sd * 2 + br) * 3) * snv_dense_cap(chunk) * 4;
         e.special = reinterpret_cast<const uint4*>(lb[br].edge_in); e.special_ra = lb[br].edge_ra;
         e.L1real = B.L1;

@@ -1,6 +1,6 @@
 #!/bin/bash
-# A/B of the side-stream schedule of the dense predict path (one box, back to back)
-for v in "MURAL_TC_SIDE_STREAMS=0 MURAL_POOL_GRID=4" "MURAL_TC_SIDE_STREAMS=1" "MURAL_TC_SIDE_STREAMS=0 MURAL_POOL_GRID=4" "MURAL_TC_SIDE_STREAMS=1"; do
+# A/B variants of the dense predict path via environment switches (one box, back to back)
+for v in "X=1" "MURAL_TC_CHUNK=262144" "X=1" "MURAL_TC_CHUNK=262144"; do
   echo "== $v"
-  env $v bash scratch/bench_short.sh "$@" | head -1
+  env $v bash scratch/bench_short.sh "$@" | head -${HEADN:-1}
 done
