@@ -386,7 +386,7 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
     }
   }
   int* scr = reinterpret_cast<int*>(reinterpret_cast<char*>(d_scratch) + 128);  // zeroed once per forward call by the caller
-  LAUNCH(k_chunk_span, 32, 256, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
+  LAUNCH(k_chunk_span, 296, 256, 0, st, d_pos, d_meta, ns, m->cfg.distal_radius, cap, m->br[0].pool[0][1], m->br[1].pool[0][1],
          128 - 2 * 4, info, scr);
   const size_t smem = sizeof(float) * (2 * 3 * 16 * C + 2 * C);
   static bool conf = false;
