@@ -637,12 +637,12 @@ __global__ void __launch_bounds__(256) k_head_tc(HeadTc b0, HeadTc b1, const flo
     }
 }
 
-constexpr int N_SIDE = 3, N_SIDE_EV = 16;
+constexpr int N_SIDE = 1, N_SIDE_EV = 8;
 struct TcState {
   uint8_t* d_w = nullptr;         // all stage blobs back to back
   const uint8_t* blob[2][3] = {};  // [branch][stage]
-  // side streams of the dense path (snv_forward_tc): the passes that are not stage kernels are latency-bound and run beside each
-  // other: [0] lattice pools, [1] local branch + tail, [2] second edge pool
+  // side stream of the dense path (snv_forward_tc): the local branch runs beside the stem tables of the first chunk, the tail of
+  // chunk c beside the stem of chunk c+1
   cudaStream_t side[N_SIDE] = {};
   cudaEvent_t ev[N_SIDE_EV] = {};
   int ev_next = 0;
@@ -838,8 +838,11 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     return fm == 1 ? launch_stage<C_RB4, 1>(sa, st, role) : launch_stage<C_RB4, 0>(sa, st, role);
   };
   const bool use_lat = use_dense && !m->debug && snv_lattice_supported(m) && getenv("MURAL_NO_LATTICE") == nullptr;
-  // Dense path: the stage kernels stay in order on the caller's stream (each fills the GPU); the latency-bound passes around them
-  // go to side streams so that they overlap each other: the local branch beside the stem tables, the four pool passes of a chunk beside each other, the tail of chunk c beside the stem of chunk c+1.
+  // Dense path: everything up to stage 2 stays in order on the caller's stream; the local branch and the tail (latency-bound, and
+  // not on the path to the next chunk's stage kernels) go to a side stream: the local branch runs beside the stem tables, the tail
+  // of chunk c beside the stem of chunk c+1.  Measured and not adopted (profiles/r02_side_stream_experiments.txt): the pool passes
+  // on side streams next to the stage kernels - a persistent stage CTA that starts late behind a pool CTA holds its whole static
+  // share of tiles back.
   static int env_side = -1;
   if (env_side < 0) { const char* e = getenv("MURAL_TC_SIDE_STREAMS"); env_side = e ? atoi(e) : 1; }
   // (the per-kernel profile of bench.py times every kernel alone: one stream there)
@@ -850,7 +853,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
     for (int i = 0; i < N_SIDE; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&S->side[i], cudaStreamNonBlocking));
     for (int i = 0; i < N_SIDE_EV; ++i) CUDA_TRY(cudaEventCreateWithFlags(&S->ev[i], cudaEventDisableTiming));
   }
-  cudaStream_t s_lat = multi ? S->side[0] : st, s_loc = multi ? S->side[1] : st, s_ep = multi ? S->side[2] : st;
+  cudaStream_t s_loc = multi ? S->side[0] : st;
   // `to` continues after everything queued on `from` so far (a wait captures the record that precedes it, so the ring is safe)
   auto dep = [&](cudaStream_t from, cudaStream_t to) -> int {
     if (from == to) return 0;
@@ -989,8 +992,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         l.ps1 = B.pool[0][1];
         if (int rc = stage(RB4, 1, l, "/lattice")) return rc;
         // ... whose pool-2 maxima go to the lattice-shaped part of the stem buffer
-        if (int rc = dep(st, s_lat)) return rc;
-        LAUNCH(k_lattice_pool, 148 * pool_grid, 256, 0, s_lat, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
+        LAUNCH(k_lattice_pool, 148 * pool_grid, 256, 0, st, info, br, B.pool[1][0], reinterpret_cast<const uint4*>(lb[br].lat_out),
                reinterpret_cast<uint4*>(lb[br].lat_in), lb[br].lat_ra);
       }
       for (int br = 1; br >= 0; --br) {
@@ -1009,7 +1011,7 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         e.ps1 = B.pool[0][1]; e.pp1 = B.pool[0][2]; e.pk1 = B.pool[0][0];
         e.off0 = br ? 0 : m->L / 2 - 100; e.R = m->cfg.distal_radius; e.br = br;
         if (int rc = stage(RB4, 2, e, "/edge")) return rc;
-        // pool-2 maxima of the bins that touch edge rows (the first branch's pass runs beside the second branch's edge kernel tail)
+        // pool-2 maxima of the bins that touch edge rows
         StageArgs l = a2[br];
         l.want = 1;
         l.lat = reinterpret_cast<const uint4*>(lb[br].lat_out); l.lat_ra = lb[br].lat_ra;
@@ -1022,12 +1024,8 @@ int snv_forward_tc(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos
         l2[br] = l;
         ep[br] = EdgePool{l.lat, l.lat_ra, l.edge, l.edge_ra, reinterpret_cast<uint4*>(epool[br]), epool_ra[br], l.pos, l.meta, ns,
                           br, B.L1, B.L2, B.pool[1][0], B.pool[1][1], B.pool[1][2], nlo[br], nhi[br], l.ps1, l.pp1, l.pk1, l.off0, l.R};
-        cudaStream_t se = br ? s_ep : st;
-        if (int rc = dep(st, se)) return rc;
-        LAUNCH(k_edge_pool, 148 * pool_grid, 256, 0, se, info, ep[br]);
+        LAUNCH(k_edge_pool, 148 * pool_grid, 256, 0, st, info, ep[br]);
       }
-      if (int rc = dep(s_lat, st)) return rc;
-      if (int rc = dep(s_ep, st)) return rc;
       if (s0 > 0)
         if (int rc = dep(s_loc, st)) return rc;  // the previous chunk's tail still reads the stage-2 rows
       for (int br = 1; br >= 0; --br) {
