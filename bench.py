@@ -1015,7 +1015,7 @@ def kernel_roofline(L, step, W, K, S, mode, cfg, barrier, pos=None):
     buf = C.create_string_buffer(1 << 16)
     L.mural_profile_end(buf, len(buf))
     prof = json.loads(buf.value.decode() or "{}")
-    conv = {k: v for k, v in prof.items() if ("stage_tc" in k if mode != "fp32" else "conv" in k)}
+    conv = {k: v for k, v in prof.items() if ("stage_tc" in k if mode != "fp32" else ("conv" in k or "site_chain" in k))}
     if not conv:
         return None
     ms = sum(v["ms"] for v in conv.values()); n = sum(v["count"] for v in conv.values())

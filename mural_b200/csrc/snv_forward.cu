@@ -928,6 +928,11 @@ int snv_forward_fp32(mural_snv_model* m, const GenomeView* G, const int32_t* d_p
       float *Q = buf[1], *Rb = buf[2], *U = buf[3];
       const char* sfx = br ? "_2" : "";
       if (int rc = save_tap(m, (std::string("pool1") + sfx).c_str(), P, ns * B.L1 * C, st)) return rc;
+      if (!m->debug) {   // the whole branch in one kernel, activations in shared memory (the parity taps need the per-layer path)
+        const int rc = snv_site_chain_launch(m, br, P, br ? hlarge : hmid, ns, st);
+        if (rc > 0) return rc;
+        if (rc == 0) continue;
+      }
       // ---- stage 1 at length L1: two ResBlocks + outer skip (model_snv.py:477-479 / 499-501)
       if (int rc = conv_any(C, P, Q, nullptr, nullptr, ns, B.L1, B.rb1[0], 0, st)) return rc;
       if (int rc = conv_any(C, Q, Rb, P, nullptr, ns, B.L1, B.rb1[1], 0, st)) return rc;   // y1 = x0 + f(x0)

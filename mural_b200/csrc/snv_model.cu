@@ -111,6 +111,7 @@ extern "C" int mural_snv_model_create(const mural_snv_config_t* cfg, int device,
 extern "C" void mural_snv_model_destroy(mural_snv_model_t* m) {
   if (!m) return;
   cudaFree(m->d_prep);
+  cudaFree(m->d_chain);
   cudaFree(m->d_ws);
   cudaFree(m->d_io);
   cudaFree(m->d_auto);
@@ -339,6 +340,7 @@ extern "C" int mural_snv_model_load(mural_snv_model_t* m, const float* h_blob, i
     B.conv3 = mk(bo[br].conv3);
   }
   if (int rc = snv_tc_prepare(m, h_blob)) return rc;
+  m->chain_ready = false;
   m->loaded = true;
   return 0;
 }

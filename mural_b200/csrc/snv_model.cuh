@@ -74,6 +74,8 @@ struct mural_snv_model {
   void* tc = nullptr;
   void* mlp_tc = nullptr;
   void* tail = nullptr;  // warp-level tail kernel (snv_tail.cu)
+  uint32_t* d_chain = nullptr;  // split (hi | lo) packed conv weights of both branches for the fused per-site chain (snv_site_chain.cu)
+  bool chain_ready = false;     // cleared whenever the weights are (re)loaded
   // forward workspace (grown on demand)
   void* d_ws = nullptr;
   int64_t ws_bytes = 0;
@@ -148,6 +150,8 @@ int snv_dense_stem_launch(mural_snv_model* m, const GenomeView* G, const int32_t
                           int64_t chunk, void* mid_out, int64_t mid_ra, void* large_out, int64_t large_ra, void* d_scratch,
                           const int** d_flag, cudaStream_t st, const LatticeBufs* lattice = nullptr,
                           const ChunkInfo** d_info = nullptr);
+// fused per-site chain of one CNN branch at fp32-equivalent precision (snv_site_chain.cu); -1: shape not served
+int snv_site_chain_launch(mural_snv_model* m, int br, const float* x0, float* h, int64_t ns, cudaStream_t st);
 int snv_local_idx_launch(mural_snv_model* m, const GenomeView* G, const int32_t* d_pos, const int32_t* d_meta, int64_t n,
                          int32_t* cat32, cudaStream_t st);
 int snv_local_launch(mural_snv_model* m, const int32_t* cat32, const int64_t* cat64, int64_t ns, float* logits, int* err_flag,

@@ -53,6 +53,33 @@ def test_fp32_forward_matches_reference(kat, cuda_genome, tag):
     assert np.abs(lp - z["ref_logp"]).max() < 5e-5                          # fp32 path is far tighter
 
 
+@pytest.mark.parametrize("tag", ["hs_AT", "mm_CpG", "ex_ckpt6"])
+def test_site_chain_equals_per_layer_path(kat, cuda_genome, tag):
+    """The fused per-site chain of a CNN branch (snv_site_chain.cu: all 10 convs + 2 pools of a branch in shared memory) runs the
+    arithmetic of the per-layer fp32-equivalent kernels in the same order: log-probs equal bit for bit (MURAL_NO_SITE_CHAIN=1
+    keeps the per-layer path), for one chunk and for sites spread over several chunks."""
+    import os
+    z, cfg, state = load_snv_golden(tag)
+    m = build_model(cfg, state, int(z["n_cat"]))
+    sb = site_batch(z, cuda_genome)
+    res = {}
+    try:
+        for key, env, chunk in (("chain", None, 0), ("layers", "1", 0), ("chain_chunks", None, 50)):
+            if env is None:
+                os.environ.pop("MURAL_NO_SITE_CHAIN", None)
+            else:
+                os.environ["MURAL_NO_SITE_CHAIN"] = env
+            m.set_debug(False, chunk=chunk)
+            with torch.no_grad():
+                res[key] = m.forward(None, sb).clone()
+    finally:
+        os.environ.pop("MURAL_NO_SITE_CHAIN", None)
+        m.set_debug(False, chunk=0)
+    assert torch.isfinite(res["chain"]).all()
+    assert torch.equal(res["chain"], res["layers"]), float((res["chain"] - res["layers"]).abs().max())
+    assert torch.equal(res["chain"], res["chain_chunks"])
+
+
 def test_fp32_intermediate_taps(kat, cuda_genome):
     z, cfg, state = load_snv_golden("hs_AT")
     m = build_model(cfg, state, int(z["n_cat"]))
