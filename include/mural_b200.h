@@ -303,6 +303,11 @@ int32_t mural_bed_n_chrom(const mural_bed_t* b);
 const char* mural_bed_chrom_name(const mural_bed_t* b, int32_t i);
 int mural_bed_columns(const mural_bed_t* b, int32_t* chrom, int64_t* start, int64_t* end, int8_t* strand, int64_t* label);
 void mural_bed_destroy(mural_bed_t* b);
+/* Emission order of bed_reader (MuRaL/data/preprocessing.py:39-106): windows of `segment_center` bp anchored at the first site of
+ * the first chromosome block (at 1 for later blocks), '+' batch before '-' batch inside each window, file order inside a batch.
+ * perm [n]: file index of the k-th emitted site; batch_sizes [capacity n]: sizes of the non-empty batches, *n_batches of them. */
+int mural_segment_order(const int32_t* chrom, const int64_t* start, const int8_t* strand, int64_t n, int64_t segment_center,
+                        int64_t* perm, int64_t* batch_sizes, int64_t* n_batches);
 int mural_fasta_read(const char* path, mural_fasta_t** out);
 int32_t mural_fasta_n(const mural_fasta_t* f);
 const char* mural_fasta_name(const mural_fasta_t* f, int32_t i);

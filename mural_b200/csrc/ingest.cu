@@ -268,6 +268,53 @@ extern "C" int mural_bed_columns(const mural_bed_t* b, int32_t* chrom, int64_t* 
 }
 extern "C" void mural_bed_destroy(mural_bed_t* b) { delete b; }
 
+// Emission order of bed_reader (MuRaL/data/preprocessing.py:39-106).  The reader walks the BED in file order with a window
+// [s, s + segment_center) anchored at the first site of the first chromosome block (at 1 for every later block; a chromosome
+// that re-appears opens a new block), moves the window forward until it holds the site (it never moves back), and emits for
+// every window first its '+' sites, then its '-' sites, each in file order.  Sites that share (block, window) are therefore
+// consecutive in the file and the emission order is a stable partition of every such run — one pass, no sort.
+// perm[k] = file index of the k-th emitted site; batch_sizes (capacity n) receives the sizes of the non-empty batches.
+extern "C" int mural_segment_order(const int32_t* chrom, const int64_t* start, const int8_t* strand, int64_t n, int64_t segment_center,
+                                   int64_t* perm, int64_t* batch_sizes, int64_t* n_batches) {
+  MURAL_CHECK(n_batches != nullptr && (n == 0 || (chrom && start && strand && perm && batch_sizes)), "NULL argument");
+  MURAL_CHECK(segment_center > 0, "segment_center must be positive");
+  *n_batches = 0;
+  if (n == 0) return 0;
+  int64_t nb = 0, out = 0, run_start = 0;
+  int64_t anchor = start[0], cur_win = -1;
+  auto flush = [&](int64_t a, int64_t b) {   // file rows [a, b) share a window
+    const int64_t o0 = out;
+    for (int64_t i = a; i < b; ++i)
+      if (strand[i] == 0) perm[out++] = i;
+    const int64_t n_plus = out - o0;
+    for (int64_t i = a; i < b; ++i)
+      if (strand[i] != 0) perm[out++] = i;
+    if (n_plus) batch_sizes[nb++] = n_plus;
+    if (out - o0 - n_plus) batch_sizes[nb++] = out - o0 - n_plus;
+  };
+  for (int64_t i = 0; i < n; ++i) {
+    const bool new_block = i > 0 && chrom[i] != chrom[i - 1];
+    if (new_block) anchor = 1;
+    const int64_t a = start[i] - anchor + segment_center - 1;
+    int64_t q = a / segment_center;                    // floor division (a may be negative: a site in front of the anchor)
+    if (a % segment_center != 0 && a < 0) --q;
+    int64_t win = q - 1;                               // first window whose end is >= start
+    if (win < 0) win = 0;
+    if (new_block || i == 0) {
+      if (i > 0) flush(run_start, i);
+      run_start = i;
+      cur_win = win;
+    } else if (win > cur_win) {                        // the window only moves forward inside a block
+      flush(run_start, i);
+      run_start = i;
+      cur_win = win;
+    }
+  }
+  flush(run_start, n);
+  *n_batches = nb;
+  return 0;
+}
+
 // FASTA -> records in file order; sequence lines are stripped of surrounding whitespace and concatenated; a repeated
 // record id is an error (SeqIO.to_dict raises ValueError("Duplicate key ...")).
 extern "C" int mural_fasta_read(const char* path, mural_fasta_t** out) {

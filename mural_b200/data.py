@@ -53,7 +53,23 @@ class SiteTable:
 def segment_order(chrom, start, strand, segment_center):
     """Emission order of bed_reader (preprocessing.py:39-106): sites are grouped into windows of
     `segment_center` bp (anchored at the first site of the first chromosome, at 1 for later
-    chromosomes), '+' batch before '-' batch inside each window.  Returns (perm, batch_sizes)."""
+    chromosomes), '+' batch before '-' batch inside each window.  Returns (perm, batch_sizes).
+    One pass in the C library (mural_segment_order: a stable partition of every run of sites that share a window)."""
+    import ctypes as C
+    from . import _lib
+    chrom = np.ascontiguousarray(chrom, dtype=np.int32); start = np.ascontiguousarray(start, dtype=np.int64)
+    strand = np.ascontiguousarray(np.asarray(strand) != 0, dtype=np.int8)
+    n = len(start)
+    if n == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    perm, sizes, nb = np.empty(n, np.int64), np.empty(n, np.int64), C.c_int64(0)
+    _lib.check(_lib.lib().mural_segment_order(_lib.ptr(chrom), _lib.ptr(start), _lib.ptr(strand), n, int(segment_center),
+                                              _lib.ptr(perm), _lib.ptr(sizes), C.byref(nb)))
+    return perm, sizes[:nb.value].copy()
+
+
+def segment_order_np(chrom, start, strand, segment_center):
+    """The same order as array operations (a stable sort by (block, window, strand)); kept as the cross-check of the C pass."""
     chrom = np.asarray(chrom); start = np.asarray(start, dtype=np.int64); strand = np.asarray(strand, dtype=np.int64)
     n = len(start)
     if n == 0:

@@ -28,6 +28,24 @@ def test_segment_order_matches_oracle_state_machine(kat):
     assert len(perm) == 0 and len(sizes) == 0
 
 
+def test_segment_order_c_pass_equals_array_form():
+    """mural_segment_order (one pass, stable partition per window run) == the stable sort by (block, window, strand)."""
+    from mural_b200.data import segment_order, segment_order_np
+    rng = np.random.default_rng(11)
+    for trial in range(400):
+        n = int(rng.integers(0, 400)); nchr = int(rng.integers(1, 5))
+        ch = np.sort(rng.integers(0, nchr, n)) if trial % 3 else rng.integers(0, nchr, n)      # re-appearing chromosomes too
+        st = rng.integers(0, 8000, n)
+        if trial % 4:
+            st = np.sort(st)
+        sd = rng.integers(0, 2, n)
+        c = int(rng.integers(1, 1200))
+        a, b = segment_order(ch, st, sd, c), segment_order_np(ch, st, sd, c)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (trial, n, c)
+    with pytest.raises(RuntimeError):
+        segment_order([0], [5], [0], 0)
+
+
 def test_bed_and_fasta_ingest(tmp_path):
     from mural_b200.data import SiteTable
     from mural_b200.genome import read_fasta
