@@ -645,7 +645,7 @@ struct TcState {
   // chunk c beside the stem of chunk c+1
   cudaStream_t side[N_SIDE] = {};
   cudaEvent_t ev[N_SIDE_EV] = {};
-  int ev_next = 0;
+  unsigned ev_next = 0;   // ring position (unsigned: wraps cleanly)
 };
 
 static inline int64_t rows_of(int64_t ns, int L) { return ns * (L + 1) + 1; }
