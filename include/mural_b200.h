@@ -308,6 +308,13 @@ void mural_bed_destroy(mural_bed_t* b);
  * perm [n]: file index of the k-th emitted site; batch_sizes [capacity n]: sizes of the non-empty batches, *n_batches of them. */
 int mural_segment_order(const int32_t* chrom, const int64_t* start, const int8_t* strand, int64_t n, int64_t segment_center,
                         int64_t* perm, int64_t* batch_sizes, int64_t* n_batches);
+/* Site records in emission order from the BED columns in file order (what CombinedDatasetNP keeps per sample,
+ * MuRaL/data/preprocessing.py:850-954, reduced to 8 bytes per site): pos = start[perm], strand, label,
+ * chrom = chrom_map[chrom[perm]] (genome index of the BED's i-th chromosome) and meta = MURAL_META(strand, label, chrom).
+ * A label outside [0, 127] is an error. */
+int mural_pack_sites(const int64_t* perm, int64_t n, const int32_t* chrom, const int64_t* start, const int8_t* strand,
+                     const int64_t* label, const int64_t* chrom_map, int32_t n_chrom, int32_t* pos_out, int8_t* strand_out,
+                     int64_t* label_out, int64_t* chrom_out, int32_t* meta_out);
 int mural_fasta_read(const char* path, mural_fasta_t** out);
 int32_t mural_fasta_n(const mural_fasta_t* f);
 const char* mural_fasta_name(const mural_fasta_t* f, int32_t i);

@@ -105,6 +105,7 @@ PROTOTYPES = {
     "mural_bed_columns": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mural_bed_destroy": (None, [_vp]),
     "mural_segment_order": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "mural_pack_sites": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mural_fasta_read": (C.c_int, [C.c_char_p, _vp]),
     "mural_fasta_n": (_i32, [_vp]),
     "mural_fasta_name": (C.c_char_p, [_vp, _i32]),

@@ -2,6 +2,7 @@
 // (MuRaL/data/preprocessing.py:39-106 reads .chrom/.start/.stop/.score/.strand per record through pybedtools) and
 // `SeqIO.to_dict(SeqIO.parse(open(ref_genome), 'fasta'))` (preprocessing.py:836).  Plain or gzip files (zlib).
 // At genome-wide scale (5e7 sites, 3e9 bases) the Python readers take minutes while the network takes a second.
+#include <limits.h>
 #include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
@@ -267,6 +268,32 @@ extern "C" int mural_bed_columns(const mural_bed_t* b, int32_t* chrom, int64_t* 
   return 0;
 }
 extern "C" void mural_bed_destroy(mural_bed_t* b) { delete b; }
+
+// Site records in emission order from the BED columns in file order (the gathers + pack_meta of PackedSiteDataset in one pass):
+// pos = start[perm] (int32), strand, label, chrom = chrom_map[chrom[perm]] (genome index of the BED's chromosome), and
+// meta = strand | label << 1 | chrom << 8 (MURAL_META).  Labels outside [0, 127] or starts beyond int32 are an error.
+extern "C" int mural_pack_sites(const int64_t* perm, int64_t n, const int32_t* chrom, const int64_t* start, const int8_t* strand,
+                                const int64_t* label, const int64_t* chrom_map, int32_t n_chrom, int32_t* pos_out, int8_t* strand_out,
+                                int64_t* label_out, int64_t* chrom_out, int32_t* meta_out) {
+  MURAL_CHECK(n == 0 || (perm && chrom && start && strand && label && chrom_map && pos_out && strand_out && label_out && chrom_out && meta_out),
+              "NULL argument");
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t i = perm[k];
+    const int64_t lb = label[i], st = start[i];
+    const int32_t c = chrom[i];
+    if (lb < 0 || lb > 0x7f) MURAL_FAIL("BED score column (label) must be in [0, 127]; got " + std::to_string(lb));
+    if (st < INT32_MIN || st > INT32_MAX) MURAL_FAIL("site position does not fit 32 bits: " + std::to_string(st));
+    if (c < 0 || c >= n_chrom) MURAL_FAIL("chromosome index out of range");
+    const int64_t gc = chrom_map[c];
+    const int8_t sd = strand[i];
+    pos_out[k] = (int32_t)st;
+    strand_out[k] = sd;
+    label_out[k] = lb;
+    chrom_out[k] = gc;
+    meta_out[k] = (int32_t)((gc << 8) | ((lb & 0x7f) << 1) | (sd & 1));
+  }
+  return 0;
+}
 
 // Emission order of bed_reader (MuRaL/data/preprocessing.py:39-106).  The reader walks the BED in file order with a window
 // [s, s + segment_center) anchored at the first site of the first chromosome block (at 1 for every later block; a chromosome

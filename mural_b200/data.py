@@ -21,11 +21,11 @@ class SiteTable:
 
     def __init__(self, chrom_names, chrom, start, end, strand, label):
         self.chrom_names = list(chrom_names)           # index -> name, order of first appearance
-        self.chrom = np.asarray(chrom, dtype=np.int32)
-        self.start = np.asarray(start, dtype=np.int64)
-        self.end = np.asarray(end, dtype=np.int64)
-        self.strand = np.asarray(strand, dtype=np.int8)   # 0 '+', 1 anything else (bed_reader :97-101)
-        self.label = np.asarray(label, dtype=np.int64)
+        self.chrom = np.ascontiguousarray(chrom, dtype=np.int32)      # (contiguous: the C library reads the columns in place)
+        self.start = np.ascontiguousarray(start, dtype=np.int64)
+        self.end = np.ascontiguousarray(end, dtype=np.int64)
+        self.strand = np.ascontiguousarray(strand, dtype=np.int8)   # 0 '+', 1 anything else (bed_reader :97-101)
+        self.label = np.ascontiguousarray(label, dtype=np.int64)
 
     def __len__(self):
         return len(self.start)
@@ -134,13 +134,16 @@ class PackedSiteDataset:
                 raise KeyError(nme)                                   # seq_records[chrom] (preprocessing.py:458)
         gidx = np.array([genome.chrom_index[nme] for nme in sites.chrom_names], dtype=np.int64)
         self.perm, self.batch_sizes = segment_order(sites.chrom, sites.start, sites.strand, segment_center)
-        self.pos = sites.start[self.perm].astype(np.int32)
-        self.strand = sites.strand[self.perm].astype(np.int8)
-        self.label = sites.label[self.perm]
-        if len(self.label) and (self.label.min() < 0 or self.label.max() > 0x7f):
-            raise ValueError("BED score column (label) must be in [0, 127]; got [%d, %d]" % (self.label.min(), self.label.max()))
-        self.chrom = gidx[sites.chrom[self.perm]]
-        self.meta = pack_meta(self.strand, self.label, self.chrom)
+        if len(sites.label) and (sites.label.min() < 0 or sites.label.max() > 0x7f):
+            raise ValueError("BED score column (label) must be in [0, 127]; got [%d, %d]" % (sites.label.min(), sites.label.max()))
+        # site records in emission order: the gathers by perm and pack_meta in one pass of the C library
+        n = len(self.perm)
+        self.pos, self.strand = np.empty(n, np.int32), np.empty(n, np.int8)
+        self.label, self.chrom, self.meta = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.int32)
+        from . import _lib
+        _lib.check(_lib.lib().mural_pack_sites(_lib.ptr(self.perm), n, _lib.ptr(sites.chrom), _lib.ptr(sites.start), _lib.ptr(sites.strand),
+                                               _lib.ptr(sites.label), _lib.ptr(gidx), len(gidx), _lib.ptr(self.pos), _lib.ptr(self.strand),
+                                               _lib.ptr(self.label), _lib.ptr(self.chrom), _lib.ptr(self.meta)))
         self.batch_offsets = np.r_[0, np.cumsum(self.batch_sizes)]
         self.n = len(self.batch_sizes)
         self.distal_info = True

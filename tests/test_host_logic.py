@@ -46,6 +46,31 @@ def test_segment_order_c_pass_equals_array_form():
         segment_order([0], [5], [0], 0)
 
 
+def test_site_records_c_pass_equals_array_form():
+    """mural_pack_sites (gathers by the emission order + MURAL_META in one pass) == the numpy expressions it replaced."""
+    from mural_b200.data import PackedSiteDataset, SiteTable, pack_meta
+
+    class G:
+        chrom_index = {"chrB": 2, "chrA": 0, "chrC": 1}
+    rng = np.random.default_rng(3)
+    gidx = np.array([2, 0, 1])
+    for trial in range(60):
+        n = int(rng.integers(0, 300))
+        chrom = np.sort(rng.integers(0, 3, n)); start = rng.integers(0, 50000, n)
+        strand = rng.integers(0, 2, n); label = rng.integers(0, 128, n)
+        st = SiteTable(["chrB", "chrA", "chrC"], chrom[::1], start, start + 1, strand, label)
+        ds = PackedSiteDataset(st, G(), int(rng.integers(1, 3000)), 10, 3, 1000)
+        p = ds.perm
+        assert ds.pos.dtype == np.int32 and np.array_equal(ds.pos, start[p])
+        assert ds.strand.dtype == np.int8 and np.array_equal(ds.strand, strand[p])
+        assert ds.label.dtype == np.int64 and np.array_equal(ds.label, label[p])
+        assert np.array_equal(ds.chrom, gidx[chrom[p]])
+        assert ds.meta.dtype == np.int32 and np.array_equal(ds.meta, pack_meta(ds.strand, ds.label, ds.chrom))
+    bad = SiteTable(["chrA"], [0], [5], [6], [0], [200])
+    with pytest.raises(ValueError):
+        PackedSiteDataset(bad, G(), 100, 10, 3, 1000)
+
+
 def test_bed_and_fasta_ingest(tmp_path):
     from mural_b200.data import SiteTable
     from mural_b200.genome import read_fasta
